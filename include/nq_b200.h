@@ -1,0 +1,206 @@
+/* nq_b200.h -- C ABI of libnq_b200.so: B200 (sm_100a) kernels for numpy-quant's
+ * quantized-inference hot path.
+ *
+ * The reference (tebartsch/numpy-quant) is pure Python/NumPy and has NO FFI of
+ * its own; each entry point below replaces one NumPy routine of the reference
+ * (cited as file:line relative to the reference repository) and is what a
+ * ctypes binding in numpy_quant/numpy_quantization.py / tensor.py / model.py
+ * would call.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - sizes and strides are in ELEMENTS of the pointed-to type unless stated;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *     all work is enqueued asynchronously on it, no hidden synchronisation;
+ *   - return value 0 = success, non-zero = failure; nq_last_error() gives the
+ *     message for the calling thread.  Nothing here aborts the process.
+ *   - zero-points: `has_zp` = 0 means symmetric (the reference's `None`).
+ *   - integer results are bit-exact w.r.t. the reference under NumPy >= 2
+ *     promotion rules (SURVEY.md §8 "Numeric contract").
+ */
+#ifndef NQ_B200_H
+#define NQ_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NQ_OK 0
+#define NQ_ERR_INVALID 1
+#define NQ_ERR_CUDA 2
+#define NQ_ERR_UNSUPPORTED 3
+
+int nq_version(void);
+const char* nq_last_error(void);
+/* Fills props_host[0..3] = {SM count, cc major, cc minor, max opt-in smem bytes}. */
+int nq_device_info(int* props_host);
+
+/* ---- K1: quantize  (numpy_quantization.py:24-34, tensor.py:227-229) -----------------
+ * q = rint(clip(zp + x/scale, lo, hi)), x/scale an IEEE float32 division, the
+ * zero-point add in float64, round-half-even.  Output int8 codes (bit_width 2..8). */
+int nq_quantize_f32(const float* x, int64_t n, int bit_width, float scale, int has_zp, int64_t zp,
+                    int8_t* out, void* stream);
+
+/* Wide symmetric quantize to int64 codes: the 4*bit_width-bit Gemm / Add biases of
+ * model.py:383-389 and 405-410 (bit_width up to 32; clip bounds rounded to float32 as
+ * np.clip does for float32 data). */
+int nq_quantize_f32_i64(const float* x, int64_t n, int bit_width, float scale, int has_zp, int64_t zp,
+                        int64_t* out, void* stream);
+
+/* Strided 4-D gather + quantize into a GEMM-ready K-major operand.
+ * Logical input x[b0][b1][r][c] with element strides (s0,s1,sr,sc); output
+ * out[(b0*d1+b1)][r][c] with row stride ldo (bytes, >= C) and batch stride
+ * R*ldo.  Padding columns c in [C, ldo) are zero-filled.  If rowsum != NULL,
+ * rowsum[(b0*d1+b1)*R + r] = sum_c q  (exact int32; the `arr.sum(axis)` terms of
+ * numpy_quantization.py:52-60). */
+int nq_quantize_f32_4d(const float* x, int64_t d0, int64_t d1, int64_t R, int64_t C,
+                       int64_t s0, int64_t s1, int64_t sr, int64_t sc,
+                       int bit_width, float scale, int has_zp, int64_t zp,
+                       int8_t* out, int64_t ldo, int32_t* rowsum, void* stream);
+
+/* ---- K2: dequantize  (numpy_quantization.py:37-41, tensor.py:189-193) ------------------
+ * out = float32( float64(q - zp) * float64(scale) );  q is int8 / int32 / int64
+ * (elem_bytes = 1, 4, 8). Scalar zero-point. */
+int nq_dequantize(const void* q, int elem_bytes, int64_t n, float scale, int has_zp, int64_t zp,
+                  float* out, void* stream);
+
+/* Zero-point of a q_matmul accumulator, kept factored (numpy_quantization.py:49-61):
+ *   zp[b,m,n] = rowsum_a[b,m]*zp_b + colsum_b[b,n]*zp_a - zp_a*zp_b*K
+ * (terms dropped when the corresponding operand is symmetric). */
+typedef struct nq_acc_zp {
+    int has_zp_a, has_zp_b;
+    int64_t zp_a, zp_b;
+    int64_t k;                     /* contraction length (a.shape[-1])                */
+    const int32_t* rowsum_a;       /* [batch*M]; required iff has_zp_b                */
+    const int32_t* colsum_b;       /* [batchB*N]; required iff has_zp_a               */
+    int64_t colsum_batch_stride;   /* N, or 0 when B is shared across the batch       */
+} nq_acc_zp;
+
+/* Dequantize an int32 accumulator [batch, M, N] (row stride ldacc) with the factored
+ * zero-point above; output float32 [batch, M, N] contiguous. */
+int nq_dequantize_acc(const int32_t* acc, int64_t batch, int64_t M, int64_t N, int64_t ldacc,
+                      float scale, const nq_acc_zp* zp, float* out, void* stream);
+
+/* ---- K3: requantize  (numpy_quantization.py:64-72, tensor.py:195-199, model.py:544-548) --
+ * q = clip(rint(zp_out + (1/s_out) * dequantize(acc + bias_q)), lo, hi) -> int8.
+ * bias_q (int64[N], may be NULL) is the Gemm bias added in the integer domain
+ * (tensor.py:183-187). */
+int nq_requantize_acc(const int32_t* acc, int64_t batch, int64_t M, int64_t N, int64_t ldacc,
+                      float scale, const nq_acc_zp* zp, const int64_t* bias_q,
+                      int out_bits, float out_scale, int has_out_zp, int64_t out_zp,
+                      int8_t* out, void* stream);
+
+/* rowsum[r] = sum_{c<C} q[r*ld + c]  (int32). Used for rowsum(A) and colsum(B) of
+ * K-major operands (numpy_quantization.py:52,55,58-59). */
+int nq_rowsum_s8(const int8_t* q, int64_t rows, int64_t C, int64_t ld, int32_t* rowsum, void* stream);
+
+/* ---- K4/K5: integer GEMM on tcgen05 (numpy_quantization.py:44-61, tensor.py:205-210) ----
+ * C[b] = A[b] (M x K, K-major, row stride lda bytes) * B[b]^T (N x K, K-major, row
+ * stride ldb bytes); exact int32 accumulation on the tensor cores (kind::i8),
+ * operands fetched by TMA (lda, ldb, batch strides multiples of 16 bytes, bases
+ * 16-byte aligned; K itself is arbitrary -- the tail is zero-filled by TMA).
+ * batch strides in elements; stride_b = 0 shares B across the batch.
+ * Epilogue modes:
+ *   NQ_EPI_RAW      C int32 [batch, M, ldc]
+ *   NQ_EPI_DEQUANT  C float32 = dequantize(acc, scale, zp) (+ bias_f32[n])      (K2 fused;
+ *                   model.py:528-538 followed by the bias Add of the graph)
+ *   NQ_EPI_REQUANT  C int8 = requantize(acc + bias_q[n])                         (K3 fused) */
+#define NQ_EPI_RAW 0
+#define NQ_EPI_DEQUANT 1
+#define NQ_EPI_REQUANT 2
+
+typedef struct nq_epilogue {
+    int mode;
+    float scale;                   /* float32(scale_a * scale_b)                       */
+    nq_acc_zp zp;
+    const float* bias_f32;         /* [N] or NULL (DEQUANT)                            */
+    const int64_t* bias_q;         /* [N] or NULL (REQUANT)                            */
+    int out_bits;                  /* REQUANT                                          */
+    float out_scale;
+    int has_out_zp;
+    int64_t out_zp;
+} nq_epilogue;
+
+int nq_qgemm_s8(const int8_t* A, const int8_t* B, void* C,
+                int64_t M, int64_t N, int64_t K, int64_t batch,
+                int64_t lda, int64_t ldb, int64_t ldc,
+                int64_t stride_a, int64_t stride_b, int64_t stride_c,
+                const nq_epilogue* ep, void* stream);
+
+/* Plain CUDA-core integer GEMM with the same arguments (RAW epilogue only): the
+ * on-device cross-check for the tensor-core kernel at sizes the CPU oracle cannot reach. */
+int nq_qgemm_s8_simt(const int8_t* A, const int8_t* B, int32_t* C,
+                     int64_t M, int64_t N, int64_t K, int64_t batch,
+                     int64_t lda, int64_t ldb, int64_t ldc,
+                     int64_t stride_a, int64_t stride_b, int64_t stride_c, void* stream);
+
+/* ---- K6: im2col for Conv (numpy_helper.py:18-92, tensor.py:256-264) ----------------------
+ * x[B,C,H,W] (int8 codes or float32; elem_bytes 1 or 4) -> patches
+ * out[B*OH*OW][kh][kw][c] with row stride ldo elements; positions that fall in the
+ * padding take `pad_value` (the zero-point in the integer domain, 0.0f bits for float).
+ * pads = (ph0, pw0, ph1, pw1); OH = ceil((H-kh+ph0+ph1+1)/sh). */
+int nq_im2col(const void* x, int elem_bytes, int64_t B, int64_t C, int64_t H, int64_t W,
+              int kh, int kw, int ph0, int pw0, int ph1, int pw1, int sh, int sw,
+              int32_t pad_value, void* out, int64_t ldo, void* stream);
+
+/* ---- K11: sub-byte storage (no reference counterpart; contract unpack(pack(q)) == q) ------
+ * n int8 codes of `bit_width` (2..8) bits <-> little-endian bitstream of
+ * ceil(n*bit_width/8) bytes (two's-complement fields). */
+int nq_pack_s8(const int8_t* q, int64_t n, int bit_width, uint8_t* packed, void* stream);
+int nq_unpack_s8(const uint8_t* packed, int64_t n, int bit_width, int8_t* q, void* stream);
+
+/* ---- K10: calibration statistics (model.py:332-336, tensor.py:232-236) -------------------
+ * minmax[2*slot] = min(x), minmax[2*slot+1] = max(x). Slots must be initialised with
+ * nq_minmax_init (+inf, -inf). */
+int nq_minmax_init(float* minmax, int64_t n_slots, void* stream);
+int nq_minmax_f32(const float* x, int64_t n, float* minmax, int64_t slot, void* stream);
+
+/* ---- K7-K9: float32 glue ops of the fake-quant path (tensor.py:47-152, model.py:134-152,
+ *      numpy_helper.py:95-112).  IEEE round-to-nearest, no FMA contraction, no fast-math. */
+#define NQ_UN_NEG 0
+#define NQ_UN_EXP 1
+#define NQ_UN_ERF 2      /* A&S 7.1.26 polynomial of numpy_helper.erf, not libm erff */
+#define NQ_UN_TANH 3
+#define NQ_UN_SIGMOID 4  /* 1 / (1 + exp(-x))                                        */
+#define NQ_UN_RELU 5     /* (x > 0) * x   (yields -0.0 for negative x)               */
+#define NQ_UN_SQRT 6
+#define NQ_UN_INV 7      /* 1 / x                                                    */
+#define NQ_UN_COPY 8
+int nq_unary_f32(int op, const float* x, int64_t n, float* out, void* stream);
+
+#define NQ_BIN_ADD 0
+#define NQ_BIN_MUL 1
+#define NQ_BIN_DIV 2
+/* out[i] = a[ia(i)] op b[ib(i)] over a contiguous 4-D output of dims d[4]; sa/sb are the
+ * element strides of a and b per output dim (0 = broadcast). */
+int nq_binary_f32(int op, const float* a, const int64_t* sa_host, const float* b, const int64_t* sb_host,
+                  const int64_t* dims_host, float* out, void* stream);
+
+/* GELU as spelled in the ViT graph: ((x / sqrt2) -> erf -> + 1) * x * 0.5, each step
+ * rounded to float32 exactly like the five separate ONNX nodes. */
+int nq_gelu_erf_f32(const float* x, int64_t n, float div_const, float add_const, float mul_const,
+                    float* out, void* stream);
+
+/* LayerNormalization over the last axis (model.py:134-152): two-pass mean / biased
+ * variance, d * (1/sqrt(var+eps)) * gamma + beta. x rows have stride ldx. */
+int nq_layernorm_f32(const float* x, int64_t rows, int64_t cols, int64_t ldx, const float* gamma,
+                     const float* beta, float eps, float* out, void* stream);
+
+/* Softmax over the last axis (tensor.py:139-146): exp(x - max) / sum. */
+int nq_softmax_f32(const float* x, int64_t rows, int64_t cols, int64_t ldx, float* out, void* stream);
+
+/* Row reductions over the last axis: op 0 = max, 1 = sum, 2 = mean (tensor.py:124-137). */
+int nq_reduce_rows_f32(int op, const float* x, int64_t rows, int64_t cols, float* out, void* stream);
+
+/* Strided 4-D copy into a contiguous tensor (Transpose / Expand / Slice / Concat pieces);
+ * elem_bytes 1, 4 or 8. out_offset/ld describe a contiguous destination written at
+ * out + out_offset with its own 4-D element strides so. */
+int nq_copy_4d(const void* x, int elem_bytes, const int64_t* dims_host, const int64_t* sx_host,
+               void* out, const int64_t* so_host, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NQ_B200_H */

@@ -1,0 +1,507 @@
+// K7-K9: float32 glue of the fake-quant path (LayerNorm, Softmax, GELU-erf chain,
+// broadcasting elementwise ops, strided copies) and K6 im2col.  Every arithmetic step is
+// an explicitly rounded IEEE op (__fadd_rn/__fmul_rn/__fdiv_rn): no FMA contraction, so the
+// elementwise chains reproduce NumPy's float32 ufunc results op for op.
+#include "common.cuh"
+
+namespace nq {
+
+// ---- the reference's erf: Abramowitz & Stegun 7.1.26 (numpy_helper.py:95-112) ----------
+__device__ __forceinline__ float erf_as(float x) {
+    const float sgn = (x > 0.f) ? 1.f : ((x < 0.f) ? -1.f : x);        // np.sign (keeps 0 / NaN)
+    const float ax = fabsf(x);
+    const float a1 = 0.254829592f, a2 = -0.284496736f, a3 = 1.421413741f, a4 = -1.453152027f, a5 = 1.061405429f;
+    const float p = 0.3275911f;
+    const float t = __fdiv_rn(1.0f, __fadd_rn(1.0f, __fmul_rn(p, ax)));
+    float y = __fadd_rn(__fmul_rn(a5, t), a4);
+    y = __fadd_rn(__fmul_rn(y, t), a3);
+    y = __fadd_rn(__fmul_rn(y, t), a2);
+    y = __fadd_rn(__fmul_rn(y, t), a1);
+    y = __fmul_rn(y, t);
+    const float e = expf(-__fmul_rn(ax, ax));
+    y = __fadd_rn(1.0f, -__fmul_rn(y, e));
+    return __fmul_rn(sgn, y);
+}
+
+template <int OP>
+__device__ __forceinline__ float unary_op(float x) {
+    if (OP == NQ_UN_NEG) return -x;
+    if (OP == NQ_UN_EXP) return expf(x);
+    if (OP == NQ_UN_ERF) return erf_as(x);
+    if (OP == NQ_UN_TANH) return tanhf(x);
+    if (OP == NQ_UN_SIGMOID) return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x)));
+    if (OP == NQ_UN_RELU) return __fmul_rn((x > 0.f) ? 1.0f : 0.0f, x);
+    if (OP == NQ_UN_SQRT) return __fsqrt_rn(x);
+    if (OP == NQ_UN_INV) return __fdiv_rn(1.0f, x);
+    return x;
+}
+
+template <int OP>
+__global__ void __launch_bounds__(256) unary_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ out,
+                                                   int vec) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t done = 0;
+    if (vec) {
+        const int64_t n4 = n >> 2;
+        const float4* x4 = reinterpret_cast<const float4*>(x);
+        float4* o4 = reinterpret_cast<float4*>(out);
+        for (int64_t i = tid; i < n4; i += stride) {
+            float4 v = __ldcs(x4 + i);
+            v.x = unary_op<OP>(v.x);
+            v.y = unary_op<OP>(v.y);
+            v.z = unary_op<OP>(v.z);
+            v.w = unary_op<OP>(v.w);
+            __stcs(o4 + i, v);
+        }
+        done = n4 << 2;
+    }
+    for (int64_t i = done + tid; i < n; i += stride) out[i] = unary_op<OP>(x[i]);
+}
+
+__device__ __forceinline__ float gelu_chain(float x, float c_div, float c_add, float c_mul) {
+    // Div -> Erf -> Add -> Mul(x, .) -> Mul(., 0.5): five float32 roundings like the five ONNX nodes
+    float u = erf_as(__fdiv_rn(x, c_div));
+    u = __fadd_rn(u, c_add);
+    u = __fmul_rn(x, u);
+    return __fmul_rn(u, c_mul);
+}
+
+__global__ void __launch_bounds__(256) gelu_kernel(const float* __restrict__ x, int64_t n, float c_div, float c_add,
+                                                  float c_mul, float* __restrict__ out, int vec) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t done = 0;
+    if (vec) {
+        const int64_t n4 = n >> 2;
+        const float4* x4 = reinterpret_cast<const float4*>(x);
+        float4* o4 = reinterpret_cast<float4*>(out);
+        for (int64_t i = tid; i < n4; i += stride) {
+            float4 v = __ldcs(x4 + i);
+            v.x = gelu_chain(v.x, c_div, c_add, c_mul);
+            v.y = gelu_chain(v.y, c_div, c_add, c_mul);
+            v.z = gelu_chain(v.z, c_div, c_add, c_mul);
+            v.w = gelu_chain(v.w, c_div, c_add, c_mul);
+            __stcs(o4 + i, v);
+        }
+        done = n4 << 2;
+    }
+    for (int64_t i = done + tid; i < n; i += stride) out[i] = gelu_chain(x[i], c_div, c_add, c_mul);
+}
+
+// ---- broadcasting binary ops ------------------------------------------------------------
+template <int OP>
+__device__ __forceinline__ float binary_op(float a, float b) {
+    if (OP == NQ_BIN_ADD) return __fadd_rn(a, b);
+    if (OP == NQ_BIN_MUL) return __fmul_rn(a, b);
+    return __fdiv_rn(a, b);
+}
+
+struct Dims4 {
+    int64_t d[4], sa[4], sb[4];
+};
+
+// MODE 0: generic strided; 1: a,b,out contiguous same shape (float4); 2: a contiguous, b a
+// row vector over the last dim (bias) (float4); 3: a contiguous, b a scalar.
+template <int OP, int MODE>
+__global__ void __launch_bounds__(256) binary_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                    Dims4 g, int64_t n, float* __restrict__ out) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (MODE == 0) {
+        for (int64_t i = tid; i < n; i += stride) {
+            int64_t r = i;
+            const int64_t i3 = r % g.d[3];
+            r /= g.d[3];
+            const int64_t i2 = r % g.d[2];
+            r /= g.d[2];
+            const int64_t i1 = r % g.d[1];
+            const int64_t i0 = r / g.d[1];
+            const float va = a[i0 * g.sa[0] + i1 * g.sa[1] + i2 * g.sa[2] + i3 * g.sa[3]];
+            const float vb = b[i0 * g.sb[0] + i1 * g.sb[1] + i2 * g.sb[2] + i3 * g.sb[3]];
+            out[i] = binary_op<OP>(va, vb);
+        }
+    } else {
+        const int64_t n4 = n >> 2;
+        const float4* a4 = reinterpret_cast<const float4*>(a);
+        float4* o4 = reinterpret_cast<float4*>(out);
+        const int64_t c4 = g.d[3] >> 2;
+        float sb = (MODE == 3) ? b[0] : 0.f;
+        for (int64_t i = tid; i < n4; i += stride) {
+            float4 va = __ldcs(a4 + i), vb;
+            if (MODE == 1) vb = __ldcs(reinterpret_cast<const float4*>(b) + i);
+            else if (MODE == 2) vb = __ldg(reinterpret_cast<const float4*>(b) + (i % c4));
+            else vb = make_float4(sb, sb, sb, sb);
+            va.x = binary_op<OP>(va.x, vb.x);
+            va.y = binary_op<OP>(va.y, vb.y);
+            va.z = binary_op<OP>(va.z, vb.z);
+            va.w = binary_op<OP>(va.w, vb.w);
+            __stcs(o4 + i, va);
+        }
+    }
+}
+
+// ---- LayerNorm / Softmax / row reductions: one warp per row, values kept in registers ----
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = __fadd_rn(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+template <int NV>   // NV float4 per lane: cols <= 128*NV, cols % 4 == 0, 16-B aligned rows
+__global__ void __launch_bounds__(256) layernorm_vec_kernel(const float* __restrict__ x, int64_t rows, int cols,
+                                                           int64_t ldx, const float* __restrict__ gamma,
+                                                           const float* __restrict__ beta, float eps,
+                                                           float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int c4 = cols >> 2;
+    const float fn = (float)cols;
+    for (int64_t row = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); row < rows; row += warps) {
+        const float4* src = reinterpret_cast<const float4*>(x + row * ldx);
+        float4 v[NV];
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            const int c = lane + j * 32;
+            v[j] = (c < c4) ? __ldcs(src + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+            s = __fadd_rn(s, __fadd_rn(__fadd_rn(v[j].x, v[j].y), __fadd_rn(v[j].z, v[j].w)));
+        }
+        const float mean = __fdiv_rn(warp_sum(s), fn);
+        float ss = 0.f;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            const int c = lane + j * 32;
+            if (c < c4) {
+                v[j].x = __fadd_rn(v[j].x, -mean);
+                v[j].y = __fadd_rn(v[j].y, -mean);
+                v[j].z = __fadd_rn(v[j].z, -mean);
+                v[j].w = __fadd_rn(v[j].w, -mean);
+                ss = __fadd_rn(ss, __fadd_rn(__fadd_rn(__fmul_rn(v[j].x, v[j].x), __fmul_rn(v[j].y, v[j].y)),
+                                             __fadd_rn(__fmul_rn(v[j].z, v[j].z), __fmul_rn(v[j].w, v[j].w))));
+            }
+        }
+        const float var = __fdiv_rn(warp_sum(ss), fn);
+        const float inv = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(var, eps)));
+        float4* dst = reinterpret_cast<float4*>(out + row * (int64_t)cols);
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            const int c = lane + j * 32;
+            if (c < c4) {
+                const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + c);
+                const float4 bt = __ldg(reinterpret_cast<const float4*>(beta) + c);
+                float4 o;
+                o.x = __fadd_rn(__fmul_rn(__fmul_rn(v[j].x, inv), gm.x), bt.x);
+                o.y = __fadd_rn(__fmul_rn(__fmul_rn(v[j].y, inv), gm.y), bt.y);
+                o.z = __fadd_rn(__fmul_rn(__fmul_rn(v[j].z, inv), gm.z), bt.z);
+                o.w = __fadd_rn(__fmul_rn(__fmul_rn(v[j].w, inv), gm.w), bt.w);
+                __stcs(dst + c, o);
+            }
+        }
+    }
+}
+
+// generic fallback: any cols / alignment, re-reads the row (L1/L2 resident)
+__global__ void __launch_bounds__(256) layernorm_generic_kernel(const float* __restrict__ x, int64_t rows, int64_t cols,
+                                                               int64_t ldx, const float* __restrict__ gamma,
+                                                               const float* __restrict__ beta, float eps,
+                                                               float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const float fn = (float)cols;
+    for (int64_t row = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); row < rows; row += warps) {
+        const float* src = x + row * ldx;
+        float s = 0.f;
+        for (int64_t c = lane; c < cols; c += 32) s = __fadd_rn(s, src[c]);
+        const float mean = __fdiv_rn(warp_sum(s), fn);
+        float ss = 0.f;
+        for (int64_t c = lane; c < cols; c += 32) {
+            const float d = __fadd_rn(src[c], -mean);
+            ss = __fadd_rn(ss, __fmul_rn(d, d));
+        }
+        const float var = __fdiv_rn(warp_sum(ss), fn);
+        const float inv = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(var, eps)));
+        for (int64_t c = lane; c < cols; c += 32) {
+            const float d = __fadd_rn(src[c], -mean);
+            out[row * cols + c] = __fadd_rn(__fmul_rn(__fmul_rn(d, inv), gamma[c]), beta[c]);
+        }
+    }
+}
+
+template <int NV>   // NV scalars per lane: cols <= 32*NV
+__global__ void __launch_bounds__(256) softmax_kernel(const float* __restrict__ x, int64_t rows, int cols, int64_t ldx,
+                                                     float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t row = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); row < rows; row += warps) {
+        const float* src = x + row * ldx;
+        float v[NV];
+        float m = __int_as_float(0xff800000);
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            const int c = lane + j * 32;
+            v[j] = (c < cols) ? src[c] : __int_as_float(0xff800000);
+            m = fmaxf(m, v[j]);
+        }
+        m = warp_max(m);
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            const int c = lane + j * 32;
+            if (c < cols) {
+                v[j] = expf(__fadd_rn(v[j], -m));
+                s = __fadd_rn(s, v[j]);
+            }
+        }
+        s = warp_sum(s);
+        float* dst = out + row * (int64_t)cols;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            const int c = lane + j * 32;
+            if (c < cols) dst[c] = __fdiv_rn(v[j], s);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) softmax_generic_kernel(const float* __restrict__ x, int64_t rows, int64_t cols,
+                                                             int64_t ldx, float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t row = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); row < rows; row += warps) {
+        const float* src = x + row * ldx;
+        float m = __int_as_float(0xff800000);
+        for (int64_t c = lane; c < cols; c += 32) m = fmaxf(m, src[c]);
+        m = warp_max(m);
+        float s = 0.f;
+        for (int64_t c = lane; c < cols; c += 32) s = __fadd_rn(s, expf(__fadd_rn(src[c], -m)));
+        s = warp_sum(s);
+        for (int64_t c = lane; c < cols; c += 32) out[row * cols + c] = __fdiv_rn(expf(__fadd_rn(src[c], -m)), s);
+    }
+}
+
+__global__ void __launch_bounds__(256) reduce_rows_kernel(int op, const float* __restrict__ x, int64_t rows,
+                                                         int64_t cols, float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t row = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); row < rows; row += warps) {
+        const float* src = x + row * cols;
+        float acc = (op == 0) ? __int_as_float(0xff800000) : 0.f;
+        for (int64_t c = lane; c < cols; c += 32) acc = (op == 0) ? fmaxf(acc, src[c]) : __fadd_rn(acc, src[c]);
+        acc = (op == 0) ? warp_max(acc) : warp_sum(acc);
+        if (lane == 0) out[row] = (op == 2) ? __fdiv_rn(acc, (float)cols) : acc;
+    }
+}
+
+// ---- strided 4-D copy ----------------------------------------------------------------------
+struct Copy4 {
+    int64_t d[4], sx[4], so[4];
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) copy4d_kernel(const T* __restrict__ x, Copy4 g, int64_t n, T* __restrict__ out) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        int64_t r = i;
+        const int64_t i3 = r % g.d[3];
+        r /= g.d[3];
+        const int64_t i2 = r % g.d[2];
+        r /= g.d[2];
+        const int64_t i1 = r % g.d[1];
+        const int64_t i0 = r / g.d[1];
+        out[i0 * g.so[0] + i1 * g.so[1] + i2 * g.so[2] + i3 * g.so[3]] =
+            x[i0 * g.sx[0] + i1 * g.sx[1] + i2 * g.sx[2] + i3 * g.sx[3]];
+    }
+}
+
+// ---- K6 im2col: x[B,C,H,W] -> rows (b, oh, ow), cols (i, j, c) ------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) im2col_kernel(const T* __restrict__ x, int64_t B, int C, int H, int W, int kh,
+                                                    int kw, int ph0, int pw0, int sh, int sw, int OH, int OW,
+                                                    T pad, T* __restrict__ out, int64_t ldo) {
+    const int64_t kcols = (int64_t)kh * kw * C;
+    const int64_t total = B * OH * OW * ldo;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int64_t col = i % ldo;
+        const int64_t row = i / ldo;
+        T v = (T)0;
+        if (col < kcols) {
+            const int c = (int)(col % C);
+            const int j = (int)((col / C) % kw);
+            const int ii = (int)(col / ((int64_t)C * kw));
+            const int ow = (int)(row % OW);
+            const int oh = (int)((row / OW) % OH);
+            const int64_t b = row / ((int64_t)OW * OH);
+            const int h = oh * sh + ii - ph0, w = ow * sw + j - pw0;
+            v = (h >= 0 && h < H && w >= 0 && w < W) ? x[((b * C + c) * H + h) * (int64_t)W + w] : pad;
+        }
+        out[i] = v;
+    }
+}
+
+}  // namespace nq
+
+using namespace nq;
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+template <int OP>
+static void launch_unary(const float* x, int64_t n, float* out, cudaStream_t s) {
+    const int vec = aligned16(x) && aligned16(out);
+    unary_kernel<OP><<<stream_grid((n + 3) / 4, 256), 256, 0, s>>>(x, n, out, vec);
+}
+
+extern "C" int nq_unary_f32(int op, const float* x, int64_t n, float* out, void* stream) {
+    if (n <= 0) return NQ_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (op) {
+        case NQ_UN_NEG: launch_unary<NQ_UN_NEG>(x, n, out, s); break;
+        case NQ_UN_EXP: launch_unary<NQ_UN_EXP>(x, n, out, s); break;
+        case NQ_UN_ERF: launch_unary<NQ_UN_ERF>(x, n, out, s); break;
+        case NQ_UN_TANH: launch_unary<NQ_UN_TANH>(x, n, out, s); break;
+        case NQ_UN_SIGMOID: launch_unary<NQ_UN_SIGMOID>(x, n, out, s); break;
+        case NQ_UN_RELU: launch_unary<NQ_UN_RELU>(x, n, out, s); break;
+        case NQ_UN_SQRT: launch_unary<NQ_UN_SQRT>(x, n, out, s); break;
+        case NQ_UN_INV: launch_unary<NQ_UN_INV>(x, n, out, s); break;
+        case NQ_UN_COPY: launch_unary<NQ_UN_COPY>(x, n, out, s); break;
+        default: NQ_REQUIRE(false, "nq_unary_f32: unknown op %d", op);
+    }
+    NQ_CHECK_LAUNCH("nq_unary_f32");
+    return NQ_OK;
+}
+
+extern "C" int nq_gelu_erf_f32(const float* x, int64_t n, float div_const, float add_const, float mul_const,
+                               float* out, void* stream) {
+    if (n <= 0) return NQ_OK;
+    const int vec = aligned16(x) && aligned16(out);
+    gelu_kernel<<<stream_grid((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(x, n, div_const, add_const,
+                                                                                mul_const, out, vec);
+    NQ_CHECK_LAUNCH("nq_gelu_erf_f32");
+    return NQ_OK;
+}
+
+template <int OP>
+static void launch_binary(const float* a, const float* b, const Dims4& g, int64_t n, float* out, cudaStream_t s) {
+    auto contig = [&](const int64_t* st) {
+        int64_t e = 1;
+        for (int i = 3; i >= 0; --i) {
+            if (g.d[i] != 1 && st[i] != e) return false;
+            e *= g.d[i];
+        }
+        return true;
+    };
+    const bool a_c = contig(g.sa), al = aligned16(a) && aligned16(out) && (n % 4 == 0);
+    const bool b_scalar = [&] { for (int i = 0; i < 4; ++i) if (g.d[i] != 1 && g.sb[i] != 0) return false; return true; }();
+    const bool b_row = (g.sb[3] == 1 || g.d[3] == 1) && [&] { for (int i = 0; i < 3; ++i) if (g.d[i] != 1 && g.sb[i] != 0) return false; return true; }();
+    const int grid4 = stream_grid((n + 3) / 4, 256), grid1 = stream_grid(n, 256);
+    if (a_c && al && contig(g.sb) && aligned16(b)) binary_kernel<OP, 1><<<grid4, 256, 0, s>>>(a, b, g, n, out);
+    else if (a_c && al && b_scalar) binary_kernel<OP, 3><<<grid4, 256, 0, s>>>(a, b, g, n, out);
+    else if (a_c && al && b_row && (g.d[3] % 4 == 0) && aligned16(b)) binary_kernel<OP, 2><<<grid4, 256, 0, s>>>(a, b, g, n, out);
+    else binary_kernel<OP, 0><<<grid1, 256, 0, s>>>(a, b, g, n, out);
+}
+
+extern "C" int nq_binary_f32(int op, const float* a, const int64_t* sa_host, const float* b, const int64_t* sb_host,
+                             const int64_t* dims_host, float* out, void* stream) {
+    Dims4 g;
+    int64_t n = 1;
+    for (int i = 0; i < 4; ++i) {
+        g.d[i] = dims_host[i];
+        g.sa[i] = sa_host[i];
+        g.sb[i] = sb_host[i];
+        n *= g.d[i];
+    }
+    if (n <= 0) return NQ_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (op == NQ_BIN_ADD) launch_binary<NQ_BIN_ADD>(a, b, g, n, out, s);
+    else if (op == NQ_BIN_MUL) launch_binary<NQ_BIN_MUL>(a, b, g, n, out, s);
+    else if (op == NQ_BIN_DIV) launch_binary<NQ_BIN_DIV>(a, b, g, n, out, s);
+    else NQ_REQUIRE(false, "nq_binary_f32: unknown op %d", op);
+    NQ_CHECK_LAUNCH("nq_binary_f32");
+    return NQ_OK;
+}
+
+extern "C" int nq_layernorm_f32(const float* x, int64_t rows, int64_t cols, int64_t ldx, const float* gamma,
+                                const float* beta, float eps, float* out, void* stream) {
+    if (rows <= 0 || cols <= 0) return NQ_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int grid = stream_grid(rows * 32, 256);
+    const bool vec = (cols % 4 == 0) && (ldx % 4 == 0) && aligned16(x) && aligned16(out) && aligned16(gamma) && aligned16(beta);
+    if (vec && cols <= 512) layernorm_vec_kernel<4><<<grid, 256, 0, s>>>(x, rows, (int)cols, ldx, gamma, beta, eps, out);
+    else if (vec && cols <= 1024) layernorm_vec_kernel<8><<<grid, 256, 0, s>>>(x, rows, (int)cols, ldx, gamma, beta, eps, out);
+    else if (vec && cols <= 4096) layernorm_vec_kernel<32><<<grid, 256, 0, s>>>(x, rows, (int)cols, ldx, gamma, beta, eps, out);
+    else layernorm_generic_kernel<<<grid, 256, 0, s>>>(x, rows, cols, ldx, gamma, beta, eps, out);
+    NQ_CHECK_LAUNCH("nq_layernorm_f32");
+    return NQ_OK;
+}
+
+extern "C" int nq_softmax_f32(const float* x, int64_t rows, int64_t cols, int64_t ldx, float* out, void* stream) {
+    if (rows <= 0 || cols <= 0) return NQ_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int grid = stream_grid(rows * 32, 256);
+    if (cols <= 128) softmax_kernel<4><<<grid, 256, 0, s>>>(x, rows, (int)cols, ldx, out);
+    else if (cols <= 256) softmax_kernel<8><<<grid, 256, 0, s>>>(x, rows, (int)cols, ldx, out);
+    else if (cols <= 1024) softmax_kernel<32><<<grid, 256, 0, s>>>(x, rows, (int)cols, ldx, out);
+    else softmax_generic_kernel<<<grid, 256, 0, s>>>(x, rows, cols, ldx, out);
+    NQ_CHECK_LAUNCH("nq_softmax_f32");
+    return NQ_OK;
+}
+
+extern "C" int nq_reduce_rows_f32(int op, const float* x, int64_t rows, int64_t cols, float* out, void* stream) {
+    NQ_REQUIRE(op >= 0 && op <= 2, "nq_reduce_rows_f32: unknown op %d", op);
+    if (rows <= 0) return NQ_OK;
+    reduce_rows_kernel<<<stream_grid(rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(op, x, rows, cols, out);
+    NQ_CHECK_LAUNCH("nq_reduce_rows_f32");
+    return NQ_OK;
+}
+
+extern "C" int nq_copy_4d(const void* x, int elem_bytes, const int64_t* dims_host, const int64_t* sx_host, void* out,
+                          const int64_t* so_host, void* stream) {
+    Copy4 g;
+    int64_t n = 1;
+    for (int i = 0; i < 4; ++i) {
+        g.d[i] = dims_host[i];
+        g.sx[i] = sx_host[i];
+        g.so[i] = so_host[i];
+        n *= g.d[i];
+    }
+    if (n <= 0) return NQ_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int grid = stream_grid(n, 256);
+    if (elem_bytes == 1) copy4d_kernel<int8_t><<<grid, 256, 0, s>>>((const int8_t*)x, g, n, (int8_t*)out);
+    else if (elem_bytes == 4) copy4d_kernel<int32_t><<<grid, 256, 0, s>>>((const int32_t*)x, g, n, (int32_t*)out);
+    else if (elem_bytes == 8) copy4d_kernel<int64_t><<<grid, 256, 0, s>>>((const int64_t*)x, g, n, (int64_t*)out);
+    else NQ_REQUIRE(false, "nq_copy_4d: elem_bytes %d not in {1,4,8}", elem_bytes);
+    NQ_CHECK_LAUNCH("nq_copy_4d");
+    return NQ_OK;
+}
+
+extern "C" int nq_im2col(const void* x, int elem_bytes, int64_t B, int64_t C, int64_t H, int64_t W, int kh, int kw,
+                         int ph0, int pw0, int ph1, int pw1, int sh, int sw, int32_t pad_value, void* out,
+                         int64_t ldo, void* stream) {
+    NQ_REQUIRE(sh > 0 && sw > 0 && kh > 0 && kw > 0, "nq_im2col: bad kernel/stride");
+    // ceil((h - kh + ph0 + ph1 + 1) / sh)  (numpy_helper.py:37-38)
+    const int64_t OH = (H - kh + ph0 + ph1 + 1 + sh - 1) / sh, OW = (W - kw + pw0 + pw1 + 1 + sw - 1) / sw;
+    NQ_REQUIRE(OH > 0 && OW > 0, "nq_im2col: empty output");
+    NQ_REQUIRE(ldo >= (int64_t)kh * kw * C, "nq_im2col: ldo too small");
+    const int64_t total = B * OH * OW * ldo;
+    const int grid = stream_grid(total, 256);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (elem_bytes == 1) {
+        im2col_kernel<int8_t><<<grid, 256, 0, s>>>((const int8_t*)x, B, (int)C, (int)H, (int)W, kh, kw, ph0, pw0, sh, sw,
+                                                   (int)OH, (int)OW, (int8_t)pad_value, (int8_t*)out, ldo);
+    } else if (elem_bytes == 4) {
+        float padf;
+        memcpy(&padf, &pad_value, 4);
+        im2col_kernel<float><<<grid, 256, 0, s>>>((const float*)x, B, (int)C, (int)H, (int)W, kh, kw, ph0, pw0, sh, sw,
+                                                  (int)OH, (int)OW, padf, (float*)out, ldo);
+    } else {
+        NQ_REQUIRE(false, "nq_im2col: elem_bytes %d not in {1,4}", elem_bytes);
+    }
+    NQ_CHECK_LAUNCH("nq_im2col");
+    return NQ_OK;
+}

@@ -1,0 +1,506 @@
+// K1 quantize, K2 dequantize, K3 requantize, K10 min/max, K11 pack/unpack, row sums.
+// All HBM-bound: 16-byte vector accesses, grid-stride over whole waves of the 148 SMs.
+#include "common.cuh"
+
+namespace nq {
+
+// ------------------------------------------------------------------ K1 contiguous
+template <bool ASYM>
+__global__ void __launch_bounds__(256) quantize_contig_kernel(const float* __restrict__ x, int64_t n,
+                                                             float scale, double zp, float lo, float hi,
+                                                             int8_t* __restrict__ out) {
+    // 16 elements per thread-iteration: four 16-B loads in flight, one 16-B store.
+    const int64_t n16 = n >> 4;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    int4* o4 = reinterpret_cast<int4*>(out);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) {
+        float4 v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = __ldcs(x4 + i * 4 + j);
+        int w[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int q0 = quantize_one<ASYM>(v[j].x, scale, zp, lo, hi);
+            int q1 = quantize_one<ASYM>(v[j].y, scale, zp, lo, hi);
+            int q2 = quantize_one<ASYM>(v[j].z, scale, zp, lo, hi);
+            int q3 = quantize_one<ASYM>(v[j].w, scale, zp, lo, hi);
+            w[j] = (q0 & 0xff) | ((q1 & 0xff) << 8) | ((q2 & 0xff) << 16) | ((q3 & 0xff) << 24);
+        }
+        __stcs(o4 + i, make_int4(w[0], w[1], w[2], w[3]));
+    }
+    // tail (< 16 elements) by the first threads of the grid
+    const int64_t base = n16 << 4;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (base + t < n) out[base + t] = (int8_t)quantize_one<ASYM>(x[base + t], scale, zp, lo, hi);
+}
+
+template <bool ASYM>
+__global__ void __launch_bounds__(256) quantize_scalar_kernel(const float* __restrict__ x, int64_t n, float scale,
+                                                             double zp, float lo, float hi,
+                                                             int8_t* __restrict__ out) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        out[i] = (int8_t)quantize_one<ASYM>(x[i], scale, zp, lo, hi);
+}
+
+// wide symmetric/asymmetric quantize to int64 codes (4*bit_width-bit biases, model.py:383-389, 405-410)
+__global__ void quantize_i64_kernel(const float* __restrict__ x, int64_t n, float scale, int has_zp, double zp,
+                                    float lo, float hi, int64_t* __restrict__ out) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        float t = __fdiv_rn(x[i], scale);
+        if (has_zp) {
+            double u = fmin(fmax(zp + (double)t, (double)lo), (double)hi);
+            out[i] = __double2ll_rn(u);
+        } else {
+            t = fminf(fmaxf(t, lo), hi);          // lo/hi already rounded to float32 like np.clip does
+            out[i] = __float2ll_rn(t);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ K1 strided 4-D -> K-major operand
+// One warp per output row (b, r): lanes sweep the C (=K) axis, so reads are coalesced when
+// sc == 1 and the row sum falls out of a shuffle reduction.
+template <bool ASYM>
+__global__ void __launch_bounds__(256) quantize_rows_kernel(const float* __restrict__ x, int64_t d1, int64_t R,
+                                                           int64_t C, int64_t s0, int64_t s1, int64_t sr,
+                                                           int64_t sc, int64_t rows_total, float scale, double zp,
+                                                           float lo, float hi, int8_t* __restrict__ out,
+                                                           int64_t ldo, int32_t* __restrict__ rowsum) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t row = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); row < rows_total; row += warps) {
+        const int64_t r = row % R;
+        const int64_t b = row / R;
+        const float* src = x + (b / d1) * s0 + (b % d1) * s1 + r * sr;
+        int8_t* dst = out + row * ldo;
+        int sum = 0;
+        if (sc == 1 && ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && (ldo & 3) == 0) {
+            const int64_t c4 = C >> 2;
+            for (int64_t c = lane; c < c4; c += 32) {
+                float4 v = *reinterpret_cast<const float4*>(src + c * 4);
+                int q0 = quantize_one<ASYM>(v.x, scale, zp, lo, hi);
+                int q1 = quantize_one<ASYM>(v.y, scale, zp, lo, hi);
+                int q2 = quantize_one<ASYM>(v.z, scale, zp, lo, hi);
+                int q3 = quantize_one<ASYM>(v.w, scale, zp, lo, hi);
+                sum += q0 + q1 + q2 + q3;
+                *reinterpret_cast<int*>(dst + c * 4) =
+                    (q0 & 0xff) | ((q1 & 0xff) << 8) | ((q2 & 0xff) << 16) | ((q3 & 0xff) << 24);
+            }
+            for (int64_t c = (c4 << 2) + lane; c < ldo; c += 32) {
+                int q = c < C ? quantize_one<ASYM>(src[c], scale, zp, lo, hi) : 0;
+                sum += q;
+                dst[c] = (int8_t)q;
+            }
+        } else {
+            for (int64_t c = lane; c < ldo; c += 32) {
+                int q = c < C ? quantize_one<ASYM>(src[c * sc], scale, zp, lo, hi) : 0;
+                sum += q;
+                dst[c] = (int8_t)q;
+            }
+        }
+        if (rowsum) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            if (lane == 0) rowsum[row] = sum;
+        }
+    }
+}
+
+// Transposing variant: the input is contiguous along r (sr == 1), e.g. a [K, N] weight or V
+// read as rows = N, cols = K.  32x32 tiles through shared memory keep both sides coalesced.
+template <bool ASYM>
+__global__ void __launch_bounds__(256) quantize_transpose_kernel(const float* __restrict__ x, int64_t d1, int64_t R,
+                                                                int64_t C, int64_t s0, int64_t s1, int64_t sc,
+                                                                float scale, double zp, float lo, float hi,
+                                                                int8_t* __restrict__ out, int64_t ldo,
+                                                                int32_t* __restrict__ rowsum) {
+    __shared__ int8_t tile[32][36];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;           // 32 x 8
+    const int64_t b = blockIdx.z;
+    const int64_t r0 = (int64_t)blockIdx.x * 32, c0 = (int64_t)blockIdx.y * 32;
+    const float* src = x + (b / d1) * s0 + (b % d1) * s1;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int64_t c = c0 + ty + j * 8, r = r0 + tx;               // lanes along r (unit stride)
+        int q = 0;
+        if (c < C && r < R) q = quantize_one<ASYM>(src[c * sc + r], scale, zp, lo, hi);
+        tile[ty + j * 8][tx] = (int8_t)q;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int64_t r = r0 + ty + j * 8, c = c0 + tx;               // lanes along c for the store
+        const int q = tile[tx][ty + j * 8];
+        if (r < R && c < ldo) out[(b * R + r) * ldo + c] = (int8_t)q;
+        if (rowsum) {
+            int s = q;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (tx == 0 && r < R) atomicAdd(rowsum + b * R + r, s);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ K2
+template <typename T>
+__global__ void __launch_bounds__(256) dequantize_kernel(const T* __restrict__ q, int64_t n, float scale, int64_t zp,
+                                                        float* __restrict__ out) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        out[i] = dequantize_one((int64_t)q[i] - zp, scale);
+}
+
+__global__ void __launch_bounds__(256) dequantize_s8x16_kernel(const int8_t* __restrict__ q, int64_t n16, float scale,
+                                                              int zp, float* __restrict__ out) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int4* q4 = reinterpret_cast<const int4*>(q);
+    float4* o4 = reinterpret_cast<float4*>(out);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) {
+        int4 v = __ldcs(q4 + i);
+        int w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float4 f;
+            f.x = __fmul_rn((float)((int)(int8_t)(w[j]) - zp), scale);
+            f.y = __fmul_rn((float)((int)(int8_t)(w[j] >> 8) - zp), scale);
+            f.z = __fmul_rn((float)((int)(int8_t)(w[j] >> 16) - zp), scale);
+            f.w = __fmul_rn((float)((int)(int8_t)(w[j] >> 24) - zp), scale);
+            __stcs(o4 + i * 4 + j, f);
+        }
+    }
+}
+
+__device__ __forceinline__ int64_t acc_zero_point(const AccZp& z, int64_t b, int64_t m, int64_t n, int64_t M) {
+    int64_t v = -z.kterm;
+    if (z.use_row) v += (int64_t)z.rowsum_a[b * M + m] * z.zp_b;
+    if (z.use_col) v += (int64_t)z.colsum_b[b * z.cs_stride + n] * z.zp_a;
+    return v;
+}
+
+// acc [batch, M, N] (ld) -> f32 / int8; one thread per 4 consecutive n when aligned.
+template <int MODE, bool ASYM_OUT>   // MODE 1 dequant -> f32, 2 requant -> s8
+__global__ void __launch_bounds__(256) acc_post_kernel(const int32_t* __restrict__ acc, int64_t batch, int64_t M,
+                                                      int64_t N, int64_t ldacc, float scale, AccZp z,
+                                                      const int64_t* __restrict__ bias_q, float inv_out_scale,
+                                                      double out_zp, float lo, float hi, void* __restrict__ out) {
+    const int64_t total = batch * M * N;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int64_t n = i % N;
+        const int64_t bm = i / N;
+        const int64_t m = bm % M, b = bm / M;
+        int64_t a = acc[bm * ldacc + n];
+        if (MODE == 2 && bias_q) a += bias_q[n];
+        const float d = dequantize_one(a - acc_zero_point(z, b, m, n, M), scale);
+        if (MODE == 1) {
+            reinterpret_cast<float*>(out)[i] = d;
+        } else {
+            reinterpret_cast<int8_t*>(out)[i] = (int8_t)requantize_one<ASYM_OUT>(d, inv_out_scale, out_zp, lo, hi);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ row sums of a K-major s8 operand
+__global__ void __launch_bounds__(256) rowsum_s8_kernel(const int8_t* __restrict__ q, int64_t rows, int64_t C,
+                                                       int64_t ld, int32_t* __restrict__ rowsum) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t row = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); row < rows; row += warps) {
+        const int8_t* src = q + row * ld;
+        int sum = 0;
+        if ((ld & 15) == 0 && (reinterpret_cast<uintptr_t>(q) & 15) == 0) {
+            const int64_t c16 = C >> 4;
+            for (int64_t c = lane; c < c16; c += 32) {
+                int4 v = *reinterpret_cast<const int4*>(src + c * 16);
+                sum = __dp4a(v.x, 0x01010101, sum);
+                sum = __dp4a(v.y, 0x01010101, sum);
+                sum = __dp4a(v.z, 0x01010101, sum);
+                sum = __dp4a(v.w, 0x01010101, sum);
+            }
+            for (int64_t c = (c16 << 4) + lane; c < C; c += 32) sum += src[c];
+        } else {
+            for (int64_t c = lane; c < C; c += 32) sum += src[c];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        if (lane == 0) rowsum[row] = sum;
+    }
+}
+
+// ------------------------------------------------------------------ K10 min / max
+__device__ __forceinline__ void atomic_min_f32(float* addr, float v) {
+    if (v >= 0.f) atomicMin(reinterpret_cast<int*>(addr), __float_as_int(v));
+    else atomicMax(reinterpret_cast<unsigned*>(addr), __float_as_uint(v));
+}
+__device__ __forceinline__ void atomic_max_f32(float* addr, float v) {
+    if (v >= 0.f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+    else atomicMin(reinterpret_cast<unsigned*>(addr), __float_as_uint(v));
+}
+
+__global__ void minmax_init_kernel(float* mm, int64_t n_slots) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_slots) {
+        mm[2 * i] = __int_as_float(0x7f800000);
+        mm[2 * i + 1] = __int_as_float(0xff800000);
+    }
+}
+
+__global__ void __launch_bounds__(256) minmax_kernel(const float* __restrict__ x, int64_t n, float* mm) {
+    float lo = __int_as_float(0x7f800000), hi = __int_as_float(0xff800000);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if ((reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+        const int64_t n4 = n >> 2;
+        const float4* x4 = reinterpret_cast<const float4*>(x);
+        for (int64_t i = tid; i < n4; i += stride) {
+            float4 v = __ldcs(x4 + i);
+            lo = fminf(fminf(lo, v.x), fminf(v.y, fminf(v.z, v.w)));
+            hi = fmaxf(fmaxf(hi, v.x), fmaxf(v.y, fmaxf(v.z, v.w)));
+        }
+        for (int64_t i = (n4 << 2) + tid; i < n; i += stride) {
+            lo = fminf(lo, x[i]);
+            hi = fmaxf(hi, x[i]);
+        }
+    } else {
+        for (int64_t i = tid; i < n; i += stride) {
+            lo = fminf(lo, x[i]);
+            hi = fmaxf(hi, x[i]);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    __shared__ float slo[8], shi[8];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) {
+        slo[w] = lo;
+        shi[w] = hi;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < (int)(blockDim.x >> 5); ++i) {
+            lo = fminf(lo, slo[i]);
+            hi = fmaxf(hi, shi[i]);
+        }
+        // -0.0 and +0.0 compare equal in NumPy's min/max; normalise so the bit tricks agree
+        if (lo == 0.f) lo = 0.f;
+        if (hi == 0.f) hi = 0.f;
+        atomic_min_f32(mm, lo);
+        atomic_max_f32(mm + 1, hi);
+    }
+}
+
+// ------------------------------------------------------------------ K11 pack / unpack
+// Eight codes <-> `bits` bytes, little-endian bitstream of two's-complement fields.
+__global__ void __launch_bounds__(256) pack_kernel(const int8_t* __restrict__ q, int64_t n, int bits,
+                                                  uint8_t* __restrict__ packed) {
+    const int64_t groups = (n + 7) >> 3;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const unsigned mask = (1u << bits) - 1u;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += stride) {
+        unsigned long long word = 0;
+        const int64_t base = g << 3;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            unsigned v = (base + j < n) ? ((unsigned)(int)q[base + j] & mask) : 0u;
+            word |= (unsigned long long)v << (j * bits);
+        }
+        const int64_t total_bytes = (n * bits + 7) >> 3;
+        for (int j = 0; j < bits; ++j) {
+            const int64_t o = g * bits + j;
+            if (o < total_bytes) packed[o] = (uint8_t)(word >> (8 * j));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) unpack_kernel(const uint8_t* __restrict__ packed, int64_t n, int bits,
+                                                    int8_t* __restrict__ q) {
+    const int64_t groups = (n + 7) >> 3;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t total_bytes = (n * bits + 7) >> 3;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += stride) {
+        unsigned long long word = 0;
+        for (int j = 0; j < bits; ++j) {
+            const int64_t o = g * bits + j;
+            if (o < total_bytes) word |= (unsigned long long)packed[o] << (8 * j);
+        }
+        const int64_t base = g << 3;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (base + j < n) {
+                int v = (int)((word >> (j * bits)) & ((1u << bits) - 1u));
+                v = (v << (32 - bits)) >> (32 - bits);         // sign-extend the field
+                q[base + j] = (int8_t)v;
+            }
+        }
+    }
+}
+
+}  // namespace nq
+
+using namespace nq;
+
+static inline void qrange(int bits, float* lo, float* hi) {
+    *lo = -ldexpf(1.f, bits - 1);
+    *hi = ldexpf(1.f, bits - 1) - 1.f;
+}
+
+extern "C" int nq_quantize_f32(const float* x, int64_t n, int bit_width, float scale, int has_zp, int64_t zp,
+                               int8_t* out, void* stream) {
+    NQ_REQUIRE(bit_width >= 2 && bit_width <= 8, "nq_quantize_f32: bit_width %d outside 2..8", bit_width);
+    if (n <= 0) return NQ_OK;
+    float lo, hi;
+    qrange(bit_width, &lo, &hi);
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool vec = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+    if (vec) {
+        const int grid = stream_grid((n + 15) / 16, 256);
+        if (has_zp) quantize_contig_kernel<true><<<grid, 256, 0, s>>>(x, n, scale, (double)zp, lo, hi, out);
+        else quantize_contig_kernel<false><<<grid, 256, 0, s>>>(x, n, scale, 0.0, lo, hi, out);
+    } else {
+        const int grid = stream_grid(n, 256);
+        if (has_zp) quantize_scalar_kernel<true><<<grid, 256, 0, s>>>(x, n, scale, (double)zp, lo, hi, out);
+        else quantize_scalar_kernel<false><<<grid, 256, 0, s>>>(x, n, scale, 0.0, lo, hi, out);
+    }
+    NQ_CHECK_LAUNCH("nq_quantize_f32");
+    return NQ_OK;
+}
+
+extern "C" int nq_quantize_f32_i64(const float* x, int64_t n, int bit_width, float scale, int has_zp, int64_t zp,
+                                   int64_t* out, void* stream) {
+    NQ_REQUIRE(bit_width >= 2 && bit_width <= 32, "nq_quantize_f32_i64: bit_width %d outside 2..32", bit_width);
+    if (n <= 0) return NQ_OK;
+    // np.clip converts the Python-float bounds to the array dtype: float32 when symmetric
+    // (2^31-1 rounds to 2^31), float64 when the zero-point add promoted the data.
+    NQ_REQUIRE(!has_zp, "nq_quantize_f32_i64: asymmetric wide quantization is not used by the reference path");
+    (void)zp;
+    const double dlo = -ldexp(1.0, bit_width - 1), dhi = ldexp(1.0, bit_width - 1) - 1.0;
+    quantize_i64_kernel<<<stream_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(x, n, scale, 0, 0.0, (float)dlo,
+                                                                              (float)dhi, out);
+    NQ_CHECK_LAUNCH("nq_quantize_f32_i64");
+    return NQ_OK;
+}
+
+extern "C" int nq_quantize_f32_4d(const float* x, int64_t d0, int64_t d1, int64_t R, int64_t C, int64_t s0,
+                                  int64_t s1, int64_t sr, int64_t sc, int bit_width, float scale, int has_zp,
+                                  int64_t zp, int8_t* out, int64_t ldo, int32_t* rowsum, void* stream) {
+    NQ_REQUIRE(bit_width >= 2 && bit_width <= 8, "nq_quantize_f32_4d: bit_width %d outside 2..8", bit_width);
+    NQ_REQUIRE(ldo >= C, "nq_quantize_f32_4d: ldo %lld < C %lld", (long long)ldo, (long long)C);
+    const int64_t batch = d0 * d1, rows = batch * R;
+    if (rows <= 0 || C <= 0) return NQ_OK;
+    float lo, hi;
+    qrange(bit_width, &lo, &hi);
+    cudaStream_t s = (cudaStream_t)stream;
+    const double dzp = has_zp ? (double)zp : 0.0;
+    if (sr == 1 && sc != 1 && batch <= 65535) {
+        if (rowsum) {
+            cudaError_t e = cudaMemsetAsync(rowsum, 0, sizeof(int32_t) * rows, s);
+            if (e != cudaSuccess) return cuda_fail(e, "nq_quantize_f32_4d memset");
+        }
+        dim3 grid((unsigned)((R + 31) / 32), (unsigned)((ldo + 31) / 32), (unsigned)batch);
+        NQ_REQUIRE(grid.y <= 65535, "nq_quantize_f32_4d: C too large for the transposing path");
+        if (has_zp) quantize_transpose_kernel<true><<<grid, 256, 0, s>>>(x, d1, R, C, s0, s1, sc, scale, dzp, lo, hi, out, ldo, rowsum);
+        else quantize_transpose_kernel<false><<<grid, 256, 0, s>>>(x, d1, R, C, s0, s1, sc, scale, dzp, lo, hi, out, ldo, rowsum);
+    } else {
+        const int grid = stream_grid(rows * 32, 256);
+        if (has_zp) quantize_rows_kernel<true><<<grid, 256, 0, s>>>(x, d1, R, C, s0, s1, sr, sc, rows, scale, dzp, lo, hi, out, ldo, rowsum);
+        else quantize_rows_kernel<false><<<grid, 256, 0, s>>>(x, d1, R, C, s0, s1, sr, sc, rows, scale, dzp, lo, hi, out, ldo, rowsum);
+    }
+    NQ_CHECK_LAUNCH("nq_quantize_f32_4d");
+    return NQ_OK;
+}
+
+extern "C" int nq_dequantize(const void* q, int elem_bytes, int64_t n, float scale, int has_zp, int64_t zp,
+                             float* out, void* stream) {
+    if (n <= 0) return NQ_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t z = has_zp ? zp : 0;
+    if (elem_bytes == 1) {
+        const bool vec = ((reinterpret_cast<uintptr_t>(q) & 15) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0) &&
+                         z > -(1 << 23) && z < (1 << 23);
+        const int64_t n16 = vec ? (n >> 4) : 0;
+        if (n16) dequantize_s8x16_kernel<<<stream_grid(n16, 256), 256, 0, s>>>((const int8_t*)q, n16, scale, (int)z, out);
+        const int64_t done = n16 << 4;
+        if (done < n)
+            dequantize_kernel<int8_t><<<stream_grid(n - done, 256), 256, 0, s>>>((const int8_t*)q + done, n - done, scale, z, out + done);
+    } else if (elem_bytes == 4) {
+        dequantize_kernel<int32_t><<<stream_grid(n, 256), 256, 0, s>>>((const int32_t*)q, n, scale, z, out);
+    } else if (elem_bytes == 8) {
+        dequantize_kernel<int64_t><<<stream_grid(n, 256), 256, 0, s>>>((const int64_t*)q, n, scale, z, out);
+    } else {
+        NQ_REQUIRE(false, "nq_dequantize: elem_bytes %d not in {1,4,8}", elem_bytes);
+    }
+    NQ_CHECK_LAUNCH("nq_dequantize");
+    return NQ_OK;
+}
+
+extern "C" int nq_dequantize_acc(const int32_t* acc, int64_t batch, int64_t M, int64_t N, int64_t ldacc,
+                                 float scale, const nq_acc_zp* zp, float* out, void* stream) {
+    if (batch * M * N <= 0) return NQ_OK;
+    if (int rc = check_acc_zp(zp)) return rc;
+    acc_post_kernel<1, false><<<stream_grid(batch * M * N, 256), 256, 0, (cudaStream_t)stream>>>(
+        acc, batch, M, N, ldacc, scale, make_acc_zp(zp), nullptr, 0.f, 0.0, 0.f, 0.f, out);
+    NQ_CHECK_LAUNCH("nq_dequantize_acc");
+    return NQ_OK;
+}
+
+extern "C" int nq_requantize_acc(const int32_t* acc, int64_t batch, int64_t M, int64_t N, int64_t ldacc,
+                                 float scale, const nq_acc_zp* zp, const int64_t* bias_q, int out_bits,
+                                 float out_scale, int has_out_zp, int64_t out_zp, int8_t* out, void* stream) {
+    NQ_REQUIRE(out_bits >= 2 && out_bits <= 8, "nq_requantize_acc: out_bits %d outside 2..8", out_bits);
+    if (batch * M * N <= 0) return NQ_OK;
+    if (int rc = check_acc_zp(zp)) return rc;
+    float lo, hi;
+    qrange(out_bits, &lo, &hi);
+    const float inv = 1.0f / out_scale;            // float32(1) / float32 scale, IEEE division (host)
+    const int grid = stream_grid(batch * M * N, 256);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (has_out_zp)
+        acc_post_kernel<2, true><<<grid, 256, 0, s>>>(acc, batch, M, N, ldacc, scale, make_acc_zp(zp), bias_q, inv, (double)out_zp, lo, hi, out);
+    else
+        acc_post_kernel<2, false><<<grid, 256, 0, s>>>(acc, batch, M, N, ldacc, scale, make_acc_zp(zp), bias_q, inv, 0.0, lo, hi, out);
+    NQ_CHECK_LAUNCH("nq_requantize_acc");
+    return NQ_OK;
+}
+
+extern "C" int nq_rowsum_s8(const int8_t* q, int64_t rows, int64_t C, int64_t ld, int32_t* rowsum, void* stream) {
+    if (rows <= 0) return NQ_OK;
+    rowsum_s8_kernel<<<stream_grid(rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(q, rows, C, ld, rowsum);
+    NQ_CHECK_LAUNCH("nq_rowsum_s8");
+    return NQ_OK;
+}
+
+extern "C" int nq_minmax_init(float* minmax, int64_t n_slots, void* stream) {
+    if (n_slots <= 0) return NQ_OK;
+    minmax_init_kernel<<<(unsigned)((n_slots + 255) / 256), 256, 0, (cudaStream_t)stream>>>(minmax, n_slots);
+    NQ_CHECK_LAUNCH("nq_minmax_init");
+    return NQ_OK;
+}
+
+extern "C" int nq_minmax_f32(const float* x, int64_t n, float* minmax, int64_t slot, void* stream) {
+    if (n <= 0) return NQ_OK;
+    minmax_kernel<<<stream_grid((n + 3) / 4, 256, 4), 256, 0, (cudaStream_t)stream>>>(x, n, minmax + 2 * slot);
+    NQ_CHECK_LAUNCH("nq_minmax_f32");
+    return NQ_OK;
+}
+
+extern "C" int nq_pack_s8(const int8_t* q, int64_t n, int bit_width, uint8_t* packed, void* stream) {
+    NQ_REQUIRE(bit_width >= 2 && bit_width <= 8, "nq_pack_s8: bit_width %d outside 2..8", bit_width);
+    if (n <= 0) return NQ_OK;
+    pack_kernel<<<stream_grid((n + 7) / 8, 256), 256, 0, (cudaStream_t)stream>>>(q, n, bit_width, packed);
+    NQ_CHECK_LAUNCH("nq_pack_s8");
+    return NQ_OK;
+}
+
+extern "C" int nq_unpack_s8(const uint8_t* packed, int64_t n, int bit_width, int8_t* q, void* stream) {
+    NQ_REQUIRE(bit_width >= 2 && bit_width <= 8, "nq_unpack_s8: bit_width %d outside 2..8", bit_width);
+    if (n <= 0) return NQ_OK;
+    unpack_kernel<<<stream_grid((n + 7) / 8, 256), 256, 0, (cudaStream_t)stream>>>(packed, n, bit_width, q);
+    NQ_CHECK_LAUNCH("nq_unpack_s8");
+    return NQ_OK;
+}

@@ -1,0 +1,397 @@
+"""Thin Python launchers over the C ABI: torch tensors in, torch tensors out.
+
+torch is plumbing here (device allocation, the current CUDA stream); every byte of
+arithmetic on the quantized path happens inside libnq_b200.so.  All launchers are
+asynchronous on `torch.cuda.current_stream()`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import AccZp, Epilogue, call
+
+LAUNCHES = 0          # kernels enqueued through this module (bench.py reports it as gpu_launches)
+
+
+def _count(n: int = 1) -> None:
+    global LAUNCHES
+    LAUNCHES += n
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _need_cuda(t: torch.Tensor, dtype=None) -> None:
+    if not t.is_cuda:
+        raise _lib.NqError("numpy_quant_b200 kernels need CUDA tensors (no CPU fallback)")
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError(f"expected {dtype}, got {t.dtype}")
+
+
+def round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+# --------------------------------------------------------------------------- K1
+def quantize(x: torch.Tensor, bits: int, scale, zp) -> torch.Tensor:
+    """float32 (contiguous) -> int8 codes, same shape (numpy_quantization.py:24-34)."""
+    _need_cuda(x, torch.float32)
+    x = x.contiguous()
+    out = torch.empty(x.shape, dtype=torch.int8, device=x.device)
+    call("nq_quantize_f32", x.data_ptr(), x.numel(), bits, float(scale), int(zp is not None),
+         0 if zp is None else int(zp), out.data_ptr(), _stream())
+    _count()
+    return out
+
+
+def quantize_i64(x: torch.Tensor, bits: int, scale) -> torch.Tensor:
+    """Symmetric wide quantize (4*bit_width-bit biases) -> int64 codes."""
+    _need_cuda(x, torch.float32)
+    x = x.contiguous()
+    out = torch.empty(x.shape, dtype=torch.int64, device=x.device)
+    call("nq_quantize_f32_i64", x.data_ptr(), x.numel(), bits, float(scale), 0, 0, out.data_ptr(), _stream())
+    _count()
+    return out
+
+
+@dataclass
+class Operand:
+    """K-major int8 GEMM operand: data[batch, rows, ld] with `k` valid columns per row."""
+    data: torch.Tensor
+    batch_shape: tuple
+    rows: int
+    k: int
+    ld: int
+    rowsum: Optional[torch.Tensor] = None      # int32 [batch, rows]: sum over k of each row
+
+    @property
+    def batch(self) -> int:
+        return int(np.prod(self.batch_shape)) if self.batch_shape else 1
+
+
+def quantize_operand(x: torch.Tensor, role: str, bits: int, scale, zp, want_rowsum: bool) -> Operand:
+    """Quantize a (possibly strided, <= 4-D) float32 matrix stack straight into the
+    K-major layout the tensor-core GEMM reads.
+
+    role 'A': x[..., M, K] -> rows = M;   role 'B': x[..., K, N] -> rows = N (transposed on the fly).
+    """
+    _need_cuda(x, torch.float32)
+    if x.dim() < 2:
+        raise ValueError("matmul operands need >= 2 dims")
+    if x.dim() > 4:
+        x = x.reshape(-1, *x.shape[-3:])
+    lead = tuple(x.shape[:-2])
+    st = list(x.stride())
+    d = [1] * (4 - x.dim()) + list(x.shape)
+    s = [0] * (4 - x.dim()) + st
+    if role == "A":
+        R, Cc, sr, sc = d[2], d[3], s[2], s[3]
+    else:
+        R, Cc, sr, sc = d[3], d[2], s[3], s[2]
+    ld = round_up(Cc, 16)
+    batch = d[0] * d[1]
+    out = torch.empty((batch, R, ld), dtype=torch.int8, device=x.device)
+    rs = torch.empty((batch, R), dtype=torch.int32, device=x.device) if want_rowsum else None
+    call("nq_quantize_f32_4d", x.data_ptr(), d[0], d[1], R, Cc, s[0], s[1], sr, sc, bits, float(scale),
+         int(zp is not None), 0 if zp is None else int(zp), out.data_ptr(), ld, _ptr(rs), _stream())
+    _count(2 if (want_rowsum and sr == 1 and sc != 1) else 1)
+    return Operand(out, lead, R, Cc, ld, rs)
+
+
+def operand_from_codes(q: torch.Tensor, role: str, want_rowsum: bool) -> Operand:
+    """int8 codes [..., M, K] (role A) / [..., K, N] (role B) -> K-major Operand (copy + pad)."""
+    _need_cuda(q, torch.int8)
+    if q.dim() > 4:
+        q = q.reshape(-1, *q.shape[-3:])
+    lead = tuple(q.shape[:-2])
+    d = [1] * (4 - q.dim()) + list(q.shape)
+    s = [0] * (4 - q.dim()) + list(q.stride())
+    if role == "B":
+        d[2], d[3] = d[3], d[2]
+        s[2], s[3] = s[3], s[2]
+    R, K = d[2], d[3]
+    ld = round_up(K, 16)
+    batch = d[0] * d[1]
+    out = torch.zeros((batch, R, ld), dtype=torch.int8, device=q.device)
+    so = [d[1] * R * ld, R * ld, ld, 1]
+    call("nq_copy_4d", q.data_ptr(), 1, _lib.i64x4(d), _lib.i64x4(s), out.data_ptr(), _lib.i64x4(so), _stream())
+    _count()
+    op = Operand(out, lead, R, K, ld, None)
+    if want_rowsum:
+        op.rowsum = rowsum(op)
+    return op
+
+
+def rowsum(op: Operand) -> torch.Tensor:
+    rs = torch.empty((op.batch, op.rows), dtype=torch.int32, device=op.data.device)
+    call("nq_rowsum_s8", op.data.data_ptr(), op.batch * op.rows, op.k, op.ld, rs.data_ptr(), _stream())
+    _count()
+    return rs
+
+
+# --------------------------------------------------------------------------- K2 / K3
+def dequantize(q: torch.Tensor, scale, zp) -> torch.Tensor:
+    _need_cuda(q)
+    q = q.contiguous()
+    eb = {torch.int8: 1, torch.int32: 4, torch.int64: 8}[q.dtype]
+    out = torch.empty(q.shape, dtype=torch.float32, device=q.device)
+    call("nq_dequantize", q.data_ptr(), eb, q.numel(), float(scale), int(zp is not None),
+         0 if zp is None else int(zp), out.data_ptr(), _stream())
+    _count()
+    return out
+
+
+@dataclass
+class AccZeroPoint:
+    """Factored zero-point of a q_matmul accumulator (numpy_quantization.py:49-61)."""
+    zp_a: Optional[int]
+    zp_b: Optional[int]
+    k: int
+    rowsum_a: Optional[torch.Tensor]       # int32 [batch, M]
+    colsum_b: Optional[torch.Tensor]       # int32 [batchB, N]
+    colsum_shared: bool                    # B shared across the batch
+
+    def c_struct(self, n: int) -> AccZp:
+        z = AccZp()
+        z.has_zp_a = int(self.zp_a is not None)
+        z.has_zp_b = int(self.zp_b is not None)
+        z.zp_a = 0 if self.zp_a is None else int(self.zp_a)
+        z.zp_b = 0 if self.zp_b is None else int(self.zp_b)
+        z.k = int(self.k)
+        z.rowsum_a = _ptr(self.rowsum_a) if self.zp_b is not None else None
+        z.colsum_b = _ptr(self.colsum_b) if self.zp_a is not None else None
+        z.colsum_batch_stride = 0 if self.colsum_shared else n
+        return z
+
+    @property
+    def is_none(self) -> bool:
+        return self.zp_a is None and self.zp_b is None
+
+
+def dequantize_acc(acc: torch.Tensor, scale, azp: AccZeroPoint) -> torch.Tensor:
+    """int32 accumulator [batch, M, N] -> float32 with the factored zero-point."""
+    _need_cuda(acc, torch.int32)
+    b, m, n = acc.shape
+    out = torch.empty((b, m, n), dtype=torch.float32, device=acc.device)
+    z = azp.c_struct(n)
+    call("nq_dequantize_acc", acc.data_ptr(), b, m, n, acc.stride(1), float(scale), C.byref(z), out.data_ptr(),
+         _stream())
+    _count()
+    return out
+
+
+def requantize_acc(acc: torch.Tensor, scale, azp: AccZeroPoint, bias_q: Optional[torch.Tensor], bits: int,
+                   out_scale, out_zp) -> torch.Tensor:
+    _need_cuda(acc, torch.int32)
+    b, m, n = acc.shape
+    out = torch.empty((b, m, n), dtype=torch.int8, device=acc.device)
+    z = azp.c_struct(n)
+    call("nq_requantize_acc", acc.data_ptr(), b, m, n, acc.stride(1), float(scale), C.byref(z), _ptr(bias_q), bits,
+         float(out_scale), int(out_zp is not None), 0 if out_zp is None else int(out_zp), out.data_ptr(), _stream())
+    _count()
+    return out
+
+
+# --------------------------------------------------------------------------- K4 / K5
+def qgemm(a: Operand, b: Operand, mode: int = _lib.EPI_RAW, scale: float = 1.0,
+          azp: Optional[AccZeroPoint] = None, bias_f32: Optional[torch.Tensor] = None,
+          bias_q: Optional[torch.Tensor] = None, out_bits: int = 8, out_scale: float = 1.0, out_zp=None,
+          simt: bool = False) -> torch.Tensor:
+    """C[batch, M, N] = A[batch, M, K] . B[batch|1, N, K]^T on the tcgen05 tensor cores."""
+    assert a.k == b.k, f"contraction mismatch {a.k} vs {b.k}"
+    batch = max(a.batch, b.batch)
+    assert a.batch in (1, batch) and b.batch in (1, batch)
+    M, N, K = a.rows, b.rows, a.k
+    dtype = {_lib.EPI_RAW: torch.int32, _lib.EPI_DEQUANT: torch.float32, _lib.EPI_REQUANT: torch.int8}[mode]
+    out = torch.empty((batch, M, N), dtype=dtype, device=a.data.device)
+    sa = 0 if (a.batch == 1 and batch > 1) else M * a.ld
+    sb = 0 if (b.batch == 1 and batch > 1) else N * b.ld
+    if simt:
+        assert mode == _lib.EPI_RAW
+        call("nq_qgemm_s8_simt", a.data.data_ptr(), b.data.data_ptr(), out.data_ptr(), M, N, K, batch, a.ld, b.ld, N,
+             sa, sb, M * N, _stream())
+        _count()
+        return out
+    ep = Epilogue()
+    ep.mode = mode
+    ep.scale = float(scale)
+    if azp is not None:
+        ep.zp = azp.c_struct(N)
+    ep.bias_f32 = _ptr(bias_f32)
+    ep.bias_q = _ptr(bias_q)
+    ep.out_bits = out_bits
+    ep.out_scale = float(out_scale)
+    ep.has_out_zp = int(out_zp is not None)
+    ep.out_zp = 0 if out_zp is None else int(out_zp)
+    call("nq_qgemm_s8", a.data.data_ptr(), b.data.data_ptr(), out.data_ptr(), M, N, K, batch, a.ld, b.ld, N,
+         sa, sb, M * N, C.byref(ep), _stream())
+    _count()
+    return out
+
+
+# --------------------------------------------------------------------------- K10 / K11
+def minmax_slots(n_slots: int, device) -> torch.Tensor:
+    mm = torch.empty((n_slots, 2), dtype=torch.float32, device=device)
+    call("nq_minmax_init", mm.data_ptr(), n_slots, _stream())
+    _count()
+    return mm
+
+
+def minmax_into(x: torch.Tensor, mm: torch.Tensor, slot: int) -> None:
+    _need_cuda(x, torch.float32)
+    x = x.contiguous()
+    call("nq_minmax_f32", x.data_ptr(), x.numel(), mm.data_ptr(), slot, _stream())
+    _count()
+
+
+def pack(q: torch.Tensor, bits: int) -> torch.Tensor:
+    _need_cuda(q, torch.int8)
+    q = q.contiguous()
+    out = torch.empty(((q.numel() * bits + 7) // 8,), dtype=torch.uint8, device=q.device)
+    call("nq_pack_s8", q.data_ptr(), q.numel(), bits, out.data_ptr(), _stream())
+    _count()
+    return out
+
+
+def unpack(packed: torch.Tensor, n: int, bits: int) -> torch.Tensor:
+    _need_cuda(packed, torch.uint8)
+    out = torch.empty((n,), dtype=torch.int8, device=packed.device)
+    call("nq_unpack_s8", packed.data_ptr(), n, bits, out.data_ptr(), _stream())
+    _count()
+    return out
+
+
+# --------------------------------------------------------------------------- K7-K9 float glue
+def unary(op: str, x: torch.Tensor) -> torch.Tensor:
+    _need_cuda(x, torch.float32)
+    x = x.contiguous()
+    out = torch.empty_like(x)
+    call("nq_unary_f32", _lib.UN[op], x.data_ptr(), x.numel(), out.data_ptr(), _stream())
+    _count()
+    return out
+
+
+def gelu_erf(x: torch.Tensor, c_div: float, c_add: float, c_mul: float) -> torch.Tensor:
+    _need_cuda(x, torch.float32)
+    x = x.contiguous()
+    out = torch.empty_like(x)
+    call("nq_gelu_erf_f32", x.data_ptr(), x.numel(), float(c_div), float(c_add), float(c_mul), out.data_ptr(),
+         _stream())
+    _count()
+    return out
+
+
+def _pad4(shape, strides):
+    n = len(shape)
+    return [1] * (4 - n) + list(shape), [0] * (4 - n) + list(strides)
+
+
+def _collapse_to_4d(t: torch.Tensor, shape) -> torch.Tensor:
+    """Broadcast `t` to `shape` (as a stride-0 view) and make it at most 4-D."""
+    v = t.expand(shape)
+    if v.dim() > 4:
+        v = v.reshape(-1, *shape[-3:])          # may copy for exotic stride patterns (not on the hot path)
+    return v
+
+
+def binary(op: str, a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """NumPy-style broadcasting float32 binary op (tensor.py:80-104)."""
+    _need_cuda(a, torch.float32)
+    _need_cuda(b, torch.float32)
+    shape = torch.broadcast_shapes(a.shape, b.shape)
+    out = torch.empty(shape, dtype=torch.float32, device=a.device)
+    if out.numel() == 0:
+        return out
+    va, vb = _collapse_to_4d(a, shape), _collapse_to_4d(b, shape)
+    d, sa = _pad4(va.shape, va.stride())
+    _, sb = _pad4(vb.shape, vb.stride())
+    sa = [0 if dd == 1 else ss for dd, ss in zip(d, sa)]
+    sb = [0 if dd == 1 else ss for dd, ss in zip(d, sb)]
+    call("nq_binary_f32", _lib.BIN[op], va.data_ptr(), _lib.i64x4(sa), vb.data_ptr(), _lib.i64x4(sb), _lib.i64x4(d),
+         out.data_ptr(), _stream())
+    _count()
+    return out
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float) -> torch.Tensor:
+    _need_cuda(x, torch.float32)
+    x = x.contiguous()
+    cols = x.shape[-1]
+    out = torch.empty_like(x)
+    call("nq_layernorm_f32", x.data_ptr(), x.numel() // cols, cols, cols, gamma.contiguous().data_ptr(),
+         beta.contiguous().data_ptr(), float(eps), out.data_ptr(), _stream())
+    _count()
+    return out
+
+
+def softmax_lastdim(x: torch.Tensor) -> torch.Tensor:
+    _need_cuda(x, torch.float32)
+    x = x.contiguous()
+    cols = x.shape[-1]
+    out = torch.empty_like(x)
+    call("nq_softmax_f32", x.data_ptr(), x.numel() // cols, cols, cols, out.data_ptr(), _stream())
+    _count()
+    return out
+
+
+def reduce_lastdim(op: str, x: torch.Tensor, keepdims: bool) -> torch.Tensor:
+    _need_cuda(x, torch.float32)
+    x = x.contiguous()
+    cols = x.shape[-1]
+    out = torch.empty(x.shape[:-1], dtype=torch.float32, device=x.device)
+    call("nq_reduce_rows_f32", {"max": 0, "sum": 1, "mean": 2}[op], x.data_ptr(), x.numel() // cols, cols,
+         out.data_ptr(), _stream())
+    _count()
+    return out.unsqueeze(-1) if keepdims else out
+
+
+def materialize(x: torch.Tensor) -> torch.Tensor:
+    """Contiguous copy of a strided view (Transpose / Expand / Slice) with our own copy kernel."""
+    _need_cuda(x)
+    if x.is_contiguous():
+        return x
+    out = torch.empty(x.shape, dtype=x.dtype, device=x.device)
+    if x.numel() == 0:
+        return out
+    v = x if x.dim() <= 4 else None
+    if v is None:
+        return x.contiguous()                    # > 4-D strided views never occur on the quantized path
+    d, sx = _pad4(v.shape, v.stride())
+    so = [d[1] * d[2] * d[3], d[2] * d[3], d[3], 1]
+    call("nq_copy_4d", v.data_ptr(), x.element_size(), _lib.i64x4(d), _lib.i64x4(sx), out.data_ptr(),
+         _lib.i64x4(so), _stream())
+    _count()
+    return out
+
+
+def im2col(x: torch.Tensor, kh: int, kw: int, pads, strides, pad_value=0) -> tuple[torch.Tensor, int, int]:
+    """x[B,C,H,W] (int8 or float32) -> patches [B*OH*OW, ld] in (kh, kw, c) order (numpy_helper.py:18-92)."""
+    _need_cuda(x)
+    x = x.contiguous()
+    B, Cc, H, W = x.shape
+    ph0, pw0, ph1, pw1 = (int(p) for p in pads)
+    sh, sw = (int(s) for s in strides)
+    OH = -((H - kh + ph0 + ph1 + 1) // -sh)
+    OW = -((W - kw + pw0 + pw1 + 1) // -sw)
+    k = kh * kw * Cc
+    if x.dtype == torch.int8:
+        ld, eb, pv = round_up(k, 16), 1, int(pad_value)
+    else:
+        ld, eb = k, 4
+        pv = int(np.float32(pad_value).view(np.int32))
+    out = torch.empty((B * OH * OW, ld), dtype=x.dtype, device=x.device)
+    call("nq_im2col", x.data_ptr(), eb, B, Cc, H, W, kh, kw, ph0, pw0, ph1, pw1, sh, sw, pv, out.data_ptr(), ld,
+         _stream())
+    _count()
+    return out, OH, OW

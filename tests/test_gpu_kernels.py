@@ -1,0 +1,306 @@
+"""Kernel-level parity: every C-ABI entry point of libnq_b200.so against the oracle /
+the golden vectors of the unmodified reference.  Integer results bit-exact; float results
+within 1e-5 relative (tolerance stated per test)."""
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+if not torch.cuda.is_available():
+    pytest.skip("needs a CUDA device", allow_module_level=True)
+
+from numpy_quant_b200 import _lib, kernels as K  # noqa: E402
+from oracle import ref_quant as rq  # noqa: E402
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+DEV = torch.device("cuda:0")
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+def host(t):
+    return t.detach().cpu().numpy()
+
+
+def _zp(flag, val):
+    return None if int(flag) == 0 else int(val)
+
+
+@pytest.fixture(scope="module")
+def kv():
+    return np.load(os.path.join(G, "kernels.npz"))
+
+
+def test_library_is_the_native_one():
+    lib = _lib.load()
+    assert lib.nq_version() >= 100
+    info = (_lib.C.c_int * 4)()
+    _lib.call("nq_device_info", info)
+    assert info[1] == 10, f"expected a compute-capability 10.x device, got {info[1]}.{info[2]}"
+
+
+# ----------------------------------------------------------------------------- K1
+@pytest.mark.parametrize("bits", range(2, 9))
+@pytest.mark.parametrize("asym", [False, True])
+def test_quantize_golden(kv, bits, asym):
+    tag = f"b{bits}_{'a' if asym else 's'}"
+    scale, zp = kv[f"q_scale_{tag}"], _zp(kv[f"q_zpf_{tag}"], kv[f"q_zp_{tag}"])
+    q = K.quantize(dev(kv[f"q_in_{tag}"]), bits, scale, zp)
+    np.testing.assert_array_equal(host(q).astype(np.int64), kv[f"q_out_{tag}"])
+    np.testing.assert_array_equal(host(K.dequantize(q, scale, zp)), kv[f"dq_out_{tag}"])
+
+
+@pytest.mark.parametrize("bits,asym", [(8, True), (8, False), (4, True), (2, False)])
+def test_quantize_large_vs_oracle(bits, asym):
+    rng = np.random.default_rng(bits * 2 + asym)
+    x = (rng.normal(size=(1 << 20) + 13) * 2).astype(np.float32)
+    scale, zp = rq.quant_parameters(x.min(), x.max(), bits, asym)
+    # plant exact ties: (k + 0.5) * scale and neighbours
+    k = np.arange(-300, 300, dtype=np.float32)
+    x[: k.size] = (k + np.float32(0.5)) * np.float32(scale)
+    ref = rq.quantize(x, bits, scale, zp)
+    got = host(K.quantize(dev(x), bits, scale, zp)).astype(np.int64)
+    np.testing.assert_array_equal(got, ref)
+    # unaligned view -> scalar kernel path
+    got2 = host(K.quantize(dev(x)[3:], bits, scale, zp)).astype(np.int64)
+    np.testing.assert_array_equal(got2, ref[3:])
+
+
+def test_quantize_operand_layouts():
+    rng = np.random.default_rng(5)
+    x = rng.normal(size=(2, 3, 37, 50)).astype(np.float32)
+    scale, zp = rq.quant_parameters(x.min(), x.max(), 8, True)
+    ref = rq.quantize(x, 8, scale, zp)
+    xd = dev(x)
+    a = K.quantize_operand(xd, "A", 8, scale, zp, True)                     # rows = 37, k = 50
+    assert a.data.shape == (6, 37, 64) and a.ld == 64
+    np.testing.assert_array_equal(host(a.data)[:, :, :50].astype(np.int64), ref.reshape(6, 37, 50))
+    assert not host(a.data)[:, :, 50:].any()
+    np.testing.assert_array_equal(host(a.rowsum).astype(np.int64), ref.reshape(6, 37, 50).sum(-1))
+    b = K.quantize_operand(xd, "B", 8, scale, zp, True)                     # rows = 50 (N), k = 37
+    np.testing.assert_array_equal(host(b.data)[:, :, :37].astype(np.int64), ref.reshape(6, 37, 50).transpose(0, 2, 1))
+    np.testing.assert_array_equal(host(b.rowsum).astype(np.int64), ref.reshape(6, 37, 50).sum(-2))
+    # strided view (the attention K^T pattern): [B, S, H, D] -> permute(0, 2, 3, 1) as operand B
+    base = rng.normal(size=(2, 11, 3, 8)).astype(np.float32)
+    view = dev(base).permute(0, 2, 3, 1)                                   # [2, 3, 8, 11] = [.., K=8, N=11]
+    refv = rq.quantize(base.transpose(0, 2, 3, 1), 8, scale, zp)
+    ob = K.quantize_operand(view, "B", 8, scale, zp, True)
+    np.testing.assert_array_equal(host(ob.data)[:, :, :8].astype(np.int64), refv.reshape(6, 8, 11).transpose(0, 2, 1))
+    np.testing.assert_array_equal(host(ob.rowsum).astype(np.int64), refv.reshape(6, 8, 11).sum(-2))
+    # symmetric 2-D weight [K, N] as operand B
+    w = rng.normal(size=(70, 33)).astype(np.float32)
+    ws, _ = rq.quant_parameters(w.min(), w.max(), 4, False)
+    ow = K.quantize_operand(dev(w), "B", 4, ws, None, True)
+    refw = rq.quantize(w, 4, ws, None)
+    np.testing.assert_array_equal(host(ow.data)[0, :, :70].astype(np.int64), refw.T)
+    np.testing.assert_array_equal(host(ow.rowsum)[0].astype(np.int64), refw.sum(0))
+
+
+def test_quantize_wide_bias():
+    rng = np.random.default_rng(7)
+    b = rng.normal(size=1000).astype(np.float32)
+    for bits, scale in ((32, np.float32(2.5e-4)), (16, np.float32(0.07)), (8, np.float32(3.4)), (32, np.float32(1e-12))):
+        ref = rq.quantize(b, bits, scale, None)
+        np.testing.assert_array_equal(host(K.quantize_i64(dev(b), bits, scale)), ref)
+
+
+# ----------------------------------------------------------------------------- K2 / K3
+def test_dequantize_wide_and_acc(kv):
+    acc, sc = kv["acc"], kv["acc_scale"]
+    np.testing.assert_array_equal(host(K.dequantize(dev(acc), sc, None)), kv["acc_dq_none"])
+    np.testing.assert_array_equal(host(K.dequantize(dev(acc.astype(np.int32)), sc, None)), kv["acc_dq_none"])
+    np.testing.assert_array_equal(host(K.dequantize(dev(acc), sc, -77)), rq.dequantize(acc, sc, np.int64(-77)))
+    # factored zero-point: rowsum*zp_b + colsum*zp_a - zp_a*zp_b*k  == zrow + zcol - 77
+    zrow, zcol = kv["acc_zrow"], kv["acc_zcol"]
+    azp = K.AccZeroPoint(zp_a=1, zp_b=1, k=77, rowsum_a=dev(zrow.astype(np.int32).reshape(1, -1)),
+                         colsum_b=dev(zcol.astype(np.int32).reshape(1, -1)), colsum_shared=True)
+    got = K.dequantize_acc(dev(acc.astype(np.int32))[None], sc, azp)
+    np.testing.assert_array_equal(host(got)[0], kv["acc_dq_full"])
+    for bits in range(2, 9):
+        for asym in (False, True):
+            tag = f"b{bits}_{'a' if asym else 's'}"
+            got = K.requantize_acc(dev(acc.astype(np.int32))[None], sc, azp, None, bits, kv[f"rq_scale_{tag}"],
+                                   _zp(kv[f"rq_zpf_{tag}"], kv[f"rq_zp_{tag}"]))
+            np.testing.assert_array_equal(host(got)[0].astype(np.int64), kv[f"rq_out_{tag}"], err_msg=tag)
+
+
+# ----------------------------------------------------------------------------- K4 / K5
+GEMM_SHAPES = [  # (batch, M, N, K, shared_B)
+    (1, 3, 1, 3, False), (1, 5, 2, 5, False), (1, 128, 256, 128, False), (1, 129, 257, 129, False),
+    (1, 300, 768, 768, False), (1, 256, 1000, 768, False), (1, 1000, 200, 3072, False),
+    (24, 197, 197, 64, False), (24, 197, 64, 197, False), (3, 70, 130, 96, True), (2, 1, 1, 1, False),
+]
+
+
+@pytest.mark.parametrize("batch,M,N,Kd,shared", GEMM_SHAPES)
+def test_qgemm_raw_bit_exact(batch, M, N, Kd, shared):
+    rng = np.random.default_rng(M * 7 + N * 3 + Kd)
+    a = rng.integers(-128, 128, size=(batch, M, Kd)).astype(np.int8)
+    b = rng.integers(-128, 128, size=(1 if shared else batch, Kd, N)).astype(np.int8)
+    ref = np.matmul(a.astype(np.int64), b.astype(np.int64))
+    oa = K.operand_from_codes(dev(a), "A", False)
+    ob = K.operand_from_codes(dev(b), "B", False)
+    got = host(K.qgemm(oa, ob)).astype(np.int64)
+    np.testing.assert_array_equal(got, ref)
+    np.testing.assert_array_equal(host(K.qgemm(oa, ob, simt=True)).astype(np.int64), ref)
+
+
+def test_qgemm_extreme_values_and_persistence():
+    # all -128 x -128 over K=4096 stresses the accumulator; > 148*2 tiles exercises the
+    # TMEM double buffer and the smem ring wrap-around of the persistent loop
+    M, N, Kd = 128 * 40, 256 * 9, 4096
+    a = torch.full((1, M, Kd), -128, dtype=torch.int8, device=DEV)
+    b = torch.full((1, Kd, N), -128, dtype=torch.int8, device=DEV)
+    a[0, 5, 7] = 127
+    got = K.qgemm(K.operand_from_codes(a, "A", False), K.operand_from_codes(b, "B", False))
+    assert int(got[0, 0, 0]) == 128 * 128 * Kd
+    assert int(got[0, 5, 3]) == 128 * 128 * (Kd - 1) - 127 * 128
+    assert bool((got[0, 6:] == 128 * 128 * Kd).all())
+
+
+def test_qgemm_4096_cubed_vs_cuda_core_gemm():
+    g = torch.Generator(device="cuda").manual_seed(0)
+    a = torch.randint(-128, 128, (1, 4096, 4096), generator=g, device=DEV, dtype=torch.int8)
+    b = torch.randint(-128, 128, (1, 4096, 4096), generator=g, device=DEV, dtype=torch.int8)
+    oa, ob = K.operand_from_codes(a, "A", False), K.operand_from_codes(b, "B", False)
+    assert torch.equal(K.qgemm(oa, ob), K.qgemm(oa, ob, simt=True))
+
+
+@pytest.mark.parametrize("za,zb", [(None, None), (None, -3), (5, None), (5, -3)])
+@pytest.mark.parametrize("bits", [8, 4])
+def test_qgemm_fused_epilogues(za, zb, bits):
+    rng = np.random.default_rng(11)
+    lo, hi = -2 ** (bits - 1), 2 ** (bits - 1) - 1
+    batch, M, N, Kd = 3, 150, 200, 320
+    a = rng.integers(lo, hi + 1, size=(batch, M, Kd)).astype(np.int64)
+    b = rng.integers(lo, hi + 1, size=(batch, Kd, N)).astype(np.int64)
+    sa, sb = np.float32(0.021), np.float32(0.0043)
+    acc, s, z = rq.q_matmul(a, sa, None if za is None else np.int64(za), b, sb, None if zb is None else np.int64(zb))
+    oa = K.operand_from_codes(dev(a.astype(np.int8)), "A", zb is not None)
+    ob = K.operand_from_codes(dev(b.astype(np.int8)), "B", za is not None)
+    azp = K.AccZeroPoint(za, zb, Kd, oa.rowsum, ob.rowsum, False)
+    # DEQUANT (+ float bias)
+    bias = rng.normal(size=N).astype(np.float32)
+    want = rq.dequantize(acc, s, z)
+    got = K.qgemm(oa, ob, _lib.EPI_DEQUANT, s, azp)
+    np.testing.assert_array_equal(host(got), want)
+    got = K.qgemm(oa, ob, _lib.EPI_DEQUANT, s, azp, bias_f32=dev(bias))
+    np.testing.assert_array_equal(host(got), bias + want)
+    # the unfused route must agree too
+    raw = K.qgemm(oa, ob)
+    np.testing.assert_array_equal(host(K.dequantize_acc(raw, s, azp)), want)
+    # REQUANT with an int64 bias (Gemm), asymmetric and symmetric outputs
+    bq = rng.integers(-20000, 20000, size=N).astype(np.int64)
+    d = rq.dequantize(acc + bq, s, z)
+    for asym in (True, False):
+        so, zo = rq.quant_parameters(d.min(), d.max(), bits, asym)
+        want_q = rq.requantize(acc + bq, s, z, so, zo, bits)
+        got_q = K.qgemm(oa, ob, _lib.EPI_REQUANT, s, azp, bias_q=dev(bq), out_bits=bits, out_scale=so,
+                        out_zp=None if zo is None else int(zo))
+        np.testing.assert_array_equal(host(got_q).astype(np.int64), want_q)
+        np.testing.assert_array_equal(
+            host(K.requantize_acc(raw, s, azp, dev(bq), bits, so, None if zo is None else int(zo))).astype(np.int64), want_q)
+
+
+def test_qgemm_rejects_bad_arguments():
+    a = torch.zeros((1, 4, 8), dtype=torch.int8, device=DEV)
+    ep = _lib.Epilogue()
+    with pytest.raises(_lib.NqError, match="multiples of 16"):
+        _lib.call("nq_qgemm_s8", a.data_ptr(), a.data_ptr(), a.data_ptr(), 4, 4, 8, 1, 8, 8, 4, 0, 0, 0,
+                  _lib.C.byref(ep), None)
+
+
+# ----------------------------------------------------------------------------- K7-K9
+def test_float_glue_vs_numpy(kv):
+    rng = np.random.default_rng(3)
+    np.testing.assert_allclose(host(K.unary("erf", dev(kv["erf_in"]))), kv["erf_out"], rtol=1e-5, atol=1e-7)
+    x = (rng.normal(size=(7, 33, 768)) * 2).astype(np.float32)
+    xd = dev(x)
+    for name, fn in (("exp", np.exp), ("tanh", np.tanh), ("sqrt", lambda v: np.sqrt(np.abs(v))),
+                     ("inv", lambda v: 1 / v), ("neg", lambda v: -v), ("relu", lambda v: (v > 0) * v),
+                     ("sigmoid", lambda v: 1 / (1.0 + np.exp(-v)))):
+        arg = dev(np.abs(x)) if name == "sqrt" else xd
+        np.testing.assert_allclose(host(K.unary(name, arg)), fn(x), rtol=1e-5, atol=1e-30, err_msg=name)
+    assert np.signbit(host(K.unary("relu", dev(np.array([-1.0, 2.0], np.float32))))[0])        # -0.0 quirk
+    # GELU chain == five separate float32 ops
+    c1, c2, c3 = np.float32(1.4142135381698608), np.float32(1.0), np.float32(0.5)
+    want = (x * (rq.erf_poly(x / c1) + c2)) * c3
+    np.testing.assert_allclose(host(K.gelu_erf(xd, c1, c2, c3)), want, rtol=1e-5, atol=1e-6)
+    # broadcasting binaries are bit-exact (single IEEE op each)
+    y = rng.normal(size=(7, 33, 768)).astype(np.float32)
+    bias = rng.normal(size=768).astype(np.float32)
+    np.testing.assert_array_equal(host(K.binary("add", xd, dev(y))), x + y)
+    np.testing.assert_array_equal(host(K.binary("add", dev(bias), xd)), bias + x)
+    np.testing.assert_array_equal(host(K.binary("mul", xd, dev(bias))), x * bias)
+    np.testing.assert_array_equal(host(K.binary("div", xd, dev(np.array(8.0, np.float32)))), x / np.float32(8))
+    col = rng.normal(size=(7, 33, 1)).astype(np.float32)
+    np.testing.assert_array_equal(host(K.binary("mul", xd, dev(col))), x * col)
+    np.testing.assert_array_equal(host(K.binary("add", xd.transpose(0, 1), dev(y).transpose(0, 1))),
+                                  (x + y).transpose(1, 0, 2))
+    # LayerNorm (model.py:134-152) and Softmax (tensor.py:139-146): 1e-5 relative
+    g, b = (1 + rng.normal(size=768) * 0.02).astype(np.float32), (rng.normal(size=768) * 0.02).astype(np.float32)
+    mean = x.mean(-1, keepdims=True)
+    d = x - mean
+    want = d * (1 / np.sqrt((d * d).mean(-1, keepdims=True) + np.float32(1e-12))) * g + b
+    np.testing.assert_allclose(host(K.layernorm(xd, dev(g), dev(b), 1e-12)), want, rtol=1e-5, atol=2e-6)
+    x2 = rng.normal(size=(5, 12, 197, 197)).astype(np.float32) * 3
+    e = np.exp(x2 - x2.max(-1, keepdims=True))
+    np.testing.assert_allclose(host(K.softmax_lastdim(dev(x2))), e / e.sum(-1, keepdims=True), rtol=1e-5, atol=1e-10)
+    for cols in (5, 130, 300, 1500):
+        x3 = rng.normal(size=(9, cols)).astype(np.float32)
+        e = np.exp(x3 - x3.max(-1, keepdims=True))
+        np.testing.assert_allclose(host(K.softmax_lastdim(dev(x3))), e / e.sum(-1, keepdims=True), rtol=1e-5)
+        g3, b3 = rng.normal(size=cols).astype(np.float32), rng.normal(size=cols).astype(np.float32)
+        d = x3 - x3.mean(-1, keepdims=True)
+        want = d * (1 / np.sqrt((d * d).mean(-1, keepdims=True) + np.float32(1e-5))) * g3 + b3
+        np.testing.assert_allclose(host(K.layernorm(dev(x3), dev(g3), dev(b3), 1e-5)), want, rtol=2e-5, atol=2e-6)
+        np.testing.assert_allclose(host(K.reduce_lastdim("mean", dev(x3), True)), x3.mean(-1, keepdims=True),
+                                   rtol=1e-5, atol=1e-7)
+        np.testing.assert_array_equal(host(K.reduce_lastdim("max", dev(x3), False)), x3.max(-1))
+
+
+def test_copy_and_im2col(kv):
+    rng = np.random.default_rng(9)
+    x = rng.normal(size=(2, 5, 3, 8)).astype(np.float32)
+    np.testing.assert_array_equal(host(K.materialize(dev(x).permute(0, 2, 3, 1))), x.transpose(0, 2, 3, 1))
+    np.testing.assert_array_equal(host(K.materialize(dev(x)[:, 1:4, :, ::2])), x[:, 1:4, :, ::2])
+    cx, cw, cb = kv["conv_x"], kv["conv_w"], kv["conv_b"]
+    cols, oh, ow = K.im2col(dev(cx), 3, 2, (0, 2, 2, 1), (2, 1))
+    wmat = cw.transpose(2, 3, 1, 0).reshape(-1, 2)
+    y = (host(cols) @ wmat).reshape(2, oh, ow, 2).transpose(0, 3, 1, 2) + cb[None, :, None, None]
+    np.testing.assert_allclose(y, kv["conv_y"], rtol=1e-5, atol=1e-5)
+    q = rng.integers(-128, 128, size=(2, 3, 9, 10)).astype(np.int8)
+    qc, oh, ow = K.im2col(dev(q), 3, 2, (0, 2, 2, 1), (2, 1), pad_value=-7)
+    qp = np.pad(q.transpose(0, 2, 3, 1), ((0, 0), (0, 2), (2, 1), (0, 0)), constant_values=-7)
+    ref = np.stack([qp[:, i * 2:i * 2 + 3, j:j + 2, :].reshape(2, -1) for i in range(oh) for j in range(ow)], 1)
+    np.testing.assert_array_equal(host(qc)[:, :18].reshape(2, oh * ow, 18), ref)
+
+
+# ----------------------------------------------------------------------------- K10 / K11
+def test_minmax_and_pack_roundtrip():
+    rng = np.random.default_rng(2)
+    mm = K.minmax_slots(3, DEV)
+    xs = [rng.normal(size=n).astype(np.float32) for n in (1, 1000, (1 << 20) + 5)]
+    xs[1] = -np.abs(xs[1]) - 1                                  # all-negative tensor
+    for i, x in enumerate(xs):
+        K.minmax_into(dev(x), mm, i)
+    got = host(mm)
+    for i, x in enumerate(xs):
+        assert got[i, 0] == x.min() and got[i, 1] == x.max()
+    for bits in range(2, 9):
+        lo, hi = -2 ** (bits - 1), 2 ** (bits - 1) - 1
+        for n in (1, 7, 8, 9, 4096, 100003):
+            q = rng.integers(lo, hi + 1, size=n).astype(np.int8)
+            p = K.pack(dev(q), bits)
+            assert p.numel() == (n * bits + 7) // 8
+            np.testing.assert_array_equal(host(K.unpack(p, n, bits)), q)
+            # layout contract: little-endian bitstream of two's-complement fields
+            bitsream = np.unpackbits(host(p), bitorder="little")[: n * bits].reshape(n, bits)
+            val = (bitsream * (1 << np.arange(bits))).sum(1)
+            val = np.where(val >= 2 ** (bits - 1), val - 2 ** bits, val)
+            np.testing.assert_array_equal(val, q)
