@@ -1,0 +1,140 @@
+#!/usr/bin/env python
+"""Config 5 microbench: standalone qGEMM 4096^3 and the quantize / dequantize / requantize
+kernels on 4096^2 (and the ViT-B b256 shapes), each timed alone with CUDA events after an L2
+flush, reported against the measured peaks.  One JSON line per case on stdout.
+
+    python benchmarks/microbench.py [--quick]
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from numpy_quant_b200 import _lib, kernels as K  # noqa: E402
+
+DEV = torch.device("cuda:0")
+try:
+    PEAKS = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+except Exception:
+    PEAKS = {}
+HBM = PEAKS.get("hbm_gbs", 6650.0)
+BF16 = PEAKS.get("bf16_tflops", 1590.0)
+FLUSH = torch.empty(256 << 20, dtype=torch.uint8, device=DEV)
+
+
+def timed(fn, iters=10, warmup=3):
+    for _ in range(warmup):
+        fn()
+    ts = []
+    for _ in range(iters):
+        FLUSH.fill_(1)                                  # evict L2 (256 MB > 126 MB)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return float(np.median(ts)), float(np.min(ts))
+
+
+def emit(**kw):
+    print(json.dumps(kw), flush=True)
+
+
+def gemm_case(M, N, Kd, batch=1, mode=_lib.EPI_RAW, label=""):
+    g = torch.Generator(device="cuda").manual_seed(0)
+    a = torch.randint(-128, 128, (batch, M, Kd), generator=g, device=DEV, dtype=torch.int8)
+    b = torch.randint(-128, 128, (1, Kd, N), generator=g, device=DEV, dtype=torch.int8)
+    oa, ob = K.operand_from_codes(a, "A", True), K.operand_from_codes(b, "B", True)
+    azp = K.AccZeroPoint(3, None, Kd, None, ob.rowsum, True)
+    kw = dict(mode=mode, scale=1e-4, azp=azp)
+    if mode == _lib.EPI_REQUANT:
+        kw.update(out_bits=8, out_scale=0.05, out_zp=-3)
+    med, best = timed(lambda: K.qgemm(oa, ob, **kw))
+    ops = 2.0 * batch * M * N * Kd
+    out_b = {0: 4, 1: 4, 2: 1}[mode]
+    byts = batch * M * Kd + N * Kd + batch * M * N * out_b
+    emit(case=f"qgemm {label or ''}".strip(), M=M, N=N, K=Kd, batch=batch, epilogue=["raw_s32", "dequant_f32", "requant_s8"][mode],
+         ms_median=med, ms_best=best, tops=ops / med / 1e9, frac_of_2x_bf16_measured=ops / med / 1e9 / (2 * BF16),
+         frac_of_nominal_4500=ops / med / 1e9 / 4500.0, hbm_gbs_implied=byts / med / 1e6)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--quick", action="store_true")
+    args = ap.parse_args()
+    emit(case="peaks", hbm_gbs=HBM, bf16_tflops=BF16, source="MEASURED_PEAKS.json" if PEAKS else "fallback")
+    # library int8 GEMM (cuBLASLt through torch._int_mm) as a second, measured int8 reference point
+    try:
+        n = 8192
+        a = torch.randint(-128, 128, (n, n), device=DEV, dtype=torch.int8)
+        b = torch.randint(-128, 128, (n, n), device=DEV, dtype=torch.int8).t().contiguous().t()
+        med, best = timed(lambda: torch._int_mm(a, b), iters=5)
+        emit(case="library int8 gemm (torch._int_mm, cuBLASLt) 8192^3", ms_median=med, tops=2.0 * n ** 3 / med / 1e9)
+        del a, b
+    except Exception as e:  # noqa: BLE001
+        emit(case="library int8 gemm", error=str(e)[:200])
+    for mode in (_lib.EPI_RAW, _lib.EPI_DEQUANT, _lib.EPI_REQUANT):
+        gemm_case(4096, 4096, 4096, mode=mode, label="4096^3")
+    if not args.quick:
+        gemm_case(8192, 8192, 8192, label="8192^3")
+        for (M, N, Kd, lab) in ((50432, 768, 768, "ViT qkv/o"), (50432, 3072, 768, "ViT fc1"), (50432, 768, 3072, "ViT fc2")):
+            for mode in (_lib.EPI_RAW, _lib.EPI_DEQUANT, _lib.EPI_REQUANT):
+                gemm_case(M, N, Kd, mode=mode, label=lab)
+        g = torch.Generator(device="cuda").manual_seed(0)
+        for (bt, M, N, Kd, lab) in ((3072, 197, 197, 64, "ViT QK^T"), (3072, 197, 64, 197, "ViT PV")):
+            a = torch.randint(-128, 128, (bt, M, Kd), generator=g, device=DEV, dtype=torch.int8)
+            b = torch.randint(-128, 128, (bt, Kd, N), generator=g, device=DEV, dtype=torch.int8)
+            oa, ob = K.operand_from_codes(a, "A", True), K.operand_from_codes(b, "B", True)
+            azp = K.AccZeroPoint(3, -4, Kd, oa.rowsum, ob.rowsum, False)
+            med, best = timed(lambda: K.qgemm(oa, ob, _lib.EPI_DEQUANT, 1e-4, azp))
+            ops = 2.0 * bt * M * N * Kd
+            emit(case=f"qgemm {lab}", M=M, N=N, K=Kd, batch=bt, epilogue="dequant_f32", ms_median=med, tops=ops / med / 1e9,
+                 hbm_gbs_implied=(bt * (M * Kd + N * Kd) + bt * M * N * 4) / med / 1e6)
+    # HBM-bound kernels: algorithmic bytes per element as fixed in SURVEY.md §8(d)
+    shapes = [(4096, 4096)] if args.quick else [(4096, 4096), (50432, 768), (50432, 3072)]
+    for shp in shapes:
+        n = shp[0] * shp[1]
+        x = torch.randn(shp, device=DEV)
+        for asym in (True, False):
+            zp = -7 if asym else None
+            med, _ = timed(lambda: K.quantize(x, 8, 0.03, zp))
+            emit(case="quantize f32->s8", shape=shp, asym=asym, ms=med, gbs=5.0 * n / med / 1e6, frac_hbm=5.0 * n / med / 1e6 / HBM,
+                 gelem_s=n / med / 1e6)
+        med, _ = timed(lambda: K.quantize_operand(x, "A", 8, 0.03, -7, True))
+        emit(case="quantize f32->s8 operand A (+rowsum)", shape=shp, ms=med, gbs=5.0 * n / med / 1e6, frac_hbm=5.0 * n / med / 1e6 / HBM)
+        q = K.quantize(x, 8, 0.03, -7)
+        med, _ = timed(lambda: K.dequantize(q, 0.03, -7))
+        emit(case="dequantize s8->f32", shape=shp, ms=med, gbs=5.0 * n / med / 1e6, frac_hbm=5.0 * n / med / 1e6 / HBM)
+        acc = torch.randint(-2 ** 20, 2 ** 20, (1,) + shp, device=DEV, dtype=torch.int32)
+        cs = torch.randint(-1000, 1000, (1, shp[1]), device=DEV, dtype=torch.int32)
+        azp = K.AccZeroPoint(5, None, 768, None, cs, True)
+        med, _ = timed(lambda: K.dequantize_acc(acc, 1e-4, azp))
+        emit(case="dequantize s32 acc->f32 (factored zp)", shape=shp, ms=med, gbs=8.0 * n / med / 1e6, frac_hbm=8.0 * n / med / 1e6 / HBM)
+        med, _ = timed(lambda: K.requantize_acc(acc, 1e-4, azp, None, 8, 0.05, -3))
+        emit(case="requantize s32 acc->s8", shape=shp, ms=med, gbs=5.0 * n / med / 1e6, frac_hbm=5.0 * n / med / 1e6 / HBM)
+        med, _ = timed(lambda: K.gelu_erf(x, 1.4142135, 1.0, 0.5))
+        emit(case="gelu-erf chain f32", shape=shp, ms=med, gbs=8.0 * n / med / 1e6, frac_hbm=8.0 * n / med / 1e6 / HBM)
+        gm = torch.ones(shp[1], device=DEV)
+        med, _ = timed(lambda: K.layernorm(x, gm, gm, 1e-12))
+        emit(case="layernorm f32", shape=shp, ms=med, gbs=8.0 * n / med / 1e6, frac_hbm=8.0 * n / med / 1e6 / HBM)
+        med, _ = timed(lambda: K.binary("add", x, gm))
+        emit(case="bias add f32", shape=shp, ms=med, gbs=8.0 * n / med / 1e6, frac_hbm=8.0 * n / med / 1e6 / HBM)
+        for bits in (4, 2):
+            med, _ = timed(lambda: K.pack(q, bits))
+            emit(case=f"pack s8->{bits}b", shape=shp, ms=med, gbs=(1 + bits / 8) * n / med / 1e6, frac_hbm=(1 + bits / 8) * n / med / 1e6 / HBM)
+        del x, q, acc
+    if not args.quick:
+        x = torch.randn((256 * 12 * 197, 197), device=DEV)
+        n = x.numel()
+        med, _ = timed(lambda: K.softmax_lastdim(x))
+        emit(case="softmax f32 rows of 197", shape=list(x.shape), ms=med, gbs=8.0 * n / med / 1e6, frac_hbm=8.0 * n / med / 1e6 / HBM)
+
+
+if __name__ == "__main__":
+    main()

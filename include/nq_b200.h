@@ -92,6 +92,11 @@ int nq_requantize_acc(const int32_t* acc, int64_t batch, int64_t M, int64_t N, i
                       int out_bits, float out_scale, int has_out_zp, int64_t out_zp,
                       int8_t* out, void* stream);
 
+/* Tail of requantize on an already dequantized float32 tensor:
+ * q = clip(rint(zp_out + (1/s_out) * d), lo, hi)  (numpy_quantization.py:68-71). */
+int nq_requantize_f32(const float* d, int64_t n, int out_bits, float out_scale, int has_out_zp,
+                      int64_t out_zp, int8_t* out, void* stream);
+
 /* rowsum[r] = sum_{c<C} q[r*ld + c]  (int32). Used for rowsum(A) and colsum(B) of
  * K-major operands (numpy_quantization.py:52,55,58-59). */
 int nq_rowsum_s8(const int8_t* q, int64_t rows, int64_t C, int64_t ld, int32_t* rowsum, void* stream);

@@ -42,6 +42,7 @@ _SIGNATURES = {
     "nq_dequantize": [vp, C.c_int, i64, f32, C.c_int, i64, vp, vp],
     "nq_dequantize_acc": [vp, i64, i64, i64, i64, f32, C.POINTER(AccZp), vp, vp],
     "nq_requantize_acc": [vp, i64, i64, i64, i64, f32, C.POINTER(AccZp), vp, C.c_int, f32, C.c_int, i64, vp, vp],
+    "nq_requantize_f32": [vp, i64, C.c_int, f32, C.c_int, i64, vp, vp],
     "nq_rowsum_s8": [vp, i64, i64, i64, vp, vp],
     "nq_qgemm_s8": [vp, vp, vp, i64, i64, i64, i64, i64, i64, i64, i64, i64, i64, C.POINTER(Epilogue), vp],
     "nq_qgemm_s8_simt": [vp, vp, vp, i64, i64, i64, i64, i64, i64, i64, i64, i64, i64, vp],

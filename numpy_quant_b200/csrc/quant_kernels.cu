@@ -203,6 +203,15 @@ __global__ void __launch_bounds__(256) acc_post_kernel(const int32_t* __restrict
     }
 }
 
+// requantize tail on an already dequantized tensor: clip(rint(zp + (1/s) * d))
+template <bool ASYM>
+__global__ void __launch_bounds__(256) requantize_f32_kernel(const float* __restrict__ d, int64_t n, float inv,
+                                                            double zp, float lo, float hi, int8_t* __restrict__ out) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        out[i] = (int8_t)requantize_one<ASYM>(d[i], inv, zp, lo, hi);
+}
+
 // ------------------------------------------------------------------ row sums of a K-major s8 operand
 __global__ void __launch_bounds__(256) rowsum_s8_kernel(const int8_t* __restrict__ q, int64_t rows, int64_t C,
                                                        int64_t ld, int32_t* __restrict__ rowsum) {
@@ -465,6 +474,21 @@ extern "C" int nq_requantize_acc(const int32_t* acc, int64_t batch, int64_t M, i
     else
         acc_post_kernel<2, false><<<grid, 256, 0, s>>>(acc, batch, M, N, ldacc, scale, make_acc_zp(zp), bias_q, inv, 0.0, lo, hi, out);
     NQ_CHECK_LAUNCH("nq_requantize_acc");
+    return NQ_OK;
+}
+
+extern "C" int nq_requantize_f32(const float* d, int64_t n, int out_bits, float out_scale, int has_out_zp,
+                                 int64_t out_zp, int8_t* out, void* stream) {
+    NQ_REQUIRE(out_bits >= 2 && out_bits <= 8, "nq_requantize_f32: out_bits %d outside 2..8", out_bits);
+    if (n <= 0) return NQ_OK;
+    float lo, hi;
+    qrange(out_bits, &lo, &hi);
+    const float inv = 1.0f / out_scale;
+    const int grid = stream_grid(n, 256);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (has_out_zp) requantize_f32_kernel<true><<<grid, 256, 0, s>>>(d, n, inv, (double)out_zp, lo, hi, out);
+    else requantize_f32_kernel<false><<<grid, 256, 0, s>>>(d, n, inv, 0.0, lo, hi, out);
+    NQ_CHECK_LAUNCH("nq_requantize_f32");
     return NQ_OK;
 }
 

@@ -17,6 +17,7 @@ from . import _lib
 from ._lib import AccZp, Epilogue, call
 
 LAUNCHES = 0          # kernels enqueued through this module (bench.py reports it as gpu_launches)
+GEMM_TIMER = None     # optional list: (ops, start_event, end_event) per tensor-core GEMM launch
 
 
 def _count(n: int = 1) -> None:
@@ -203,6 +204,17 @@ def requantize_acc(acc: torch.Tensor, scale, azp: AccZeroPoint, bias_q: Optional
     return out
 
 
+def requantize_f32(d: torch.Tensor, bits: int, out_scale, out_zp) -> torch.Tensor:
+    """clip(rint(zp + (1/s) * d)) on a dequantized float32 tensor -> int8 codes."""
+    _need_cuda(d, torch.float32)
+    d = d.contiguous()
+    out = torch.empty(d.shape, dtype=torch.int8, device=d.device)
+    call("nq_requantize_f32", d.data_ptr(), d.numel(), bits, float(out_scale), int(out_zp is not None),
+         0 if out_zp is None else int(out_zp), out.data_ptr(), _stream())
+    _count()
+    return out
+
+
 # --------------------------------------------------------------------------- K4 / K5
 def qgemm(a: Operand, b: Operand, mode: int = _lib.EPI_RAW, scale: float = 1.0,
           azp: Optional[AccZeroPoint] = None, bias_f32: Optional[torch.Tensor] = None,
@@ -234,8 +246,15 @@ def qgemm(a: Operand, b: Operand, mode: int = _lib.EPI_RAW, scale: float = 1.0,
     ep.out_scale = float(out_scale)
     ep.has_out_zp = int(out_zp is not None)
     ep.out_zp = 0 if out_zp is None else int(out_zp)
+    timer = GEMM_TIMER
+    if timer is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     call("nq_qgemm_s8", a.data.data_ptr(), b.data.data_ptr(), out.data_ptr(), M, N, K, batch, a.ld, b.ld, N,
          sa, sb, M * N, C.byref(ep), _stream())
+    if timer is not None:
+        e1.record()
+        timer.append((2 * batch * M * N * K, e0, e1))
     _count()
     return out
 

@@ -1,0 +1,224 @@
+"""End-to-end parity of the drop-in API (Model.from_onnx / quantize / __call__) on the GPU
+against the golden vectors of the unmodified reference and against the oracle."""
+import os
+import warnings
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+if not torch.cuda.is_available():
+    pytest.skip("needs a CUDA device", allow_module_level=True)
+
+from numpy_quant_b200 import onnx_lite as ol, zoo  # noqa: E402
+from numpy_quant_b200.model import Constant, Model, QModel, QuantizationParams  # noqa: E402
+from numpy_quant_b200.tensor import FTensor, QTensor, quantize_tensor, quantize_tensor_min_max, tensor_min_max  # noqa: E402
+from numpy_quant_b200.numpy_quantization import quant_parameters  # noqa: E402
+from oracle import ref_graph as rg, ref_quant as rq  # noqa: E402
+
+warnings.simplefilter("ignore")
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def gv():
+    return np.load(os.path.join(G, "graphs.npz"))
+
+
+def inject_oracle_params(qmodel: QModel, fmodel: Model, plan: rg.QPlan):
+    """Give the product model the oracle's exact quantization parameters (parity
+    'using the same qparams'): calibration min/max come from a float pass whose summation order
+    differs by ulps, which is a float (1e-5) matter, not part of the integer contract."""
+    fconst = {v.name: v for v in fmodel.values if isinstance(v, Constant)}
+    for name, (s, z) in plan.qparams.items():
+        qmodel.quant_params[name] = QuantizationParams(s, z)
+    for v in qmodel.values:
+        if isinstance(v, Constant):
+            oq = plan.qconsts[v.name]
+            v.data = quantize_tensor(fconst[v.name].data, oq.bits, oq.scale, oq.zp)
+            np.testing.assert_array_equal(v.data.data, oq.a, err_msg=v.name)
+    qmodel._const_deq.clear()
+
+
+def check_qparams_close(qmodel, plan, rtol=2e-5):
+    for name, (s, z) in plan.qparams.items():
+        p = qmodel.quant_params[name]
+        if not np.isfinite(s) or s == 0:
+            continue
+        np.testing.assert_allclose(np.float64(p.scale), np.float64(s), rtol=rtol, err_msg=name)
+        assert (p.zero_point is None) == (z is None), name
+        if z is not None:
+            assert abs(int(p.zero_point) - int(z)) <= 1, name
+
+
+@pytest.mark.parametrize("bits", [2, 3, 4, 5, 6, 7, 8])
+def test_mlp_reference_onnx_file(gv, bits):
+    proto = ol.load(os.path.join(G, "mlp.onnx"))
+    x = gv["mlp/x"]
+    model = Model.from_onnx(proto)
+    fout = model([x])[0]
+    np.testing.assert_allclose(fout, gv[f"mlp/b{bits}/fout0"], rtol=1e-5, atol=1e-7)
+    q = model.quantize([x], bit_width=bits)
+    plan = rg.calibrate(rg.import_graph(proto, ol), [x], bits)
+    check_qparams_close(q, plan)
+    inject_oracle_params(q, model, plan)
+    out = q([x])[0]
+    by = {v.name: v for v in q.values}
+    pre = f"mlp/b{bits}"
+    # integer values: bit-exact
+    np.testing.assert_array_equal(by["input"].data.data, gv[f"{pre}/val_q/input"])
+    np.testing.assert_array_equal(by["/fc1/Gemm_output_0"].data.data, gv[f"{pre}/val_q//fc1/Gemm_output_0"])
+    np.testing.assert_array_equal(by["/fc2/Gemm_output_0"].data.data, gv[f"{pre}/val_q//fc2/Gemm_output_0"])
+    assert by["/fc1/Gemm_output_0"].data.bit_width == bits
+    np.testing.assert_array_equal(by["/relu/Relu_output_0"].data.data, gv[f"{pre}/val_f//relu/Relu_output_0"])
+    np.testing.assert_allclose(out, gv[f"{pre}/out0"], rtol=1e-5, atol=1e-7)
+
+
+def test_gemm_matmul_conv_graphs(gv):
+    proto = zoo.gemm_graph(3, 4, 2, seed=0)
+    x = gv["gemm/x"]
+    m = Model.from_onnx(proto)
+    q = m.quantize([x], 8)
+    plan = rg.calibrate(rg.import_graph(proto, ol), [x], 8)
+    check_qparams_close(q, plan)
+    inject_oracle_params(q, m, plan)
+    np.testing.assert_array_equal(q([x])[0], gv["gemm/b8/out0"])           # int path end to end: exact
+    np.testing.assert_array_equal({v.name: v for v in q.values}["output"].data.data, gv["gemm/b8/val_q/output"])
+
+    a, b = gv["matmul/a"], gv["matmul/b"]
+    proto = zoo.matmul_graph(a.shape, b.shape)
+    m = Model.from_onnx(proto)
+    q = m.quantize([a, b], 8)
+    plan = rg.calibrate(rg.import_graph(proto, ol), [a, b], 8)
+    inject_oracle_params(q, m, plan)
+    out = q([a, b])[0]
+    np.testing.assert_array_equal(out, gv["matmul/b8/out0"])
+    acc = {v.name: v for v in q.values}["output"].data
+    np.testing.assert_array_equal(acc.data, gv["matmul/b8/val_q/output"])                 # raw accumulator
+    np.testing.assert_array_equal(np.broadcast_to(acc.zero_point, acc.data.shape), gv["matmul/b8/val_qzp/output"])
+    assert acc.bit_width == 32
+
+    proto = zoo.conv_graph(2, 3, (9, 10), 2, (3, 2), (0, 2, 2, 1), (2, 1), seed=0)
+    x = gv["conv/x"]
+    m = Model.from_onnx(proto)
+    np.testing.assert_allclose(m([x])[0], gv["conv/b8/fout0"], rtol=1e-5, atol=1e-5)
+    q = m.quantize([x], 8)
+    plan = rg.calibrate(rg.import_graph(proto, ol), [x], 8)
+    inject_oracle_params(q, m, plan)
+    # integer im2col conv == the reference's fake-quant float conv up to float32 summation rounding
+    np.testing.assert_allclose(q([x])[0], gv["conv/b8/out0"], rtol=1e-5, atol=2e-5)
+
+
+VIT_CFG = dict(batch=2, image_size=32, patch_size=16, hidden=32, heads=4, intermediate=64, layers=2, classes=10)
+
+
+@pytest.mark.parametrize("bits", [8, 4])
+def test_small_vit(gv, bits):
+    proto = zoo.vit_graph(seed=0, **VIT_CFG)
+    x = gv["vit/x"]
+    model = Model.from_onnx(proto)
+    fout = model([x])[0]
+    np.testing.assert_allclose(fout, gv[f"vit/b{bits}/fout0"], rtol=1e-4, atol=1e-5)
+    q = model.quantize([x], bit_width=bits)
+    plan = rg.calibrate(rg.import_graph(proto, ol), [x], bits)
+    check_qparams_close(q, plan, rtol=1e-4)
+    inject_oracle_params(q, model, plan)
+    out = q([x])[0]
+    by = {v.name: v for v in q.values}
+    pre = f"vit/b{bits}"
+    np.testing.assert_array_equal(by["inputs"].data.data, rq.quantize(x, bits, *plan.qparams["inputs"]))
+    # first encoder inputs are float-parity values
+    emb = "/vit/embeddings/Add_output_0"
+    np.testing.assert_allclose(by[emb].data.data, gv[f"{pre}/val_f/{emb}"], rtol=1e-5, atol=1e-5)
+    ln = "/vit/encoder/layer.0/layernorm_before/LayerNormalization_output_0"
+    np.testing.assert_allclose(by[ln].data.data, gv[f"{pre}/val_f/{ln}"], rtol=1e-4, atol=1e-5)
+    # integer accumulators downstream: identical except where a float input sat within an ulp of a
+    # rounding boundary (bounded fraction, |difference| explained by single-code flips)
+    a0 = "/vit/encoder/layer.0/attention/attention"
+    qm = by[a0 + "/query/MatMul_output_0"].data
+    ref = gv[f"{pre}/val_q/{a0}/query/MatMul_output_0"]
+    assert qm.bit_width == 4 * bits
+    mism = np.mean(qm.data != ref)
+    assert mism < 0.02, f"query accumulator mismatch fraction {mism}"
+    out_scale = float(plan.qparams["logits"][0])
+    want = gv[f"{pre}/out0"]
+    assert np.abs(out - want).max() <= 4 * out_scale and np.abs(out - want).mean() <= 0.5 * out_scale
+    # retain=False (freed intermediates + fused GELU) is bit-identical to the retained run
+    out2 = q([x], retain=False)[0]
+    np.testing.assert_array_equal(out2, out)
+    assert by[a0 + "/query/MatMul_output_0"].data is None
+    # profile contract: dict of op type -> seconds with the two extra buckets (model.py:497-499)
+    out3, prof = q([x], profile=True)
+    np.testing.assert_array_equal(out3[0], out)
+    assert {"TinyqQuant", "TinyqDequant", "MatMul", "Gemm", "Softmax", "LayerNormalization"} <= set(prof)
+    assert all(isinstance(v, float) and v >= 0 for v in prof.values())
+
+
+def test_quantized_matmul_surface_known_answers():
+    """test_quantization.py:40-149 restated on the device tensors, plus KA-1 literals."""
+    k = np.load(os.path.join(G, "ka1.npz"))
+    w, x = FTensor(k["w"]), FTensor(k["x"])
+    y = w.matmul(x)
+    ys, yz = quant_parameters(*tensor_min_max(y), bit_width=8, asymmetric=True)
+    assert np.float32(ys) == k["y_scale"] and int(yz) == int(k["y_zp"])
+    for wa in (False, True):
+        for xa in (False, True):
+            tag = f"{int(wa)}{int(xa)}"
+            qw = quantize_tensor_min_max(w, 8, wa)
+            qx = quantize_tensor_min_max(x, 8, xa)
+            np.testing.assert_array_equal(qw.data, k[f"qw_{tag}"])
+            np.testing.assert_array_equal(qx.data, k[f"qx_{tag}"])
+            r = qw.matmul(qx)
+            assert r.bit_width == 32 and np.float32(r.scale) == k[f"accs_{tag}"]
+            np.testing.assert_array_equal(r.dequantize().data, k[f"dq_{tag}"])
+            np.testing.assert_array_equal(r.requantize(8, ys, yz).data, k[f"rq_{tag}"])
+            np.testing.assert_array_equal(r.data, k[f"acc_{tag}"])
+            if int(k[f"acczf_{tag}"]):
+                np.testing.assert_array_equal(np.broadcast_to(r.zero_point, r.data.shape),
+                                              np.broadcast_to(k[f"accz_{tag}"], r.data.shape))
+            else:
+                assert r.zero_point is None
+            np.testing.assert_allclose(r.dequantize().data, k["w"] @ k["x"], rtol=0.5)
+    # broadcast batch dims (2,1,4,3) x (1,2,3,4), all sym/asym combos, vs the oracle
+    rng = np.random.default_rng(0)
+    wd, xd = rng.random((2, 1, 4, 3)).astype(np.float32), rng.random((1, 2, 3, 4)).astype(np.float32)
+    for wa in (False, True):
+        for xa in (False, True):
+            qw = quantize_tensor_min_max(FTensor(wd), 8, wa)
+            qx = quantize_tensor_min_max(FTensor(xd), 8, xa)
+            acc, s, z = rq.q_matmul(qw.data, qw.scale, qw.zero_point, qx.data, qx.scale, qx.zero_point)
+            r = qw.matmul(qx)
+            np.testing.assert_array_equal(r.data, acc)
+            np.testing.assert_array_equal(r.dequantize().data, rq.dequantize(acc, s, z))
+
+
+def test_api_errors_match_reference():
+    with pytest.raises(ValueError):
+        FTensor(np.zeros(3, np.float64))                       # tensor.py:49-50
+    with pytest.raises(ValueError):
+        QTensor(np.zeros(3, np.int32), 8, np.float32(1.0))     # tensor.py:158-159
+    m = Model.from_onnx(zoo.gemm_graph(3, 4, 2))
+    with pytest.raises(ValueError):
+        m([np.zeros((3, 4), np.float64)])                      # model.py:300-305
+    with pytest.raises(AssertionError):
+        a = QTensor(np.zeros((2, 2), np.int64), 8, np.float32(1.0))
+        b = QTensor(np.zeros((2, 2), np.int64), 4, np.float32(1.0))
+        a.matmul(b)                                            # tensor.py:206
+    from numpy_quant_b200.model import onnx_operator_implementation
+    with pytest.raises(ValueError, match="not supported"):
+        onnx_operator_implementation("Foo", [], {})            # model.py:213
+
+
+def test_no_device_memory_leak_over_repeated_quantize():
+    """test/long_running/test_delete.py: 100x quantize must not accumulate memory."""
+    proto = zoo.vit_graph(seed=0, **VIT_CFG)
+    x = np.random.default_rng(1).normal(size=(2, 3, 32, 32)).astype(np.float32)
+    model = Model.from_onnx(proto)
+    model.quantize([x], 8)
+    torch.cuda.synchronize()
+    base = torch.cuda.memory_allocated()
+    for _ in range(30):
+        model.quantize([x], 8)
+    torch.cuda.synchronize()
+    assert torch.cuda.memory_allocated() <= base * 1.5 + (1 << 20)
