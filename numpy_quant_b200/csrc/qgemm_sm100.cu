@@ -5,8 +5,9 @@
 //   warp 0      TMA producer   (cp.async.bulk.tensor 3-D, 128B swizzle, K-major tiles)
 //   warp 1      MMA issuer     (one elected thread, tcgen05.mma cta_group::1, M=128, N=BN, K=32)
 //   warp 2      TMEM allocator (2 accumulator buffers of BN int32 columns)
-//   warps 4-7   epilogue       (tcgen05.ld 32x32b -> zero-point correction -> dequant /
-//                               requant -> per-warp smem transpose -> coalesced stores)
+//   warps 4-11  epilogue       (tcgen05.ld 32x32b -> per-warp swizzled smem transpose ->
+//                               zero-point correction + dequant(+bias) on the row-contiguous
+//                               read-back -> 16-byte coalesced stores; requant -> int8 codes)
 // smem ring of STAGES x (A 128x128 B + B BNx128 B); mbarrier full/empty per stage and
 // tmem_full/tmem_empty per accumulator buffer, so the epilogue of tile i overlaps the
 // main loop of tile i+1.
@@ -19,8 +20,8 @@ namespace nq {
 constexpr int BM = 128;          // rows of A per tile == TMEM lanes
 constexpr int BK = 128;          // int8 elements per stage along K == one 128-byte swizzle row
 constexpr int UMMA_K = 32;       // K per tcgen05.mma for 8-bit operands
-constexpr int NUM_THREADS = 256;
-constexpr int EPI_PITCH = 36;    // words per staged row (32 + 4 pad): conflict-free 16-B accesses
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_THREADS = 128 + 32 * NUM_EPI_WARPS;
 
 template <int BN> struct Cfg {
     static constexpr int STAGES = (BN == 256) ? 4 : 6;
@@ -28,7 +29,7 @@ template <int BN> struct Cfg {
     static constexpr int B_BYTES = BN * BK;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-    static constexpr int EPI_BYTES = 4 * 32 * EPI_PITCH * 4;
+    static constexpr int EPI_BYTES = NUM_EPI_WARPS * (32 * 32 * 4 + 32 * 4);   // staging slabs + row terms
     static constexpr int BAR_BYTES = 256;
     static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES;
 };
@@ -38,6 +39,7 @@ struct GemmParams {
     int64_t ldc, stride_c;
     int a_batched, b_batched;        // 0 -> operand shared across the batch (TMA batch coord 0)
     int mode;
+    int fast32;                      // zero-point arithmetic provably fits int32 (host-checked bound)
     float scale;
     AccZp zp;
     const float* bias_f32;
@@ -126,6 +128,18 @@ __host__ __device__ constexpr uint32_t make_idesc(int bn) {
 }
 
 // ------------------------------------------------------------------ epilogue math
+// dequantize with 32-bit zero-point arithmetic: identical bits to f32(f64(d) * f64(scale)).
+// |d| < 2^22 converts through the 1.5*2^23 magic constant (integer add + FADD, full rate)
+// instead of I2F; larger values take the conversion / float64 routes.
+__device__ __forceinline__ float deq_fast(int a, int rt, int ct, float scale) {
+    const int d = a - rt - ct;
+    float f;
+    if ((unsigned)(d + 0x400000) < 0x800000u) f = __fadd_rn(__int_as_float(0x4B400000 + d), -12582912.0f);
+    else if (d >= -16777216 && d <= 16777216) f = (float)d;
+    else return (float)((double)d * (double)scale);
+    return __fmul_rn(f, scale);
+}
+
 __device__ __forceinline__ int64_t tile_zp(const AccZp& z, int64_t rowterm, int64_t b, int64_t n) {
     int64_t v = rowterm;
     if (z.use_col) v += (int64_t)__ldg(z.colsum_b + b * z.cs_stride + n) * z.zp_a;
@@ -166,7 +180,7 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(smem_u32(tfull_bar + i), 1);
-            mbar_init(smem_u32(tempty_bar + i), 4);            // one arrival per epilogue warp
+            mbar_init(smem_u32(tempty_bar + i), NUM_EPI_WARPS);  // one arrival per epilogue warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -242,25 +256,41 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
         }
         __syncwarp();
     } else if (warp >= 4) {
-        // ===================== epilogue =====================
-        const int q = warp & 3;                                           // TMEM lane quarter
-        uint32_t* stg = epi + q * 32 * EPI_PITCH;
+        // ===================== epilogue (8 warps) =====================
+        // warp -> TMEM lane quarter q (hardware rule: warp_id % 4) and column-chunk parity h:
+        // two warps share a quarter and take alternate 32-column chunks.
+        const int q = warp & 3;
+        const int h = (warp - 4) >> 2;
+        const int ew = warp - 4;
+        uint32_t* stg = epi + ew * (32 * 32);                            // 32 rows x 32 words, XOR-swizzled
+        int32_t* stg_row = reinterpret_cast<int32_t*>(epi + NUM_EPI_WARPS * 32 * 32) + ew * 32;
         int acc = 0;
         uint32_t acc_phase = 0;
         const AccZp z = p.zp;
+        const bool c_aligned = ((p.ldc & 3) == 0) && ((p.stride_c & 3) == 0) &&
+                               ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+        const int cl = lane & 7, rsub = lane >> 3;                       // read-back: chunk of 4 cols, row in group
+        const bool cs_vec = z.use_col && ((reinterpret_cast<uintptr_t>(z.colsum_b) & 15) == 0) && ((z.cs_stride & 3) == 0);
+        const bool bias_vec = p.bias_f32 && ((reinterpret_cast<uintptr_t>(p.bias_f32) & 15) == 0);
         for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
             const int64_t b = t / tiles_per_batch, r = t % tiles_per_batch;
             const int64_t m0 = (r / n_tiles) * BM, n0 = (r % n_tiles) * BN;
             mbar_wait(smem_u32(tfull_bar + acc), acc_phase);
             tc_fence_after();
-            const int64_t m = m0 + q * 32 + lane;                         // this thread's output row
+            const int64_t mrow0 = m0 + q * 32;
+            const int64_t m = mrow0 + lane;                               // this thread's accumulator row
             const bool row_ok = m < p.M;
             int64_t rowterm = -z.kterm;
             if (z.use_row && row_ok) rowterm += (int64_t)__ldg(z.rowsum_a + b * p.M + m) * z.zp_b;
+            if (p.fast32) {
+                __syncwarp();
+                stg_row[lane] = (int32_t)rowterm;
+            }
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
             const int64_t crow_base = b * p.stride_c;
+            const int32_t* cs_b = z.use_col ? z.colsum_b + b * z.cs_stride : nullptr;
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
+            for (int c = h; c < BN / 32; c += 2) {
                 const int64_t nc = n0 + c * 32;
                 if (nc >= p.N) break;                                     // warp-uniform
                 uint32_t v[32];
@@ -292,44 +322,87 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                             for (int j = 0; j < 32 && nc + j < p.N; ++j) dst[j] = (int8_t)(w[j >> 2] >> ((j & 3) * 8));
                         }
                     }
-                } else {
-                    // 32-bit outputs: transform in registers, transpose through this warp's smem
-                    // slab so that global stores are row-contiguous.
-                    if (p.mode == NQ_EPI_DEQUANT) {
+                    continue;
+                }
+                const bool fast_deq = (p.mode == NQ_EPI_DEQUANT) && p.fast32;
+                if (p.mode == NQ_EPI_DEQUANT && !fast_deq) {
+                    // general path (64-bit zero-point arithmetic) in registers, before the transpose
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const int64_t n = nc + j;
-                            float d = 0.f;
-                            if (n < p.N) {
-                                d = dequantize_one((int64_t)(int32_t)v[j] - tile_zp(z, rowterm, b, n), p.scale);
-                                if (p.bias_f32) d = __fadd_rn(__ldg(p.bias_f32 + n), d);
-                            }
-                            v[j] = __float_as_uint(d);
+                    for (int j = 0; j < 32; ++j) {
+                        const int64_t n = nc + j;
+                        float d = 0.f;
+                        if (n < p.N) {
+                            d = dequantize_one((int64_t)(int32_t)v[j] - tile_zp(z, rowterm, b, n), p.scale);
+                            if (p.bias_f32) d = __fadd_rn(__ldg(p.bias_f32 + n), d);
+                        }
+                        v[j] = __float_as_uint(d);
+                    }
+                }
+                // transpose through this warp's smem slab (16-byte chunks XOR-swizzled by row: both the
+                // row-per-thread writes and the 4-rows-per-instruction reads are bank-conflict free)
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    *reinterpret_cast<uint4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) =
+                        make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                __syncwarp();
+                uint32_t* cbase = reinterpret_cast<uint32_t*>(p.C) + crow_base + nc;
+                if (c_aligned && nc + 32 <= p.N) {
+                    // each store instruction covers 4 rows x 128 B; this lane owns 4 fixed columns
+                    int ct[4] = {0, 0, 0, 0};
+                    float bs[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (fast_deq) {
+                        if (cs_b) {
+                            int4 c4;
+                            if (cs_vec) c4 = __ldg(reinterpret_cast<const int4*>(cs_b + nc) + cl);
+                            else c4 = make_int4(__ldg(cs_b + nc + cl * 4), __ldg(cs_b + nc + cl * 4 + 1),
+                                                __ldg(cs_b + nc + cl * 4 + 2), __ldg(cs_b + nc + cl * 4 + 3));
+                            ct[0] = c4.x * (int)z.zp_a; ct[1] = c4.y * (int)z.zp_a;
+                            ct[2] = c4.z * (int)z.zp_a; ct[3] = c4.w * (int)z.zp_a;
+                        }
+                        if (p.bias_f32) {
+                            const float* bp = p.bias_f32 + nc + cl * 4;
+                            float4 b4;
+                            if (bias_vec) b4 = __ldg(reinterpret_cast<const float4*>(bp));
+                            else b4 = make_float4(__ldg(bp), __ldg(bp + 1), __ldg(bp + 2), __ldg(bp + 3));
+                            bs[0] = b4.x; bs[1] = b4.y; bs[2] = b4.z; bs[3] = b4.w;
                         }
                     }
-                    __syncwarp();
 #pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        *reinterpret_cast<uint4*>(stg + lane * EPI_PITCH + j * 4) =
-                            make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                    __syncwarp();
-                    uint32_t* cbase = reinterpret_cast<uint32_t*>(p.C) + crow_base + nc;
-                    const bool vec_ok = (nc + 32 <= p.N) && ((p.ldc & 3) == 0) && ((p.stride_c & 3) == 0) &&
-                                        ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
-                    if (vec_ok) {
-                        // each instruction stores 4 rows x 128 B
-#pragma unroll
-                        for (int it = 0; it < 8; ++it) {
-                            const int rr = it * 4 + (lane >> 3);
-                            const int64_t mm = m0 + q * 32 + rr;
-                            const uint4 val = *reinterpret_cast<const uint4*>(stg + rr * EPI_PITCH + (lane & 7) * 4);
-                            if (mm < p.M) *reinterpret_cast<uint4*>(cbase + mm * p.ldc + (lane & 7) * 4) = val;
+                    for (int it = 0; it < 8; ++it) {
+                        const int rr = it * 4 + rsub;
+                        uint4 val = *reinterpret_cast<const uint4*>(stg + rr * 32 + ((cl ^ (rr & 7)) << 2));
+                        if (fast_deq) {
+                            const int rt = stg_row[rr];
+                            float f0 = deq_fast((int)val.x, rt, ct[0], p.scale), f1 = deq_fast((int)val.y, rt, ct[1], p.scale);
+                            float f2 = deq_fast((int)val.z, rt, ct[2], p.scale), f3 = deq_fast((int)val.w, rt, ct[3], p.scale);
+                            if (p.bias_f32) {
+                                f0 = __fadd_rn(bs[0], f0); f1 = __fadd_rn(bs[1], f1);
+                                f2 = __fadd_rn(bs[2], f2); f3 = __fadd_rn(bs[3], f3);
+                            }
+                            val = make_uint4(__float_as_uint(f0), __float_as_uint(f1), __float_as_uint(f2), __float_as_uint(f3));
                         }
-                    } else {
-                        for (int rr = 0; rr < 32; ++rr) {
-                            const int64_t mm = m0 + q * 32 + rr;
-                            if (mm < p.M && nc + lane < p.N) cbase[mm * p.ldc + lane] = stg[rr * EPI_PITCH + lane];
+                        if (mrow0 + rr < p.M) *reinterpret_cast<uint4*>(cbase + (mrow0 + rr) * p.ldc + (cl << 2)) = val;
+                    }
+                } else {
+                    // ragged / unaligned: one column per lane, 32 rows, 128-byte coalesced scalar stores
+                    const bool col_ok = nc + lane < p.N;
+                    int ct = 0;
+                    float bs = 0.f;
+                    if (fast_deq && col_ok) {
+                        if (cs_b) ct = __ldg(cs_b + nc + lane) * (int)z.zp_a;
+                        if (p.bias_f32) bs = __ldg(p.bias_f32 + nc + lane);
+                    }
+                    const int lch = lane >> 2, lw = lane & 3;
+#pragma unroll 4
+                    for (int rr = 0; rr < 32; ++rr) {
+                        uint32_t val = stg[rr * 32 + (((lch ^ (rr & 7)) << 2) | lw)];
+                        if (fast_deq) {
+                            float f = deq_fast((int)val, stg_row[rr], ct, p.scale);
+                            if (p.bias_f32) f = __fadd_rn(bs, f);
+                            val = __float_as_uint(f);
                         }
+                        if (col_ok && mrow0 + rr < p.M) cbase[(mrow0 + rr) * p.ldc + lane] = val;
                     }
                 }
             }
@@ -446,6 +519,12 @@ extern "C" int nq_qgemm_s8(const int8_t* A, const int8_t* B, void* Cout, int64_t
     p.mode = ep->mode;
     p.scale = ep->scale;
     p.zp = (ep->mode == NQ_EPI_RAW) ? AccZp{} : make_acc_zp(&ep->zp);
+    {
+        // |acc| + |rowsum*zp_b - zp_a*zp_b*K| + |colsum*zp_a| with 8-bit operands (|q| <= 128)
+        const long double za = (long double)llabs(p.zp.zp_a), zb = (long double)llabs(p.zp.zp_b);
+        const long double bound = 16384.0L * K + 128.0L * K * (za + zb) + za * zb * K;
+        p.fast32 = (ep->mode == NQ_EPI_DEQUANT) && bound < 2147483000.0L;
+    }
     p.bias_f32 = ep->bias_f32;
     p.bias_q = ep->bias_q;
     p.C = Cout;

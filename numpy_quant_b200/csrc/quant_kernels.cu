@@ -5,43 +5,50 @@
 namespace nq {
 
 // ------------------------------------------------------------------ K1 contiguous
-template <bool ASYM>
-__global__ void __launch_bounds__(256) quantize_contig_kernel(const float* __restrict__ x, int64_t n,
-                                                             float scale, double zp, float lo, float hi,
+struct QArgs {
+    float scale, zpf, lo, hi;
+    double zp;
+    int zp_odd;
+};
+
+// Each thread-iteration: four fully coalesced 16-B loads (512 B per warp each) in flight, four
+// coalesced 4-B stores of packed codes.
+template <int QMODE>
+__global__ void __launch_bounds__(256) quantize_contig_kernel(const float* __restrict__ x, int64_t n, QArgs a,
                                                              int8_t* __restrict__ out) {
-    // 16 elements per thread-iteration: four 16-B loads in flight, one 16-B store.
-    const int64_t n16 = n >> 4;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t n4 = n >> 2;                                  // float4 groups
     const float4* x4 = reinterpret_cast<const float4*>(x);
-    int4* o4 = reinterpret_cast<int4*>(out);
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) {
+    int* o32 = reinterpret_cast<int*>(out);
+    const int64_t tile = (int64_t)blockDim.x * 4;
+    const bool odd = a.zp_odd != 0;
+    for (int64_t base = (int64_t)blockIdx.x * tile; base < n4; base += (int64_t)gridDim.x * tile) {
         float4 v[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) v[j] = __ldcs(x4 + i * 4 + j);
-        int w[4];
+        for (int j = 0; j < 4; ++j) {
+            const int64_t i = base + j * blockDim.x + threadIdx.x;
+            v[j] = (i < n4) ? __ldcs(x4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            int q0 = quantize_one<ASYM>(v[j].x, scale, zp, lo, hi);
-            int q1 = quantize_one<ASYM>(v[j].y, scale, zp, lo, hi);
-            int q2 = quantize_one<ASYM>(v[j].z, scale, zp, lo, hi);
-            int q3 = quantize_one<ASYM>(v[j].w, scale, zp, lo, hi);
-            w[j] = (q0 & 0xff) | ((q1 & 0xff) << 8) | ((q2 & 0xff) << 16) | ((q3 & 0xff) << 24);
+            const int64_t i = base + j * blockDim.x + threadIdx.x;
+            if (i < n4)
+                __stcs(o32 + i, pack4_codes(quantize_code<QMODE>(v[j].x, a.scale, a.zp, a.zpf, odd, a.lo, a.hi),
+                                            quantize_code<QMODE>(v[j].y, a.scale, a.zp, a.zpf, odd, a.lo, a.hi),
+                                            quantize_code<QMODE>(v[j].z, a.scale, a.zp, a.zpf, odd, a.lo, a.hi),
+                                            quantize_code<QMODE>(v[j].w, a.scale, a.zp, a.zpf, odd, a.lo, a.hi)));
         }
-        __stcs(o4 + i, make_int4(w[0], w[1], w[2], w[3]));
     }
-    // tail (< 16 elements) by the first threads of the grid
-    const int64_t base = n16 << 4;
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (base + t < n) out[base + t] = (int8_t)quantize_one<ASYM>(x[base + t], scale, zp, lo, hi);
+    const int64_t t = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // tail (< 4 elements)
+    if (t < n) out[t] = (int8_t)quantize_code<QMODE>(x[t], a.scale, a.zp, a.zpf, odd, a.lo, a.hi);
 }
 
-template <bool ASYM>
-__global__ void __launch_bounds__(256) quantize_scalar_kernel(const float* __restrict__ x, int64_t n, float scale,
-                                                             double zp, float lo, float hi,
+template <int QMODE>
+__global__ void __launch_bounds__(256) quantize_scalar_kernel(const float* __restrict__ x, int64_t n, QArgs a,
                                                              int8_t* __restrict__ out) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const bool odd = a.zp_odd != 0;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-        out[i] = (int8_t)quantize_one<ASYM>(x[i], scale, zp, lo, hi);
+        out[i] = (int8_t)quantize_code<QMODE>(x[i], a.scale, a.zp, a.zpf, odd, a.lo, a.hi);
 }
 
 // wide symmetric/asymmetric quantize to int64 codes (4*bit_width-bit biases, model.py:383-389, 405-410)
@@ -62,15 +69,16 @@ __global__ void quantize_i64_kernel(const float* __restrict__ x, int64_t n, floa
 
 // ------------------------------------------------------------------ K1 strided 4-D -> K-major operand
 // One warp per output row (b, r): lanes sweep the C (=K) axis, so reads are coalesced when
-// sc == 1 and the row sum falls out of a shuffle reduction.
-template <bool ASYM>
+// sc == 1 and the row sum falls out of a dp4a + shuffle reduction.
+template <int QMODE>
 __global__ void __launch_bounds__(256) quantize_rows_kernel(const float* __restrict__ x, int64_t d1, int64_t R,
                                                            int64_t C, int64_t s0, int64_t s1, int64_t sr,
-                                                           int64_t sc, int64_t rows_total, float scale, double zp,
-                                                           float lo, float hi, int8_t* __restrict__ out,
-                                                           int64_t ldo, int32_t* __restrict__ rowsum) {
+                                                           int64_t sc, int64_t rows_total, QArgs a,
+                                                           int8_t* __restrict__ out, int64_t ldo,
+                                                           int32_t* __restrict__ rowsum) {
     const int lane = threadIdx.x & 31;
     const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const bool odd = a.zp_odd != 0;
     for (int64_t row = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); row < rows_total; row += warps) {
         const int64_t r = row % R;
         const int64_t b = row / R;
@@ -80,23 +88,22 @@ __global__ void __launch_bounds__(256) quantize_rows_kernel(const float* __restr
         if (sc == 1 && ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && (ldo & 3) == 0) {
             const int64_t c4 = C >> 2;
             for (int64_t c = lane; c < c4; c += 32) {
-                float4 v = *reinterpret_cast<const float4*>(src + c * 4);
-                int q0 = quantize_one<ASYM>(v.x, scale, zp, lo, hi);
-                int q1 = quantize_one<ASYM>(v.y, scale, zp, lo, hi);
-                int q2 = quantize_one<ASYM>(v.z, scale, zp, lo, hi);
-                int q3 = quantize_one<ASYM>(v.w, scale, zp, lo, hi);
-                sum += q0 + q1 + q2 + q3;
-                *reinterpret_cast<int*>(dst + c * 4) =
-                    (q0 & 0xff) | ((q1 & 0xff) << 8) | ((q2 & 0xff) << 16) | ((q3 & 0xff) << 24);
+                const float4 v = __ldcs(reinterpret_cast<const float4*>(src) + c);
+                const int w = pack4_codes(quantize_code<QMODE>(v.x, a.scale, a.zp, a.zpf, odd, a.lo, a.hi),
+                                          quantize_code<QMODE>(v.y, a.scale, a.zp, a.zpf, odd, a.lo, a.hi),
+                                          quantize_code<QMODE>(v.z, a.scale, a.zp, a.zpf, odd, a.lo, a.hi),
+                                          quantize_code<QMODE>(v.w, a.scale, a.zp, a.zpf, odd, a.lo, a.hi));
+                sum = __dp4a(w, 0x01010101, sum);
+                reinterpret_cast<int*>(dst)[c] = w;
             }
             for (int64_t c = (c4 << 2) + lane; c < ldo; c += 32) {
-                int q = c < C ? quantize_one<ASYM>(src[c], scale, zp, lo, hi) : 0;
+                const int q = c < C ? (int)(int8_t)quantize_code<QMODE>(src[c], a.scale, a.zp, a.zpf, odd, a.lo, a.hi) : 0;
                 sum += q;
                 dst[c] = (int8_t)q;
             }
         } else {
             for (int64_t c = lane; c < ldo; c += 32) {
-                int q = c < C ? quantize_one<ASYM>(src[c * sc], scale, zp, lo, hi) : 0;
+                const int q = c < C ? (int)(int8_t)quantize_code<QMODE>(src[c * sc], a.scale, a.zp, a.zpf, odd, a.lo, a.hi) : 0;
                 sum += q;
                 dst[c] = (int8_t)q;
             }
@@ -111,12 +118,12 @@ __global__ void __launch_bounds__(256) quantize_rows_kernel(const float* __restr
 
 // Transposing variant: the input is contiguous along r (sr == 1), e.g. a [K, N] weight or V
 // read as rows = N, cols = K.  32x32 tiles through shared memory keep both sides coalesced.
-template <bool ASYM>
+template <int QMODE>
 __global__ void __launch_bounds__(256) quantize_transpose_kernel(const float* __restrict__ x, int64_t d1, int64_t R,
                                                                 int64_t C, int64_t s0, int64_t s1, int64_t sc,
-                                                                float scale, double zp, float lo, float hi,
-                                                                int8_t* __restrict__ out, int64_t ldo,
+                                                                QArgs a, int8_t* __restrict__ out, int64_t ldo,
                                                                 int32_t* __restrict__ rowsum) {
+    const bool odd = a.zp_odd != 0;
     __shared__ int8_t tile[32][36];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;           // 32 x 8
     const int64_t b = blockIdx.z;
@@ -126,7 +133,7 @@ __global__ void __launch_bounds__(256) quantize_transpose_kernel(const float* __
     for (int j = 0; j < 4; ++j) {
         const int64_t c = c0 + ty + j * 8, r = r0 + tx;               // lanes along r (unit stride)
         int q = 0;
-        if (c < C && r < R) q = quantize_one<ASYM>(src[c * sc + r], scale, zp, lo, hi);
+        if (c < C && r < R) q = (int)(int8_t)quantize_code<QMODE>(src[c * sc + r], a.scale, a.zp, a.zpf, odd, a.lo, a.hi);
         tile[ty + j * 8][tx] = (int8_t)q;
     }
     __syncthreads();
@@ -153,22 +160,31 @@ __global__ void __launch_bounds__(256) dequantize_kernel(const T* __restrict__ q
         out[i] = dequantize_one((int64_t)q[i] - zp, scale);
 }
 
-__global__ void __launch_bounds__(256) dequantize_s8x16_kernel(const int8_t* __restrict__ q, int64_t n16, float scale,
-                                                              int zp, float* __restrict__ out) {
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    const int4* q4 = reinterpret_cast<const int4*>(q);
+// int8 codes -> float32: one 32-bit load (4 codes) and one 16-byte store per thread-iteration,
+// four iterations in flight; both sides fully coalesced.
+__global__ void __launch_bounds__(256) dequantize_s8x4_kernel(const int8_t* __restrict__ q, int64_t n4, float scale,
+                                                             int zp, float* __restrict__ out) {
+    const int* q32 = reinterpret_cast<const int*>(q);
     float4* o4 = reinterpret_cast<float4*>(out);
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) {
-        int4 v = __ldcs(q4 + i);
-        int w[4] = {v.x, v.y, v.z, v.w};
+    const int64_t tile = (int64_t)blockDim.x * 4;
+    for (int64_t base = (int64_t)blockIdx.x * tile; base < n4; base += (int64_t)gridDim.x * tile) {
+        int w[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            float4 f;
-            f.x = __fmul_rn((float)((int)(int8_t)(w[j]) - zp), scale);
-            f.y = __fmul_rn((float)((int)(int8_t)(w[j] >> 8) - zp), scale);
-            f.z = __fmul_rn((float)((int)(int8_t)(w[j] >> 16) - zp), scale);
-            f.w = __fmul_rn((float)((int)(int8_t)(w[j] >> 24) - zp), scale);
-            __stcs(o4 + i * 4 + j, f);
+            const int64_t i = base + j * blockDim.x + threadIdx.x;
+            w[j] = (i < n4) ? __ldcs(q32 + i) : 0;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int64_t i = base + j * blockDim.x + threadIdx.x;
+            if (i < n4) {
+                float4 f;
+                f.x = __fmul_rn((float)((int)(int8_t)(w[j]) - zp), scale);
+                f.y = __fmul_rn((float)((int)(int8_t)(w[j] >> 8) - zp), scale);
+                f.z = __fmul_rn((float)((int)(int8_t)(w[j] >> 16) - zp), scale);
+                f.w = __fmul_rn((float)((int)(int8_t)(w[j] >> 24) - zp), scale);
+                __stcs(o4 + i, f);
+            }
         }
     }
 }
@@ -359,22 +375,40 @@ static inline void qrange(int bits, float* lo, float* hi) {
     *hi = ldexpf(1.f, bits - 1) - 1.f;
 }
 
+static inline QArgs make_qargs(int bits, float scale, int has_zp, int64_t zp, int* qmode) {
+    QArgs a;
+    a.scale = scale;
+    qrange(bits, &a.lo, &a.hi);
+    a.zp = has_zp ? (double)zp : 0.0;
+    a.zpf = has_zp ? (float)zp : 0.f;
+    a.zp_odd = has_zp ? (int)(zp & 1) : 0;
+    // the float32-exact route needs |zp| < 2^20 (see quantize_asym_f32); NQ_QUANT_F64=1 forces float64
+    static const bool force64 = getenv("NQ_QUANT_F64") != nullptr;
+    *qmode = !has_zp ? 0 : ((!force64 && zp > -(1 << 20) && zp < (1 << 20)) ? 1 : 2);
+    return a;
+}
+
+#define NQ_DISPATCH_QMODE(qmode, KERNEL, ...)            \
+    do {                                                 \
+        if ((qmode) == 0) KERNEL<0> __VA_ARGS__;         \
+        else if ((qmode) == 1) KERNEL<1> __VA_ARGS__;    \
+        else KERNEL<2> __VA_ARGS__;                      \
+    } while (0)
+
 extern "C" int nq_quantize_f32(const float* x, int64_t n, int bit_width, float scale, int has_zp, int64_t zp,
                                int8_t* out, void* stream) {
     NQ_REQUIRE(bit_width >= 2 && bit_width <= 8, "nq_quantize_f32: bit_width %d outside 2..8", bit_width);
     if (n <= 0) return NQ_OK;
-    float lo, hi;
-    qrange(bit_width, &lo, &hi);
+    int qmode;
+    const QArgs a = make_qargs(bit_width, scale, has_zp, zp, &qmode);
     cudaStream_t s = (cudaStream_t)stream;
-    const bool vec = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+    const bool vec = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && ((reinterpret_cast<uintptr_t>(out) & 3) == 0);
     if (vec) {
         const int grid = stream_grid((n + 15) / 16, 256);
-        if (has_zp) quantize_contig_kernel<true><<<grid, 256, 0, s>>>(x, n, scale, (double)zp, lo, hi, out);
-        else quantize_contig_kernel<false><<<grid, 256, 0, s>>>(x, n, scale, 0.0, lo, hi, out);
+        NQ_DISPATCH_QMODE(qmode, quantize_contig_kernel, <<<grid, 256, 0, s>>>(x, n, a, out));
     } else {
         const int grid = stream_grid(n, 256);
-        if (has_zp) quantize_scalar_kernel<true><<<grid, 256, 0, s>>>(x, n, scale, (double)zp, lo, hi, out);
-        else quantize_scalar_kernel<false><<<grid, 256, 0, s>>>(x, n, scale, 0.0, lo, hi, out);
+        NQ_DISPATCH_QMODE(qmode, quantize_scalar_kernel, <<<grid, 256, 0, s>>>(x, n, a, out));
     }
     NQ_CHECK_LAUNCH("nq_quantize_f32");
     return NQ_OK;
@@ -402,10 +436,9 @@ extern "C" int nq_quantize_f32_4d(const float* x, int64_t d0, int64_t d1, int64_
     NQ_REQUIRE(ldo >= C, "nq_quantize_f32_4d: ldo %lld < C %lld", (long long)ldo, (long long)C);
     const int64_t batch = d0 * d1, rows = batch * R;
     if (rows <= 0 || C <= 0) return NQ_OK;
-    float lo, hi;
-    qrange(bit_width, &lo, &hi);
+    int qmode;
+    const QArgs a = make_qargs(bit_width, scale, has_zp, zp, &qmode);
     cudaStream_t s = (cudaStream_t)stream;
-    const double dzp = has_zp ? (double)zp : 0.0;
     if (sr == 1 && sc != 1 && batch <= 65535) {
         if (rowsum) {
             cudaError_t e = cudaMemsetAsync(rowsum, 0, sizeof(int32_t) * rows, s);
@@ -413,12 +446,10 @@ extern "C" int nq_quantize_f32_4d(const float* x, int64_t d0, int64_t d1, int64_
         }
         dim3 grid((unsigned)((R + 31) / 32), (unsigned)((ldo + 31) / 32), (unsigned)batch);
         NQ_REQUIRE(grid.y <= 65535, "nq_quantize_f32_4d: C too large for the transposing path");
-        if (has_zp) quantize_transpose_kernel<true><<<grid, 256, 0, s>>>(x, d1, R, C, s0, s1, sc, scale, dzp, lo, hi, out, ldo, rowsum);
-        else quantize_transpose_kernel<false><<<grid, 256, 0, s>>>(x, d1, R, C, s0, s1, sc, scale, dzp, lo, hi, out, ldo, rowsum);
+        NQ_DISPATCH_QMODE(qmode, quantize_transpose_kernel, <<<grid, 256, 0, s>>>(x, d1, R, C, s0, s1, sc, a, out, ldo, rowsum));
     } else {
         const int grid = stream_grid(rows * 32, 256);
-        if (has_zp) quantize_rows_kernel<true><<<grid, 256, 0, s>>>(x, d1, R, C, s0, s1, sr, sc, rows, scale, dzp, lo, hi, out, ldo, rowsum);
-        else quantize_rows_kernel<false><<<grid, 256, 0, s>>>(x, d1, R, C, s0, s1, sr, sc, rows, scale, dzp, lo, hi, out, ldo, rowsum);
+        NQ_DISPATCH_QMODE(qmode, quantize_rows_kernel, <<<grid, 256, 0, s>>>(x, d1, R, C, s0, s1, sr, sc, rows, a, out, ldo, rowsum));
     }
     NQ_CHECK_LAUNCH("nq_quantize_f32_4d");
     return NQ_OK;
@@ -430,11 +461,11 @@ extern "C" int nq_dequantize(const void* q, int elem_bytes, int64_t n, float sca
     cudaStream_t s = (cudaStream_t)stream;
     const int64_t z = has_zp ? zp : 0;
     if (elem_bytes == 1) {
-        const bool vec = ((reinterpret_cast<uintptr_t>(q) & 15) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0) &&
+        const bool vec = ((reinterpret_cast<uintptr_t>(q) & 3) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0) &&
                          z > -(1 << 23) && z < (1 << 23);
-        const int64_t n16 = vec ? (n >> 4) : 0;
-        if (n16) dequantize_s8x16_kernel<<<stream_grid(n16, 256), 256, 0, s>>>((const int8_t*)q, n16, scale, (int)z, out);
-        const int64_t done = n16 << 4;
+        const int64_t n4 = vec ? (n >> 2) : 0;
+        if (n4) dequantize_s8x4_kernel<<<stream_grid((n4 + 3) / 4, 256), 256, 0, s>>>((const int8_t*)q, n4, scale, (int)z, out);
+        const int64_t done = n4 << 2;
         if (done < n)
             dequantize_kernel<int8_t><<<stream_grid(n - done, 256), 256, 0, s>>>((const int8_t*)q + done, n - done, scale, z, out + done);
     } else if (elem_bytes == 4) {

@@ -71,6 +71,35 @@ def test_quantize_large_vs_oracle(bits, asym):
     np.testing.assert_array_equal(got2, ref[3:])
 
 
+@pytest.mark.parametrize("zp", [None, 0, -7, -8, 5, 130, -131, (1 << 20) - 1, 1 << 21, -(1 << 22) - 1])
+def test_quantize_exact_ties_and_zero_point_parity(zp):
+    """x / scale lands exactly on k + 0.5 (power-of-two scale): the float32-exact route must
+    break ties like the reference's float64 `rint(zp + t)` for even and odd, small and huge
+    zero-points (|zp| >= 2^20 switches to the float64 kernel)."""
+    scale = np.float32(0.25)
+    k = np.arange(-70000, 70000, dtype=np.float32)
+    centre = 0.0 if zp is None else -float(zp)
+    t = np.concatenate([k + 0.5, k, k + 0.25, centre + (k[69000:71000] + 0.5), centre + k[69900:70100] * 0.5,
+                        [1e30, -1e30, 3e9, -3e9, 1e-30, -1e-30, 0.0, -0.0, 0.49999997, -0.49999997, 0.50000006]])
+    x = (t.astype(np.float32) * scale).astype(np.float32)
+    for bits in (8, 5, 2):
+        ref = rq.quantize(x, bits, scale, None if zp is None else np.int64(zp))
+        got = host(K.quantize(dev(x), bits, scale, zp)).astype(np.int64)
+        np.testing.assert_array_equal(got, ref, err_msg=f"bits={bits} zp={zp}")
+    # non-power-of-two scale: ordinary data plus values straddling the rounding boundaries
+    rng = np.random.default_rng(abs(hash(zp)) % 1000)
+    s2 = np.float32(0.0371)
+    base = ((np.arange(-300, 300) + 0.5) * s2).astype(np.float32)
+    x2 = np.concatenate([np.nextafter(base, np.float32(np.inf)), base, np.nextafter(base, np.float32(-np.inf)),
+                         (rng.normal(size=100000) * 3).astype(np.float32)]).astype(np.float32)
+    if zp is not None:
+        x2 = np.concatenate([x2, (x2 - np.float32(zp) * s2).astype(np.float32)])
+    ref = rq.quantize(x2, 8, s2, None if zp is None else np.int64(zp))
+    op = K.quantize_operand(dev(x2).view(1, -1), "A", 8, s2, zp, True)
+    np.testing.assert_array_equal(host(op.data)[0, 0, : x2.size].astype(np.int64), ref)
+    assert int(op.rowsum[0, 0]) == int(ref.sum())
+
+
 def test_quantize_operand_layouts():
     rng = np.random.default_rng(5)
     x = rng.normal(size=(2, 3, 37, 50)).astype(np.float32)
