@@ -1,0 +1,39 @@
+#!/usr/bin/env python
+"""Tiny driver for `ncu --set full` captures of the tensor-core GEMM (one launch per case)."""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from numpy_quant_b200 import _lib, kernels as K  # noqa: E402
+
+DEV = torch.device("cuda:0")
+g = torch.Generator(device="cuda").manual_seed(0)
+cases = sys.argv[1:] or ["qkv", "fc1", "qk", "pv", "raw4096"]
+for case in cases:
+    if case in ("qkv", "fc1", "fc2"):
+        M, N, Kd = {"qkv": (50432, 768, 768), "fc1": (50432, 3072, 768), "fc2": (50432, 768, 3072)}[case]
+        a = torch.randint(-128, 128, (1, M, Kd), generator=g, device=DEV, dtype=torch.int8)
+        b = torch.randint(-128, 128, (1, Kd, N), generator=g, device=DEV, dtype=torch.int8)
+        oa, ob = K.operand_from_codes(a, "A", False), K.operand_from_codes(b, "B", True)
+        azp = K.AccZeroPoint(3, None, Kd, None, ob.rowsum, True)
+        bias = torch.randn(N, device=DEV)
+        for _ in range(2):
+            out = K.qgemm(oa, ob, _lib.EPI_DEQUANT, 1e-4, azp, bias_f32=bias)
+    elif case in ("qk", "pv"):
+        bt, M, N, Kd = (3072, 197, 197, 64) if case == "qk" else (3072, 197, 64, 197)
+        a = torch.randint(-128, 128, (bt, M, Kd), generator=g, device=DEV, dtype=torch.int8)
+        b = torch.randint(-128, 128, (bt, Kd, N), generator=g, device=DEV, dtype=torch.int8)
+        oa, ob = K.operand_from_codes(a, "A", True), K.operand_from_codes(b, "B", True)
+        azp = K.AccZeroPoint(3, -4, Kd, oa.rowsum, ob.rowsum, False)
+        for _ in range(2):
+            out = K.qgemm(oa, ob, _lib.EPI_DEQUANT, 1e-4, azp)
+    else:
+        a = torch.randint(-128, 128, (1, 4096, 4096), generator=g, device=DEV, dtype=torch.int8)
+        oa, ob = K.operand_from_codes(a, "A", False), K.operand_from_codes(a, "B", False)
+        for _ in range(2):
+            out = K.qgemm(oa, ob)
+    torch.cuda.synchronize()
+    print(case, "ok", tuple(out.shape))

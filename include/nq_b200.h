@@ -196,6 +196,24 @@ int nq_layernorm_f32(const float* x, int64_t rows, int64_t cols, int64_t ldx, co
 /* Softmax over the last axis (tensor.py:139-146): exp(x - max) / sum. */
 int nq_softmax_f32(const float* x, int64_t rows, int64_t cols, int64_t ldx, float* out, void* stream);
 
+/* Softmax preceded by the graph's Div(x, c) (attention scores / sqrt(d)): exp(x/c - max) / sum. */
+int nq_softmax_div_f32(const float* x, int64_t rows, int64_t cols, int64_t ldx, float div_const, float* out,
+                       void* stream);
+
+/* Producer -> quantize fusions (executor `retain=False`): the float op of the graph node(s)
+ * and the quantize of the consuming MatMul (model.py:503-513) in one pass; the output is the
+ * int8 K-major GEMM operand row (row stride ldo bytes, zero padded) plus optional row sums.
+ * Same float32 roundings as running the two kernels back to back. */
+int nq_layernorm_quantize_f32(const float* x, int64_t rows, int64_t cols, int64_t ldx, const float* gamma,
+                              const float* beta, float eps, int bit_width, float scale, int has_zp, int64_t zp,
+                              int8_t* out, int64_t ldo, int32_t* rowsum, void* stream);
+int nq_softmax_quantize_f32(const float* x, int64_t rows, int64_t cols, int64_t ldx, int has_div, float div_const,
+                            int bit_width, float scale, int has_zp, int64_t zp,
+                            int8_t* out, int64_t ldo, int32_t* rowsum, void* stream);
+int nq_gelu_quantize_f32(const float* x, int64_t rows, int64_t cols, int64_t ldx, float div_const, float add_const,
+                         float mul_const, int bit_width, float scale, int has_zp, int64_t zp,
+                         int8_t* out, int64_t ldo, int32_t* rowsum, void* stream);
+
 /* Row reductions over the last axis: op 0 = max, 1 = sum, 2 = mean (tensor.py:124-137). */
 int nq_reduce_rows_f32(int op, const float* x, int64_t rows, int64_t cols, float* out, void* stream);
 

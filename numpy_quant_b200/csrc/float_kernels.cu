@@ -153,11 +153,17 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 
-template <int NV>   // NV float4 per lane: cols <= 128*NV, cols % 4 == 0, 16-B aligned rows
+// NV float4 per lane: cols <= 128*NV, cols % 4 == 0, 16-B aligned rows.
+// QMODE -1: float32 output.  QMODE 0/1/2: the normalised row is quantized on the fly and written
+// as an int8 K-major GEMM operand row (row stride ldo, zero padded, optional row sum) -- the
+// LayerNormalization -> quantize pair of the graph in one pass, same roundings as the two kernels.
+template <int NV, int QMODE>
 __global__ void __launch_bounds__(256) layernorm_vec_kernel(const float* __restrict__ x, int64_t rows, int cols,
                                                            int64_t ldx, const float* __restrict__ gamma,
                                                            const float* __restrict__ beta, float eps,
-                                                           float* __restrict__ out) {
+                                                           float* __restrict__ out, QArgs qa,
+                                                           int8_t* __restrict__ qout, int64_t ldo,
+                                                           int32_t* __restrict__ rowsum) {
     const int lane = threadIdx.x & 31;
     const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int c4 = cols >> 2;
@@ -188,7 +194,9 @@ __global__ void __launch_bounds__(256) layernorm_vec_kernel(const float* __restr
         }
         const float var = __fdiv_rn(warp_sum(ss), fn);
         const float inv = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(var, eps)));
-        float4* dst = reinterpret_cast<float4*>(out + row * (int64_t)cols);
+        float4* dst = (QMODE < 0) ? reinterpret_cast<float4*>(out + row * (int64_t)cols) : nullptr;
+        int* qdst = (QMODE >= 0) ? reinterpret_cast<int*>(qout + row * ldo) : nullptr;
+        int qsum = 0;
 #pragma unroll
         for (int j = 0; j < NV; ++j) {
             const int c = lane + j * 32;
@@ -200,7 +208,22 @@ __global__ void __launch_bounds__(256) layernorm_vec_kernel(const float* __restr
                 o.y = __fadd_rn(__fmul_rn(__fmul_rn(v[j].y, inv), gm.y), bt.y);
                 o.z = __fadd_rn(__fmul_rn(__fmul_rn(v[j].z, inv), gm.z), bt.z);
                 o.w = __fadd_rn(__fmul_rn(__fmul_rn(v[j].w, inv), gm.w), bt.w);
-                __stcs(dst + c, o);
+                if (QMODE < 0) {
+                    __stcs(dst + c, o);
+                } else {
+                    constexpr int QM = QMODE < 0 ? 0 : QMODE;
+                    const int w = pack4_codes(qcode<QM>(o.x, qa), qcode<QM>(o.y, qa), qcode<QM>(o.z, qa), qcode<QM>(o.w, qa));
+                    qsum = __dp4a(w, 0x01010101, qsum);
+                    qdst[c] = w;
+                }
+            }
+        }
+        if (QMODE >= 0) {
+            for (int64_t c = c4 + lane; c < (ldo >> 2); c += 32) qdst[c] = 0;      // zero the K padding
+            if (rowsum) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) qsum += __shfl_xor_sync(0xffffffffu, qsum, o);
+                if (lane == 0) rowsum[row] = qsum;
             }
         }
     }
@@ -233,9 +256,14 @@ __global__ void __launch_bounds__(256) layernorm_generic_kernel(const float* __r
     }
 }
 
-template <int NV>   // NV scalars per lane: cols <= 32*NV
+// NV scalars per lane: cols <= 32*NV.  `has_div`: the graph's Div(x, c) that precedes the Softmax
+// (attention scores / sqrt(d)) applied on load.  QMODE as in layernorm_vec_kernel: the Softmax ->
+// quantize pair written straight as an int8 GEMM operand row.
+template <int NV, int QMODE>
 __global__ void __launch_bounds__(256) softmax_kernel(const float* __restrict__ x, int64_t rows, int cols, int64_t ldx,
-                                                     float* __restrict__ out) {
+                                                     int has_div, float div_c, float* __restrict__ out, QArgs qa,
+                                                     int8_t* __restrict__ qout, int64_t ldo,
+                                                     int32_t* __restrict__ rowsum) {
     const int lane = threadIdx.x & 31;
     const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t row = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); row < rows; row += warps) {
@@ -245,7 +273,7 @@ __global__ void __launch_bounds__(256) softmax_kernel(const float* __restrict__ 
 #pragma unroll
         for (int j = 0; j < NV; ++j) {
             const int c = lane + j * 32;
-            v[j] = (c < cols) ? src[c] : __int_as_float(0xff800000);
+            v[j] = (c < cols) ? (has_div ? __fdiv_rn(src[c], div_c) : src[c]) : __int_as_float(0xff800000);
             m = fmaxf(m, v[j]);
         }
         m = warp_max(m);
@@ -259,11 +287,71 @@ __global__ void __launch_bounds__(256) softmax_kernel(const float* __restrict__ 
             }
         }
         s = warp_sum(s);
-        float* dst = out + row * (int64_t)cols;
+        if (QMODE < 0) {
+            float* dst = out + row * (int64_t)cols;
 #pragma unroll
-        for (int j = 0; j < NV; ++j) {
-            const int c = lane + j * 32;
-            if (c < cols) dst[c] = __fdiv_rn(v[j], s);
+            for (int j = 0; j < NV; ++j) {
+                const int c = lane + j * 32;
+                if (c < cols) dst[c] = __fdiv_rn(v[j], s);
+            }
+        } else {
+            constexpr int QM = QMODE < 0 ? 0 : QMODE;
+            int8_t* qdst = qout + row * ldo;
+            int qsum = 0;
+#pragma unroll
+            for (int j = 0; j < NV; ++j) {
+                const int c = lane + j * 32;
+                if (c < ldo) {
+                    const int q = (c < cols) ? (int)(int8_t)qcode<QM>(__fdiv_rn(v[j], s), qa) : 0;
+                    qsum += q;
+                    qdst[c] = (int8_t)q;
+                }
+            }
+            if (rowsum) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) qsum += __shfl_xor_sync(0xffffffffu, qsum, o);
+                if (lane == 0) rowsum[row] = qsum;
+            }
+        }
+    }
+}
+
+// GELU chain -> quantize: warp per row, streaming (any cols); int8 operand row + optional row sum.
+template <int QMODE>
+__global__ void __launch_bounds__(256) gelu_quantize_kernel(const float* __restrict__ x, int64_t rows, int64_t cols,
+                                                           int64_t ldx, float c_div, float c_add, float c_mul,
+                                                           QArgs qa, int8_t* __restrict__ qout, int64_t ldo,
+                                                           int32_t* __restrict__ rowsum) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const bool vec = ((ldx & 3) == 0) && ((ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+    for (int64_t row = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); row < rows; row += warps) {
+        const float* src = x + row * ldx;
+        int8_t* dst = qout + row * ldo;
+        int qsum = 0;
+        int64_t done = 0;
+        if (vec) {
+            const int64_t c4 = cols >> 2;
+            for (int64_t c = lane; c < c4; c += 32) {
+                const float4 v = __ldcs(reinterpret_cast<const float4*>(src) + c);
+                const int w = pack4_codes(qcode<QMODE>(gelu_chain(v.x, c_div, c_add, c_mul), qa),
+                                          qcode<QMODE>(gelu_chain(v.y, c_div, c_add, c_mul), qa),
+                                          qcode<QMODE>(gelu_chain(v.z, c_div, c_add, c_mul), qa),
+                                          qcode<QMODE>(gelu_chain(v.w, c_div, c_add, c_mul), qa));
+                qsum = __dp4a(w, 0x01010101, qsum);
+                reinterpret_cast<int*>(dst)[c] = w;
+            }
+            done = c4 << 2;
+        }
+        for (int64_t c = done + lane; c < ldo; c += 32) {
+            const int q = (c < cols) ? (int)(int8_t)qcode<QMODE>(gelu_chain(src[c], c_div, c_add, c_mul), qa) : 0;
+            qsum += q;
+            dst[c] = (int8_t)q;
+        }
+        if (rowsum) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) qsum += __shfl_xor_sync(0xffffffffu, qsum, o);
+            if (lane == 0) rowsum[row] = qsum;
         }
     }
 }
@@ -425,29 +513,118 @@ extern "C" int nq_binary_f32(int op, const float* a, const int64_t* sa_host, con
     return NQ_OK;
 }
 
+static int launch_layernorm(const float* x, int64_t rows, int64_t cols, int64_t ldx, const float* gamma,
+                            const float* beta, float eps, float* out, int qmode, const QArgs& qa, int8_t* qout,
+                            int64_t ldo, int32_t* rowsum, cudaStream_t s) {
+    const int grid = stream_grid(rows * 32, 256);
+    const bool vec = (cols % 4 == 0) && (ldx % 4 == 0) && aligned16(x) && aligned16(gamma) && aligned16(beta) &&
+                     (qmode >= 0 ? ((ldo & 3) == 0) : aligned16(out));
+#define NQ_LN(NV)                                                                                                       \
+    do {                                                                                                                \
+        if (qmode < 0) layernorm_vec_kernel<NV, -1><<<grid, 256, 0, s>>>(x, rows, (int)cols, ldx, gamma, beta, eps, out, qa, qout, ldo, rowsum); \
+        else if (qmode == 0) layernorm_vec_kernel<NV, 0><<<grid, 256, 0, s>>>(x, rows, (int)cols, ldx, gamma, beta, eps, out, qa, qout, ldo, rowsum); \
+        else if (qmode == 1) layernorm_vec_kernel<NV, 1><<<grid, 256, 0, s>>>(x, rows, (int)cols, ldx, gamma, beta, eps, out, qa, qout, ldo, rowsum); \
+        else layernorm_vec_kernel<NV, 2><<<grid, 256, 0, s>>>(x, rows, (int)cols, ldx, gamma, beta, eps, out, qa, qout, ldo, rowsum); \
+    } while (0)
+    if (vec && cols <= 512) NQ_LN(4);
+    else if (vec && cols <= 1024) NQ_LN(8);
+    else if (vec && cols <= 4096 && qmode < 0) NQ_LN(32);
+    else if (qmode < 0) layernorm_generic_kernel<<<grid, 256, 0, s>>>(x, rows, cols, ldx, gamma, beta, eps, out);
+    else {
+        set_error("nq_layernorm_quantize_f32: needs cols %% 4 == 0, cols <= 1024 and 16-byte aligned rows");
+        return NQ_ERR_UNSUPPORTED;
+    }
+#undef NQ_LN
+    return NQ_OK;
+}
+
 extern "C" int nq_layernorm_f32(const float* x, int64_t rows, int64_t cols, int64_t ldx, const float* gamma,
                                 const float* beta, float eps, float* out, void* stream) {
     if (rows <= 0 || cols <= 0) return NQ_OK;
-    cudaStream_t s = (cudaStream_t)stream;
-    const int grid = stream_grid(rows * 32, 256);
-    const bool vec = (cols % 4 == 0) && (ldx % 4 == 0) && aligned16(x) && aligned16(out) && aligned16(gamma) && aligned16(beta);
-    if (vec && cols <= 512) layernorm_vec_kernel<4><<<grid, 256, 0, s>>>(x, rows, (int)cols, ldx, gamma, beta, eps, out);
-    else if (vec && cols <= 1024) layernorm_vec_kernel<8><<<grid, 256, 0, s>>>(x, rows, (int)cols, ldx, gamma, beta, eps, out);
-    else if (vec && cols <= 4096) layernorm_vec_kernel<32><<<grid, 256, 0, s>>>(x, rows, (int)cols, ldx, gamma, beta, eps, out);
-    else layernorm_generic_kernel<<<grid, 256, 0, s>>>(x, rows, cols, ldx, gamma, beta, eps, out);
+    QArgs qa{};
+    if (int rc = launch_layernorm(x, rows, cols, ldx, gamma, beta, eps, out, -1, qa, nullptr, 0, nullptr, (cudaStream_t)stream)) return rc;
     NQ_CHECK_LAUNCH("nq_layernorm_f32");
+    return NQ_OK;
+}
+
+extern "C" int nq_layernorm_quantize_f32(const float* x, int64_t rows, int64_t cols, int64_t ldx, const float* gamma,
+                                         const float* beta, float eps, int bit_width, float scale, int has_zp,
+                                         int64_t zp, int8_t* out, int64_t ldo, int32_t* rowsum, void* stream) {
+    NQ_REQUIRE(bit_width >= 2 && bit_width <= 8, "nq_layernorm_quantize_f32: bit_width %d outside 2..8", bit_width);
+    NQ_REQUIRE(ldo >= cols, "nq_layernorm_quantize_f32: ldo < cols");
+    if (rows <= 0 || cols <= 0) return NQ_OK;
+    int qmode;
+    const QArgs qa = make_qargs(bit_width, scale, has_zp, zp, &qmode);
+    if (int rc = launch_layernorm(x, rows, cols, ldx, gamma, beta, eps, nullptr, qmode, qa, out, ldo, rowsum, (cudaStream_t)stream)) return rc;
+    NQ_CHECK_LAUNCH("nq_layernorm_quantize_f32");
+    return NQ_OK;
+}
+
+static int launch_softmax(const float* x, int64_t rows, int64_t cols, int64_t ldx, int has_div, float div_c, float* out,
+                          int qmode, const QArgs& qa, int8_t* qout, int64_t ldo, int32_t* rowsum, cudaStream_t s) {
+    const int grid = stream_grid(rows * 32, 256);
+#define NQ_SM(NV)                                                                                                       \
+    do {                                                                                                                \
+        if (qmode < 0) softmax_kernel<NV, -1><<<grid, 256, 0, s>>>(x, rows, (int)cols, ldx, has_div, div_c, out, qa, qout, ldo, rowsum); \
+        else if (qmode == 0) softmax_kernel<NV, 0><<<grid, 256, 0, s>>>(x, rows, (int)cols, ldx, has_div, div_c, out, qa, qout, ldo, rowsum); \
+        else if (qmode == 1) softmax_kernel<NV, 1><<<grid, 256, 0, s>>>(x, rows, (int)cols, ldx, has_div, div_c, out, qa, qout, ldo, rowsum); \
+        else softmax_kernel<NV, 2><<<grid, 256, 0, s>>>(x, rows, (int)cols, ldx, has_div, div_c, out, qa, qout, ldo, rowsum); \
+    } while (0)
+    const int64_t span = qmode >= 0 ? ldo : cols;                 // the quantizing variant also writes the padding
+    if (span <= 128) NQ_SM(4);
+    else if (span <= 256) NQ_SM(8);
+    else if (span <= 1024) NQ_SM(32);
+    else if (qmode < 0 && !has_div) softmax_generic_kernel<<<grid, 256, 0, s>>>(x, rows, cols, ldx, out);
+    else {
+        set_error("fused softmax: rows longer than 1024 are not supported");
+        return NQ_ERR_UNSUPPORTED;
+    }
+#undef NQ_SM
     return NQ_OK;
 }
 
 extern "C" int nq_softmax_f32(const float* x, int64_t rows, int64_t cols, int64_t ldx, float* out, void* stream) {
     if (rows <= 0 || cols <= 0) return NQ_OK;
-    cudaStream_t s = (cudaStream_t)stream;
-    const int grid = stream_grid(rows * 32, 256);
-    if (cols <= 128) softmax_kernel<4><<<grid, 256, 0, s>>>(x, rows, (int)cols, ldx, out);
-    else if (cols <= 256) softmax_kernel<8><<<grid, 256, 0, s>>>(x, rows, (int)cols, ldx, out);
-    else if (cols <= 1024) softmax_kernel<32><<<grid, 256, 0, s>>>(x, rows, (int)cols, ldx, out);
-    else softmax_generic_kernel<<<grid, 256, 0, s>>>(x, rows, cols, ldx, out);
+    QArgs qa{};
+    if (int rc = launch_softmax(x, rows, cols, ldx, 0, 1.f, out, -1, qa, nullptr, 0, nullptr, (cudaStream_t)stream)) return rc;
     NQ_CHECK_LAUNCH("nq_softmax_f32");
+    return NQ_OK;
+}
+
+extern "C" int nq_softmax_div_f32(const float* x, int64_t rows, int64_t cols, int64_t ldx, float div_const, float* out,
+                                  void* stream) {
+    if (rows <= 0 || cols <= 0) return NQ_OK;
+    QArgs qa{};
+    if (int rc = launch_softmax(x, rows, cols, ldx, 1, div_const, out, -1, qa, nullptr, 0, nullptr, (cudaStream_t)stream)) return rc;
+    NQ_CHECK_LAUNCH("nq_softmax_div_f32");
+    return NQ_OK;
+}
+
+extern "C" int nq_softmax_quantize_f32(const float* x, int64_t rows, int64_t cols, int64_t ldx, int has_div,
+                                       float div_const, int bit_width, float scale, int has_zp, int64_t zp,
+                                       int8_t* out, int64_t ldo, int32_t* rowsum, void* stream) {
+    NQ_REQUIRE(bit_width >= 2 && bit_width <= 8, "nq_softmax_quantize_f32: bit_width %d outside 2..8", bit_width);
+    NQ_REQUIRE(ldo >= cols, "nq_softmax_quantize_f32: ldo < cols");
+    if (rows <= 0 || cols <= 0) return NQ_OK;
+    int qmode;
+    const QArgs qa = make_qargs(bit_width, scale, has_zp, zp, &qmode);
+    if (int rc = launch_softmax(x, rows, cols, ldx, has_div, div_const, nullptr, qmode, qa, out, ldo, rowsum, (cudaStream_t)stream)) return rc;
+    NQ_CHECK_LAUNCH("nq_softmax_quantize_f32");
+    return NQ_OK;
+}
+
+extern "C" int nq_gelu_quantize_f32(const float* x, int64_t rows, int64_t cols, int64_t ldx, float div_const,
+                                    float add_const, float mul_const, int bit_width, float scale, int has_zp,
+                                    int64_t zp, int8_t* out, int64_t ldo, int32_t* rowsum, void* stream) {
+    NQ_REQUIRE(bit_width >= 2 && bit_width <= 8, "nq_gelu_quantize_f32: bit_width %d outside 2..8", bit_width);
+    NQ_REQUIRE(ldo >= cols, "nq_gelu_quantize_f32: ldo < cols");
+    if (rows <= 0 || cols <= 0) return NQ_OK;
+    int qmode;
+    const QArgs qa = make_qargs(bit_width, scale, has_zp, zp, &qmode);
+    const int grid = stream_grid(rows * 32, 256);
+    cudaStream_t s = (cudaStream_t)stream;
+    NQ_DISPATCH_QMODE(qmode, gelu_quantize_kernel, <<<grid, 256, 0, s>>>(x, rows, cols, ldx, div_const, add_const, mul_const, qa, out, ldo, rowsum));
+    NQ_CHECK_LAUNCH("nq_gelu_quantize_f32");
     return NQ_OK;
 }
 

@@ -109,6 +109,23 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t* r) 
         : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// explicit shared-space accesses (a generic LD/ST through the smem window costs extra address checks)
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t a) {
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(a) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
 
 // K-major, 128-byte-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart
 // (SBO), LBO unused for swizzled K-major; descriptor version 1 (Blackwell), layout 2.
@@ -259,11 +276,12 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
         // ===================== epilogue (8 warps) =====================
         // warp -> TMEM lane quarter q (hardware rule: warp_id % 4) and column-chunk parity h:
         // two warps share a quarter and take alternate 32-column chunks.
+        constexpr int NCH = (BN / 32 + 1) / 2;                           // chunks per warp and tile
         const int q = warp & 3;
         const int h = (warp - 4) >> 2;
         const int ew = warp - 4;
-        uint32_t* stg = epi + ew * (32 * 32);                            // 32 rows x 32 words, XOR-swizzled
-        int32_t* stg_row = reinterpret_cast<int32_t*>(epi + NUM_EPI_WARPS * 32 * 32) + ew * 32;
+        const uint32_t stg = smem_u32(epi + ew * (32 * 32));              // 32 rows x 32 words, XOR-swizzled
+        const uint32_t stg_row = smem_u32(epi + NUM_EPI_WARPS * 32 * 32 + ew * 32);
         int acc = 0;
         uint32_t acc_phase = 0;
         const AccZp z = p.zp;
@@ -272,27 +290,62 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
         const int cl = lane & 7, rsub = lane >> 3;                       // read-back: chunk of 4 cols, row in group
         const bool cs_vec = z.use_col && ((reinterpret_cast<uintptr_t>(z.colsum_b) & 15) == 0) && ((z.cs_stride & 3) == 0);
         const bool bias_vec = p.bias_f32 && ((reinterpret_cast<uintptr_t>(p.bias_f32) & 15) == 0);
+        const bool fast_deq = (p.mode == NQ_EPI_DEQUANT) && p.fast32;
         for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
             const int64_t b = t / tiles_per_batch, r = t % tiles_per_batch;
             const int64_t m0 = (r / n_tiles) * BM, n0 = (r % n_tiles) * BN;
-            mbar_wait(smem_u32(tfull_bar + acc), acc_phase);
-            tc_fence_after();
             const int64_t mrow0 = m0 + q * 32;
             const int64_t m = mrow0 + lane;                               // this thread's accumulator row
             const bool row_ok = m < p.M;
+            const int32_t* cs_b = z.use_col ? z.colsum_b + b * z.cs_stride : nullptr;
+            // ---- operands of the zero-point correction, fetched BEFORE waiting for the accumulator so
+            //      their L2 latency overlaps the main loop (with 227 KB of smem there is no L1 to hit)
             int64_t rowterm = -z.kterm;
             if (z.use_row && row_ok) rowterm += (int64_t)__ldg(z.rowsum_a + b * p.M + m) * z.zp_b;
-            if (p.fast32) {
+            int ct[NCH][4];
+            float bs[NCH][4];
+            if (fast_deq) {
+#pragma unroll
+                for (int i = 0; i < NCH; ++i) {
+                    const int64_t nc = n0 + (h + 2 * i) * 32;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) { ct[i][k] = 0; bs[i][k] = 0.f; }
+                    if (h + 2 * i >= BN / 32 || nc >= p.N) continue;
+                    if (c_aligned && nc + 32 <= p.N) {
+                        if (cs_b) {
+                            int4 c4;
+                            if (cs_vec) c4 = __ldg(reinterpret_cast<const int4*>(cs_b + nc) + cl);
+                            else c4 = make_int4(__ldg(cs_b + nc + cl * 4), __ldg(cs_b + nc + cl * 4 + 1),
+                                                __ldg(cs_b + nc + cl * 4 + 2), __ldg(cs_b + nc + cl * 4 + 3));
+                            ct[i][0] = c4.x * (int)z.zp_a; ct[i][1] = c4.y * (int)z.zp_a;
+                            ct[i][2] = c4.z * (int)z.zp_a; ct[i][3] = c4.w * (int)z.zp_a;
+                        }
+                        if (p.bias_f32) {
+                            const float* bp = p.bias_f32 + nc + cl * 4;
+                            float4 b4;
+                            if (bias_vec) b4 = __ldg(reinterpret_cast<const float4*>(bp));
+                            else b4 = make_float4(__ldg(bp), __ldg(bp + 1), __ldg(bp + 2), __ldg(bp + 3));
+                            bs[i][0] = b4.x; bs[i][1] = b4.y; bs[i][2] = b4.z; bs[i][3] = b4.w;
+                        }
+                    } else if (nc + lane < p.N) {
+                        if (cs_b) ct[i][0] = __ldg(cs_b + nc + lane) * (int)z.zp_a;
+                        if (p.bias_f32) bs[i][0] = __ldg(p.bias_f32 + nc + lane);
+                    }
+                }
+            }
+            mbar_wait(smem_u32(tfull_bar + acc), acc_phase);
+            tc_fence_after();
+            if (fast_deq) {
                 __syncwarp();
-                stg_row[lane] = (int32_t)rowterm;
+                sts32(stg_row + lane * 4, (uint32_t)(int32_t)rowterm);
             }
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
             const int64_t crow_base = b * p.stride_c;
-            const int32_t* cs_b = z.use_col ? z.colsum_b + b * z.cs_stride : nullptr;
-#pragma unroll 1
-            for (int c = h; c < BN / 32; c += 2) {
+#pragma unroll
+            for (int i = 0; i < NCH; ++i) {
+                const int c = h + 2 * i;
                 const int64_t nc = n0 + c * 32;
-                if (nc >= p.N) break;                                     // warp-uniform
+                if (c >= BN / 32 || nc >= p.N) continue;                  // warp-uniform
                 uint32_t v[32];
                 tmem_ld_32x32b_x32(t_row + (uint32_t)(c * 32), v);
                 tmem_ld_wait();
@@ -324,7 +377,6 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                     }
                     continue;
                 }
-                const bool fast_deq = (p.mode == NQ_EPI_DEQUANT) && p.fast32;
                 if (p.mode == NQ_EPI_DEQUANT && !fast_deq) {
                     // general path (64-bit zero-point arithmetic) in registers, before the transpose
 #pragma unroll
@@ -343,66 +395,40 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                 __syncwarp();
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
-                    *reinterpret_cast<uint4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) =
-                        make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    sts128(stg + (uint32_t)(lane * 128 + ((j ^ (lane & 7)) << 4)), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                 __syncwarp();
                 uint32_t* cbase = reinterpret_cast<uint32_t*>(p.C) + crow_base + nc;
                 if (c_aligned && nc + 32 <= p.N) {
                     // each store instruction covers 4 rows x 128 B; this lane owns 4 fixed columns
-                    int ct[4] = {0, 0, 0, 0};
-                    float bs[4] = {0.f, 0.f, 0.f, 0.f};
-                    if (fast_deq) {
-                        if (cs_b) {
-                            int4 c4;
-                            if (cs_vec) c4 = __ldg(reinterpret_cast<const int4*>(cs_b + nc) + cl);
-                            else c4 = make_int4(__ldg(cs_b + nc + cl * 4), __ldg(cs_b + nc + cl * 4 + 1),
-                                                __ldg(cs_b + nc + cl * 4 + 2), __ldg(cs_b + nc + cl * 4 + 3));
-                            ct[0] = c4.x * (int)z.zp_a; ct[1] = c4.y * (int)z.zp_a;
-                            ct[2] = c4.z * (int)z.zp_a; ct[3] = c4.w * (int)z.zp_a;
-                        }
-                        if (p.bias_f32) {
-                            const float* bp = p.bias_f32 + nc + cl * 4;
-                            float4 b4;
-                            if (bias_vec) b4 = __ldg(reinterpret_cast<const float4*>(bp));
-                            else b4 = make_float4(__ldg(bp), __ldg(bp + 1), __ldg(bp + 2), __ldg(bp + 3));
-                            bs[0] = b4.x; bs[1] = b4.y; bs[2] = b4.z; bs[3] = b4.w;
-                        }
-                    }
 #pragma unroll
                     for (int it = 0; it < 8; ++it) {
                         const int rr = it * 4 + rsub;
-                        uint4 val = *reinterpret_cast<const uint4*>(stg + rr * 32 + ((cl ^ (rr & 7)) << 2));
+                        uint4 val = lds128(stg + (uint32_t)(rr * 128 + ((cl ^ (rr & 7)) << 4)));
                         if (fast_deq) {
-                            const int rt = stg_row[rr];
-                            float f0 = deq_fast((int)val.x, rt, ct[0], p.scale), f1 = deq_fast((int)val.y, rt, ct[1], p.scale);
-                            float f2 = deq_fast((int)val.z, rt, ct[2], p.scale), f3 = deq_fast((int)val.w, rt, ct[3], p.scale);
+                            const int rt = (int)lds32(stg_row + rr * 4);
+                            float f0 = deq_fast((int)val.x, rt, ct[i][0], p.scale), f1 = deq_fast((int)val.y, rt, ct[i][1], p.scale);
+                            float f2 = deq_fast((int)val.z, rt, ct[i][2], p.scale), f3 = deq_fast((int)val.w, rt, ct[i][3], p.scale);
                             if (p.bias_f32) {
-                                f0 = __fadd_rn(bs[0], f0); f1 = __fadd_rn(bs[1], f1);
-                                f2 = __fadd_rn(bs[2], f2); f3 = __fadd_rn(bs[3], f3);
+                                f0 = __fadd_rn(bs[i][0], f0); f1 = __fadd_rn(bs[i][1], f1);
+                                f2 = __fadd_rn(bs[i][2], f2); f3 = __fadd_rn(bs[i][3], f3);
                             }
                             val = make_uint4(__float_as_uint(f0), __float_as_uint(f1), __float_as_uint(f2), __float_as_uint(f3));
                         }
-                        if (mrow0 + rr < p.M) *reinterpret_cast<uint4*>(cbase + (mrow0 + rr) * p.ldc + (cl << 2)) = val;
+                        if (mrow0 + rr < p.M) __stcs(reinterpret_cast<uint4*>(cbase + (mrow0 + rr) * p.ldc + (cl << 2)), val);
                     }
                 } else {
                     // ragged / unaligned: one column per lane, 32 rows, 128-byte coalesced scalar stores
                     const bool col_ok = nc + lane < p.N;
-                    int ct = 0;
-                    float bs = 0.f;
-                    if (fast_deq && col_ok) {
-                        if (cs_b) ct = __ldg(cs_b + nc + lane) * (int)z.zp_a;
-                        if (p.bias_f32) bs = __ldg(p.bias_f32 + nc + lane);
-                    }
                     const int lch = lane >> 2, lw = lane & 3;
-#pragma unroll 4
+#pragma unroll 8
                     for (int rr = 0; rr < 32; ++rr) {
-                        uint32_t val = stg[rr * 32 + (((lch ^ (rr & 7)) << 2) | lw)];
+                        uint32_t val = lds32(stg + (uint32_t)(rr * 128 + (((lch ^ (rr & 7)) << 4) | (lw << 2))));
                         if (fast_deq) {
-                            float f = deq_fast((int)val, stg_row[rr], ct, p.scale);
-                            if (p.bias_f32) f = __fadd_rn(bs, f);
+                            float f = deq_fast((int)val, (int)lds32(stg_row + rr * 4), ct[i][0], p.scale);
+                            if (p.bias_f32) f = __fadd_rn(bs[i][0], f);
                             val = __float_as_uint(f);
                         }
-                        if (col_ok && mrow0 + rr < p.M) cbase[(mrow0 + rr) * p.ldc + lane] = val;
+                        if (col_ok && mrow0 + rr < p.M) __stcs(cbase + (mrow0 + rr) * p.ldc + lane, val);
                     }
                 }
             }

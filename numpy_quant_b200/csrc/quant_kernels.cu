@@ -5,12 +5,6 @@
 namespace nq {
 
 // ------------------------------------------------------------------ K1 contiguous
-struct QArgs {
-    float scale, zpf, lo, hi;
-    double zp;
-    int zp_odd;
-};
-
 // Each thread-iteration: four fully coalesced 16-B loads (512 B per warp each) in flight, four
 // coalesced 4-B stores of packed codes.
 template <int QMODE>
@@ -369,31 +363,6 @@ __global__ void __launch_bounds__(256) unpack_kernel(const uint8_t* __restrict__
 }  // namespace nq
 
 using namespace nq;
-
-static inline void qrange(int bits, float* lo, float* hi) {
-    *lo = -ldexpf(1.f, bits - 1);
-    *hi = ldexpf(1.f, bits - 1) - 1.f;
-}
-
-static inline QArgs make_qargs(int bits, float scale, int has_zp, int64_t zp, int* qmode) {
-    QArgs a;
-    a.scale = scale;
-    qrange(bits, &a.lo, &a.hi);
-    a.zp = has_zp ? (double)zp : 0.0;
-    a.zpf = has_zp ? (float)zp : 0.f;
-    a.zp_odd = has_zp ? (int)(zp & 1) : 0;
-    // the float32-exact route needs |zp| < 2^20 (see quantize_asym_f32); NQ_QUANT_F64=1 forces float64
-    static const bool force64 = getenv("NQ_QUANT_F64") != nullptr;
-    *qmode = !has_zp ? 0 : ((!force64 && zp > -(1 << 20) && zp < (1 << 20)) ? 1 : 2);
-    return a;
-}
-
-#define NQ_DISPATCH_QMODE(qmode, KERNEL, ...)            \
-    do {                                                 \
-        if ((qmode) == 0) KERNEL<0> __VA_ARGS__;         \
-        else if ((qmode) == 1) KERNEL<1> __VA_ARGS__;    \
-        else KERNEL<2> __VA_ARGS__;                      \
-    } while (0)
 
 extern "C" int nq_quantize_f32(const float* x, int64_t n, int bit_width, float scale, int has_zp, int64_t zp,
                                int8_t* out, void* stream) {

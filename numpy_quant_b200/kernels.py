@@ -364,6 +364,72 @@ def softmax_lastdim(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def softmax_div_lastdim(x: torch.Tensor, div_c: float) -> torch.Tensor:
+    """softmax(x / c) over the last axis: the graph's Div + Softmax pair in one pass."""
+    _need_cuda(x, torch.float32)
+    x = x.contiguous()
+    cols = x.shape[-1]
+    out = torch.empty_like(x)
+    call("nq_softmax_div_f32", x.data_ptr(), x.numel() // cols, cols, cols, float(div_c), out.data_ptr(), _stream())
+    _count()
+    return out
+
+
+def _rows_operand(x: torch.Tensor, want_rowsum: bool):
+    """Allocate the A-role operand for a contiguous [..., M, K] float tensor produced row by row."""
+    lead = tuple(x.shape[:-2])
+    M, Kd = int(x.shape[-2]), int(x.shape[-1])
+    batch = int(np.prod(lead)) if lead else 1
+    ld = round_up(Kd, 16)
+    out = torch.empty((batch, M, ld), dtype=torch.int8, device=x.device)
+    rs = torch.empty((batch, M), dtype=torch.int32, device=x.device) if want_rowsum else None
+    return Operand(out, lead, M, Kd, ld, rs), batch * M, Kd, ld
+
+
+def can_fuse_layernorm_quantize(x: torch.Tensor) -> bool:
+    return x.dim() >= 2 and x.is_contiguous() and x.shape[-1] % 4 == 0 and x.shape[-1] <= 1024
+
+
+def layernorm_quantize(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, bits: int, scale, zp,
+                       want_rowsum: bool) -> Operand:
+    """LayerNormalization -> quantize (operand A) in one kernel."""
+    _need_cuda(x, torch.float32)
+    op, rows, cols, ld = _rows_operand(x, want_rowsum)
+    call("nq_layernorm_quantize_f32", x.data_ptr(), rows, cols, cols, gamma.contiguous().data_ptr(),
+         beta.contiguous().data_ptr(), float(eps), bits, float(scale), int(zp is not None), 0 if zp is None else int(zp),
+         op.data.data_ptr(), ld, _ptr(op.rowsum), _stream())
+    _count()
+    return op
+
+
+def can_fuse_softmax_quantize(x: torch.Tensor) -> bool:
+    return x.dim() >= 2 and x.is_contiguous() and round_up(int(x.shape[-1]), 16) <= 1024
+
+
+def softmax_quantize(x: torch.Tensor, div_c, bits: int, scale, zp, want_rowsum: bool) -> Operand:
+    """[Div ->] Softmax -> quantize (operand A) in one kernel."""
+    _need_cuda(x, torch.float32)
+    op, rows, cols, ld = _rows_operand(x, want_rowsum)
+    call("nq_softmax_quantize_f32", x.data_ptr(), rows, cols, cols, int(div_c is not None),
+         1.0 if div_c is None else float(div_c), bits, float(scale), int(zp is not None), 0 if zp is None else int(zp),
+         op.data.data_ptr(), ld, _ptr(op.rowsum), _stream())
+    _count()
+    return op
+
+
+def gelu_quantize(x: torch.Tensor, c_div: float, c_add: float, c_mul: float, bits: int, scale, zp,
+                  want_rowsum: bool) -> Operand:
+    """GELU chain -> quantize (operand A) in one kernel."""
+    _need_cuda(x, torch.float32)
+    x = x.contiguous()
+    op, rows, cols, ld = _rows_operand(x, want_rowsum)
+    call("nq_gelu_quantize_f32", x.data_ptr(), rows, cols, cols, float(c_div), float(c_add), float(c_mul), bits,
+         float(scale), int(zp is not None), 0 if zp is None else int(zp), op.data.data_ptr(), ld, _ptr(op.rowsum),
+         _stream())
+    _count()
+    return op
+
+
 def reduce_lastdim(op: str, x: torch.Tensor, keepdims: bool) -> torch.Tensor:
     _need_cuda(x, torch.float32)
     x = x.contiguous()

@@ -20,7 +20,8 @@ import torch
 from . import kernels as K
 from . import onnx_lite
 from .numpy_quantization import quant_parameters
-from .tensor import (FTensor, ITensor, QTensor, Tensor, concat, fconv2d, qconv2d, quantize_tensor, where)
+from .tensor import (FTensor, ITensor, QTensor, Tensor, concat, fconv2d, qconv2d, qtensor_from_operand,
+                     quantize_tensor, where)
 
 
 class Constant:
@@ -424,10 +425,8 @@ class QModel(Model):
         super().__init__(nodes, values, inputs, outputs)
         self.bit_width = bit_width
         self.quant_params = quant_params
-        self._gelu = find_gelu_chains(nodes)
-        self._gelu_skip = {name for spec in self._gelu.values() for name in spec[4]}
-        self._gelu_last = {spec[5] for spec in self._gelu.values()}
         self._const_deq: dict = {}
+        self._plan = None
 
     def __repr__(self):
         return (f"QModel(nodes={self.nodes}, values={self.values}, inputs={self.inputs}, outputs={self.values}, "
@@ -453,6 +452,48 @@ class QModel(Model):
         res += ")\n"
         return res
 
+    # ------------------------------------------------------------------ fusion plan (retain=False)
+    def _feeds_only_matmul_lhs(self, value: Value) -> bool:
+        """True when every consumer of `value` is a MatMul taking it as its left operand, so the
+        float tensor itself is never needed -- only its quantized GEMM operand."""
+        if not value.outputs or any(value is o for o in self.outputs):
+            return False
+        return all(n.op == "MatMul" and n.inputs[0] is value and n.inputs[1] is not value for n in value.outputs)
+
+    def _build_plan(self) -> dict:
+        """Static multi-node patterns of the graph, looked up by node name at run time:
+          gelu[div]      Div -> Erf -> Add -> Mul -> Mul chain        -> one kernel at the Div node
+          softmax[div]   Div(x, scalar) -> Softmax(last axis)          -> one kernel at the Div node
+          skip           nodes whose work is done by a fused step
+          emit[node]     fused result is handed to this node's output
+          quantize_out   producers (LayerNorm / Softmax / GELU) whose output only feeds MatMul left
+                         operands: they emit the int8 GEMM operand directly instead of float32
+        """
+        producers = {o.name: n for n in self.nodes for o in n.outputs}
+        by_name = {n.name: n for n in self.nodes}
+        plan = dict(gelu=find_gelu_chains(self.nodes), softmax={}, skip=set(), emit={}, quantize_out=set(), node=by_name)
+        for first, spec in plan["gelu"].items():
+            plan["skip"].update(spec[4])
+            plan["emit"][spec[5]] = first
+        for n in self.nodes:
+            if n.op == "Div" and len(n.outputs[0].outputs) == 1 and first_not_in(n.name, plan["gelu"]):
+                c = _scalar_const(n.inputs[1], producers)
+                sm = n.outputs[0].outputs[0]
+                if c is not None and sm.op == "Softmax" and sm.attrs.get("axis", -1) == -1 \
+                        and not any(n.outputs[0] is o for o in self.outputs):
+                    plan["softmax"][n.name] = (n.inputs[0], c, sm.name)
+                    plan["emit"][sm.name] = n.name
+        emitters = {}
+        for n in self.nodes:
+            if n.op == "LayerNormalization" or (n.op == "Softmax" and n.attrs.get("axis", -1) == -1):
+                emitters[n.name] = n.outputs[0]
+        for first, spec in plan["gelu"].items():
+            emitters[spec[5]] = by_name[spec[5]].outputs[0]
+        for name, out in emitters.items():
+            if self._feeds_only_matmul_lhs(out):
+                plan["quantize_out"].add(name)
+        return plan
+
     # ------------------------------------------------------------------------------
     def _dequantized(self, value: Value) -> FTensor:
         """Dequantize a value for a float consumer; constants are immutable, so cached."""
@@ -463,6 +504,18 @@ class QModel(Model):
                 self._const_deq[value.name] = d
             return d[1]
         return value.data.dequantize()
+
+    def _rowsum_needed(self, value: Value) -> bool:
+        """Row sums of a left operand are needed iff some consuming MatMul has an asymmetric right operand."""
+        for n in value.outputs:
+            if n.op in ("MatMul", "Gemm") and n.inputs[0] is value:
+                other = n.inputs[1]
+                if isinstance(other.data, QTensor):
+                    if other.data._zp is not None:
+                        return True
+                elif self.quant_params[other.name].zero_point is not None:
+                    return True
+        return False
 
     def _quantized_operand(self, value: Value, role: Optional[str], other: Value, cache: dict) -> QTensor:
         """Quantize a float activation for an integer MatMul / Gemm (model.py:503-527), straight
@@ -479,12 +532,18 @@ class QModel(Model):
             cache[key] = q
         return q
 
+    def _emit_operand(self, out: Value, op, shape, cache: dict) -> None:
+        """Register a fused producer's int8 operand as the quantized form of `out` (left operand)."""
+        qp = self.quant_params[out.name]
+        cache[(out.name, "A")] = qtensor_from_operand(op, "A", shape, self.bit_width, qp.scale, qp.zero_point)
+
     def __call__(self, inputs: List[np.ndarray], profile=False, *, retain: bool = True,
                  device_outputs: bool = False):
         """Quantized interpreter (reference model.py:486-565).
 
         retain=True  keeps every intermediate on `Variable.data` like the reference.
-        retain=False frees a value after its last consumer and runs GELU chains as one kernel.
+        retain=False frees a value after its last consumer and fuses multi-node patterns
+                     (GELU chain, Div+Softmax, producer->quantize); results are bit-identical.
         device_outputs=True returns CUDA tensors (no device->host copy, no synchronisation).
         """
         for array, variable in zip(inputs, self.inputs):
@@ -511,49 +570,87 @@ class QModel(Model):
                 torch.cuda.synchronize()
                 times[key] += time() - t0
 
+        fused = not retain
+        if fused and self._plan is None:
+            self._plan = self._build_plan()
+        plan = self._plan if fused else dict(gelu={}, softmax={}, skip=set(), emit={}, quantize_out=set(), node={})
         qcache: dict = {}
+        stash: dict = {}
         remaining = None
-        if not retain:
+        if fused:
             remaining = {v.name: len(v.outputs) for v in self.values if isinstance(v, Variable)}
             keep = {o.name for o in self.outputs} | {n.outputs[0].name for n in self.nodes if n.op == "Constant"}
+        bits = self.bit_width
 
-        gelu_stash: dict = {}
+        def as_float(v: Value) -> FTensor:
+            return v.data if isinstance(v.data, FTensor) else self._dequantized(v)
+
         for node in self.nodes:
-            if (not retain) and node.name in self._gelu:
-                x, c1, c2, c3, _, last = self._gelu[node.name]
-                xin = x.data if isinstance(x.data, FTensor) else self._dequantized(x)
+            name = node.name
+            out0 = node.outputs[0] if node.outputs else None
+            if name in plan["gelu"]:
+                # ---- GELU chain in one kernel (optionally emitting the next MatMul's int8 operand)
+                x, c1, c2, c3, _, last = plan["gelu"][name]
+                xin = as_float(x)
                 t0 = tick()
-                gelu_stash[last] = xin.gelu_erf(c1, c2, c3)
+                lastv = plan["node"][last].outputs[0] if last in plan["quantize_out"] else None
+                if lastv is not None and xin.device_tensor.dim() >= 2:
+                    qp = self.quant_params[lastv.name]
+                    op = K.gelu_quantize(xin.device_tensor, c1, c2, c3, bits, float(qp.scale), _zp_int(qp.zero_point),
+                                         self._rowsum_needed(lastv))
+                    self._emit_operand(lastv, op, tuple(xin.device_tensor.shape), qcache)
+                    stash[last] = None
+                else:
+                    stash[last] = xin.gelu_erf(c1, c2, c3)
                 tock("Erf", t0)
                 outputs_data = [None]
-            elif (not retain) and node.name in self._gelu_skip:
+            elif name in plan["softmax"]:
+                # ---- Div + Softmax (+ quantize) in one kernel
+                x, c, sm_name = plan["softmax"][name]
+                xin = as_float(x)
+                t0 = tick()
+                smv = plan["node"][sm_name].outputs[0]
+                xt = xin.device_tensor
+                if sm_name in plan["quantize_out"] and K.can_fuse_softmax_quantize(xt):
+                    qp = self.quant_params[smv.name]
+                    op = K.softmax_quantize(xt, c, bits, float(qp.scale), _zp_int(qp.zero_point), self._rowsum_needed(smv))
+                    self._emit_operand(smv, op, tuple(xt.shape), qcache)
+                    stash[sm_name] = None
+                else:
+                    stash[sm_name] = FTensor(K.softmax_div_lastdim(xt, c))
+                tock("Softmax", t0)
                 outputs_data = [None]
-            elif (not retain) and node.name in self._gelu_last:
-                outputs_data = [gelu_stash.pop(node.name)]
-            elif node.op == "Constant" and node.outputs[0].data is not None:
-                outputs_data = [node.outputs[0].data]           # immutable: uploaded once, reused
+            elif name in plan["skip"]:
+                outputs_data = [None]
+            elif name in plan["emit"]:
+                outputs_data = [stash.pop(name)]
+            elif node.op == "Constant" and out0.data is not None:
+                outputs_data = [out0.data]                      # immutable: uploaded once, reused
             elif node.op in ("MatMul", "Gemm"):
                 inputs_data = []
                 for pos, i in enumerate(node.inputs):
-                    if isinstance(i.data, FTensor):
-                        role = None
-                        if pos < 2 and len(i.data.device_tensor.shape) >= 2:
-                            trans = node.op == "Gemm" and node.attrs.get("transA" if pos == 0 else "transB")
-                            role = ("A" if pos == 0 else "B") if not trans else None
+                    role = None
+                    if pos < 2:
+                        trans = node.op == "Gemm" and node.attrs.get("transA" if pos == 0 else "transB")
+                        role = ("A" if pos == 0 else "B") if not trans else None
+                    pre = qcache.get((i.name, role)) if role else None
+                    if pre is not None and not isinstance(i.data, QTensor):
+                        inputs_data.append(pre)
+                    elif isinstance(i.data, FTensor):
                         t0 = tick()
-                        if role is not None:
+                        if role is not None and i.data.device_tensor.dim() >= 2:
                             inputs_data.append(self._quantized_operand(i, role, node.inputs[1 - pos], qcache))
                         else:
                             qp = self.quant_params[i.name]
-                            inputs_data.append(quantize_tensor(i.data, self.bit_width, qp.scale, qp.zero_point))
+                            inputs_data.append(quantize_tensor(i.data, bits, qp.scale, qp.zero_point))
                         tock("TinyqQuant", t0)
                     else:
                         inputs_data.append(i.data)
                 t0 = tick()
                 outputs_data = onnx_operator_implementation(node.op, inputs_data, node.attrs)
                 if node.op == "Gemm":
-                    qp = self.quant_params[node.outputs[0].name]
-                    outputs_data = [outputs_data[0].requantize(self.bit_width, qp.scale, qp.zero_point)]
+                    qp = self.quant_params[out0.name]
+                    outputs_data = [outputs_data[0].requantize(bits, qp.scale, qp.zero_point)]
                 tock(node.op, t0)
             elif node.op == "Add" and self._is_bias_add(node):
                 # dequantize(acc) + dequantize(bias): both folded into the GEMM epilogue
@@ -571,6 +668,31 @@ class QModel(Model):
                 tock("TinyqDequant", t0)
                 t0 = tick()
                 outputs_data = onnx_operator_implementation(node.op, [node.inputs[0].data, node.inputs[1].data, b], node.attrs)
+                tock(node.op, t0)
+            elif fused and node.op == "LayerNormalization" and name in plan["quantize_out"] \
+                    and isinstance(node.inputs[0].data, FTensor) \
+                    and K.can_fuse_layernorm_quantize(node.inputs[0].data.device_tensor) \
+                    and node.attrs["axis"] in (-1, node.inputs[0].data.device_tensor.dim() - 1):
+                # ---- LayerNorm -> quantize: only the int8 operand is written
+                t0 = tick()
+                g, b = as_float(node.inputs[1]), as_float(node.inputs[2])
+                tock("TinyqDequant", t0)
+                t0 = tick()
+                xt = node.inputs[0].data.device_tensor
+                qp = self.quant_params[out0.name]
+                op = K.layernorm_quantize(xt, g.device_tensor, b.device_tensor, node.attrs["epsilon"], bits,
+                                          float(qp.scale), _zp_int(qp.zero_point), self._rowsum_needed(out0))
+                self._emit_operand(out0, op, tuple(xt.shape), qcache)
+                outputs_data = [None]
+                tock(node.op, t0)
+            elif fused and node.op == "Softmax" and name in plan["quantize_out"] and isinstance(node.inputs[0].data, FTensor) \
+                    and node.attrs.get("axis", -1) == -1 and K.can_fuse_softmax_quantize(node.inputs[0].data.device_tensor):
+                t0 = tick()
+                xt = node.inputs[0].data.device_tensor
+                qp = self.quant_params[out0.name]
+                op = K.softmax_quantize(xt, None, bits, float(qp.scale), _zp_int(qp.zero_point), self._rowsum_needed(out0))
+                self._emit_operand(out0, op, tuple(xt.shape), qcache)
+                outputs_data = [None]
                 tock(node.op, t0)
             else:
                 inputs_data = []
@@ -591,7 +713,7 @@ class QModel(Model):
                 for i in node.inputs:
                     if i.name in remaining:
                         remaining[i.name] -= 1
-                        if remaining[i.name] <= 0 and i.name not in keep and i not in self.inputs:
+                        if remaining[i.name] <= 0 and i.name not in keep and not any(i is v for v in self.inputs):
                             i.data = None
                             qcache.pop((i.name, "A"), None)
                             qcache.pop((i.name, "B"), None)
@@ -618,3 +740,11 @@ class QModel(Model):
                     and len(bias.data.shape) == 1 and bias.data.shape[0] == acc.data._lazy["b"].rows:
                 return True
         return False
+
+
+def first_not_in(name: str, table: dict) -> bool:
+    return name not in table
+
+
+def _zp_int(zero_point):
+    return None if zero_point is None else int(np.asarray(zero_point).reshape(-1)[0])

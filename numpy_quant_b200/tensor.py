@@ -518,9 +518,14 @@ def quantize_tensor(tensor: FTensor, bit_width: int, scale: np.float32, zero_poi
     if role is None or t.dim() < 2:
         return QTensor(K.quantize(t, bit_width, float(scale), zi), bit_width, scale=scale, zero_point=zero_point)
     op = K.quantize_operand(t, role, bit_width, float(scale), zi, want_rowsum)
+    return qtensor_from_operand(op, role, tuple(t.shape), bit_width, scale, zero_point)
+
+
+def qtensor_from_operand(op: K.Operand, role: str, shape: tuple, bit_width: int, scale, zero_point) -> QTensor:
+    """Wrap codes that exist only in the K-major GEMM operand layout (`.data` un-pads on demand)."""
     out = QTensor(None, bit_width, scale=scale, zero_point=zero_point)
     out._ops[role] = op
-    out._oplayout = (op, role, tuple(t.shape))
+    out._oplayout = (op, role, tuple(shape))
     return out
 
 

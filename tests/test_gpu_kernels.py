@@ -293,6 +293,35 @@ def test_float_glue_vs_numpy(kv):
         np.testing.assert_array_equal(host(K.reduce_lastdim("max", dev(x3), False)), x3.max(-1))
 
 
+@pytest.mark.parametrize("zp", [None, -3, 6])
+def test_fused_producer_quantize_kernels_equal_the_two_step_route(zp):
+    """LayerNorm->quantize, [Div->]Softmax->quantize, GELU->quantize emit exactly the codes (and row
+    sums) that the float kernel followed by quantize_operand produces."""
+    rng = np.random.default_rng(17)
+    x = (rng.normal(size=(3, 50, 768)) * 2).astype(np.float32)
+    g, b = (1 + rng.normal(size=768) * 0.1).astype(np.float32), (rng.normal(size=768) * 0.1).astype(np.float32)
+    xd, gd, bd = dev(x), dev(g), dev(b)
+    ref = K.quantize_operand(K.layernorm(xd, gd, bd, 1e-12), "A", 8, 0.03, zp, True)
+    got = K.layernorm_quantize(xd, gd, bd, 1e-12, 8, 0.03, zp, True)
+    assert torch.equal(got.data, ref.data) and torch.equal(got.rowsum, ref.rowsum)
+    s = (rng.normal(size=(2, 4, 197, 197)) * 5).astype(np.float32)
+    sd = dev(s)
+    for div in (None, 8.0):
+        f = K.softmax_lastdim(K.binary("div", sd, dev(np.array(div, np.float32)))) if div else K.softmax_lastdim(sd)
+        if div:
+            assert torch.equal(K.softmax_div_lastdim(sd, div), f)
+        ref = K.quantize_operand(f, "A", 8, 1.0 / 255, zp, True)
+        got = K.softmax_quantize(sd, div, 8, 1.0 / 255, zp, True)
+        assert got.ld == 208 and torch.equal(got.data, ref.data) and torch.equal(got.rowsum, ref.rowsum)
+    for shape in ((3, 50, 3072), (5, 7, 30)):
+        h = (rng.normal(size=shape) * 2).astype(np.float32)
+        hd = dev(h)
+        c = (1.4142135381698608, 1.0, 0.5)
+        ref = K.quantize_operand(K.gelu_erf(hd, *c), "A", 4, 0.2, zp, True)
+        got = K.gelu_quantize(hd, *c, 4, 0.2, zp, True)
+        assert torch.equal(got.data, ref.data) and torch.equal(got.rowsum, ref.rowsum)
+
+
 def test_copy_and_im2col(kv):
     rng = np.random.default_rng(9)
     x = rng.normal(size=(2, 5, 3, 8)).astype(np.float32)
