@@ -67,6 +67,7 @@ def gemm_case(M, N, Kd, batch=1, mode=_lib.EPI_RAW, label=""):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--gemm-only", action="store_true")
     args = ap.parse_args()
     emit(case="peaks", hbm_gbs=HBM, bf16_tflops=BF16, source="MEASURED_PEAKS.json" if PEAKS else "fallback")
     # library int8 GEMM (cuBLASLt through torch._int_mm) as a second, measured int8 reference point
@@ -96,6 +97,8 @@ def main():
             ops = 2.0 * bt * M * N * Kd
             emit(case=f"qgemm {lab}", M=M, N=N, K=Kd, batch=bt, epilogue="dequant_f32", ms_median=med, tops=ops / med / 1e9,
                  hbm_gbs_implied=(bt * (M * Kd + N * Kd) + bt * M * N * 4) / med / 1e6)
+    if args.gemm_only:
+        return
     # HBM-bound kernels: algorithmic bytes per element as fixed in SURVEY.md §8(d)
     shapes = [(4096, 4096)] if args.quick else [(4096, 4096), (50432, 768), (50432, 3072)]
     for shp in shapes:

@@ -109,8 +109,8 @@ int nq_rowsum_s8(const int8_t* q, int64_t rows, int64_t C, int64_t ld, int32_t* 
  * batch strides in elements; stride_b = 0 shares B across the batch.
  * Epilogue modes:
  *   NQ_EPI_RAW      C int32 [batch, M, ldc]
- *   NQ_EPI_DEQUANT  C float32 = dequantize(acc, scale, zp) (+ bias_f32[n])      (K2 fused;
- *                   model.py:528-538 followed by the bias Add of the graph)
+ *   NQ_EPI_DEQUANT  C float32 = dequantize(acc, scale, zp) (+ bias_f32[n]) (+ residual)  (K2 fused;
+ *                   model.py:528-538 followed by the bias Add / residual Add of the graph)
  *   NQ_EPI_REQUANT  C int8 = requantize(acc + bias_q[n])                         (K3 fused) */
 #define NQ_EPI_RAW 0
 #define NQ_EPI_DEQUANT 1
@@ -126,6 +126,10 @@ typedef struct nq_epilogue {
     float out_scale;
     int has_out_zp;
     int64_t out_zp;
+    const float* residual;         /* [batch, M, N] float32 or NULL (DEQUANT): the graph's residual Add,
+                                      out = (bias + dequant) + residual                 */
+    int64_t ld_residual;           /* row stride of residual (elements)                */
+    int64_t stride_residual;       /* batch stride of residual (elements)              */
 } nq_epilogue;
 
 int nq_qgemm_s8(const int8_t* A, const int8_t* B, void* C,

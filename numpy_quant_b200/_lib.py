@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libnq_b200.so")
+LIB_PATH = os.environ.get("NQ_B200_LIB") or os.path.join(HERE, "libnq_b200.so")   # override: A/B runs of older builds
 
 i64, i32, f32, vp = C.c_int64, C.c_int32, C.c_float, C.c_void_p
 
@@ -24,7 +24,8 @@ class AccZp(C.Structure):
 class Epilogue(C.Structure):
     """struct nq_epilogue"""
     _fields_ = [("mode", C.c_int), ("scale", f32), ("zp", AccZp), ("bias_f32", vp), ("bias_q", vp),
-                ("out_bits", C.c_int), ("out_scale", f32), ("has_out_zp", C.c_int), ("out_zp", i64)]
+                ("out_bits", C.c_int), ("out_scale", f32), ("has_out_zp", C.c_int), ("out_zp", i64),
+                ("residual", vp), ("ld_residual", i64), ("stride_residual", i64)]
 
 
 EPI_RAW, EPI_DEQUANT, EPI_REQUANT = 0, 1, 2
@@ -83,6 +84,8 @@ def load() -> C.CDLL:
                           "(nvcc, sm_100a). There is no CPU or PyTorch fallback.")
         lib = C.CDLL(LIB_PATH)
         for name, argtypes in _SIGNATURES.items():
+            if "NQ_B200_LIB" in os.environ and not hasattr(lib, name):
+                continue                       # an older build under A/B test may lack newer entry points
             fn = getattr(lib, name)            # AttributeError if the symbol is not exported
             fn.argtypes = argtypes
             fn.restype = _RESTYPE.get(name, C.c_int)

@@ -43,6 +43,8 @@ struct GemmParams {
     float scale;
     AccZp zp;
     const float* bias_f32;
+    const float* residual;           // DEQUANT: out = (bias + dequant) + residual[b, m, n]
+    int64_t ldr, stride_r;
     const int64_t* bias_q;
     float inv_out_scale;
     double out_zp;
@@ -109,22 +111,17 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t* r) 
         : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-// explicit shared-space accesses (a generic LD/ST through the smem window costs extra address checks)
-__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+// Read-only global loads as volatile asm: the compiler keeps them where they are written (ahead of the
+// accumulator wait), so their latency overlaps the main loop instead of being sunk to the first use.
+__device__ __forceinline__ int4 ldg_v4(const void* p) {
+    int4 r;
+    asm volatile("ld.global.nc.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
 }
-__device__ __forceinline__ void sts32(uint32_t addr, uint32_t a) {
-    asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(a) : "memory");
-}
-__device__ __forceinline__ uint4 lds128(uint32_t addr) {
-    uint4 v;
-    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
-    return v;
-}
-__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
-    uint32_t v;
-    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
-    return v;
+__device__ __forceinline__ int ldg_s32(const void* p) {
+    int r;
+    asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
 }
 
 // K-major, 128-byte-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart
@@ -169,7 +166,7 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
     using C = Cfg<BN>;
     extern __shared__ uint8_t smem_raw[];
     // 128B swizzle atoms need 1024-byte aligned tiles
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps .shared provenance
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + C::STAGES * C::A_BYTES;
     uint32_t* epi = reinterpret_cast<uint32_t*>(smem + C::STAGES * C::STAGE_BYTES);
@@ -280,8 +277,8 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
         const int q = warp & 3;
         const int h = (warp - 4) >> 2;
         const int ew = warp - 4;
-        const uint32_t stg = smem_u32(epi + ew * (32 * 32));              // 32 rows x 32 words, XOR-swizzled
-        const uint32_t stg_row = smem_u32(epi + NUM_EPI_WARPS * 32 * 32 + ew * 32);
+        uint32_t* stg = epi + ew * (32 * 32);                             // 32 rows x 32 words, XOR-swizzled
+        uint32_t* stg_row = epi + NUM_EPI_WARPS * 32 * 32 + ew * 32;
         int acc = 0;
         uint32_t acc_phase = 0;
         const AccZp z = p.zp;
@@ -291,6 +288,8 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
         const bool cs_vec = z.use_col && ((reinterpret_cast<uintptr_t>(z.colsum_b) & 15) == 0) && ((z.cs_stride & 3) == 0);
         const bool bias_vec = p.bias_f32 && ((reinterpret_cast<uintptr_t>(p.bias_f32) & 15) == 0);
         const bool fast_deq = (p.mode == NQ_EPI_DEQUANT) && p.fast32;
+        const bool res_vec = p.residual && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0) && ((p.ldr & 3) == 0) &&
+                             ((p.stride_r & 3) == 0);
         for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
             const int64_t b = t / tiles_per_batch, r = t % tiles_per_batch;
             const int64_t m0 = (r / n_tiles) * BM, n0 = (r % n_tiles) * BN;
@@ -301,7 +300,7 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
             // ---- operands of the zero-point correction, fetched BEFORE waiting for the accumulator so
             //      their L2 latency overlaps the main loop (with 227 KB of smem there is no L1 to hit)
             int64_t rowterm = -z.kterm;
-            if (z.use_row && row_ok) rowterm += (int64_t)__ldg(z.rowsum_a + b * p.M + m) * z.zp_b;
+            if (z.use_row && row_ok) rowterm += (int64_t)ldg_s32(z.rowsum_a + b * p.M + m) * z.zp_b;
             int ct[NCH][4];
             float bs[NCH][4];
             if (fast_deq) {
@@ -314,30 +313,36 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                     if (c_aligned && nc + 32 <= p.N) {
                         if (cs_b) {
                             int4 c4;
-                            if (cs_vec) c4 = __ldg(reinterpret_cast<const int4*>(cs_b + nc) + cl);
-                            else c4 = make_int4(__ldg(cs_b + nc + cl * 4), __ldg(cs_b + nc + cl * 4 + 1),
-                                                __ldg(cs_b + nc + cl * 4 + 2), __ldg(cs_b + nc + cl * 4 + 3));
-                            ct[i][0] = c4.x * (int)z.zp_a; ct[i][1] = c4.y * (int)z.zp_a;
-                            ct[i][2] = c4.z * (int)z.zp_a; ct[i][3] = c4.w * (int)z.zp_a;
+                            if (cs_vec) c4 = ldg_v4(cs_b + nc + cl * 4);
+                            else c4 = make_int4(ldg_s32(cs_b + nc + cl * 4), ldg_s32(cs_b + nc + cl * 4 + 1),
+                                                ldg_s32(cs_b + nc + cl * 4 + 2), ldg_s32(cs_b + nc + cl * 4 + 3));
+                            ct[i][0] = c4.x; ct[i][1] = c4.y; ct[i][2] = c4.z; ct[i][3] = c4.w;
                         }
                         if (p.bias_f32) {
                             const float* bp = p.bias_f32 + nc + cl * 4;
-                            float4 b4;
-                            if (bias_vec) b4 = __ldg(reinterpret_cast<const float4*>(bp));
-                            else b4 = make_float4(__ldg(bp), __ldg(bp + 1), __ldg(bp + 2), __ldg(bp + 3));
-                            bs[i][0] = b4.x; bs[i][1] = b4.y; bs[i][2] = b4.z; bs[i][3] = b4.w;
+                            int4 b4;
+                            if (bias_vec) b4 = ldg_v4(bp);
+                            else b4 = make_int4(ldg_s32(bp), ldg_s32(bp + 1), ldg_s32(bp + 2), ldg_s32(bp + 3));
+                            bs[i][0] = __int_as_float(b4.x); bs[i][1] = __int_as_float(b4.y);
+                            bs[i][2] = __int_as_float(b4.z); bs[i][3] = __int_as_float(b4.w);
                         }
                     } else if (nc + lane < p.N) {
-                        if (cs_b) ct[i][0] = __ldg(cs_b + nc + lane) * (int)z.zp_a;
-                        if (p.bias_f32) bs[i][0] = __ldg(p.bias_f32 + nc + lane);
+                        if (cs_b) ct[i][0] = ldg_s32(cs_b + nc + lane);
+                        if (p.bias_f32) bs[i][0] = __int_as_float(ldg_s32(p.bias_f32 + nc + lane));
                     }
                 }
             }
             mbar_wait(smem_u32(tfull_bar + acc), acc_phase);
             tc_fence_after();
             if (fast_deq) {
+                if (cs_b) {
+#pragma unroll
+                    for (int i = 0; i < NCH; ++i)
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) ct[i][k] *= (int)z.zp_a;
+                }
                 __syncwarp();
-                sts32(stg_row + lane * 4, (uint32_t)(int32_t)rowterm);
+                stg_row[lane] = (uint32_t)(int32_t)rowterm;
             }
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
             const int64_t crow_base = b * p.stride_c;
@@ -348,6 +353,18 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                 if (c >= BN / 32 || nc >= p.N) continue;                  // warp-uniform
                 uint32_t v[32];
                 tmem_ld_32x32b_x32(t_row + (uint32_t)(c * 32), v);
+                const bool vec_chunk = c_aligned && nc + 32 <= p.N;
+                const bool res_fast = fast_deq && p.residual != nullptr;
+                float4 res[8];
+                if (res_fast && vec_chunk && res_vec) {
+                    // residual tile rows for the read-back below; in flight while TMEM drains
+                    const float* rbase = p.residual + b * p.stride_r + nc + (cl << 2);
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const int64_t mm = mrow0 + it * 4 + rsub;
+                        res[it] = (mm < p.M) ? __ldcs(reinterpret_cast<const float4*>(rbase + mm * p.ldr)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
                 tmem_ld_wait();
                 if (p.mode == NQ_EPI_REQUANT) {
                     // int8 codes: 32 bytes per row, written straight from the owning thread
@@ -386,6 +403,7 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                         if (n < p.N) {
                             d = dequantize_one((int64_t)(int32_t)v[j] - tile_zp(z, rowterm, b, n), p.scale);
                             if (p.bias_f32) d = __fadd_rn(__ldg(p.bias_f32 + n), d);
+                            if (p.residual && row_ok) d = __fadd_rn(d, __ldg(p.residual + b * p.stride_r + m * p.ldr + n));
                         }
                         v[j] = __float_as_uint(d);
                     }
@@ -395,26 +413,38 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                 __syncwarp();
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
-                    sts128(stg + (uint32_t)(lane * 128 + ((j ^ (lane & 7)) << 4)), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    *reinterpret_cast<uint4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) =
+                        make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                 __syncwarp();
                 uint32_t* cbase = reinterpret_cast<uint32_t*>(p.C) + crow_base + nc;
-                if (c_aligned && nc + 32 <= p.N) {
+                if (vec_chunk) {
                     // each store instruction covers 4 rows x 128 B; this lane owns 4 fixed columns
 #pragma unroll
                     for (int it = 0; it < 8; ++it) {
                         const int rr = it * 4 + rsub;
-                        uint4 val = lds128(stg + (uint32_t)(rr * 128 + ((cl ^ (rr & 7)) << 4)));
+                        uint4 val = *reinterpret_cast<const uint4*>(stg + rr * 32 + ((cl ^ (rr & 7)) << 2));
                         if (fast_deq) {
-                            const int rt = (int)lds32(stg_row + rr * 4);
+                            const int rt = (int)stg_row[rr];
                             float f0 = deq_fast((int)val.x, rt, ct[i][0], p.scale), f1 = deq_fast((int)val.y, rt, ct[i][1], p.scale);
                             float f2 = deq_fast((int)val.z, rt, ct[i][2], p.scale), f3 = deq_fast((int)val.w, rt, ct[i][3], p.scale);
                             if (p.bias_f32) {
                                 f0 = __fadd_rn(bs[i][0], f0); f1 = __fadd_rn(bs[i][1], f1);
                                 f2 = __fadd_rn(bs[i][2], f2); f3 = __fadd_rn(bs[i][3], f3);
                             }
+                            if (res_fast) {
+                                float4 rv;
+                                if (res_vec) rv = res[it];
+                                else {
+                                    const float* rp = p.residual + b * p.stride_r + (mrow0 + rr) * p.ldr + nc + (cl << 2);
+                                    rv = (mrow0 + rr < p.M) ? make_float4(__ldg(rp), __ldg(rp + 1), __ldg(rp + 2), __ldg(rp + 3))
+                                                            : make_float4(0.f, 0.f, 0.f, 0.f);
+                                }
+                                f0 = __fadd_rn(f0, rv.x); f1 = __fadd_rn(f1, rv.y);
+                                f2 = __fadd_rn(f2, rv.z); f3 = __fadd_rn(f3, rv.w);
+                            }
                             val = make_uint4(__float_as_uint(f0), __float_as_uint(f1), __float_as_uint(f2), __float_as_uint(f3));
                         }
-                        if (mrow0 + rr < p.M) __stcs(reinterpret_cast<uint4*>(cbase + (mrow0 + rr) * p.ldc + (cl << 2)), val);
+                        if (mrow0 + rr < p.M) *reinterpret_cast<uint4*>(cbase + (mrow0 + rr) * p.ldc + (cl << 2)) = val;
                     }
                 } else {
                     // ragged / unaligned: one column per lane, 32 rows, 128-byte coalesced scalar stores
@@ -422,13 +452,15 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                     const int lch = lane >> 2, lw = lane & 3;
 #pragma unroll 8
                     for (int rr = 0; rr < 32; ++rr) {
-                        uint32_t val = lds32(stg + (uint32_t)(rr * 128 + (((lch ^ (rr & 7)) << 4) | (lw << 2))));
+                        uint32_t val = stg[rr * 32 + (((lch ^ (rr & 7)) << 2) | lw)];
                         if (fast_deq) {
-                            float f = deq_fast((int)val, (int)lds32(stg_row + rr * 4), ct[i][0], p.scale);
+                            float f = deq_fast((int)val, (int)stg_row[rr], ct[i][0], p.scale);
                             if (p.bias_f32) f = __fadd_rn(bs[i][0], f);
+                            if (res_fast && col_ok && mrow0 + rr < p.M)
+                                f = __fadd_rn(f, __ldg(p.residual + b * p.stride_r + (mrow0 + rr) * p.ldr + nc + lane));
                             val = __float_as_uint(f);
                         }
-                        if (col_ok && mrow0 + rr < p.M) __stcs(cbase + (mrow0 + rr) * p.ldc + lane, val);
+                        if (col_ok && mrow0 + rr < p.M) cbase[(mrow0 + rr) * p.ldc + lane] = val;
                     }
                 }
             }
@@ -553,6 +585,10 @@ extern "C" int nq_qgemm_s8(const int8_t* A, const int8_t* B, void* Cout, int64_t
     }
     p.bias_f32 = ep->bias_f32;
     p.bias_q = ep->bias_q;
+    p.residual = (ep->mode == NQ_EPI_DEQUANT) ? ep->residual : nullptr;
+    p.ldr = ep->ld_residual;
+    p.stride_r = ep->stride_residual;
+    NQ_REQUIRE(!p.residual || p.ldr >= N, "nq_qgemm_s8: ld_residual < N");
     p.C = Cout;
     if (ep->mode == NQ_EPI_REQUANT) {
         NQ_REQUIRE(ep->out_bits >= 2 && ep->out_bits <= 8, "nq_qgemm_s8: out_bits %d outside 2..8", ep->out_bits);

@@ -48,7 +48,7 @@ def round_up(x: int, m: int) -> int:
 def quantize(x: torch.Tensor, bits: int, scale, zp) -> torch.Tensor:
     """float32 (contiguous) -> int8 codes, same shape (numpy_quantization.py:24-34)."""
     _need_cuda(x, torch.float32)
-    x = x.contiguous()
+    x = materialize(x)
     out = torch.empty(x.shape, dtype=torch.int8, device=x.device)
     call("nq_quantize_f32", x.data_ptr(), x.numel(), bits, float(scale), int(zp is not None),
          0 if zp is None else int(zp), out.data_ptr(), _stream())
@@ -59,7 +59,7 @@ def quantize(x: torch.Tensor, bits: int, scale, zp) -> torch.Tensor:
 def quantize_i64(x: torch.Tensor, bits: int, scale) -> torch.Tensor:
     """Symmetric wide quantize (4*bit_width-bit biases) -> int64 codes."""
     _need_cuda(x, torch.float32)
-    x = x.contiguous()
+    x = materialize(x)
     out = torch.empty(x.shape, dtype=torch.int64, device=x.device)
     call("nq_quantize_f32_i64", x.data_ptr(), x.numel(), bits, float(scale), 0, 0, out.data_ptr(), _stream())
     _count()
@@ -144,7 +144,7 @@ def rowsum(op: Operand) -> torch.Tensor:
 # --------------------------------------------------------------------------- K2 / K3
 def dequantize(q: torch.Tensor, scale, zp) -> torch.Tensor:
     _need_cuda(q)
-    q = q.contiguous()
+    q = materialize(q)
     eb = {torch.int8: 1, torch.int32: 4, torch.int64: 8}[q.dtype]
     out = torch.empty(q.shape, dtype=torch.float32, device=q.device)
     call("nq_dequantize", q.data_ptr(), eb, q.numel(), float(scale), int(zp is not None),
@@ -219,14 +219,17 @@ def requantize_f32(d: torch.Tensor, bits: int, out_scale, out_zp) -> torch.Tenso
 def qgemm(a: Operand, b: Operand, mode: int = _lib.EPI_RAW, scale: float = 1.0,
           azp: Optional[AccZeroPoint] = None, bias_f32: Optional[torch.Tensor] = None,
           bias_q: Optional[torch.Tensor] = None, out_bits: int = 8, out_scale: float = 1.0, out_zp=None,
-          simt: bool = False) -> torch.Tensor:
+          simt: bool = False, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
     """C[batch, M, N] = A[batch, M, K] . B[batch|1, N, K]^T on the tcgen05 tensor cores."""
     assert a.k == b.k, f"contraction mismatch {a.k} vs {b.k}"
     batch = max(a.batch, b.batch)
     assert a.batch in (1, batch) and b.batch in (1, batch)
     M, N, K = a.rows, b.rows, a.k
     dtype = {_lib.EPI_RAW: torch.int32, _lib.EPI_DEQUANT: torch.float32, _lib.EPI_REQUANT: torch.int8}[mode]
-    out = torch.empty((batch, M, N), dtype=dtype, device=a.data.device)
+    # 32-bit outputs get rows padded to a 16-byte multiple so the epilogue can use its vector-store
+    # path for ragged N (attention scores, N = 197); callers see a [batch, M, N] view of it
+    ldn = N if (simt or mode == _lib.EPI_REQUANT or N % 4 == 0) else round_up(N, 4)
+    out = torch.empty((batch, M, ldn), dtype=dtype, device=a.data.device)
     sa = 0 if (a.batch == 1 and batch > 1) else M * a.ld
     sb = 0 if (b.batch == 1 and batch > 1) else N * b.ld
     if simt:
@@ -242,6 +245,13 @@ def qgemm(a: Operand, b: Operand, mode: int = _lib.EPI_RAW, scale: float = 1.0,
         ep.zp = azp.c_struct(N)
     ep.bias_f32 = _ptr(bias_f32)
     ep.bias_q = _ptr(bias_q)
+    if residual is not None:
+        # float32 [batch, M, N] rows with one uniform row stride (contiguous or row-padded)
+        assert mode == _lib.EPI_DEQUANT and residual.dtype == torch.float32 and residual.numel() == batch * M * N
+        residual, ldr = rows_layout(residual)
+        ep.residual = residual.data_ptr()
+        ep.ld_residual = ldr
+        ep.stride_residual = M * ldr
     ep.out_bits = out_bits
     ep.out_scale = float(out_scale)
     ep.has_out_zp = int(out_zp is not None)
@@ -250,13 +260,13 @@ def qgemm(a: Operand, b: Operand, mode: int = _lib.EPI_RAW, scale: float = 1.0,
     if timer is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-    call("nq_qgemm_s8", a.data.data_ptr(), b.data.data_ptr(), out.data_ptr(), M, N, K, batch, a.ld, b.ld, N,
-         sa, sb, M * N, C.byref(ep), _stream())
+    call("nq_qgemm_s8", a.data.data_ptr(), b.data.data_ptr(), out.data_ptr(), M, N, K, batch, a.ld, b.ld, ldn,
+         sa, sb, M * ldn, C.byref(ep), _stream())
     if timer is not None:
         e1.record()
         timer.append((2 * batch * M * N * K, e0, e1))
     _count()
-    return out
+    return out if ldn == N else out[:, :, :N]
 
 
 # --------------------------------------------------------------------------- K10 / K11
@@ -269,14 +279,14 @@ def minmax_slots(n_slots: int, device) -> torch.Tensor:
 
 def minmax_into(x: torch.Tensor, mm: torch.Tensor, slot: int) -> None:
     _need_cuda(x, torch.float32)
-    x = x.contiguous()
+    x = materialize(x)
     call("nq_minmax_f32", x.data_ptr(), x.numel(), mm.data_ptr(), slot, _stream())
     _count()
 
 
 def pack(q: torch.Tensor, bits: int) -> torch.Tensor:
     _need_cuda(q, torch.int8)
-    q = q.contiguous()
+    q = materialize(q)
     out = torch.empty(((q.numel() * bits + 7) // 8,), dtype=torch.uint8, device=q.device)
     call("nq_pack_s8", q.data_ptr(), q.numel(), bits, out.data_ptr(), _stream())
     _count()
@@ -294,7 +304,7 @@ def unpack(packed: torch.Tensor, n: int, bits: int) -> torch.Tensor:
 # --------------------------------------------------------------------------- K7-K9 float glue
 def unary(op: str, x: torch.Tensor) -> torch.Tensor:
     _need_cuda(x, torch.float32)
-    x = x.contiguous()
+    x = materialize(x)
     out = torch.empty_like(x)
     call("nq_unary_f32", _lib.UN[op], x.data_ptr(), x.numel(), out.data_ptr(), _stream())
     _count()
@@ -303,7 +313,7 @@ def unary(op: str, x: torch.Tensor) -> torch.Tensor:
 
 def gelu_erf(x: torch.Tensor, c_div: float, c_add: float, c_mul: float) -> torch.Tensor:
     _need_cuda(x, torch.float32)
-    x = x.contiguous()
+    x = materialize(x)
     out = torch.empty_like(x)
     call("nq_gelu_erf_f32", x.data_ptr(), x.numel(), float(c_div), float(c_add), float(c_mul), out.data_ptr(),
          _stream())
@@ -345,7 +355,7 @@ def binary(op: str, a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
 
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float) -> torch.Tensor:
     _need_cuda(x, torch.float32)
-    x = x.contiguous()
+    x = materialize(x)
     cols = x.shape[-1]
     out = torch.empty_like(x)
     call("nq_layernorm_f32", x.data_ptr(), x.numel() // cols, cols, cols, gamma.contiguous().data_ptr(),
@@ -356,21 +366,37 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
 
 def softmax_lastdim(x: torch.Tensor) -> torch.Tensor:
     _need_cuda(x, torch.float32)
-    x = x.contiguous()
+    x, ldx = rows_layout(x)
     cols = x.shape[-1]
-    out = torch.empty_like(x)
-    call("nq_softmax_f32", x.data_ptr(), x.numel() // cols, cols, cols, out.data_ptr(), _stream())
+    out = torch.empty(x.shape, dtype=torch.float32, device=x.device)
+    call("nq_softmax_f32", x.data_ptr(), x.numel() // cols, cols, ldx, out.data_ptr(), _stream())
     _count()
     return out
+
+
+def rows_layout(x: torch.Tensor):
+    """(tensor, ldx): `x` seen as rows of its last axis with ONE uniform row stride (e.g. the padded
+    GEMM output view); falls back to a contiguous copy when the leading dims do not collapse."""
+    if x.is_contiguous():
+        return x, int(x.shape[-1])
+    ok = x.dim() >= 2 and x.stride(-1) == 1
+    if ok:
+        ld = x.stride(-2)
+        ok = ld >= x.shape[-1] and all(x.shape[i] == 1 or x.stride(i) == x.stride(i + 1) * x.shape[i + 1]
+                                       for i in range(x.dim() - 2))
+    if ok:
+        return x, int(ld)
+    x = materialize(x)
+    return x, int(x.shape[-1])
 
 
 def softmax_div_lastdim(x: torch.Tensor, div_c: float) -> torch.Tensor:
     """softmax(x / c) over the last axis: the graph's Div + Softmax pair in one pass."""
     _need_cuda(x, torch.float32)
-    x = x.contiguous()
+    x, ldx = rows_layout(x)
     cols = x.shape[-1]
-    out = torch.empty_like(x)
-    call("nq_softmax_div_f32", x.data_ptr(), x.numel() // cols, cols, cols, float(div_c), out.data_ptr(), _stream())
+    out = torch.empty(x.shape, dtype=torch.float32, device=x.device)
+    call("nq_softmax_div_f32", x.data_ptr(), x.numel() // cols, cols, ldx, float(div_c), out.data_ptr(), _stream())
     _count()
     return out
 
@@ -403,14 +429,15 @@ def layernorm_quantize(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor,
 
 
 def can_fuse_softmax_quantize(x: torch.Tensor) -> bool:
-    return x.dim() >= 2 and x.is_contiguous() and round_up(int(x.shape[-1]), 16) <= 1024
+    return x.dim() >= 2 and round_up(int(x.shape[-1]), 16) <= 1024
 
 
 def softmax_quantize(x: torch.Tensor, div_c, bits: int, scale, zp, want_rowsum: bool) -> Operand:
     """[Div ->] Softmax -> quantize (operand A) in one kernel."""
     _need_cuda(x, torch.float32)
+    x, ldx = rows_layout(x)
     op, rows, cols, ld = _rows_operand(x, want_rowsum)
-    call("nq_softmax_quantize_f32", x.data_ptr(), rows, cols, cols, int(div_c is not None),
+    call("nq_softmax_quantize_f32", x.data_ptr(), rows, cols, ldx, int(div_c is not None),
          1.0 if div_c is None else float(div_c), bits, float(scale), int(zp is not None), 0 if zp is None else int(zp),
          op.data.data_ptr(), ld, _ptr(op.rowsum), _stream())
     _count()
@@ -421,7 +448,7 @@ def gelu_quantize(x: torch.Tensor, c_div: float, c_add: float, c_mul: float, bit
                   want_rowsum: bool) -> Operand:
     """GELU chain -> quantize (operand A) in one kernel."""
     _need_cuda(x, torch.float32)
-    x = x.contiguous()
+    x = materialize(x)
     op, rows, cols, ld = _rows_operand(x, want_rowsum)
     call("nq_gelu_quantize_f32", x.data_ptr(), rows, cols, cols, float(c_div), float(c_add), float(c_mul), bits,
          float(scale), int(zp is not None), 0 if zp is None else int(zp), op.data.data_ptr(), ld, _ptr(op.rowsum),
@@ -432,7 +459,7 @@ def gelu_quantize(x: torch.Tensor, c_div: float, c_add: float, c_mul: float, bit
 
 def reduce_lastdim(op: str, x: torch.Tensor, keepdims: bool) -> torch.Tensor:
     _need_cuda(x, torch.float32)
-    x = x.contiguous()
+    x = materialize(x)
     cols = x.shape[-1]
     out = torch.empty(x.shape[:-1], dtype=torch.float32, device=x.device)
     call("nq_reduce_rows_f32", {"max": 0, "sum": 1, "mean": 2}[op], x.data_ptr(), x.numel() // cols, cols,
@@ -463,7 +490,7 @@ def materialize(x: torch.Tensor) -> torch.Tensor:
 def im2col(x: torch.Tensor, kh: int, kw: int, pads, strides, pad_value=0) -> tuple[torch.Tensor, int, int]:
     """x[B,C,H,W] (int8 or float32) -> patches [B*OH*OW, ld] in (kh, kw, c) order (numpy_helper.py:18-92)."""
     _need_cuda(x)
-    x = x.contiguous()
+    x = materialize(x)
     B, Cc, H, W = x.shape
     ph0, pw0, ph1, pw1 = (int(p) for p in pads)
     sh, sw = (int(s) for s in strides)

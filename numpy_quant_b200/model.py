@@ -471,7 +471,8 @@ class QModel(Model):
         """
         producers = {o.name: n for n in self.nodes for o in n.outputs}
         by_name = {n.name: n for n in self.nodes}
-        plan = dict(gelu=find_gelu_chains(self.nodes), softmax={}, skip=set(), emit={}, quantize_out=set(), node=by_name)
+        plan = dict(gelu=find_gelu_chains(self.nodes), softmax={}, skip=set(), emit={}, quantize_out=set(), node=by_name,
+                    residual={})
         for first, spec in plan["gelu"].items():
             plan["skip"].update(spec[4])
             plan["emit"][spec[5]] = first
@@ -483,6 +484,22 @@ class QModel(Model):
                         and not any(n.outputs[0] is o for o in self.outputs):
                     plan["softmax"][n.name] = (n.inputs[0], c, sm.name)
                     plan["emit"][sm.name] = n.name
+        # bias Add (folded into the GEMM epilogue) whose only consumer is a residual Add
+        for n in self.nodes:
+            if n.op != "Add" or len(n.outputs[0].outputs) != 1 or any(n.outputs[0] is o for o in self.outputs):
+                continue
+            a, b = n.inputs
+            if not ((isinstance(a, Constant) and isinstance(b, Variable)) or (isinstance(b, Constant) and isinstance(a, Variable))):
+                continue
+            acc_v = b if isinstance(a, Constant) else a
+            if not acc_v.inputs or acc_v.inputs[0].op != "MatMul":
+                continue
+            add2 = n.outputs[0].outputs[0]
+            if add2.op != "Add" or add2.name in plan["emit"] or add2.name in plan["skip"]:
+                continue
+            other = [v for v in add2.inputs if v is not n.outputs[0]]
+            if len(other) == 1 and isinstance(other[0], Variable):
+                plan["residual"][n.name] = (other[0], add2.name)
         emitters = {}
         for n in self.nodes:
             if n.op == "LayerNormalization" or (n.op == "Softmax" and n.attrs.get("axis", -1) == -1):
@@ -573,7 +590,8 @@ class QModel(Model):
         fused = not retain
         if fused and self._plan is None:
             self._plan = self._build_plan()
-        plan = self._plan if fused else dict(gelu={}, softmax={}, skip=set(), emit={}, quantize_out=set(), node={})
+        plan = self._plan if fused else dict(gelu={}, softmax={}, skip=set(), emit={}, quantize_out=set(), node={},
+                                             residual={})
         qcache: dict = {}
         stash: dict = {}
         remaining = None
@@ -622,7 +640,7 @@ class QModel(Model):
                 outputs_data = [None]
             elif name in plan["skip"]:
                 outputs_data = [None]
-            elif name in plan["emit"]:
+            elif name in plan["emit"] or name in stash:
                 outputs_data = [stash.pop(name)]
             elif node.op == "Constant" and out0.data is not None:
                 outputs_data = [out0.data]                      # immutable: uploaded once, reused
@@ -660,7 +678,14 @@ class QModel(Model):
                 b = self._dequantized(bias)
                 tock("TinyqDequant", t0)
                 t0 = tick()
-                outputs_data = [acc.data.dequantize(bias=b)]
+                res_spec = plan["residual"].get(name)
+                resid = res_spec[0].data if res_spec else None
+                if isinstance(resid, FTensor) and tuple(resid.device_tensor.shape) == tuple(acc.data.shape):
+                    # (bias + dequant) + residual in the same epilogue; handed to the residual Add's output
+                    stash[res_spec[1]] = acc.data.dequantize(bias=b, residual=resid)
+                    outputs_data = [None]
+                else:
+                    outputs_data = [acc.data.dequantize(bias=b)]
                 tock(node.op, t0)
             elif node.op == "Conv" and isinstance(node.inputs[0].data, QTensor) and isinstance(node.inputs[1].data, QTensor):
                 t0 = tick()

@@ -387,16 +387,18 @@ class QTensor:
         return QTensor(a + b, self.bit_width, self.scale, self.zero_point)
 
     # -- K2 ----------------------------------------------------------------------------
-    def dequantize(self, bias: Optional[FTensor] = None) -> FTensor:
-        """tensor.py:189-193. `bias` (float32 [N]) optionally fuses the bias Add that follows."""
+    def dequantize(self, bias: Optional[FTensor] = None, residual: Optional[FTensor] = None) -> FTensor:
+        """tensor.py:189-193. `bias` (float32 [N]) and `residual` (float32, result shape) optionally
+        fuse the bias Add / residual Add that follow in the graph: (bias + dequant) + residual."""
         if self._pending() and self._lazy.get("bias_q") is None:
-            if bias is None and self._deq is not None:
+            if bias is None and residual is None and self._deq is not None:
                 return self._deq
             L = self._lazy
             out = K.qgemm(L["a"], L["b"], _lib.EPI_DEQUANT, float(self.scale), self._zp,
-                          bias_f32=None if bias is None else bias.device_tensor.contiguous())
+                          bias_f32=None if bias is None else bias.device_tensor.contiguous(),
+                          residual=None if residual is None else residual.device_tensor)
             res = FTensor(out.view(*L["batch_shape"], L["a"].rows, L["b"].rows))
-            if bias is None:
+            if bias is None and residual is None:
                 self._deq = res
             return res
         q = self._codes()
@@ -412,7 +414,9 @@ class QTensor:
             # array zero-point supplied by a caller: integer subtract, then scalar dequantize
             zt = _to_device(np.broadcast_to(np.asarray(z, dtype=np.int64), tuple(q.shape)).copy())
             res = FTensor(K.dequantize(K.materialize(q).to(torch.int64) - zt, float(self.scale), None))
-        return res if bias is None else res + bias
+        if bias is not None:
+            res = bias + res
+        return res if residual is None else res + residual
 
     # -- K3 ----------------------------------------------------------------------------
     def requantize(self, bit_width: int, scale: np.float32, zero_point: np.int64):

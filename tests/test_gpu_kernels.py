@@ -236,6 +236,38 @@ def test_qgemm_fused_epilogues(za, zb, bits):
             host(K.requantize_acc(raw, s, azp, dev(bq), bits, so, None if zo is None else int(zo))).astype(np.int64), want_q)
 
 
+def test_qgemm_residual_epilogue_and_ragged_output_rows():
+    """(bias + dequant) + residual in the epilogue == the three separate float ops; ragged N (197) is
+    written through a row-padded buffer and returned as a strided view."""
+    rng = np.random.default_rng(23)
+    for (batch, M, N, Kd) in ((1, 300, 768, 256), (6, 197, 197, 64), (2, 70, 50, 40)):
+        a = rng.integers(-128, 128, size=(batch, M, Kd)).astype(np.int64)
+        b = rng.integers(-128, 128, size=(1, Kd, N)).astype(np.int64)
+        acc, s, z = rq.q_matmul(a, np.float32(0.02), np.int64(-9), b, np.float32(0.004), None)
+        bias = rng.normal(size=N).astype(np.float32)
+        resid = rng.normal(size=(batch, M, N)).astype(np.float32)
+        oa = K.operand_from_codes(dev(a.astype(np.int8)), "A", False)
+        ob = K.operand_from_codes(dev(b.astype(np.int8)), "B", True)
+        azp = K.AccZeroPoint(-9, None, Kd, None, ob.rowsum, True)
+        got = K.qgemm(oa, ob, _lib.EPI_DEQUANT, s, azp, bias_f32=dev(bias), residual=dev(resid))
+        assert tuple(got.shape) == (batch, M, N)
+        want = (bias + rq.dequantize(acc, s, z)) + resid
+        np.testing.assert_array_equal(host(got), want)
+        if N % 4:
+            assert got.stride(1) == K.round_up(N, 4) and not got.is_contiguous()
+            # the padded view feeds the row kernels directly
+            e = np.exp(want / np.float32(8) - (want / np.float32(8)).max(-1, keepdims=True))
+            np.testing.assert_allclose(host(K.softmax_div_lastdim(got, 8.0)), e / e.sum(-1, keepdims=True), rtol=1e-5)
+            ref = K.quantize_operand(K.softmax_div_lastdim(got, 8.0), "A", 8, 1 / 255, -128, True)
+            fq = K.softmax_quantize(got, 8.0, 8, 1 / 255, -128, True)
+            assert torch.equal(fq.data, ref.data) and torch.equal(fq.rowsum, ref.rowsum)
+        # residual given as a strided (row-padded) view
+        rp = torch.zeros((batch, M, N + 4), device=DEV)
+        rp[:, :, :N] = dev(resid)
+        got2 = K.qgemm(oa, ob, _lib.EPI_DEQUANT, s, azp, bias_f32=dev(bias), residual=rp[:, :, :N])
+        np.testing.assert_array_equal(host(got2), want)
+
+
 def test_qgemm_rejects_bad_arguments():
     a = torch.zeros((1, 4, 8), dtype=torch.int8, device=DEV)
     ep = _lib.Epilogue()
