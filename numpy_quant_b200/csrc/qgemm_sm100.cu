@@ -145,13 +145,14 @@ __host__ __device__ constexpr uint32_t make_idesc(int bn) {
 // dequantize with 32-bit zero-point arithmetic: identical bits to f32(f64(d) * f64(scale)).
 // |d| < 2^22 converts through the 1.5*2^23 magic constant (integer add + FADD, full rate)
 // instead of I2F; larger values take the conversion / float64 routes.
+__device__ __noinline__ float deq_slow(int d, float scale) {       // rare: |d| >= 2^22, kept out of line
+    if (d >= -16777216 && d <= 16777216) return __fmul_rn((float)d, scale);
+    return (float)((double)d * (double)scale);
+}
 __device__ __forceinline__ float deq_fast(int a, int rt, int ct, float scale) {
     const int d = a - rt - ct;
-    float f;
-    if ((unsigned)(d + 0x400000) < 0x800000u) f = __fadd_rn(__int_as_float(0x4B400000 + d), -12582912.0f);
-    else if (d >= -16777216 && d <= 16777216) f = (float)d;
-    else return (float)((double)d * (double)scale);
-    return __fmul_rn(f, scale);
+    if (__builtin_expect((unsigned)(d + 0x400000) >= 0x800000u, 0)) return deq_slow(d, scale);
+    return __fmul_rn(__fadd_rn(__int_as_float(0x4B400000 + d), -12582912.0f), scale);
 }
 
 __device__ __forceinline__ int64_t tile_zp(const AccZp& z, int64_t rowterm, int64_t b, int64_t n) {
@@ -160,7 +161,9 @@ __device__ __forceinline__ int64_t tile_zp(const AccZp& z, int64_t rowterm, int6
     return v;
 }
 
-template <int BN>
+constexpr int EM_RAW = 0, EM_DEQ_FAST = 1, EM_DEQ_GENERAL = 2, EM_REQUANT = 3;
+
+template <int BN, int EMODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
     using C = Cfg<BN>;
@@ -179,9 +182,11 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-    const int64_t m_tiles = (p.M + BM - 1) / BM, n_tiles = (p.N + BN - 1) / BN;
-    const int64_t tiles_per_batch = m_tiles * n_tiles, total_tiles = tiles_per_batch * p.batch;
-    const int64_t k_blocks = (p.K + BK - 1) / BK;
+    // tile bookkeeping in 32 bits (host guarantees total_tiles < 2^31): 64-bit divides are long
+    // emulated sequences that would otherwise sit in every role's tile loop
+    const uint32_t m_tiles = (uint32_t)((p.M + BM - 1) / BM), n_tiles = (uint32_t)((p.N + BN - 1) / BN);
+    const uint32_t tiles_per_batch = m_tiles * n_tiles, total_tiles = tiles_per_batch * (uint32_t)p.batch;
+    const uint32_t k_blocks = (uint32_t)((p.K + BK - 1) / BK);
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
@@ -214,11 +219,11 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-                const int64_t b = t / tiles_per_batch, r = t % tiles_per_batch;
+            for (uint32_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                const uint32_t b = t / tiles_per_batch, r = t % tiles_per_batch;
                 const int m0 = (int)(r / n_tiles) * BM, n0 = (int)(r % n_tiles) * BN;
                 const int ba = p.a_batched ? (int)b : 0, bb = p.b_batched ? (int)b : 0;
-                for (int64_t kb = 0; kb < k_blocks; ++kb) {
+                for (uint32_t kb = 0; kb < k_blocks; ++kb) {
                     mbar_wait(smem_u32(empty_bar + stage), phase ^ 1);
                     const uint32_t fb = smem_u32(full_bar + stage);
                     mbar_expect_tx(fb, C::STAGE_BYTES);
@@ -240,11 +245,11 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            for (uint32_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
                 mbar_wait(smem_u32(tempty_bar + acc), acc_phase ^ 1);     // epilogue drained this buffer
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-                for (int64_t kb = 0; kb < k_blocks; ++kb) {
+                for (uint32_t kb = 0; kb < k_blocks; ++kb) {
                     mbar_wait(smem_u32(full_bar + stage), phase);
                     tc_fence_after();
                     const uint64_t adesc = make_smem_desc(smem_u32(smem_a + stage * C::A_BYTES));
@@ -271,9 +276,9 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
         __syncwarp();
     } else if (warp >= 4) {
         // ===================== epilogue (8 warps) =====================
-        // warp -> TMEM lane quarter q (hardware rule: warp_id % 4) and column-chunk parity h:
-        // two warps share a quarter and take alternate 32-column chunks.
-        constexpr int NCH = (BN / 32 + 1) / 2;                           // chunks per warp and tile
+        // warp -> TMEM lane quarter q (hardware rule: warp_id % 4) and column-chunk parity h: two
+        // warps share a quarter and take alternate 32-column chunks.  EMODE is a template parameter so
+        // that each instantiation carries only its own epilogue (the loop body stays I-cache resident).
         const int q = warp & 3;
         const int h = (warp - 4) >> 2;
         const int ew = warp - 4;
@@ -287,86 +292,80 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
         const int cl = lane & 7, rsub = lane >> 3;                       // read-back: chunk of 4 cols, row in group
         const bool cs_vec = z.use_col && ((reinterpret_cast<uintptr_t>(z.colsum_b) & 15) == 0) && ((z.cs_stride & 3) == 0);
         const bool bias_vec = p.bias_f32 && ((reinterpret_cast<uintptr_t>(p.bias_f32) & 15) == 0);
-        const bool fast_deq = (p.mode == NQ_EPI_DEQUANT) && p.fast32;
         const bool res_vec = p.residual && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0) && ((p.ldr & 3) == 0) &&
                              ((p.stride_r & 3) == 0);
-        for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-            const int64_t b = t / tiles_per_batch, r = t % tiles_per_batch;
-            const int64_t m0 = (r / n_tiles) * BM, n0 = (r % n_tiles) * BN;
+        const int zpa = (int)z.zp_a;
+        for (uint32_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            const int64_t b = t / tiles_per_batch;
+            const uint32_t r = t % tiles_per_batch;
+            const int64_t m0 = (int64_t)(r / n_tiles) * BM, n0 = (int64_t)(r % n_tiles) * BN;
             const int64_t mrow0 = m0 + q * 32;
             const int64_t m = mrow0 + lane;                               // this thread's accumulator row
             const bool row_ok = m < p.M;
             const int32_t* cs_b = z.use_col ? z.colsum_b + b * z.cs_stride : nullptr;
-            // ---- operands of the zero-point correction, fetched BEFORE waiting for the accumulator so
-            //      their L2 latency overlaps the main loop (with 227 KB of smem there is no L1 to hit)
             int64_t rowterm = -z.kterm;
             if (z.use_row && row_ok) rowterm += (int64_t)ldg_s32(z.rowsum_a + b * p.M + m) * z.zp_b;
-            int ct[NCH][4];
-            float bs[NCH][4];
-            if (fast_deq) {
-#pragma unroll
-                for (int i = 0; i < NCH; ++i) {
-                    const int64_t nc = n0 + (h + 2 * i) * 32;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) { ct[i][k] = 0; bs[i][k] = 0.f; }
-                    if (h + 2 * i >= BN / 32 || nc >= p.N) continue;
-                    if (c_aligned && nc + 32 <= p.N) {
-                        if (cs_b) {
-                            int4 c4;
-                            if (cs_vec) c4 = ldg_v4(cs_b + nc + cl * 4);
-                            else c4 = make_int4(ldg_s32(cs_b + nc + cl * 4), ldg_s32(cs_b + nc + cl * 4 + 1),
-                                                ldg_s32(cs_b + nc + cl * 4 + 2), ldg_s32(cs_b + nc + cl * 4 + 3));
-                            ct[i][0] = c4.x; ct[i][1] = c4.y; ct[i][2] = c4.z; ct[i][3] = c4.w;
-                        }
-                        if (p.bias_f32) {
-                            const float* bp = p.bias_f32 + nc + cl * 4;
-                            int4 b4;
-                            if (bias_vec) b4 = ldg_v4(bp);
-                            else b4 = make_int4(ldg_s32(bp), ldg_s32(bp + 1), ldg_s32(bp + 2), ldg_s32(bp + 3));
-                            bs[i][0] = __int_as_float(b4.x); bs[i][1] = __int_as_float(b4.y);
-                            bs[i][2] = __int_as_float(b4.z); bs[i][3] = __int_as_float(b4.w);
-                        }
-                    } else if (nc + lane < p.N) {
-                        if (cs_b) ct[i][0] = ldg_s32(cs_b + nc + lane);
-                        if (p.bias_f32) bs[i][0] = __int_as_float(ldg_s32(p.bias_f32 + nc + lane));
+            // Column operands of the zero-point correction / bias for the NEXT chunk are always in
+            // flight one chunk ahead (first chunk: issued before waiting for the accumulator), so their
+            // L2 latency never sits on the critical path (227 KB of smem leaves no L1 to hit).
+            int4 ct_n = make_int4(0, 0, 0, 0), bs_n = make_int4(0, 0, 0, 0);
+            auto fetch_cols = [&](int c) {
+                ct_n = make_int4(0, 0, 0, 0);
+                bs_n = make_int4(0, 0, 0, 0);
+                const int64_t nc = n0 + c * 32;
+                if (c >= BN / 32 || nc >= p.N) return;
+                if (c_aligned && nc + 32 <= p.N) {
+                    if (cs_b) ct_n = cs_vec ? ldg_v4(cs_b + nc + cl * 4)
+                                            : make_int4(ldg_s32(cs_b + nc + cl * 4), ldg_s32(cs_b + nc + cl * 4 + 1),
+                                                        ldg_s32(cs_b + nc + cl * 4 + 2), ldg_s32(cs_b + nc + cl * 4 + 3));
+                    if (p.bias_f32) {
+                        const float* bp = p.bias_f32 + nc + cl * 4;
+                        bs_n = bias_vec ? ldg_v4(bp) : make_int4(ldg_s32(bp), ldg_s32(bp + 1), ldg_s32(bp + 2), ldg_s32(bp + 3));
                     }
+                } else if (nc + lane < p.N) {
+                    if (cs_b) ct_n.x = ldg_s32(cs_b + nc + lane);
+                    if (p.bias_f32) bs_n.x = ldg_s32(p.bias_f32 + nc + lane);
                 }
-            }
+            };
+            if (EMODE == EM_DEQ_FAST) fetch_cols(h);
             mbar_wait(smem_u32(tfull_bar + acc), acc_phase);
             tc_fence_after();
-            if (fast_deq) {
-                if (cs_b) {
-#pragma unroll
-                    for (int i = 0; i < NCH; ++i)
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) ct[i][k] *= (int)z.zp_a;
-                }
+            if (EMODE == EM_DEQ_FAST) {
                 __syncwarp();
                 stg_row[lane] = (uint32_t)(int32_t)rowterm;
             }
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
             const int64_t crow_base = b * p.stride_c;
-#pragma unroll
-            for (int i = 0; i < NCH; ++i) {
-                const int c = h + 2 * i;
+            const int rows_left = (int)((p.M - mrow0) < 32 ? ((p.M - mrow0) > 0 ? (p.M - mrow0) : 0) : 32);
+#pragma unroll 1
+            for (int c = h; c < BN / 32; c += 2) {
                 const int64_t nc = n0 + c * 32;
-                if (c >= BN / 32 || nc >= p.N) continue;                  // warp-uniform
+                if (nc >= p.N) break;                                     // warp-uniform
                 uint32_t v[32];
                 tmem_ld_32x32b_x32(t_row + (uint32_t)(c * 32), v);
                 const bool vec_chunk = c_aligned && nc + 32 <= p.N;
-                const bool res_fast = fast_deq && p.residual != nullptr;
+                int ct[4];
+                float bs[4];
                 float4 res[8];
-                if (res_fast && vec_chunk && res_vec) {
-                    // residual tile rows for the read-back below; in flight while TMEM drains
-                    const float* rbase = p.residual + b * p.stride_r + nc + (cl << 2);
+                if (EMODE == EM_DEQ_FAST) {
+                    ct[0] = ct_n.x * zpa; ct[1] = ct_n.y * zpa; ct[2] = ct_n.z * zpa; ct[3] = ct_n.w * zpa;
+                    bs[0] = __int_as_float(bs_n.x); bs[1] = __int_as_float(bs_n.y);
+                    bs[2] = __int_as_float(bs_n.z); bs[3] = __int_as_float(bs_n.w);
+                    fetch_cols(c + 2);
+                    if (p.residual && vec_chunk && res_vec) {
+                        // residual tile rows for the read-back below; in flight while TMEM drains
+                        const float* rrow = p.residual + b * p.stride_r + (mrow0 + rsub) * p.ldr + nc + (cl << 2);
+                        const int64_t rstep = 4 * p.ldr;
 #pragma unroll
-                    for (int it = 0; it < 8; ++it) {
-                        const int64_t mm = mrow0 + it * 4 + rsub;
-                        res[it] = (mm < p.M) ? __ldcs(reinterpret_cast<const float4*>(rbase + mm * p.ldr)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        for (int it = 0; it < 8; ++it) {
+                            res[it] = (it * 4 + rsub < rows_left) ? __ldcs(reinterpret_cast<const float4*>(rrow))
+                                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+                            rrow += rstep;
+                        }
                     }
                 }
                 tmem_ld_wait();
-                if (p.mode == NQ_EPI_REQUANT) {
+                if (EMODE == EM_REQUANT) {
                     // int8 codes: 32 bytes per row, written straight from the owning thread
                     uint32_t w[8];
 #pragma unroll
@@ -394,7 +393,7 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                     }
                     continue;
                 }
-                if (p.mode == NQ_EPI_DEQUANT && !fast_deq) {
+                if (EMODE == EM_DEQ_GENERAL) {
                     // general path (64-bit zero-point arithmetic) in registers, before the transpose
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
@@ -419,24 +418,26 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                 uint32_t* cbase = reinterpret_cast<uint32_t*>(p.C) + crow_base + nc;
                 if (vec_chunk) {
                     // each store instruction covers 4 rows x 128 B; this lane owns 4 fixed columns
+                    uint32_t* crow = cbase + (mrow0 + rsub) * p.ldc + (cl << 2);
+                    const int64_t cstep = 4 * p.ldc;
 #pragma unroll
                     for (int it = 0; it < 8; ++it) {
                         const int rr = it * 4 + rsub;
                         uint4 val = *reinterpret_cast<const uint4*>(stg + rr * 32 + ((cl ^ (rr & 7)) << 2));
-                        if (fast_deq) {
+                        if (EMODE == EM_DEQ_FAST) {
                             const int rt = (int)stg_row[rr];
-                            float f0 = deq_fast((int)val.x, rt, ct[i][0], p.scale), f1 = deq_fast((int)val.y, rt, ct[i][1], p.scale);
-                            float f2 = deq_fast((int)val.z, rt, ct[i][2], p.scale), f3 = deq_fast((int)val.w, rt, ct[i][3], p.scale);
+                            float f0 = deq_fast((int)val.x, rt, ct[0], p.scale), f1 = deq_fast((int)val.y, rt, ct[1], p.scale);
+                            float f2 = deq_fast((int)val.z, rt, ct[2], p.scale), f3 = deq_fast((int)val.w, rt, ct[3], p.scale);
                             if (p.bias_f32) {
-                                f0 = __fadd_rn(bs[i][0], f0); f1 = __fadd_rn(bs[i][1], f1);
-                                f2 = __fadd_rn(bs[i][2], f2); f3 = __fadd_rn(bs[i][3], f3);
+                                f0 = __fadd_rn(bs[0], f0); f1 = __fadd_rn(bs[1], f1);
+                                f2 = __fadd_rn(bs[2], f2); f3 = __fadd_rn(bs[3], f3);
                             }
-                            if (res_fast) {
+                            if (p.residual) {
                                 float4 rv;
                                 if (res_vec) rv = res[it];
                                 else {
                                     const float* rp = p.residual + b * p.stride_r + (mrow0 + rr) * p.ldr + nc + (cl << 2);
-                                    rv = (mrow0 + rr < p.M) ? make_float4(__ldg(rp), __ldg(rp + 1), __ldg(rp + 2), __ldg(rp + 3))
+                                    rv = (rr < rows_left) ? make_float4(__ldg(rp), __ldg(rp + 1), __ldg(rp + 2), __ldg(rp + 3))
                                                             : make_float4(0.f, 0.f, 0.f, 0.f);
                                 }
                                 f0 = __fadd_rn(f0, rv.x); f1 = __fadd_rn(f1, rv.y);
@@ -444,23 +445,27 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                             }
                             val = make_uint4(__float_as_uint(f0), __float_as_uint(f1), __float_as_uint(f2), __float_as_uint(f3));
                         }
-                        if (mrow0 + rr < p.M) *reinterpret_cast<uint4*>(cbase + (mrow0 + rr) * p.ldc + (cl << 2)) = val;
+                        if (rr < rows_left) *reinterpret_cast<uint4*>(crow) = val;
+                        crow += cstep;
                     }
                 } else {
                     // ragged / unaligned: one column per lane, 32 rows, 128-byte coalesced scalar stores
                     const bool col_ok = nc + lane < p.N;
                     const int lch = lane >> 2, lw = lane & 3;
-#pragma unroll 8
+                    uint32_t* crow = cbase + mrow0 * p.ldc + lane;
+                    const float* rrow = p.residual ? p.residual + b * p.stride_r + mrow0 * p.ldr + nc + lane : nullptr;
+#pragma unroll 4
                     for (int rr = 0; rr < 32; ++rr) {
                         uint32_t val = stg[rr * 32 + (((lch ^ (rr & 7)) << 2) | lw)];
-                        if (fast_deq) {
-                            float f = deq_fast((int)val, (int)stg_row[rr], ct[i][0], p.scale);
-                            if (p.bias_f32) f = __fadd_rn(bs[i][0], f);
-                            if (res_fast && col_ok && mrow0 + rr < p.M)
-                                f = __fadd_rn(f, __ldg(p.residual + b * p.stride_r + (mrow0 + rr) * p.ldr + nc + lane));
+                        if (EMODE == EM_DEQ_FAST) {
+                            float f = deq_fast((int)val, (int)stg_row[rr], ct[0], p.scale);
+                            if (p.bias_f32) f = __fadd_rn(bs[0], f);
+                            if (rrow && col_ok && rr < rows_left) f = __fadd_rn(f, __ldg(rrow));
                             val = __float_as_uint(f);
                         }
-                        if (col_ok && mrow0 + rr < p.M) cbase[(mrow0 + rr) * p.ldc + lane] = val;
+                        if (col_ok && rr < rows_left) *crow = val;
+                        crow += p.ldc;
+                        if (rrow) rrow += p.ldr;
                     }
                 }
             }
@@ -533,19 +538,27 @@ static int make_operand_map(CUtensorMap* map, const int8_t* base, int64_t K, int
     return NQ_OK;
 }
 
-template <int BN>
+template <int BN, int EMODE>
 static int launch_qgemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t s) {
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(qgemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(qgemm_kernel<BN, EMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             Cfg<BN>::SMEM_BYTES);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(qgemm)");
         configured = true;
     }
     const int64_t tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN) * p.batch;
     const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
-    qgemm_kernel<BN><<<grid, NUM_THREADS, Cfg<BN>::SMEM_BYTES, s>>>(ta, tb, p);
+    qgemm_kernel<BN, EMODE><<<grid, NUM_THREADS, Cfg<BN>::SMEM_BYTES, s>>>(ta, tb, p);
     NQ_CHECK_LAUNCH("nq_qgemm_s8");
     return NQ_OK;
+}
+
+template <int BN>
+static int launch_qgemm_mode(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t s) {
+    if (p.mode == NQ_EPI_RAW) return launch_qgemm<BN, EM_RAW>(ta, tb, p, s);
+    if (p.mode == NQ_EPI_REQUANT) return launch_qgemm<BN, EM_REQUANT>(ta, tb, p, s);
+    return p.fast32 ? launch_qgemm<BN, EM_DEQ_FAST>(ta, tb, p, s) : launch_qgemm<BN, EM_DEQ_GENERAL>(ta, tb, p, s);
 }
 
 }  // namespace nq
@@ -565,6 +578,7 @@ extern "C" int nq_qgemm_s8(const int8_t* A, const int8_t* B, void* Cout, int64_t
     NQ_REQUIRE(((uintptr_t)A % 16 == 0) && ((uintptr_t)B % 16 == 0), "nq_qgemm_s8: operands must be 16-byte aligned");
     NQ_REQUIRE(ldc >= N, "nq_qgemm_s8: ldc < N");
     NQ_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31) && batch < (1ll << 31), "nq_qgemm_s8: extent too large");
+    NQ_REQUIRE(((M + 127) / 128) * ((N + 63) / 64) * batch < (1ll << 31), "nq_qgemm_s8: too many output tiles");
     NQ_REQUIRE(ep->mode >= NQ_EPI_RAW && ep->mode <= NQ_EPI_REQUANT, "nq_qgemm_s8: unknown epilogue mode %d", ep->mode);
     if (ep->mode != NQ_EPI_RAW)
         if (int rc = check_acc_zp(&ep->zp)) return rc;
@@ -604,9 +618,9 @@ extern "C" int nq_qgemm_s8(const int8_t* A, const int8_t* B, void* Cout, int64_t
     if (int rc = make_operand_map(&ta, A, K, M, p.a_batched ? batch : 1, lda, stride_a, BM)) return rc;
     if (int rc = make_operand_map(&tb, B, K, N, p.b_batched ? batch : 1, ldb, stride_b, bn)) return rc;
     cudaStream_t s = (cudaStream_t)stream;
-    if (bn == 64) return launch_qgemm<64>(ta, tb, p, s);
-    if (bn == 128) return launch_qgemm<128>(ta, tb, p, s);
-    return launch_qgemm<256>(ta, tb, p, s);
+    if (bn == 64) return launch_qgemm_mode<64>(ta, tb, p, s);
+    if (bn == 128) return launch_qgemm_mode<128>(ta, tb, p, s);
+    return launch_qgemm_mode<256>(ta, tb, p, s);
 }
 
 extern "C" int nq_qgemm_s8_simt(const int8_t* A, const int8_t* B, int32_t* Cm, int64_t M, int64_t N, int64_t K,
