@@ -130,6 +130,11 @@ typedef struct nq_epilogue {
                                       out = (bias + dequant) + residual                 */
     int64_t ld_residual;           /* row stride of residual (elements)                */
     int64_t stride_residual;       /* batch stride of residual (elements)              */
+    int64_t c_batch_inner;         /* > 1: the batch index is (outer, inner) and C[b] starts at
+                                      (b / inner) * stride_c + (b % inner) * stride_c_inner -- lets the
+                                      attention context GEMM write [B, S, H, D] directly (the graph's
+                                      Transpose(0,2,1,3) of a [B, H, S, D] result) */
+    int64_t stride_c_inner;
 } nq_epilogue;
 
 int nq_qgemm_s8(const int8_t* A, const int8_t* B, void* C,

@@ -25,7 +25,8 @@ class Epilogue(C.Structure):
     """struct nq_epilogue"""
     _fields_ = [("mode", C.c_int), ("scale", f32), ("zp", AccZp), ("bias_f32", vp), ("bias_q", vp),
                 ("out_bits", C.c_int), ("out_scale", f32), ("has_out_zp", C.c_int), ("out_zp", i64),
-                ("residual", vp), ("ld_residual", i64), ("stride_residual", i64)]
+                ("residual", vp), ("ld_residual", i64), ("stride_residual", i64),
+                ("c_batch_inner", i64), ("stride_c_inner", i64)]
 
 
 EPI_RAW, EPI_DEQUANT, EPI_REQUANT = 0, 1, 2

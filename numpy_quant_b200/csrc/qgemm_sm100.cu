@@ -37,6 +37,7 @@ template <int BN> struct Cfg {
 struct GemmParams {
     int64_t M, N, K, batch;
     int64_t ldc, stride_c;
+    int64_t c_inner, stride_c_inner; // C batch offset = (b / c_inner) * stride_c + (b % c_inner) * stride_c_inner
     int a_batched, b_batched;        // 0 -> operand shared across the batch (TMA batch coord 0)
     int mode;
     int fast32;                      // zero-point arithmetic provably fits int32 (host-checked bound)
@@ -287,7 +288,7 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
         int acc = 0;
         uint32_t acc_phase = 0;
         const AccZp z = p.zp;
-        const bool c_aligned = ((p.ldc & 3) == 0) && ((p.stride_c & 3) == 0) &&
+        const bool c_aligned = ((p.ldc & 3) == 0) && ((p.stride_c & 3) == 0) && ((p.stride_c_inner & 3) == 0) &&
                                ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
         const int cl = lane & 7, rsub = lane >> 3;                       // read-back: chunk of 4 cols, row in group
         const bool cs_vec = z.use_col && ((reinterpret_cast<uintptr_t>(z.colsum_b) & 15) == 0) && ((z.cs_stride & 3) == 0);
@@ -335,7 +336,8 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                 stg_row[lane] = (uint32_t)(int32_t)rowterm;
             }
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
-            const int64_t crow_base = b * p.stride_c;
+            const int64_t crow_base = (p.c_inner > 1) ? (b / p.c_inner) * p.stride_c + (b % p.c_inner) * p.stride_c_inner
+                                                      : b * p.stride_c;
             const int rows_left = (int)((p.M - mrow0) < 32 ? ((p.M - mrow0) > 0 ? (p.M - mrow0) : 0) : 32);
 #pragma unroll 1
             for (int c = h; c < BN / 32; c += 2) {
@@ -599,6 +601,10 @@ extern "C" int nq_qgemm_s8(const int8_t* A, const int8_t* B, void* Cout, int64_t
     }
     p.bias_f32 = ep->bias_f32;
     p.bias_q = ep->bias_q;
+    p.c_inner = ep->c_batch_inner > 1 ? ep->c_batch_inner : 1;
+    p.stride_c_inner = ep->c_batch_inner > 1 ? ep->stride_c_inner : 0;
+    NQ_REQUIRE(p.c_inner == 1 || (batch % p.c_inner == 0 && ep->mode != NQ_EPI_REQUANT),
+               "nq_qgemm_s8: c_batch_inner must divide batch (and is not available with REQUANT)");
     p.residual = (ep->mode == NQ_EPI_DEQUANT) ? ep->residual : nullptr;
     p.ldr = ep->ld_residual;
     p.stride_r = ep->stride_residual;

@@ -219,8 +219,10 @@ def requantize_f32(d: torch.Tensor, bits: int, out_scale, out_zp) -> torch.Tenso
 def qgemm(a: Operand, b: Operand, mode: int = _lib.EPI_RAW, scale: float = 1.0,
           azp: Optional[AccZeroPoint] = None, bias_f32: Optional[torch.Tensor] = None,
           bias_q: Optional[torch.Tensor] = None, out_bits: int = 8, out_scale: float = 1.0, out_zp=None,
-          simt: bool = False, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """C[batch, M, N] = A[batch, M, K] . B[batch|1, N, K]^T on the tcgen05 tensor cores."""
+          simt: bool = False, residual: Optional[torch.Tensor] = None, heads: int = 0) -> torch.Tensor:
+    """C[batch, M, N] = A[batch, M, K] . B[batch|1, N, K]^T on the tcgen05 tensor cores.
+
+    heads=H (batch = B*H): write the result as [B, M, H, N] -- i.e. already Transpose(0,2,1,3)-ed."""
     assert a.k == b.k, f"contraction mismatch {a.k} vs {b.k}"
     batch = max(a.batch, b.batch)
     assert a.batch in (1, batch) and b.batch in (1, batch)
@@ -229,7 +231,11 @@ def qgemm(a: Operand, b: Operand, mode: int = _lib.EPI_RAW, scale: float = 1.0,
     # 32-bit outputs get rows padded to a 16-byte multiple so the epilogue can use its vector-store
     # path for ragged N (attention scores, N = 197); callers see a [batch, M, N] view of it
     ldn = N if (simt or mode == _lib.EPI_REQUANT or N % 4 == 0) else round_up(N, 4)
-    out = torch.empty((batch, M, ldn), dtype=dtype, device=a.data.device)
+    if heads:
+        assert batch % heads == 0 and N % 4 == 0 and mode != _lib.EPI_REQUANT and not simt and residual is None
+        out = torch.empty((batch // heads, M, heads, N), dtype=dtype, device=a.data.device)
+    else:
+        out = torch.empty((batch, M, ldn), dtype=dtype, device=a.data.device)
     sa = 0 if (a.batch == 1 and batch > 1) else M * a.ld
     sb = 0 if (b.batch == 1 and batch > 1) else N * b.ld
     if simt:
@@ -260,13 +266,17 @@ def qgemm(a: Operand, b: Operand, mode: int = _lib.EPI_RAW, scale: float = 1.0,
     if timer is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-    call("nq_qgemm_s8", a.data.data_ptr(), b.data.data_ptr(), out.data_ptr(), M, N, K, batch, a.ld, b.ld, ldn,
-         sa, sb, M * ldn, C.byref(ep), _stream())
+    ldc, sc = ldn, M * ldn
+    if heads:
+        ep.c_batch_inner, ep.stride_c_inner = heads, N
+        ldc, sc = heads * N, M * heads * N
+    call("nq_qgemm_s8", a.data.data_ptr(), b.data.data_ptr(), out.data_ptr(), M, N, K, batch, a.ld, b.ld, ldc,
+         sa, sb, sc, C.byref(ep), _stream())
     if timer is not None:
         e1.record()
         timer.append((2 * batch * M * N * K, e0, e1))
     _count()
-    return out if ldn == N else out[:, :, :N]
+    return out if (heads or ldn == N) else out[:, :, :N]
 
 
 # --------------------------------------------------------------------------- K10 / K11

@@ -687,6 +687,11 @@ class QModel(Model):
                 else:
                     outputs_data = [acc.data.dequantize(bias=b)]
                 tock(node.op, t0)
+            elif node.op == "Transpose" and isinstance(node.inputs[0].data, QTensor) and node.inputs[0].data._pending() \
+                    and list(node.attrs["perm"]) == [0, 2, 1, 3] \
+                    and (heads_last := self._timed_heads_last(node.inputs[0].data, tick, tock)) is not None:
+                # attention context: the P.V GEMM writes [B, S, H, D] directly, no transpose copy
+                outputs_data = [heads_last]
             elif node.op == "Conv" and isinstance(node.inputs[0].data, QTensor) and isinstance(node.inputs[1].data, QTensor):
                 t0 = tick()
                 b = self._dequantized(node.inputs[2])
@@ -755,6 +760,13 @@ class QModel(Model):
         if profile:
             return output_tensors, times
         return output_tensors
+
+    @staticmethod
+    def _timed_heads_last(acc: QTensor, tick, tock):
+        t0 = tick()
+        res = acc.dequantize_heads_last()
+        tock("TinyqDequant", t0)
+        return res
 
     @staticmethod
     def _is_bias_add(node: Node) -> bool:

@@ -387,6 +387,16 @@ class QTensor:
         return QTensor(a + b, self.bit_width, self.scale, self.zero_point)
 
     # -- K2 ----------------------------------------------------------------------------
+    def dequantize_heads_last(self) -> Optional[FTensor]:
+        """dequantize().transpose(0, 2, 1, 3), materialised: a pending [B, H, S, D] accumulator is
+        written by the GEMM epilogue directly as [B, S, H, D] (the attention context layout).
+        Returns None when this accumulator does not qualify."""
+        L = self._lazy
+        if not self._pending() or L.get("bias_q") is not None or len(L["batch_shape"]) != 2 or L["b"].rows % 4:
+            return None
+        out = K.qgemm(L["a"], L["b"], _lib.EPI_DEQUANT, float(self.scale), self._zp, heads=int(L["batch_shape"][1]))
+        return FTensor(out)
+
     def dequantize(self, bias: Optional[FTensor] = None, residual: Optional[FTensor] = None) -> FTensor:
         """tensor.py:189-193. `bias` (float32 [N]) and `residual` (float32, result shape) optionally
         fuse the bias Add / residual Add that follow in the graph: (bias + dequant) + residual."""
