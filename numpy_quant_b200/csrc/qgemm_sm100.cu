@@ -5,7 +5,7 @@
 //   warp 0      TMA producer   (cp.async.bulk.tensor 3-D, 128B swizzle, K-major tiles)
 //   warp 1      MMA issuer     (one elected thread, tcgen05.mma cta_group::1, M=128, N=BN, K=32)
 //   warp 2      TMEM allocator (2 accumulator buffers of BN int32 columns)
-//   warps 4-11  epilogue       (tcgen05.ld 32x32b -> per-warp swizzled smem transpose ->
+//   warps 4-19  epilogue       (tcgen05.ld 32x32b -> per-warp swizzled smem transpose ->
 //                               zero-point correction + dequant(+bias) on the row-contiguous
 //                               read-back -> 16-byte coalesced stores; requant -> int8 codes)
 // smem ring of STAGES x (A 128x128 B + B BNx128 B); mbarrier full/empty per stage and
@@ -20,7 +20,7 @@ namespace nq {
 constexpr int BM = 128;          // rows of A per tile == TMEM lanes
 constexpr int BK = 128;          // int8 elements per stage along K == one 128-byte swizzle row
 constexpr int UMMA_K = 32;       // K per tcgen05.mma for 8-bit operands
-constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_EPI_WARPS = 16;
 constexpr int NUM_THREADS = 128 + 32 * NUM_EPI_WARPS;
 
 template <int BN> struct Cfg {
@@ -29,9 +29,10 @@ template <int BN> struct Cfg {
     static constexpr int B_BYTES = BN * BK;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-    static constexpr int EPI_BYTES = NUM_EPI_WARPS * (32 * 32 * 4 + 32 * 4);   // staging slabs + row terms
+    static constexpr int EPI_BYTES = NUM_EPI_WARPS * (32 * 16 * 4 + 32 * 4);   // staging slabs + row terms
     static constexpr int BAR_BYTES = 256;
-    static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES;
+    static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB opt-in shared memory of sm_100");
 };
 
 struct GemmParams {
@@ -111,6 +112,15 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t* r) 
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // Read-only global loads as volatile asm: the compiler keeps them where they are written (ahead of the
 // accumulator wait), so their latency overlaps the main loop instead of being sunk to the first use.
@@ -150,11 +160,6 @@ __device__ __noinline__ float deq_slow(int d, float scale) {       // rare: |d| 
     if (d >= -16777216 && d <= 16777216) return __fmul_rn((float)d, scale);
     return (float)((double)d * (double)scale);
 }
-__device__ __forceinline__ float deq_fast(int a, int rt, int ct, float scale) {
-    const int d = a - rt - ct;
-    if (__builtin_expect((unsigned)(d + 0x400000) >= 0x800000u, 0)) return deq_slow(d, scale);
-    return __fmul_rn(__fadd_rn(__int_as_float(0x4B400000 + d), -12582912.0f), scale);
-}
 
 __device__ __forceinline__ int64_t tile_zp(const AccZp& z, int64_t rowterm, int64_t b, int64_t n) {
     int64_t v = rowterm;
@@ -168,9 +173,10 @@ template <int BN, int EMODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
     using C = Cfg<BN>;
-    extern __shared__ uint8_t smem_raw[];
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 128B swizzle atoms need 1024-byte aligned tiles
-    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps .shared provenance
+    uint8_t* smem = smem_raw;
+    if ((smem_u32(smem_raw) & 1023u) != 0) __trap();      // swizzle atoms need the 1024-byte alignment requested above
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + C::STAGES * C::A_BYTES;
     uint32_t* epi = reinterpret_cast<uint32_t*>(smem + C::STAGES * C::STAGE_BYTES);
@@ -276,21 +282,26 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
         }
         __syncwarp();
     } else if (warp >= 4) {
-        // ===================== epilogue (8 warps) =====================
-        // warp -> TMEM lane quarter q (hardware rule: warp_id % 4) and column-chunk parity h: two
-        // warps share a quarter and take alternate 32-column chunks.  EMODE is a template parameter so
-        // that each instantiation carries only its own epilogue (the loop body stays I-cache resident).
+        // ===================== epilogue (16 warps) =====================
+        // The epilogue is a long dependent instruction stream per element, so it is throughput-
+        // bound by how many warps each SM sub-partition can interleave: 16 warps (4 per scheduler),
+        // each owning a TMEM lane quarter q (hardware rule: warp_id % 4) and every 4th 16-column
+        // sub-chunk (h).  Unit of work: 32 rows x 16 columns -> tcgen05.ld x16 -> XOR-swizzled smem
+        // slab (2 KB per warp) -> row-contiguous read-back (8 rows x 64 B per store instruction) with the
+        // zero-point correction, dequantize, bias and residual applied branch-free on the way out.
+        // EMODE is a template parameter so that each instantiation only carries its own path.
         const int q = warp & 3;
-        const int h = (warp - 4) >> 2;
+        const int h = (warp - 4) >> 2;                                    // 0..3
         const int ew = warp - 4;
-        uint32_t* stg = epi + ew * (32 * 32);                             // 32 rows x 32 words, XOR-swizzled
-        uint32_t* stg_row = epi + NUM_EPI_WARPS * 32 * 32 + ew * 32;
+        uint32_t* stg = epi + ew * (32 * 16);                             // 32 rows x 16 words
+        uint32_t* stg_row = epi + NUM_EPI_WARPS * 32 * 16 + ew * 32;
         int acc = 0;
         uint32_t acc_phase = 0;
         const AccZp z = p.zp;
         const bool c_aligned = ((p.ldc & 3) == 0) && ((p.stride_c & 3) == 0) && ((p.stride_c_inner & 3) == 0) &&
                                ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
-        const int cl = lane & 7, rsub = lane >> 3;                       // read-back: chunk of 4 cols, row in group
+        const int cl = lane & 3, rsub = lane >> 2;                       // vector read-back: 4-col chunk, row in group of 8
+        const int sc_col = lane & 15, sc_row = lane >> 4;                 // scalar read-back: column, row in pair
         const bool cs_vec = z.use_col && ((reinterpret_cast<uintptr_t>(z.colsum_b) & 15) == 0) && ((z.cs_stride & 3) == 0);
         const bool bias_vec = p.bias_f32 && ((reinterpret_cast<uintptr_t>(p.bias_f32) & 15) == 0);
         const bool res_vec = p.residual && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0) && ((p.ldr & 3) == 0) &&
@@ -306,16 +317,16 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
             const int32_t* cs_b = z.use_col ? z.colsum_b + b * z.cs_stride : nullptr;
             int64_t rowterm = -z.kterm;
             if (z.use_row && row_ok) rowterm += (int64_t)ldg_s32(z.rowsum_a + b * p.M + m) * z.zp_b;
-            // Column operands of the zero-point correction / bias for the NEXT chunk are always in
-            // flight one chunk ahead (first chunk: issued before waiting for the accumulator), so their
-            // L2 latency never sits on the critical path (227 KB of smem leaves no L1 to hit).
+            // Column operands (colsum for the zero-point, bias) of the NEXT sub-chunk are always in flight
+            // one step ahead (first one: issued before waiting for the accumulator): with 227 KB of
+            // smem there is no L1 to hit, so every one of these loads is an L2 round trip.
             int4 ct_n = make_int4(0, 0, 0, 0), bs_n = make_int4(0, 0, 0, 0);
-            auto fetch_cols = [&](int c) {
+            auto fetch_cols = [&](int sidx) {
                 ct_n = make_int4(0, 0, 0, 0);
                 bs_n = make_int4(0, 0, 0, 0);
-                const int64_t nc = n0 + c * 32;
-                if (c >= BN / 32 || nc >= p.N) return;
-                if (c_aligned && nc + 32 <= p.N) {
+                const int64_t nc = n0 + sidx * 16;
+                if (sidx >= BN / 16 || nc >= p.N) return;
+                if (c_aligned && nc + 16 <= p.N) {
                     if (cs_b) ct_n = cs_vec ? ldg_v4(cs_b + nc + cl * 4)
                                             : make_int4(ldg_s32(cs_b + nc + cl * 4), ldg_s32(cs_b + nc + cl * 4 + 1),
                                                         ldg_s32(cs_b + nc + cl * 4 + 2), ldg_s32(cs_b + nc + cl * 4 + 3));
@@ -323,9 +334,9 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                         const float* bp = p.bias_f32 + nc + cl * 4;
                         bs_n = bias_vec ? ldg_v4(bp) : make_int4(ldg_s32(bp), ldg_s32(bp + 1), ldg_s32(bp + 2), ldg_s32(bp + 3));
                     }
-                } else if (nc + lane < p.N) {
-                    if (cs_b) ct_n.x = ldg_s32(cs_b + nc + lane);
-                    if (p.bias_f32) bs_n.x = ldg_s32(p.bias_f32 + nc + lane);
+                } else if (nc + sc_col < p.N) {
+                    if (cs_b) ct_n.x = ldg_s32(cs_b + nc + sc_col);
+                    if (p.bias_f32) bs_n.x = ldg_s32(p.bias_f32 + nc + sc_col);
                 }
             };
             if (EMODE == EM_DEQ_FAST) fetch_cols(h);
@@ -333,45 +344,34 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
             tc_fence_after();
             if (EMODE == EM_DEQ_FAST) {
                 __syncwarp();
-                stg_row[lane] = (uint32_t)(int32_t)rowterm;
+                // row term with the int->float magic constant folded in: x = acc + rowmagic - colterm
+                stg_row[lane] = (uint32_t)(0x4B400000 - (int32_t)rowterm);
             }
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
             const int64_t crow_base = (p.c_inner > 1) ? (b / p.c_inner) * p.stride_c + (b % p.c_inner) * p.stride_c_inner
                                                       : b * p.stride_c;
             const int rows_left = (int)((p.M - mrow0) < 32 ? ((p.M - mrow0) > 0 ? (p.M - mrow0) : 0) : 32);
 #pragma unroll 1
-            for (int c = h; c < BN / 32; c += 2) {
-                const int64_t nc = n0 + c * 32;
+            for (int sidx = h; sidx < BN / 16; sidx += 4) {
+                const int64_t nc = n0 + sidx * 16;
                 if (nc >= p.N) break;                                     // warp-uniform
-                uint32_t v[32];
-                tmem_ld_32x32b_x32(t_row + (uint32_t)(c * 32), v);
-                const bool vec_chunk = c_aligned && nc + 32 <= p.N;
+                uint32_t v[16];
+                tmem_ld_32x32b_x16(t_row + (uint32_t)(sidx * 16), v);
+                const bool vec_chunk = c_aligned && nc + 16 <= p.N;
                 int ct[4];
                 float bs[4];
-                float4 res[8];
                 if (EMODE == EM_DEQ_FAST) {
                     ct[0] = ct_n.x * zpa; ct[1] = ct_n.y * zpa; ct[2] = ct_n.z * zpa; ct[3] = ct_n.w * zpa;
                     bs[0] = __int_as_float(bs_n.x); bs[1] = __int_as_float(bs_n.y);
                     bs[2] = __int_as_float(bs_n.z); bs[3] = __int_as_float(bs_n.w);
-                    fetch_cols(c + 2);
-                    if (p.residual && vec_chunk && res_vec) {
-                        // residual tile rows for the read-back below; in flight while TMEM drains
-                        const float* rrow = p.residual + b * p.stride_r + (mrow0 + rsub) * p.ldr + nc + (cl << 2);
-                        const int64_t rstep = 4 * p.ldr;
-#pragma unroll
-                        for (int it = 0; it < 8; ++it) {
-                            res[it] = (it * 4 + rsub < rows_left) ? __ldcs(reinterpret_cast<const float4*>(rrow))
-                                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
-                            rrow += rstep;
-                        }
-                    }
+                    fetch_cols(sidx + 4);
                 }
                 tmem_ld_wait();
                 if (EMODE == EM_REQUANT) {
-                    // int8 codes: 32 bytes per row, written straight from the owning thread
-                    uint32_t w[8];
+                    // int8 codes: 16 bytes per row, written straight from the owning thread
+                    uint32_t w[4];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
+                    for (int j = 0; j < 16; ++j) {
                         const int64_t n = nc + j;
                         int qv = 0;
                         if (n < p.N) {
@@ -386,11 +386,10 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                     }
                     if (row_ok) {
                         int8_t* dst = reinterpret_cast<int8_t*>(p.C) + crow_base + m * p.ldc + nc;
-                        if (nc + 32 <= p.N && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-                            reinterpret_cast<uint4*>(dst)[0] = make_uint4(w[0], w[1], w[2], w[3]);
-                            reinterpret_cast<uint4*>(dst)[1] = make_uint4(w[4], w[5], w[6], w[7]);
+                        if (nc + 16 <= p.N && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+                            *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
                         } else {
-                            for (int j = 0; j < 32 && nc + j < p.N; ++j) dst[j] = (int8_t)(w[j >> 2] >> ((j & 3) * 8));
+                            for (int j = 0; j < 16 && nc + j < p.N; ++j) dst[j] = (int8_t)(w[j >> 2] >> ((j & 3) * 8));
                         }
                     }
                     continue;
@@ -398,7 +397,7 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                 if (EMODE == EM_DEQ_GENERAL) {
                     // general path (64-bit zero-point arithmetic) in registers, before the transpose
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
+                    for (int j = 0; j < 16; ++j) {
                         const int64_t n = nc + j;
                         float d = 0.f;
                         if (n < p.N) {
@@ -409,41 +408,60 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                         v[j] = __float_as_uint(d);
                     }
                 }
-                // transpose through this warp's smem slab (16-byte chunks XOR-swizzled by row: both the
-                // row-per-thread writes and the 4-rows-per-instruction reads are bank-conflict free)
+                // transpose through this warp's smem slab: rows of 64 B, 16-byte chunks XOR-swizzled by
+                // (row >> 1) & 3 -> row-per-thread writes and 8-rows-per-instruction reads are conflict free
                 __syncwarp();
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    *reinterpret_cast<uint4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) =
+                for (int j = 0; j < 4; ++j)
+                    *reinterpret_cast<uint4*>(stg + lane * 16 + ((j ^ ((lane >> 1) & 3)) << 2)) =
                         make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                 __syncwarp();
                 uint32_t* cbase = reinterpret_cast<uint32_t*>(p.C) + crow_base + nc;
                 if (vec_chunk) {
-                    // each store instruction covers 4 rows x 128 B; this lane owns 4 fixed columns
+                    // each store instruction covers 8 rows x 64 B; this lane owns 4 fixed columns
                     uint32_t* crow = cbase + (mrow0 + rsub) * p.ldc + (cl << 2);
-                    const int64_t cstep = 4 * p.ldc;
+                    const int64_t cstep = 8 * p.ldc;
+                    const bool res_on = (EMODE == EM_DEQ_FAST) && p.residual != nullptr;
+                    const float* rrow = res_on ? p.residual + b * p.stride_r + (mrow0 + rsub) * p.ldr + nc + (cl << 2) : nullptr;
+                    const int64_t rstep = 8 * p.ldr;
+                    float4 res[4];
+                    if (res_on) {
 #pragma unroll
-                    for (int it = 0; it < 8; ++it) {
-                        const int rr = it * 4 + rsub;
-                        uint4 val = *reinterpret_cast<const uint4*>(stg + rr * 32 + ((cl ^ (rr & 7)) << 2));
+                        for (int it = 0; it < 4; ++it) {
+                            const float* rp = rrow + it * rstep;
+                            if (it * 8 + rsub >= rows_left) res[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            else if (res_vec) res[it] = __ldcs(reinterpret_cast<const float4*>(rp));
+                            else res[it] = make_float4(__ldg(rp), __ldg(rp + 1), __ldg(rp + 2), __ldg(rp + 3));
+                        }
+                    }
+#pragma unroll
+                    for (int it = 0; it < 4; ++it) {
+                        const int rr = it * 8 + rsub;
+                        uint4 val = *reinterpret_cast<const uint4*>(stg + rr * 16 + ((cl ^ ((rr >> 1) & 3)) << 2));
                         if (EMODE == EM_DEQ_FAST) {
-                            const int rt = (int)stg_row[rr];
-                            float f0 = deq_fast((int)val.x, rt, ct[0], p.scale), f1 = deq_fast((int)val.y, rt, ct[1], p.scale);
-                            float f2 = deq_fast((int)val.z, rt, ct[2], p.scale), f3 = deq_fast((int)val.w, rt, ct[3], p.scale);
+                            // x = float bits of (1.5*2^23 + d), valid while |d| < 2^22: checked once per 4
+                            const int rm = (int)stg_row[rr];
+                            const int x0 = (int)val.x + rm - ct[0], x1 = (int)val.y + rm - ct[1];
+                            const int x2 = (int)val.z + rm - ct[2], x3 = (int)val.w + rm - ct[3];
+                            const uint32_t bad = ((uint32_t)(x0 ^ 0x4B000000) | (uint32_t)(x1 ^ 0x4B000000) |
+                                                  (uint32_t)(x2 ^ 0x4B000000) | (uint32_t)(x3 ^ 0x4B000000)) & 0xFF800000u;
+                            float f0, f1, f2, f3;
+                            if (__builtin_expect(bad != 0, 0)) {
+                                f0 = deq_slow(x0 - 0x4B400000, p.scale); f1 = deq_slow(x1 - 0x4B400000, p.scale);
+                                f2 = deq_slow(x2 - 0x4B400000, p.scale); f3 = deq_slow(x3 - 0x4B400000, p.scale);
+                            } else {
+                                f0 = __fmul_rn(__fadd_rn(__int_as_float(x0), -12582912.0f), p.scale);
+                                f1 = __fmul_rn(__fadd_rn(__int_as_float(x1), -12582912.0f), p.scale);
+                                f2 = __fmul_rn(__fadd_rn(__int_as_float(x2), -12582912.0f), p.scale);
+                                f3 = __fmul_rn(__fadd_rn(__int_as_float(x3), -12582912.0f), p.scale);
+                            }
                             if (p.bias_f32) {
                                 f0 = __fadd_rn(bs[0], f0); f1 = __fadd_rn(bs[1], f1);
                                 f2 = __fadd_rn(bs[2], f2); f3 = __fadd_rn(bs[3], f3);
                             }
-                            if (p.residual) {
-                                float4 rv;
-                                if (res_vec) rv = res[it];
-                                else {
-                                    const float* rp = p.residual + b * p.stride_r + (mrow0 + rr) * p.ldr + nc + (cl << 2);
-                                    rv = (rr < rows_left) ? make_float4(__ldg(rp), __ldg(rp + 1), __ldg(rp + 2), __ldg(rp + 3))
-                                                            : make_float4(0.f, 0.f, 0.f, 0.f);
-                                }
-                                f0 = __fadd_rn(f0, rv.x); f1 = __fadd_rn(f1, rv.y);
-                                f2 = __fadd_rn(f2, rv.z); f3 = __fadd_rn(f3, rv.w);
+                            if (res_on) {
+                                f0 = __fadd_rn(f0, res[it].x); f1 = __fadd_rn(f1, res[it].y);
+                                f2 = __fadd_rn(f2, res[it].z); f3 = __fadd_rn(f3, res[it].w);
                             }
                             val = make_uint4(__float_as_uint(f0), __float_as_uint(f1), __float_as_uint(f2), __float_as_uint(f3));
                         }
@@ -451,23 +469,26 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                         crow += cstep;
                     }
                 } else {
-                    // ragged / unaligned: one column per lane, 32 rows, 128-byte coalesced scalar stores
-                    const bool col_ok = nc + lane < p.N;
-                    const int lch = lane >> 2, lw = lane & 3;
-                    uint32_t* crow = cbase + mrow0 * p.ldc + lane;
-                    const float* rrow = p.residual ? p.residual + b * p.stride_r + mrow0 * p.ldr + nc + lane : nullptr;
+                    // ragged / unaligned: one column per lane (16 columns x 2 rows per instruction)
+                    const bool col_ok = nc + sc_col < p.N;
+                    uint32_t* crow = cbase + (mrow0 + sc_row) * p.ldc + sc_col;
+                    const float* rrow = p.residual ? p.residual + b * p.stride_r + (mrow0 + sc_row) * p.ldr + nc + sc_col : nullptr;
 #pragma unroll 4
-                    for (int rr = 0; rr < 32; ++rr) {
-                        uint32_t val = stg[rr * 32 + (((lch ^ (rr & 7)) << 2) | lw)];
+                    for (int it = 0; it < 16; ++it) {
+                        const int rr = it * 2 + sc_row;
+                        uint32_t val = stg[rr * 16 + ((((sc_col >> 2) ^ ((rr >> 1) & 3)) << 2) | (sc_col & 3))];
                         if (EMODE == EM_DEQ_FAST) {
-                            float f = deq_fast((int)val, (int)stg_row[rr], ct[0], p.scale);
+                            const int x = (int)val + (int)stg_row[rr] - ct[0];
+                            float f = (((uint32_t)(x ^ 0x4B000000) & 0xFF800000u) == 0)
+                                          ? __fmul_rn(__fadd_rn(__int_as_float(x), -12582912.0f), p.scale)
+                                          : deq_slow(x - 0x4B400000, p.scale);
                             if (p.bias_f32) f = __fadd_rn(bs[0], f);
                             if (rrow && col_ok && rr < rows_left) f = __fadd_rn(f, __ldg(rrow));
                             val = __float_as_uint(f);
                         }
                         if (col_ok && rr < rows_left) *crow = val;
-                        crow += p.ldc;
-                        if (rrow) rrow += p.ldr;
+                        crow += 2 * p.ldc;
+                        if (rrow) rrow += 2 * p.ldr;
                     }
                 }
             }
