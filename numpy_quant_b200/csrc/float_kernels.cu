@@ -12,7 +12,7 @@ __device__ __forceinline__ float erf_as(float x) {
     const float ax = fabsf(x);
     const float a1 = 0.254829592f, a2 = -0.284496736f, a3 = 1.421413741f, a4 = -1.453152027f, a5 = 1.061405429f;
     const float p = 0.3275911f;
-    const float t = __fdiv_rn(1.0f, __fadd_rn(1.0f, __fmul_rn(p, ax)));
+    const float t = __frcp_rn(__fadd_rn(1.0f, __fmul_rn(p, ax)));           // 1 / y, correctly rounded
     float y = __fadd_rn(__fmul_rn(a5, t), a4);
     y = __fadd_rn(__fmul_rn(y, t), a3);
     y = __fadd_rn(__fmul_rn(y, t), a2);
@@ -59,16 +59,17 @@ __global__ void __launch_bounds__(256) unary_kernel(const float* __restrict__ x,
     for (int64_t i = done + tid; i < n; i += stride) out[i] = unary_op<OP>(x[i]);
 }
 
-__device__ __forceinline__ float gelu_chain(float x, float c_div, float c_add, float c_mul) {
+__device__ __forceinline__ float gelu_chain(float x, const FastDiv& c_div, float c_add, float c_mul) {
     // Div -> Erf -> Add -> Mul(x, .) -> Mul(., 0.5): five float32 roundings like the five ONNX nodes
-    float u = erf_as(__fdiv_rn(x, c_div));
+    float u = erf_as(div_rn(x, c_div));
     u = __fadd_rn(u, c_add);
     u = __fmul_rn(x, u);
     return __fmul_rn(u, c_mul);
 }
 
-__global__ void __launch_bounds__(256) gelu_kernel(const float* __restrict__ x, int64_t n, float c_div, float c_add,
+__global__ void __launch_bounds__(256) gelu_kernel(const float* __restrict__ x, int64_t n, float c_div_f, float c_add,
                                                   float c_mul, float* __restrict__ out, int vec) {
+    const FastDiv c_div = make_fastdiv(c_div_f);
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t done = 0;
@@ -127,6 +128,18 @@ __global__ void __launch_bounds__(256) binary_kernel(const float* __restrict__ a
         float4* o4 = reinterpret_cast<float4*>(out);
         const int64_t c4 = g.d[3] >> 2;
         float sb = (MODE == 3) ? b[0] : 0.f;
+        if (MODE == 3 && OP == NQ_BIN_DIV) {
+            const FastDiv dv = make_fastdiv(sb);
+            for (int64_t i = tid; i < n4; i += stride) {
+                float4 va = __ldcs(a4 + i);
+                va.x = div_rn(va.x, dv);
+                va.y = div_rn(va.y, dv);
+                va.z = div_rn(va.z, dv);
+                va.w = div_rn(va.w, dv);
+                __stcs(o4 + i, va);
+            }
+            return;
+        }
         for (int64_t i = tid; i < n4; i += stride) {
             float4 va = __ldcs(a4 + i), vb;
             if (MODE == 1) vb = __ldcs(reinterpret_cast<const float4*>(b) + i);
@@ -168,6 +181,7 @@ __global__ void __launch_bounds__(256) layernorm_vec_kernel(const float* __restr
     const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int c4 = cols >> 2;
     const float fn = (float)cols;
+    const Quantizer qz(qa);
     for (int64_t row = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); row < rows; row += warps) {
         const float4* src = reinterpret_cast<const float4*>(x + row * ldx);
         float4 v[NV];
@@ -212,7 +226,7 @@ __global__ void __launch_bounds__(256) layernorm_vec_kernel(const float* __restr
                     __stcs(dst + c, o);
                 } else {
                     constexpr int QM = QMODE < 0 ? 0 : QMODE;
-                    const int w = pack4_codes(qcode<QM>(o.x, qa), qcode<QM>(o.y, qa), qcode<QM>(o.z, qa), qcode<QM>(o.w, qa));
+                    const int w = pack4_codes(qz.code<QM>(o.x), qz.code<QM>(o.y), qz.code<QM>(o.z), qz.code<QM>(o.w));
                     qsum = __dp4a(w, 0x01010101, qsum);
                     qdst[c] = w;
                 }
@@ -266,6 +280,8 @@ __global__ void __launch_bounds__(256) softmax_kernel(const float* __restrict__ 
                                                      int32_t* __restrict__ rowsum) {
     const int lane = threadIdx.x & 31;
     const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const Quantizer qz(qa);
+    const FastDiv dc = make_fastdiv(has_div ? div_c : 1.0f);
     for (int64_t row = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); row < rows; row += warps) {
         const float* src = x + row * ldx;
         float v[NV];
@@ -273,7 +289,7 @@ __global__ void __launch_bounds__(256) softmax_kernel(const float* __restrict__ 
 #pragma unroll
         for (int j = 0; j < NV; ++j) {
             const int c = lane + j * 32;
-            v[j] = (c < cols) ? (has_div ? __fdiv_rn(src[c], div_c) : src[c]) : __int_as_float(0xff800000);
+            v[j] = (c < cols) ? (has_div ? div_rn(src[c], dc) : src[c]) : __int_as_float(0xff800000);
             m = fmaxf(m, v[j]);
         }
         m = warp_max(m);
@@ -287,12 +303,13 @@ __global__ void __launch_bounds__(256) softmax_kernel(const float* __restrict__ 
             }
         }
         s = warp_sum(s);
+        const FastDiv ds = make_fastdiv(s);                          // one reciprocal per row
         if (QMODE < 0) {
             float* dst = out + row * (int64_t)cols;
 #pragma unroll
             for (int j = 0; j < NV; ++j) {
                 const int c = lane + j * 32;
-                if (c < cols) dst[c] = __fdiv_rn(v[j], s);
+                if (c < cols) dst[c] = div_rn(v[j], ds);
             }
         } else {
             constexpr int QM = QMODE < 0 ? 0 : QMODE;
@@ -302,7 +319,7 @@ __global__ void __launch_bounds__(256) softmax_kernel(const float* __restrict__ 
             for (int j = 0; j < NV; ++j) {
                 const int c = lane + j * 32;
                 if (c < ldo) {
-                    const int q = (c < cols) ? (int)(int8_t)qcode<QM>(__fdiv_rn(v[j], s), qa) : 0;
+                    const int q = (c < cols) ? (int)(int8_t)qz.code<QM>(div_rn(v[j], ds)) : 0;
                     qsum += q;
                     qdst[c] = (int8_t)q;
                 }
@@ -319,9 +336,11 @@ __global__ void __launch_bounds__(256) softmax_kernel(const float* __restrict__ 
 // GELU chain -> quantize: warp per row, streaming (any cols); int8 operand row + optional row sum.
 template <int QMODE>
 __global__ void __launch_bounds__(256) gelu_quantize_kernel(const float* __restrict__ x, int64_t rows, int64_t cols,
-                                                           int64_t ldx, float c_div, float c_add, float c_mul,
+                                                           int64_t ldx, float c_div_f, float c_add, float c_mul,
                                                            QArgs qa, int8_t* __restrict__ qout, int64_t ldo,
                                                            int32_t* __restrict__ rowsum) {
+    const Quantizer qz(qa);
+    const FastDiv c_div = make_fastdiv(c_div_f);
     const int lane = threadIdx.x & 31;
     const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const bool vec = ((ldx & 3) == 0) && ((ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
@@ -334,17 +353,17 @@ __global__ void __launch_bounds__(256) gelu_quantize_kernel(const float* __restr
             const int64_t c4 = cols >> 2;
             for (int64_t c = lane; c < c4; c += 32) {
                 const float4 v = __ldcs(reinterpret_cast<const float4*>(src) + c);
-                const int w = pack4_codes(qcode<QMODE>(gelu_chain(v.x, c_div, c_add, c_mul), qa),
-                                          qcode<QMODE>(gelu_chain(v.y, c_div, c_add, c_mul), qa),
-                                          qcode<QMODE>(gelu_chain(v.z, c_div, c_add, c_mul), qa),
-                                          qcode<QMODE>(gelu_chain(v.w, c_div, c_add, c_mul), qa));
+                const int w = pack4_codes(qz.code<QMODE>(gelu_chain(v.x, c_div, c_add, c_mul)),
+                                          qz.code<QMODE>(gelu_chain(v.y, c_div, c_add, c_mul)),
+                                          qz.code<QMODE>(gelu_chain(v.z, c_div, c_add, c_mul)),
+                                          qz.code<QMODE>(gelu_chain(v.w, c_div, c_add, c_mul)));
                 qsum = __dp4a(w, 0x01010101, qsum);
                 reinterpret_cast<int*>(dst)[c] = w;
             }
             done = c4 << 2;
         }
         for (int64_t c = done + lane; c < ldo; c += 32) {
-            const int q = (c < cols) ? (int)(int8_t)qcode<QMODE>(gelu_chain(src[c], c_div, c_add, c_mul), qa) : 0;
+            const int q = (c < cols) ? (int)(int8_t)qz.code<QMODE>(gelu_chain(src[c], c_div, c_add, c_mul)) : 0;
             qsum += q;
             dst[c] = (int8_t)q;
         }
@@ -432,9 +451,43 @@ __global__ void __launch_bounds__(256) im2col_kernel(const T* __restrict__ x, in
     }
 }
 
+// counts inputs where the hoisted-reciprocal division differs from __fdiv_rn (must be 0)
+__global__ void selftest_division_kernel(uint64_t n, uint32_t seed, int mode, unsigned long long* mismatches) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    unsigned long long bad = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        // two 32-bit hashes -> raw float bit patterns (all exponents, denormals, specials)
+        uint32_t h = (uint32_t)i * 2654435761u + seed, g = (uint32_t)(i >> 32) * 40503u + (uint32_t)i * 2246822519u + seed * 3u;
+        h ^= h >> 15; h *= 2246822519u; h ^= h >> 13; h *= 3266489917u; h ^= h >> 16;
+        g ^= g >> 16; g *= 2654435761u; g ^= g >> 13; g *= 2246822519u; g ^= g >> 15;
+        float a = __uint_as_float(h), b = __uint_as_float(g);
+        if (mode == 1) {            // moderate ranges: activations / scales, with all-ones divisor mantissas mixed in
+            a = __uint_as_float((h & 0x807fffffu) | ((100u + (h >> 23) % 56u) << 23));
+            b = __uint_as_float((g & 0x007fffffu) | ((100u + (g >> 23) % 40u) << 23));
+            if ((i & 7) == 0) b = __uint_as_float(__float_as_uint(b) | 0x007fff00u);
+        }
+        if (!(fabsf(b) > 1e-30f && fabsf(b) < 1e30f)) continue;       // divisor window checked on the host side
+        const FastDiv d = make_fastdiv(b);
+        const float want = __fdiv_rn(a, b), got = div_rn(a, d);
+        if (__float_as_uint(want) != __float_as_uint(got) && !(want != want && got != got)) ++bad;
+        if (mode == 1) {
+            float q = div_for_quantize(a, d);
+            const float wc = fminf(fmaxf(want, -2097152.0f), 2097152.0f), qc = fminf(fmaxf(q, -2097152.0f), 2097152.0f);
+            if (wc != qc && !(want != want)) ++bad;
+        }
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
 }  // namespace nq
 
 using namespace nq;
+
+extern "C" int nq_selftest_division(int64_t n, int seed, int mode, unsigned long long* mismatches_dev, void* stream) {
+    selftest_division_kernel<<<sm_count() * 8, 256, 0, (cudaStream_t)stream>>>((uint64_t)n, (uint32_t)seed, mode, mismatches_dev);
+    NQ_CHECK_LAUNCH("nq_selftest_division");
+    return NQ_OK;
+}
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 

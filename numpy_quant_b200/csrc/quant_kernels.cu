@@ -14,7 +14,7 @@ __global__ void __launch_bounds__(256) quantize_contig_kernel(const float* __res
     const float4* x4 = reinterpret_cast<const float4*>(x);
     int* o32 = reinterpret_cast<int*>(out);
     const int64_t tile = (int64_t)blockDim.x * 4;
-    const bool odd = a.zp_odd != 0;
+    const Quantizer qz(a);
     for (int64_t base = (int64_t)blockIdx.x * tile; base < n4; base += (int64_t)gridDim.x * tile) {
         float4 v[4];
 #pragma unroll
@@ -26,23 +26,23 @@ __global__ void __launch_bounds__(256) quantize_contig_kernel(const float* __res
         for (int j = 0; j < 4; ++j) {
             const int64_t i = base + j * blockDim.x + threadIdx.x;
             if (i < n4)
-                __stcs(o32 + i, pack4_codes(quantize_code<QMODE>(v[j].x, a.scale, a.zp, a.zpf, odd, a.lo, a.hi),
-                                            quantize_code<QMODE>(v[j].y, a.scale, a.zp, a.zpf, odd, a.lo, a.hi),
-                                            quantize_code<QMODE>(v[j].z, a.scale, a.zp, a.zpf, odd, a.lo, a.hi),
-                                            quantize_code<QMODE>(v[j].w, a.scale, a.zp, a.zpf, odd, a.lo, a.hi)));
+                __stcs(o32 + i, pack4_codes(qz.code<QMODE>(v[j].x),
+                                            qz.code<QMODE>(v[j].y),
+                                            qz.code<QMODE>(v[j].z),
+                                            qz.code<QMODE>(v[j].w)));
         }
     }
     const int64_t t = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // tail (< 4 elements)
-    if (t < n) out[t] = (int8_t)quantize_code<QMODE>(x[t], a.scale, a.zp, a.zpf, odd, a.lo, a.hi);
+    if (t < n) out[t] = (int8_t)qz.code<QMODE>(x[t]);
 }
 
 template <int QMODE>
 __global__ void __launch_bounds__(256) quantize_scalar_kernel(const float* __restrict__ x, int64_t n, QArgs a,
                                                              int8_t* __restrict__ out) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    const bool odd = a.zp_odd != 0;
+    const Quantizer qz(a);
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-        out[i] = (int8_t)quantize_code<QMODE>(x[i], a.scale, a.zp, a.zpf, odd, a.lo, a.hi);
+        out[i] = (int8_t)qz.code<QMODE>(x[i]);
 }
 
 // wide symmetric/asymmetric quantize to int64 codes (4*bit_width-bit biases, model.py:383-389, 405-410)
@@ -62,50 +62,51 @@ __global__ void quantize_i64_kernel(const float* __restrict__ x, int64_t n, floa
 }
 
 // ------------------------------------------------------------------ K1 strided 4-D -> K-major operand
-// One warp per output row (b, r): lanes sweep the C (=K) axis, so reads are coalesced when
-// sc == 1 and the row sum falls out of a dp4a + shuffle reduction.
+// `lpr` lanes (8 / 16 / 32) cooperate on one output row (b, r) and sweep its C (=K) axis, so reads
+// are coalesced when sc == 1, short rows (attention heads: C = 64) still fill the warp, and the
+// row sum falls out of a dp4a + sub-warp shuffle reduction.
 template <int QMODE>
-__global__ void __launch_bounds__(256) quantize_rows_kernel(const float* __restrict__ x, int64_t d1, int64_t R,
+__global__ void __launch_bounds__(256) quantize_rows_kernel(const float* __restrict__ x, uint32_t d1, uint32_t R,
                                                            int64_t C, int64_t s0, int64_t s1, int64_t sr,
-                                                           int64_t sc, int64_t rows_total, QArgs a,
+                                                           int64_t sc, uint32_t rows_total, QArgs a,
                                                            int8_t* __restrict__ out, int64_t ldo,
-                                                           int32_t* __restrict__ rowsum) {
+                                                           int32_t* __restrict__ rowsum, int lpr) {
     const int lane = threadIdx.x & 31;
-    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    const bool odd = a.zp_odd != 0;
-    for (int64_t row = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); row < rows_total; row += warps) {
-        const int64_t r = row % R;
-        const int64_t b = row / R;
-        const float* src = x + (b / d1) * s0 + (b % d1) * s1 + r * sr;
-        int8_t* dst = out + row * ldo;
+    const int sub = lane & (lpr - 1), rsel = lane / lpr, rpw = 32 / lpr;
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    const Quantizer qz(a);
+    for (uint32_t row0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * rpw; row0 < rows_total; row0 += warps * rpw) {
+        const uint32_t row = row0 + rsel;
+        const bool valid = row < rows_total;
         int sum = 0;
-        if (sc == 1 && ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && (ldo & 3) == 0) {
-            const int64_t c4 = C >> 2;
-            for (int64_t c = lane; c < c4; c += 32) {
-                const float4 v = __ldcs(reinterpret_cast<const float4*>(src) + c);
-                const int w = pack4_codes(quantize_code<QMODE>(v.x, a.scale, a.zp, a.zpf, odd, a.lo, a.hi),
-                                          quantize_code<QMODE>(v.y, a.scale, a.zp, a.zpf, odd, a.lo, a.hi),
-                                          quantize_code<QMODE>(v.z, a.scale, a.zp, a.zpf, odd, a.lo, a.hi),
-                                          quantize_code<QMODE>(v.w, a.scale, a.zp, a.zpf, odd, a.lo, a.hi));
-                sum = __dp4a(w, 0x01010101, sum);
-                reinterpret_cast<int*>(dst)[c] = w;
-            }
-            for (int64_t c = (c4 << 2) + lane; c < ldo; c += 32) {
-                const int q = c < C ? (int)(int8_t)quantize_code<QMODE>(src[c], a.scale, a.zp, a.zpf, odd, a.lo, a.hi) : 0;
-                sum += q;
-                dst[c] = (int8_t)q;
-            }
-        } else {
-            for (int64_t c = lane; c < ldo; c += 32) {
-                const int q = c < C ? (int)(int8_t)quantize_code<QMODE>(src[c * sc], a.scale, a.zp, a.zpf, odd, a.lo, a.hi) : 0;
-                sum += q;
-                dst[c] = (int8_t)q;
+        if (valid) {
+            const uint32_t r = row % R, b = row / R;
+            const float* src = x + (int64_t)(b / d1) * s0 + (int64_t)(b % d1) * s1 + (int64_t)r * sr;
+            int8_t* dst = out + (int64_t)row * ldo;
+            if (sc == 1 && ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && (ldo & 3) == 0) {
+                const int c4 = (int)(C >> 2);
+                for (int c = sub; c < c4; c += lpr) {
+                    const float4 v = __ldcs(reinterpret_cast<const float4*>(src) + c);
+                    const int w = pack4_codes(qz.code<QMODE>(v.x), qz.code<QMODE>(v.y), qz.code<QMODE>(v.z), qz.code<QMODE>(v.w));
+                    sum = __dp4a(w, 0x01010101, sum);
+                    reinterpret_cast<int*>(dst)[c] = w;
+                }
+                for (int64_t c = ((int64_t)c4 << 2) + sub; c < ldo; c += lpr) {
+                    const int q = c < C ? (int)(int8_t)qz.code<QMODE>(src[c]) : 0;
+                    sum += q;
+                    dst[c] = (int8_t)q;
+                }
+            } else {
+                for (int64_t c = sub; c < ldo; c += lpr) {
+                    const int q = c < C ? (int)(int8_t)qz.code<QMODE>(src[c * sc]) : 0;
+                    sum += q;
+                    dst[c] = (int8_t)q;
+                }
             }
         }
         if (rowsum) {
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-            if (lane == 0) rowsum[row] = sum;
+            for (int o = lpr >> 1; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            if (sub == 0 && valid) rowsum[row] = sum;
         }
     }
 }
@@ -117,7 +118,7 @@ __global__ void __launch_bounds__(256) quantize_transpose_kernel(const float* __
                                                                 int64_t C, int64_t s0, int64_t s1, int64_t sc,
                                                                 QArgs a, int8_t* __restrict__ out, int64_t ldo,
                                                                 int32_t* __restrict__ rowsum) {
-    const bool odd = a.zp_odd != 0;
+    const Quantizer qz(a);
     __shared__ int8_t tile[32][36];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;           // 32 x 8
     const int64_t b = blockIdx.z;
@@ -127,7 +128,7 @@ __global__ void __launch_bounds__(256) quantize_transpose_kernel(const float* __
     for (int j = 0; j < 4; ++j) {
         const int64_t c = c0 + ty + j * 8, r = r0 + tx;               // lanes along r (unit stride)
         int q = 0;
-        if (c < C && r < R) q = (int)(int8_t)quantize_code<QMODE>(src[c * sc + r], a.scale, a.zp, a.zpf, odd, a.lo, a.hi);
+        if (c < C && r < R) q = (int)(int8_t)qz.code<QMODE>(src[c * sc + r]);
         tile[ty + j * 8][tx] = (int8_t)q;
     }
     __syncthreads();
@@ -417,8 +418,11 @@ extern "C" int nq_quantize_f32_4d(const float* x, int64_t d0, int64_t d1, int64_
         NQ_REQUIRE(grid.y <= 65535, "nq_quantize_f32_4d: C too large for the transposing path");
         NQ_DISPATCH_QMODE(qmode, quantize_transpose_kernel, <<<grid, 256, 0, s>>>(x, d1, R, C, s0, s1, sc, a, out, ldo, rowsum));
     } else {
-        const int grid = stream_grid(rows * 32, 256);
-        NQ_DISPATCH_QMODE(qmode, quantize_rows_kernel, <<<grid, 256, 0, s>>>(x, d1, R, C, s0, s1, sr, sc, rows, a, out, ldo, rowsum));
+        NQ_REQUIRE(rows < (1ll << 31) && R < (1ll << 31) && d1 < (1ll << 31), "nq_quantize_f32_4d: too many rows");
+        const int64_t c4 = C >> 2;
+        const int lpr = (sc == 1 && c4 <= 8) ? 8 : (sc == 1 && c4 <= 16) ? 16 : 32;
+        const int grid = stream_grid(rows * lpr, 256);
+        NQ_DISPATCH_QMODE(qmode, quantize_rows_kernel, <<<grid, 256, 0, s>>>(x, (uint32_t)d1, (uint32_t)R, C, s0, s1, sr, sc, (uint32_t)rows, a, out, ldo, rowsum, lpr));
     }
     NQ_CHECK_LAUNCH("nq_quantize_f32_4d");
     return NQ_OK;

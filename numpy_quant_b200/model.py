@@ -249,8 +249,8 @@ class Model:
     def release(self) -> None:
         """Drop every intermediate held on `Variable.data` (frees HBM; constants stay)."""
         for value in self.values:
-            if isinstance(value, Variable):
-                value.data = None
+            if isinstance(value, Variable) and not (value.inputs and value.inputs[0].op == "Constant"):
+                value.data = None           # outputs of Constant nodes are immutable uploads: kept
 
     @classmethod
     def from_onnx(cls, onnx_model):
@@ -427,6 +427,8 @@ class QModel(Model):
         self.quant_params = quant_params
         self._const_deq: dict = {}
         self._plan = None
+        self._graphs: dict = {}
+        self._graph_launches: dict = {}
 
     def __repr__(self):
         return (f"QModel(nodes={self.nodes}, values={self.values}, inputs={self.inputs}, outputs={self.values}, "
@@ -554,15 +556,70 @@ class QModel(Model):
         qp = self.quant_params[out.name]
         cache[(out.name, "A")] = qtensor_from_operand(op, "A", shape, self.bit_width, qp.scale, qp.zero_point)
 
+    # ------------------------------------------------------------------ CUDA-graph replay
+    def _graph_call(self, inputs: list, device_outputs: bool):
+        """Capture the fused forward (retain=False) once per input signature into a CUDA graph and
+        replay it: ~200 kernel launches become one graph launch, so the host interpreter loop
+        (Python + ctypes per node) disappears from the steady state.  Quantization parameters are
+        static after calibration, so the launch sequence depends on shapes only."""
+        key = tuple((tuple(a.shape), str(a.dtype)) for a in inputs)
+        entry = self._graphs.get(key)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        if entry is None:
+            for a in inputs:
+                if not (isinstance(a, torch.Tensor) or a.dtype == np.float32):
+                    raise ValueError("graph=True supports float32 inputs only")
+            static_in = [torch.empty(tuple(a.shape), dtype=torch.float32, device=dev) for a in inputs]
+            for s_in, a in zip(static_in, inputs):
+                s_in.copy_(a if isinstance(a, torch.Tensor) else torch.from_numpy(a))
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):                     # warm-up outside capture: constants, operand
+                for _ in range(2):                            # caches, function attributes, allocator pool
+                    self(static_in, retain=False, device_outputs=True)
+            torch.cuda.current_stream().wait_stream(side)
+            self.release()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                static_out = self(static_in, retain=False, device_outputs=True)
+            self.release()
+            entry = (graph, static_in, static_out)
+            self._graphs[key] = entry
+        graph, static_in, static_out = entry
+        for s_in, a in zip(static_in, inputs):
+            if isinstance(a, torch.Tensor):
+                if a.data_ptr() != s_in.data_ptr():
+                    s_in.copy_(a, non_blocking=True)
+            else:
+                s_in.copy_(torch.from_numpy(a), non_blocking=True)
+        graph.replay()
+        K._count(self._graph_launches.setdefault(key, 0))
+        if device_outputs:
+            return list(static_out)
+        return [o.cpu().numpy() for o in static_out]
+
     def __call__(self, inputs: List[np.ndarray], profile=False, *, retain: bool = True,
-                 device_outputs: bool = False):
+                 device_outputs: bool = False, graph: bool = False):
         """Quantized interpreter (reference model.py:486-565).
 
         retain=True  keeps every intermediate on `Variable.data` like the reference.
         retain=False frees a value after its last consumer and fuses multi-node patterns
                      (GELU chain, Div+Softmax, producer->quantize); results are bit-identical.
         device_outputs=True returns CUDA tensors (no device->host copy, no synchronisation).
+        graph=True   (implies retain=False) replays the forward as one CUDA graph.
         """
+        if graph:
+            if profile:
+                raise ValueError("profile=True needs the eager interpreter (graph=False)")
+            if not torch.cuda.is_current_stream_capturing():
+                key = tuple((tuple(a.shape), str(a.dtype)) for a in inputs)
+                if key not in self._graphs:
+                    before = K.LAUNCHES
+                    out = self._graph_call(inputs, device_outputs)
+                    # launches of one forward = (2 warm-ups + 1 capture) / 3
+                    self._graph_launches[key] = (K.LAUNCHES - before) // 3
+                    return out
+                return self._graph_call(inputs, device_outputs)
         for array, variable in zip(inputs, self.inputs):
             qparams = self.quant_params[variable.name]
             if isinstance(array, torch.Tensor) or array.dtype == np.float32:

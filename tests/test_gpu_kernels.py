@@ -100,6 +100,21 @@ def test_quantize_exact_ties_and_zero_point_parity(zp):
     assert int(op.rowsum[0, 0]) == int(ref.sum())
 
 
+def test_hoisted_reciprocal_division_equals_ieee_division():
+    """The kernels divide by per-tensor constants through a hoisted correctly-rounded reciprocal and
+    two fused residual corrections; it must give the bits of IEEE division (np.float32 '/') always."""
+    cnt = torch.zeros(1, dtype=torch.int64, device=DEV)
+    for mode, n in ((0, 1 << 28), (1, 1 << 28)):
+        for seed in (1, 2):
+            _lib.call("nq_selftest_division", n, seed, mode, cnt.data_ptr(), None)
+    assert int(cnt.item()) == 0, f"{int(cnt.item())} quotients differ from __fdiv_rn"
+    # and end to end through a kernel that uses it: Div by a scalar vs NumPy
+    rng = np.random.default_rng(4)
+    x = (rng.normal(size=1 << 20) * rng.choice([1e-3, 1.0, 1e3], size=1 << 20)).astype(np.float32)
+    for c in (8.0, 1.4142135381698608, 0.0371, 3.0, 1e-7, 123456.7):
+        np.testing.assert_array_equal(host(K.binary("div", dev(x), dev(np.array(c, np.float32)))), x / np.float32(c))
+
+
 def test_quantize_operand_layouts():
     rng = np.random.default_rng(5)
     x = rng.normal(size=(2, 3, 37, 50)).astype(np.float32)
@@ -121,6 +136,14 @@ def test_quantize_operand_layouts():
     ob = K.quantize_operand(view, "B", 8, scale, zp, True)
     np.testing.assert_array_equal(host(ob.data)[:, :, :8].astype(np.int64), refv.reshape(6, 8, 11).transpose(0, 2, 1))
     np.testing.assert_array_equal(host(ob.rowsum).astype(np.int64), refv.reshape(6, 8, 11).sum(-2))
+    # short rows (attention head dim): sub-warp rows, strided head view [B, S, H, D] -> [B, H, S, D]
+    for D in (64, 32, 20):
+        hx = rng.normal(size=(3, 197, 4, D)).astype(np.float32)
+        hv = dev(hx).permute(0, 2, 1, 3)
+        oh = K.quantize_operand(hv, "A", 8, scale, zp, True)
+        refh = rq.quantize(hx.transpose(0, 2, 1, 3), 8, scale, zp).reshape(12, 197, D)
+        np.testing.assert_array_equal(host(oh.data)[:, :, :D].astype(np.int64), refh)
+        np.testing.assert_array_equal(host(oh.rowsum).astype(np.int64), refh.sum(-1))
     # symmetric 2-D weight [K, N] as operand B
     w = rng.normal(size=(70, 33)).astype(np.float32)
     ws, _ = rq.quant_parameters(w.min(), w.max(), 4, False)

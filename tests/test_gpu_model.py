@@ -148,6 +148,12 @@ def test_small_vit(gv, bits):
     out2 = q([x], retain=False)[0]
     np.testing.assert_array_equal(out2, out)
     assert by[a0 + "/query/MatMul_output_0"].data is None
+    # CUDA-graph replay of the fused forward: identical bits, also for a second, different input
+    out4 = q([x], graph=True)[0]
+    np.testing.assert_array_equal(out4, out)
+    x_b = (x[::-1] * np.float32(0.5)).copy()
+    np.testing.assert_array_equal(q([x_b], graph=True)[0], q([x_b], retain=False)[0])
+    np.testing.assert_array_equal(q([x], graph=True)[0], out)
     # profile contract: dict of op type -> seconds with the two extra buckets (model.py:497-499)
     out3, prof = q([x], profile=True)
     np.testing.assert_array_equal(out3[0], out)
