@@ -115,6 +115,8 @@ int nq_rowsum_s8(const int8_t* q, int64_t rows, int64_t C, int64_t ld, int32_t* 
 #define NQ_EPI_RAW 0
 #define NQ_EPI_DEQUANT 1
 #define NQ_EPI_REQUANT 2
+#define NQ_EPI_QUANT 3   /* float result (dequant + bias) quantized for, and scattered into the K-major int8
+                            operand of, the NEXT MatMul -- removes the float32 round trip (see q_* fields) */
 
 typedef struct nq_epilogue {
     int mode;
@@ -135,6 +137,15 @@ typedef struct nq_epilogue {
                                       attention context GEMM write [B, S, H, D] directly (the graph's
                                       Transpose(0,2,1,3) of a [B, H, S, D] result) */
     int64_t stride_c_inner;
+    /* NQ_EPI_QUANT: code = quantize(bias + dequant; out_scale, out_zp, out_bits) (numpy_quantization.py:24-34
+     * applied to the float value the graph would have produced); C is the int8 destination.  With
+     * m = mb*q_rows_per_image + ms, n = nh*q_cols_per_head + nd and batch b = bo*c_batch_inner + bi, the
+     * code goes to byte C[bo*q_off[0] + bi*q_off[1] + mb*q_off[2] + ms*q_off[3] + nh*q_off[4] + nd*q_off[5]]
+     * and, if q_rowsum != NULL, is added to q_rowsum[same decomposition with q_rs[]] (int32, caller-zeroed):
+     * q_rs[5] == 0 accumulates along n (row sums), q_rs[3] == 0 along m (column sums). */
+    int64_t q_rows_per_image, q_cols_per_head;
+    int64_t q_off[6], q_rs[6];
+    int32_t* q_rowsum;
 } nq_epilogue;
 
 int nq_qgemm_s8(const int8_t* A, const int8_t* B, void* C,

@@ -26,10 +26,12 @@ class Epilogue(C.Structure):
     _fields_ = [("mode", C.c_int), ("scale", f32), ("zp", AccZp), ("bias_f32", vp), ("bias_q", vp),
                 ("out_bits", C.c_int), ("out_scale", f32), ("has_out_zp", C.c_int), ("out_zp", i64),
                 ("residual", vp), ("ld_residual", i64), ("stride_residual", i64),
-                ("c_batch_inner", i64), ("stride_c_inner", i64)]
+                ("c_batch_inner", i64), ("stride_c_inner", i64),
+                ("q_rows_per_image", i64), ("q_cols_per_head", i64), ("q_off", i64 * 6), ("q_rs", i64 * 6),
+                ("q_rowsum", vp)]
 
 
-EPI_RAW, EPI_DEQUANT, EPI_REQUANT = 0, 1, 2
+EPI_RAW, EPI_DEQUANT, EPI_REQUANT, EPI_QUANT = 0, 1, 2, 3
 UN = dict(neg=0, exp=1, erf=2, tanh=3, sigmoid=4, relu=5, sqrt=6, inv=7, copy=8)
 BIN = dict(add=0, mul=1, div=2)
 

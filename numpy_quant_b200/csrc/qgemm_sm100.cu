@@ -53,6 +53,12 @@ struct GemmParams {
     int asym_out;
     float lo, hi;
     void* C;
+    // QUANT_OUT: float result quantized and scattered as the next GEMM's int8 operand
+    QArgs qargs;
+    uint32_t q_S, q_D;               // rows per image (m = mb*S + ms), columns per head (n = nh*D + nd)
+    int64_t q_off[6];                // byte offset  = bo*[0] + bi*[1] + mb*[2] + ms*[3] + nh*[4] + nd*[5]
+    int64_t q_rs[6];                 // row-sum slot = same decomposition
+    int32_t* q_rowsum;
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -167,7 +173,7 @@ __device__ __forceinline__ int64_t tile_zp(const AccZp& z, int64_t rowterm, int6
     return v;
 }
 
-constexpr int EM_RAW = 0, EM_DEQ_FAST = 1, EM_DEQ_GENERAL = 2, EM_REQUANT = 3;
+constexpr int EM_RAW = 0, EM_DEQ_FAST = 1, EM_DEQ_GENERAL = 2, EM_REQUANT = 3, EM_QUANT_SYM = 4, EM_QUANT_ASYM = 5;
 
 template <int BN, int EMODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -307,6 +313,10 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
         const bool res_vec = p.residual && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0) && ((p.ldr & 3) == 0) &&
                              ((p.stride_r & 3) == 0);
         const int zpa = (int)z.zp_a;
+        constexpr bool QUANT = (EMODE == EM_QUANT_SYM || EMODE == EM_QUANT_ASYM);
+        constexpr bool FASTF = (EMODE == EM_DEQ_FAST) || QUANT;          // float result via the 32-bit fast path
+        constexpr int QM = (EMODE == EM_QUANT_ASYM) ? 1 : 0;
+        const Quantizer qz(p.qargs);
         for (uint32_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
             const int64_t b = t / tiles_per_batch;
             const uint32_t r = t % tiles_per_batch;
@@ -326,7 +336,7 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                 bs_n = make_int4(0, 0, 0, 0);
                 const int64_t nc = n0 + sidx * 16;
                 if (sidx >= BN / 16 || nc >= p.N) return;
-                if (c_aligned && nc + 16 <= p.N) {
+                if (QUANT || (c_aligned && nc + 16 <= p.N)) {
                     if (cs_b) ct_n = cs_vec ? ldg_v4(cs_b + nc + cl * 4)
                                             : make_int4(ldg_s32(cs_b + nc + cl * 4), ldg_s32(cs_b + nc + cl * 4 + 1),
                                                         ldg_s32(cs_b + nc + cl * 4 + 2), ldg_s32(cs_b + nc + cl * 4 + 3));
@@ -339,10 +349,10 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                     if (p.bias_f32) bs_n.x = ldg_s32(p.bias_f32 + nc + sc_col);
                 }
             };
-            if (EMODE == EM_DEQ_FAST) fetch_cols(h);
+            if (FASTF) fetch_cols(h);
             mbar_wait(smem_u32(tfull_bar + acc), acc_phase);
             tc_fence_after();
-            if (EMODE == EM_DEQ_FAST) {
+            if (FASTF) {
                 __syncwarp();
                 // row term with the int->float magic constant folded in: x = acc + rowmagic - colterm
                 stg_row[lane] = (uint32_t)(0x4B400000 - (int32_t)rowterm);
@@ -351,16 +361,29 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
             const int64_t crow_base = (p.c_inner > 1) ? (b / p.c_inner) * p.stride_c + (b % p.c_inner) * p.stride_c_inner
                                                       : b * p.stride_c;
             const int rows_left = (int)((p.M - mrow0) < 32 ? ((p.M - mrow0) > 0 ? (p.M - mrow0) : 0) : 32);
+            // QUANT: image / row-in-image of this lane's first read-back row, batch part of the offsets
+            uint32_t q_mb0 = 0, q_ms0 = 0;
+            int64_t q_base = 0, q_rsbase = 0;
+            bool q_uniform = false;
+            if (QUANT) {
+                const uint32_t mfirst = (uint32_t)(mrow0 + rsub);
+                q_mb0 = mfirst / p.q_S;
+                q_ms0 = mfirst - q_mb0 * p.q_S;
+                const int64_t bo = b / p.c_inner, bi = b % p.c_inner;
+                q_base = bo * p.q_off[0] + bi * p.q_off[1];
+                q_rsbase = bo * p.q_rs[0] + bi * p.q_rs[1];
+                q_uniform = rows_left == 32 && ((uint32_t)mrow0 / p.q_S) == ((uint32_t)(mrow0 + 31) / p.q_S);
+            }
 #pragma unroll 1
             for (int sidx = h; sidx < BN / 16; sidx += 4) {
                 const int64_t nc = n0 + sidx * 16;
                 if (nc >= p.N) break;                                     // warp-uniform
                 uint32_t v[16];
                 tmem_ld_32x32b_x16(t_row + (uint32_t)(sidx * 16), v);
-                const bool vec_chunk = c_aligned && nc + 16 <= p.N;
+                const bool vec_chunk = QUANT || (c_aligned && nc + 16 <= p.N);
                 int ct[4];
                 float bs[4];
-                if (EMODE == EM_DEQ_FAST) {
+                if (FASTF) {
                     ct[0] = ct_n.x * zpa; ct[1] = ct_n.y * zpa; ct[2] = ct_n.z * zpa; ct[3] = ct_n.w * zpa;
                     bs[0] = __int_as_float(bs_n.x); bs[1] = __int_as_float(bs_n.y);
                     bs[2] = __int_as_float(bs_n.z); bs[3] = __int_as_float(bs_n.w);
@@ -422,6 +445,16 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                     uint32_t* crow = cbase + (mrow0 + rsub) * p.ldc + (cl << 2);
                     const int64_t cstep = 8 * p.ldc;
                     const bool res_on = (EMODE == EM_DEQ_FAST) && p.residual != nullptr;
+                    // QUANT: column part of the scatter offsets for this lane's 4 columns (one head)
+                    uint32_t q_mb = q_mb0, q_ms = q_ms0;
+                    int64_t q_col = 0, q_rscol = 0;
+                    int colacc[4] = {0, 0, 0, 0};
+                    if (QUANT) {
+                        const uint32_t n_l = (uint32_t)(nc + (cl << 2));
+                        const uint32_t nh = n_l / p.q_D, nd = n_l - nh * p.q_D;
+                        q_col = nh * p.q_off[4] + nd * p.q_off[5];
+                        q_rscol = nh * p.q_rs[4] + nd * p.q_rs[5];
+                    }
                     const float* rrow = res_on ? p.residual + b * p.stride_r + (mrow0 + rsub) * p.ldr + nc + (cl << 2) : nullptr;
                     const int64_t rstep = 8 * p.ldr;
                     float4 res[4];
@@ -438,7 +471,7 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                     for (int it = 0; it < 4; ++it) {
                         const int rr = it * 8 + rsub;
                         uint4 val = *reinterpret_cast<const uint4*>(stg + rr * 16 + ((cl ^ ((rr >> 1) & 3)) << 2));
-                        if (EMODE == EM_DEQ_FAST) {
+                        if (FASTF) {
                             // x = float bits of (1.5*2^23 + d), valid while |d| < 2^22: checked once per 4
                             const int rm = (int)stg_row[rr];
                             const int x0 = (int)val.x + rm - ct[0], x1 = (int)val.y + rm - ct[1];
@@ -463,10 +496,60 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                                 f0 = __fadd_rn(f0, res[it].x); f1 = __fadd_rn(f1, res[it].y);
                                 f2 = __fadd_rn(f2, res[it].z); f3 = __fadd_rn(f3, res[it].w);
                             }
+                            if (QUANT) {
+                                // quantize for the consuming MatMul and scatter into its K-major operand
+                                const bool rv = rr < rows_left;
+                                const int w = pack4_codes(qz.code<QM>(f0), qz.code<QM>(f1), qz.code<QM>(f2), qz.code<QM>(f3));
+                                if (rv) {
+                                    int8_t* dst = reinterpret_cast<int8_t*>(p.C) + q_base + (int64_t)q_mb * p.q_off[2] +
+                                                  (int64_t)q_ms * p.q_off[3] + q_col;
+                                    if (p.q_off[5] == 1) {
+                                        *reinterpret_cast<int*>(dst) = w;
+                                    } else {
+                                        dst[0] = (int8_t)w;
+                                        dst[p.q_off[5]] = (int8_t)(w >> 8);
+                                        dst[2 * p.q_off[5]] = (int8_t)(w >> 16);
+                                        dst[3 * p.q_off[5]] = (int8_t)(w >> 24);
+                                    }
+                                }
+                                if (p.q_rowsum) {
+                                    if (p.q_rs[5] == 0) {          // sums along the columns (K axis = n): one slot per row
+                                        int s4 = rv ? __dp4a(w, 0x01010101, 0) : 0;
+                                        s4 += __shfl_xor_sync(0xffffffffu, s4, 1);
+                                        s4 += __shfl_xor_sync(0xffffffffu, s4, 2);
+                                        if (cl == 0 && rv)
+                                            atomicAdd(p.q_rowsum + q_rsbase + (int64_t)q_mb * p.q_rs[2] + (int64_t)q_ms * p.q_rs[3] + q_rscol, s4);
+                                    } else if (q_uniform) {        // sums along the rows (K axis = m): one slot per column
+                                        colacc[0] += (int)(int8_t)w; colacc[1] += (int)(int8_t)(w >> 8);
+                                        colacc[2] += (int)(int8_t)(w >> 16); colacc[3] += (int)(int8_t)(w >> 24);
+                                    } else if (rv) {               // slab straddles two images: per-element atomics
+                                        int32_t* rsp = p.q_rowsum + q_rsbase + (int64_t)q_mb * p.q_rs[2] + (int64_t)q_ms * p.q_rs[3] + q_rscol;
+                                        atomicAdd(rsp, (int)(int8_t)w);
+                                        atomicAdd(rsp + p.q_rs[5], (int)(int8_t)(w >> 8));
+                                        atomicAdd(rsp + 2 * p.q_rs[5], (int)(int8_t)(w >> 16));
+                                        atomicAdd(rsp + 3 * p.q_rs[5], (int)(int8_t)(w >> 24));
+                                    }
+                                }
+                                q_ms += 8;
+                                while (q_ms >= p.q_S) { q_ms -= p.q_S; ++q_mb; }
+                                continue;
+                            }
                             val = make_uint4(__float_as_uint(f0), __float_as_uint(f1), __float_as_uint(f2), __float_as_uint(f3));
                         }
                         if (rr < rows_left) *reinterpret_cast<uint4*>(crow) = val;
                         crow += cstep;
+                    }
+                    if (QUANT && p.q_rowsum && p.q_rs[5] != 0 && q_uniform) {
+                        // column sums of the whole 32-row slab: reduce over the 8 lanes that share `cl`
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            int v2 = colacc[k];
+                            v2 += __shfl_xor_sync(0xffffffffu, v2, 4);
+                            v2 += __shfl_xor_sync(0xffffffffu, v2, 8);
+                            v2 += __shfl_xor_sync(0xffffffffu, v2, 16);
+                            if (rsub == 0)
+                                atomicAdd(p.q_rowsum + q_rsbase + (int64_t)q_mb0 * p.q_rs[2] + q_rscol + k * p.q_rs[5], v2);
+                        }
                     }
                 } else {
                     // ragged / unaligned: one column per lane (16 columns x 2 rows per instruction)
@@ -581,6 +664,8 @@ template <int BN>
 static int launch_qgemm_mode(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t s) {
     if (p.mode == NQ_EPI_RAW) return launch_qgemm<BN, EM_RAW>(ta, tb, p, s);
     if (p.mode == NQ_EPI_REQUANT) return launch_qgemm<BN, EM_REQUANT>(ta, tb, p, s);
+    if (p.mode == NQ_EPI_QUANT)
+        return p.asym_out ? launch_qgemm<BN, EM_QUANT_ASYM>(ta, tb, p, s) : launch_qgemm<BN, EM_QUANT_SYM>(ta, tb, p, s);
     return p.fast32 ? launch_qgemm<BN, EM_DEQ_FAST>(ta, tb, p, s) : launch_qgemm<BN, EM_DEQ_GENERAL>(ta, tb, p, s);
 }
 
@@ -602,7 +687,7 @@ extern "C" int nq_qgemm_s8(const int8_t* A, const int8_t* B, void* Cout, int64_t
     NQ_REQUIRE(ldc >= N, "nq_qgemm_s8: ldc < N");
     NQ_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31) && batch < (1ll << 31), "nq_qgemm_s8: extent too large");
     NQ_REQUIRE(((M + 127) / 128) * ((N + 63) / 64) * batch < (1ll << 31), "nq_qgemm_s8: too many output tiles");
-    NQ_REQUIRE(ep->mode >= NQ_EPI_RAW && ep->mode <= NQ_EPI_REQUANT, "nq_qgemm_s8: unknown epilogue mode %d", ep->mode);
+    NQ_REQUIRE(ep->mode >= NQ_EPI_RAW && ep->mode <= NQ_EPI_QUANT, "nq_qgemm_s8: unknown epilogue mode %d", ep->mode);
     if (ep->mode != NQ_EPI_RAW)
         if (int rc = check_acc_zp(&ep->zp)) return rc;
 
@@ -618,12 +703,30 @@ extern "C" int nq_qgemm_s8(const int8_t* A, const int8_t* B, void* Cout, int64_t
         // |acc| + |rowsum*zp_b - zp_a*zp_b*K| + |colsum*zp_a| with 8-bit operands (|q| <= 128)
         const long double za = (long double)llabs(p.zp.zp_a), zb = (long double)llabs(p.zp.zp_b);
         const long double bound = 16384.0L * K + 128.0L * K * (za + zb) + za * zb * K;
-        p.fast32 = (ep->mode == NQ_EPI_DEQUANT) && bound < 2147483000.0L;
+        p.fast32 = (ep->mode == NQ_EPI_DEQUANT || ep->mode == NQ_EPI_QUANT) && bound < 2147483000.0L;
+    }
+    if (ep->mode == NQ_EPI_QUANT) {
+        NQ_REQUIRE(p.fast32, "nq_qgemm_s8: QUANT epilogue needs the 32-bit zero-point bound (K or zero-points too large)");
+        NQ_REQUIRE(N % 16 == 0 && ep->q_cols_per_head > 0 && ep->q_cols_per_head % 16 == 0 && ep->q_rows_per_image > 0,
+                   "nq_qgemm_s8: QUANT epilogue needs N and cols_per_head multiples of 16");
+        NQ_REQUIRE(ep->out_bits >= 2 && ep->out_bits <= 8, "nq_qgemm_s8: out_bits %d outside 2..8", ep->out_bits);
+        int qmode;
+        p.qargs = make_qargs(ep->out_bits, ep->out_scale, ep->has_out_zp, ep->out_zp, &qmode);
+        NQ_REQUIRE(qmode != 2, "nq_qgemm_s8: QUANT epilogue needs |out_zp| < 2^20");
+        p.asym_out = ep->has_out_zp;
+        p.q_S = (uint32_t)ep->q_rows_per_image;
+        p.q_D = (uint32_t)ep->q_cols_per_head;
+        for (int i = 0; i < 6; ++i) {
+            p.q_off[i] = ep->q_off[i];
+            p.q_rs[i] = ep->q_rs[i];
+        }
+        p.q_rowsum = ep->q_rowsum;
     }
     p.bias_f32 = ep->bias_f32;
     p.bias_q = ep->bias_q;
     p.c_inner = ep->c_batch_inner > 1 ? ep->c_batch_inner : 1;
     p.stride_c_inner = ep->c_batch_inner > 1 ? ep->stride_c_inner : 0;
+    if (ep->mode == NQ_EPI_QUANT) p.c_inner = ep->c_batch_inner > 1 ? ep->c_batch_inner : 1;
     NQ_REQUIRE(p.c_inner == 1 || (batch % p.c_inner == 0 && ep->mode != NQ_EPI_REQUANT),
                "nq_qgemm_s8: c_batch_inner must divide batch (and is not available with REQUANT)");
     p.residual = (ep->mode == NQ_EPI_DEQUANT) ? ep->residual : nullptr;

@@ -279,6 +279,79 @@ def qgemm(a: Operand, b: Operand, mode: int = _lib.EPI_RAW, scale: float = 1.0,
     return out if (heads or ldn == N) else out[:, :, :N]
 
 
+def qgemm_to_operand(a: Operand, b: Operand, scale: float, azp: AccZeroPoint, bias_f32: Optional[torch.Tensor],
+                     bits: int, out_scale, out_zp, kind: str, heads: int, seq: int, want_rowsum: bool) -> Operand:
+    """GEMM whose epilogue quantizes the float result (bias + dequant) with the consumer's parameters
+    and scatters the codes straight into the K-major operand of the NEXT MatMul (NQ_EPI_QUANT).
+
+      kind 'split_rows'  GEMM [B*S, H*D] -> operand [B*H, S, D]      (attention Q as A, K^T as B)
+      kind 'split_cols'  GEMM [B*S, H*D] -> operand [B*H, D, S]      (attention V as B)
+      kind 'merge_heads' batched GEMM (B*H) x [S, D] -> operand [B, S, H*D] as one [B*S, H*D] matrix
+    """
+    assert a.k == b.k
+    batch = max(a.batch, b.batch)
+    M, N, Kd = a.rows, b.rows, a.k
+    dev = a.data.device
+    ep = Epilogue()
+    ep.mode = _lib.EPI_QUANT
+    ep.scale = float(scale)
+    ep.zp = azp.c_struct(N)
+    ep.bias_f32 = _ptr(bias_f32)
+    ep.out_bits, ep.out_scale = bits, float(out_scale)
+    ep.has_out_zp, ep.out_zp = int(out_zp is not None), 0 if out_zp is None else int(out_zp)
+    if kind in ("split_rows", "split_cols"):
+        assert batch == 1 and M % seq == 0 and N % heads == 0
+        B, S, H, D = M // seq, seq, heads, N // heads
+        if kind == "split_rows":
+            ld = round_up(D, 16)
+            out = torch.empty((B * H, S, ld), dtype=torch.int8, device=dev)
+            res = Operand(out, (B, H), S, D, ld, None)
+            off = [0, 0, H * S * ld, ld, S * ld, 1]
+            rs = [0, 0, H * S, 1, S, 0]
+            n_rs = B * H * S
+        else:
+            ld = round_up(S, 16)
+            out = torch.empty((B * H, D, ld), dtype=torch.int8, device=dev)
+            res = Operand(out, (B, H), D, S, ld, None)
+            off = [0, 0, H * D * ld, 1, D * ld, ld]
+            rs = [0, 0, H * D, 0, D, 1]
+            n_rs = B * H * D
+        ep.q_rows_per_image, ep.q_cols_per_head = S, D
+    elif kind == "merge_heads":
+        assert batch % heads == 0
+        B, S, H, D = batch // heads, M, heads, N
+        ld = H * D
+        assert ld % 16 == 0
+        out = torch.empty((1, B * S, ld), dtype=torch.int8, device=dev)
+        res = Operand(out, (), B * S, ld, ld, None)
+        off = [S * H * D, D, 0, H * D, 0, 1]
+        rs = [S, 0, 0, 1, 0, 0]
+        n_rs = B * S
+        ep.q_rows_per_image, ep.q_cols_per_head = S, D
+        ep.c_batch_inner = H
+    else:
+        raise ValueError(kind)
+    for i in range(6):
+        ep.q_off[i], ep.q_rs[i] = off[i], rs[i]
+    if want_rowsum:
+        res.rowsum = torch.zeros((n_rs,), dtype=torch.int32, device=dev).view(res.batch, res.rows)
+        ep.q_rowsum = res.rowsum.data_ptr()
+        _count()
+    sa = 0 if (a.batch == 1 and batch > 1) else M * a.ld
+    sb = 0 if (b.batch == 1 and batch > 1) else N * b.ld
+    timer = GEMM_TIMER
+    if timer is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    call("nq_qgemm_s8", a.data.data_ptr(), b.data.data_ptr(), out.data_ptr(), M, N, Kd, batch, a.ld, b.ld, N,
+         sa, sb, M * N, C.byref(ep), _stream())
+    if timer is not None:
+        e1.record()
+        timer.append((2 * batch * M * N * Kd, e0, e1))
+    _count()
+    return res
+
+
 # --------------------------------------------------------------------------- K10 / K11
 def minmax_slots(n_slots: int, device) -> torch.Tensor:
     mm = torch.empty((n_slots, 2), dtype=torch.float32, device=device)

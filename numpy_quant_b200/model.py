@@ -474,7 +474,7 @@ class QModel(Model):
         producers = {o.name: n for n in self.nodes for o in n.outputs}
         by_name = {n.name: n for n in self.nodes}
         plan = dict(gelu=find_gelu_chains(self.nodes), softmax={}, skip=set(), emit={}, quantize_out=set(), node=by_name,
-                    residual={})
+                    residual={}, to_operand={}, merge_heads={})
         for first, spec in plan["gelu"].items():
             plan["skip"].update(spec[4])
             plan["emit"][spec[5]] = first
@@ -502,6 +502,40 @@ class QModel(Model):
             other = [v for v in add2.inputs if v is not n.outputs[0]]
             if len(other) == 1 and isinstance(other[0], Variable):
                 plan["residual"][n.name] = (other[0], add2.name)
+        # bias Add -> Reshape([B,S,H,D]) -> Transpose -> MatMul operand: the GEMM epilogue writes the
+        # consumer's int8 operand directly (attention Q / K^T / V)
+        def single(v):
+            return len(v.outputs) == 1 and not any(v is o for o in self.outputs)
+        for n in self.nodes:
+            if n.op != "Add" or n.name in plan["residual"] or not single(n.outputs[0]):
+                continue
+            a, b = n.inputs
+            if not ((isinstance(a, Constant) and isinstance(b, Variable)) or (isinstance(b, Constant) and isinstance(a, Variable))):
+                continue
+            rs = n.outputs[0].outputs[0]
+            if rs.op != "Reshape" or rs.inputs[0] is not n.outputs[0] or not single(rs.outputs[0]):
+                continue
+            tr = rs.outputs[0].outputs[0]
+            if tr.op != "Transpose" or not single(tr.outputs[0]):
+                continue
+            mm = tr.outputs[0].outputs[0]
+            if mm.op != "MatMul" or mm.inputs[0] is mm.inputs[1]:
+                continue
+            pos = 0 if mm.inputs[0] is tr.outputs[0] else 1
+            perm = [int(x) for x in tr.attrs["perm"]]
+            kind = {(0, (0, 2, 1, 3)): "split_rows", (1, (0, 2, 3, 1)): "split_rows", (1, (0, 2, 1, 3)): "split_cols"}.get(
+                (pos, tuple(perm)))
+            if kind:
+                plan["to_operand"][n.name] = dict(reshape=rs, transpose=tr, matmul=mm, pos=pos, kind=kind)
+        # P.V MatMul -> Transpose(0,2,1,3) -> Reshape([B,S,H*D]) -> MatMul left operand (attention output proj.)
+        for n in self.nodes:
+            if n.op != "Transpose" or [int(x) for x in n.attrs["perm"]] != [0, 2, 1, 3] or not single(n.outputs[0]):
+                continue
+            rs = n.outputs[0].outputs[0]
+            if rs.op != "Reshape" or rs.inputs[0] is not n.outputs[0]:
+                continue
+            if self._feeds_only_matmul_lhs(rs.outputs[0]):
+                plan["merge_heads"][n.name] = dict(reshape=rs)
         emitters = {}
         for n in self.nodes:
             if n.op == "LayerNormalization" or (n.op == "Softmax" and n.attrs.get("axis", -1) == -1):
@@ -648,7 +682,8 @@ class QModel(Model):
         if fused and self._plan is None:
             self._plan = self._build_plan()
         plan = self._plan if fused else dict(gelu={}, softmax={}, skip=set(), emit={}, quantize_out=set(), node={},
-                                             residual={})
+                                             residual={}, to_operand={}, merge_heads={})
+        dyn_skip: set = set()
         qcache: dict = {}
         stash: dict = {}
         remaining = None
@@ -695,7 +730,7 @@ class QModel(Model):
                     stash[sm_name] = FTensor(K.softmax_div_lastdim(xt, c))
                 tock("Softmax", t0)
                 outputs_data = [None]
-            elif name in plan["skip"]:
+            elif name in plan["skip"] or name in dyn_skip:
                 outputs_data = [None]
             elif name in plan["emit"] or name in stash:
                 outputs_data = [stash.pop(name)]
@@ -735,6 +770,15 @@ class QModel(Model):
                 b = self._dequantized(bias)
                 tock("TinyqDequant", t0)
                 t0 = tick()
+                spec = plan["to_operand"].get(name)
+                if spec is not None and self._emit_split_heads(acc.data, b, spec, qcache):
+                    dyn_skip.update((spec["reshape"].name, spec["transpose"].name))
+                    outputs_data = [None]
+                    tock(node.op, t0)
+                    for o, tensor in zip(node.outputs, outputs_data):
+                        o.data = tensor
+                    self._release_inputs(node, remaining, keep, qcache)
+                    continue
                 res_spec = plan["residual"].get(name)
                 resid = res_spec[0].data if res_spec else None
                 if isinstance(resid, FTensor) and tuple(resid.device_tensor.shape) == tuple(acc.data.shape):
@@ -744,6 +788,10 @@ class QModel(Model):
                 else:
                     outputs_data = [acc.data.dequantize(bias=b)]
                 tock(node.op, t0)
+            elif fused and name in plan["merge_heads"] and isinstance(node.inputs[0].data, QTensor) \
+                    and node.inputs[0].data._pending() and self._emit_merge_heads(node, plan["merge_heads"][name], qcache, tick, tock):
+                dyn_skip.add(plan["merge_heads"][name]["reshape"].name)
+                outputs_data = [None]
             elif node.op == "Transpose" and isinstance(node.inputs[0].data, QTensor) and node.inputs[0].data._pending() \
                     and list(node.attrs["perm"]) == [0, 2, 1, 3] \
                     and (heads_last := self._timed_heads_last(node.inputs[0].data, tick, tock)) is not None:
@@ -797,13 +845,7 @@ class QModel(Model):
             for o, tensor in zip(node.outputs, outputs_data):
                 o.data = tensor
             if remaining is not None:
-                for i in node.inputs:
-                    if i.name in remaining:
-                        remaining[i.name] -= 1
-                        if remaining[i.name] <= 0 and i.name not in keep and not any(i is v for v in self.inputs):
-                            i.data = None
-                            qcache.pop((i.name, "A"), None)
-                            qcache.pop((i.name, "B"), None)
+                self._release_inputs(node, remaining, keep, qcache)
 
         output_tensors = []
         for out_var in self.outputs:
@@ -818,6 +860,59 @@ class QModel(Model):
             return output_tensors, times
         return output_tensors
 
+    def _release_inputs(self, node: Node, remaining: dict, keep: set, qcache: dict) -> None:
+        """retain=False: drop a value (and its cached operands) once its last consumer has run."""
+        for i in node.inputs:
+            if i.name in remaining:
+                remaining[i.name] -= 1
+                if remaining[i.name] <= 0 and i.name not in keep and not any(i is v for v in self.inputs):
+                    i.data = None
+                    qcache.pop((i.name, "A"), None)
+                    qcache.pop((i.name, "B"), None)
+
+    def _emit_split_heads(self, acc: QTensor, bias: FTensor, spec: dict, qcache: dict) -> bool:
+        """bias Add -> Reshape -> Transpose -> MatMul operand, inside the GEMM epilogue."""
+        shape = spec["reshape"].inputs[1].data
+        if not isinstance(shape, ITensor) or np.asarray(shape.data).size != 4:
+            return False
+        B, S, H, D = (int(x) for x in np.asarray(shape.data).reshape(-1))
+        if min(B, S, H, D) <= 0 or tuple(acc.shape[-1:]) != (H * D,) or int(np.prod(acc.shape[:-1])) != B * S:
+            return False
+        tr_out = spec["transpose"].outputs[0]
+        mm, pos = spec["matmul"], spec["pos"]
+        role = "A" if pos == 0 else "B"
+        qp = self.quant_params[tr_out.name]
+        other = mm.inputs[1 - pos]
+        if isinstance(other.data, QTensor):
+            other_asym = other.data._zp is not None
+        else:
+            other_asym = self.quant_params[other.name].zero_point is not None
+        perm = [int(x) for x in spec["transpose"].attrs["perm"]]
+        logical = tuple([B, S, H, D][p] for p in perm)
+        q = acc.quantize_into_operand(bias, self.bit_width, qp.scale, qp.zero_point, spec["kind"], H, S, other_asym,
+                                      role, logical)
+        if q is None:
+            return False
+        qcache[(tr_out.name, role)] = q
+        return True
+
+    def _emit_merge_heads(self, node: Node, spec: dict, qcache: dict, tick, tock) -> bool:
+        """P.V accumulator -> Transpose(0,2,1,3) -> Reshape -> left operand of the output projection."""
+        acc = node.inputs[0].data
+        if len(acc.shape) != 4:
+            return False
+        B, H, S, D = (int(x) for x in acc.shape)
+        out = spec["reshape"].outputs[0]
+        qp = self.quant_params[out.name]
+        t0 = tick()
+        q = acc.quantize_into_operand(None, self.bit_width, qp.scale, qp.zero_point, "merge_heads", H, S,
+                                      self._rowsum_needed(out), "A", (B, S, H * D))
+        tock("TinyqQuant", t0)
+        if q is None:
+            return False
+        qcache[(out.name, "A")] = q
+        return True
+
     @staticmethod
     def _timed_heads_last(acc: QTensor, tick, tock):
         t0 = tick()
@@ -831,7 +926,7 @@ class QModel(Model):
         for acc, bias in ((a, b), (b, a)):
             if isinstance(bias, Constant) and isinstance(bias.data, QTensor) and isinstance(acc.data, QTensor) \
                     and acc.data._pending() and acc.data._lazy.get("bias_q") is None \
-                    and len(bias.data.shape) == 1 and bias.data.shape[0] == acc.data._lazy["b"].rows:
+                    and len(bias.data.shape) == 1 and bias.data.shape[0] == acc.data._lazy["N"]:
                 return True
         return False
 

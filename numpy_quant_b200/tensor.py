@@ -327,7 +327,7 @@ class QTensor:
         if self._oplayout is not None:
             return tuple(self._oplayout[2])
         L = self._lazy
-        return tuple(L["batch_shape"]) + (L["a"].rows, L["b"].rows)
+        return tuple(L["batch_shape"]) + (L["M"], L["N"])
 
     def _pending(self) -> bool:
         return self._q is None and self._lazy is not None
@@ -346,7 +346,7 @@ class QTensor:
                 acc = K.qgemm(L["a"], L["b"])
                 if L.get("bias_q") is not None:
                     acc = acc.to(torch.int64) + L["bias_q"]
-                self._q = acc.view(*L["batch_shape"], L["a"].rows, L["b"].rows)
+                self._q = acc.view(*L["batch_shape"], L["M"], L["N"])
         return self._q
 
     @property
@@ -379,7 +379,7 @@ class QTensor:
         if not isinstance(other, QTensor):
             raise ValueError(f"Cannot add QTensor with {other.__class__}")
         if self._pending() and self._lazy.get("bias_q") is None and len(other.shape) == 1 \
-                and other.shape[0] == self._lazy["b"].rows:
+                and other.shape[0] == self._lazy["N"]:
             out = QTensor(None, self.bit_width, self.scale, self._zp)
             out._lazy = dict(self._lazy, bias_q=other._codes().to(torch.int64).contiguous())
             return out
@@ -392,10 +392,37 @@ class QTensor:
         written by the GEMM epilogue directly as [B, S, H, D] (the attention context layout).
         Returns None when this accumulator does not qualify."""
         L = self._lazy
-        if not self._pending() or L.get("bias_q") is not None or len(L["batch_shape"]) != 2 or L["b"].rows % 4:
+        if not self._pending() or L.get("bias_q") is not None or len(L["batch_shape"]) != 2 or L["b"].rows % 4 \
+                or L["a"].batch != int(np.prod(L["batch_shape"])):
             return None
         out = K.qgemm(L["a"], L["b"], _lib.EPI_DEQUANT, float(self.scale), self._zp, heads=int(L["batch_shape"][1]))
         return FTensor(out)
+
+    def quantize_into_operand(self, bias: Optional[FTensor], bit_width: int, scale, zero_point, kind: str,
+                              heads: int, seq: int, want_rowsum: bool, role: str, logical_shape: tuple):
+        """dequantize (+ bias) -> [Reshape / Transpose] -> quantize for the next MatMul, all inside the
+        GEMM epilogue: the int8 K-major operand of the consumer is the only thing written.  Same float32
+        and rounding steps as the separate kernels, so the codes are identical.  Returns None when this
+        accumulator does not qualify (caller falls back to the unfused route)."""
+        L = self._lazy
+        zo = _as_opt_int(zero_point)
+        if not self._pending() or L.get("bias_q") is not None or (zo is not None and abs(zo) >= (1 << 20)):
+            return None
+        M, N = L["a"].rows, L["b"].rows
+        if kind == "merge_heads":
+            if len(L["batch_shape"]) != 2 or int(L["batch_shape"][1]) != heads or N % 16 or (heads * N) % 16 \
+                    or L["a"].batch != int(np.prod(L["batch_shape"])):
+                return None
+        else:
+            if max(L["a"].batch, L["b"].batch) != 1 or N % heads or (N // heads) % 16 or M % seq:
+                return None
+        try:
+            op = K.qgemm_to_operand(L["a"], L["b"], float(self.scale), self._zp,
+                                    None if bias is None else bias.device_tensor.contiguous(), bit_width,
+                                    float(scale), zo, kind, heads, seq, want_rowsum)
+        except _lib.NqError:
+            return None
+        return qtensor_from_operand(op, role, logical_shape, bit_width, scale, zero_point)
 
     def dequantize(self, bias: Optional[FTensor] = None, residual: Optional[FTensor] = None) -> FTensor:
         """tensor.py:189-193. `bias` (float32 [N]) and `residual` (float32, result shape) optionally
@@ -407,7 +434,7 @@ class QTensor:
             out = K.qgemm(L["a"], L["b"], _lib.EPI_DEQUANT, float(self.scale), self._zp,
                           bias_f32=None if bias is None else bias.device_tensor.contiguous(),
                           residual=None if residual is None else residual.device_tensor)
-            res = FTensor(out.view(*L["batch_shape"], L["a"].rows, L["b"].rows))
+            res = FTensor(out.view(*L["batch_shape"], L["M"], L["N"]))
             if bias is None and residual is None:
                 self._deq = res
             return res
@@ -436,7 +463,7 @@ class QTensor:
             L = self._lazy
             out = K.qgemm(L["a"], L["b"], _lib.EPI_REQUANT, float(self.scale), self._zp, bias_q=L.get("bias_q"),
                           out_bits=bit_width, out_scale=float(scale), out_zp=zo)
-            return QTensor(out.view(*L["batch_shape"], L["a"].rows, L["b"].rows), bit_width, scale, zero_point)
+            return QTensor(out.view(*L["batch_shape"], L["M"], L["N"]), bit_width, scale, zero_point)
         d = self.dequantize().device_tensor
         return QTensor(K.requantize_f32(d, bit_width, float(scale), zo), bit_width, scale, zero_point)
 
@@ -498,7 +525,16 @@ class QTensor:
         azp = K.AccZeroPoint(za, zb, opa.k, opa.rowsum if zb is not None else None,
                              opb.rowsum if za is not None else None, colsum_shared=(opb.batch == 1))
         out = QTensor(None, 4 * self.bit_width, scale, azp)
-        out._lazy = dict(a=opa, b=opb, batch_shape=batch_shape)
+        M, N = opa.rows, opb.rows
+        if opb.batch == 1 and opa.batch > 1:
+            # one weight for the whole batch: run ONE [batch*M, K] x [K, N] GEMM instead of `batch` small ones
+            # (no partially filled 128-row tiles per batch entry); the operand buffer is already contiguous
+            rs = None if opa.rowsum is None else opa.rowsum.view(1, -1)
+            opa = K.Operand(opa.data.view(1, opa.batch * opa.rows, opa.ld), (), opa.batch * opa.rows, opa.k, opa.ld, rs)
+            if azp.rowsum_a is not None:
+                azp = K.AccZeroPoint(za, zb, opa.k, rs, azp.colsum_b, azp.colsum_shared)
+                out._zp = azp
+        out._lazy = dict(a=opa, b=opb, batch_shape=batch_shape, M=M, N=N)
         return out
 
     def relu(self):

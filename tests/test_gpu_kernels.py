@@ -291,6 +291,40 @@ def test_qgemm_residual_epilogue_and_ragged_output_rows():
         np.testing.assert_array_equal(host(got2), want)
 
 
+@pytest.mark.parametrize("zp_out", [None, -11, 6])
+def test_qgemm_quantize_into_next_operand(zp_out):
+    """NQ_EPI_QUANT: bias + dequant -> quantize -> scatter into the next MatMul's K-major operand must equal
+    the unfused route (GEMM -> float32 -> reshape/transpose -> quantize_operand), codes and row sums."""
+    rng = np.random.default_rng(31)
+    B, S, H, D, Kd = 3, 197, 4, 16, 96
+    a = rng.integers(-128, 128, size=(1, B * S, Kd)).astype(np.int8)
+    w = rng.integers(-128, 128, size=(1, Kd, H * D)).astype(np.int8)
+    bias = dev(rng.normal(size=H * D).astype(np.float32))
+    oa, ob = K.operand_from_codes(dev(a), "A", False), K.operand_from_codes(dev(w), "B", True)
+    azp = K.AccZeroPoint(7, None, Kd, None, ob.rowsum, True)
+    sc, so = 3.1e-4, 0.021
+    f = K.qgemm(oa, ob, _lib.EPI_DEQUANT, sc, azp, bias_f32=bias).view(B, S, H, D)          # float reference route
+    # Q as A operand / K^T as B operand: [B, H, S, D] rows = S, k = D
+    ref = K.quantize_operand(f.permute(0, 2, 1, 3), "A", 8, so, zp_out, True)
+    got = K.qgemm_to_operand(oa, ob, sc, azp, bias, 8, so, zp_out, "split_rows", H, S, True)
+    assert got.data.shape == ref.data.shape and torch.equal(got.data, ref.data) and torch.equal(got.rowsum, ref.rowsum)
+    refb = K.quantize_operand(f.permute(0, 2, 3, 1), "B", 8, so, zp_out, True)               # K^T: same layout
+    assert torch.equal(got.data, refb.data) and torch.equal(got.rowsum, refb.rowsum)
+    # V as B operand: logical [B, H, S(K), D(N)] -> rows = D, k = S (padded to 208)
+    ref = K.quantize_operand(f.permute(0, 2, 1, 3), "B", 8, so, zp_out, True)
+    got = K.qgemm_to_operand(oa, ob, sc, azp, bias, 8, so, zp_out, "split_cols", H, S, True)
+    assert got.ld == 208 and torch.equal(got.data[:, :, :S], ref.data[:, :, :S]) and torch.equal(got.rowsum, ref.rowsum)
+    # attention context: batched (B*H) x [S, S'] . [S', D] -> [B, S, H*D] operand of the output projection
+    p8 = rng.integers(-128, 128, size=(B * H, S, 40)).astype(np.int8)
+    v8 = rng.integers(-128, 128, size=(B * H, 40, D)).astype(np.int8)
+    op_, ov_ = K.operand_from_codes(dev(p8), "A", True), K.operand_from_codes(dev(v8), "B", True)
+    azp2 = K.AccZeroPoint(-128, 9, 40, op_.rowsum, ov_.rowsum, False)
+    f2 = K.qgemm(op_, ov_, _lib.EPI_DEQUANT, sc, azp2).view(B, H, S, D).permute(0, 2, 1, 3).reshape(B, S, H * D)
+    ref = K.quantize_operand(f2, "A", 8, so, zp_out, True)
+    got = K.qgemm_to_operand(op_, ov_, sc, azp2, None, 8, so, zp_out, "merge_heads", H, S, True)
+    assert torch.equal(got.data.view(-1), ref.data.view(-1)) and torch.equal(got.rowsum.view(-1), ref.rowsum.view(-1))
+
+
 def test_qgemm_rejects_bad_arguments():
     a = torch.zeros((1, 4, 8), dtype=torch.int8, device=DEV)
     ep = _lib.Epilogue()

@@ -161,6 +161,28 @@ def test_small_vit(gv, bits):
     assert all(isinstance(v, float) and v >= 0 for v in prof.values())
 
 
+@pytest.mark.parametrize("bits", [8, 4])
+def test_fused_executor_is_bit_identical_with_epilogue_quantization(bits):
+    """Head dim 16 enables every fusion (epilogue quantize-into-operand for Q/K/V and the context,
+    residual / bias epilogues, LayerNorm / Softmax / GELU -> quantize): retain=False, graph replay and the
+    node-by-node retained run must agree bit for bit, and all agree with the oracle within the ViT bound."""
+    cfg = dict(batch=3, image_size=32, patch_size=16, hidden=64, heads=4, intermediate=128, layers=2, classes=10)
+    proto = zoo.vit_graph(seed=3, **cfg)
+    x = np.random.default_rng(5).normal(size=(3, 3, 32, 32)).astype(np.float32)
+    model = Model.from_onnx(proto)
+    q = model.quantize([x], bit_width=bits)
+    plan = rg.calibrate(rg.import_graph(proto, ol), [x], bits)
+    inject_oracle_params(q, model, plan)
+    ref = q([x])[0]
+    fused = q([x], retain=False)[0]
+    np.testing.assert_array_equal(fused, ref)
+    np.testing.assert_array_equal(q([x], graph=True)[0], ref)
+    assert q._plan["to_operand"] and q._plan["merge_heads"] and q._plan["residual"]
+    want = rg.run_quant(plan, [x])[0]
+    step = float(plan.qparams["logits"][0])
+    assert np.abs(ref - want).max() <= 4 * step
+
+
 def test_quantized_matmul_surface_known_answers():
     """test_quantization.py:40-149 restated on the device tensors, plus KA-1 literals."""
     k = np.load(os.path.join(G, "ka1.npz"))
