@@ -525,7 +525,7 @@ class QTensor:
         azp = K.AccZeroPoint(za, zb, opa.k, opa.rowsum if zb is not None else None,
                              opb.rowsum if za is not None else None, colsum_shared=(opb.batch == 1))
         out = QTensor(None, 4 * self.bit_width, scale, azp)
-        M, N = opa.rows, opb.rows
+        M, N = int(sa_shape[-2]), int(sb_shape[-1])                    # logical extents (an operand may be flat)
         if opb.batch == 1 and opa.batch > 1:
             # one weight for the whole batch: run ONE [batch*M, K] x [K, N] GEMM instead of `batch` small ones
             # (no partially filled 128-row tiles per batch entry); the operand buffer is already contiguous
