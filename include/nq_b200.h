@@ -243,6 +243,9 @@ int nq_reduce_rows_f32(int op, const float* x, int64_t rows, int64_t cols, float
 int nq_copy_4d(const void* x, int elem_bytes, const int64_t* dims_host, const int64_t* sx_host,
                void* out, const int64_t* so_host, void* stream);
 
+/* cudaMemsetAsync on `stream` (zeroing of row-sum accumulators that kernels add into). */
+int nq_memset_async(void* ptr, int value, int64_t bytes, void* stream);
+
 /* Device self-test: counts (into *mismatches_dev, uint64 on the device, caller-zeroed) the inputs among
  * n pseudo-random float pairs for which the kernels' hoisted-reciprocal IEEE division differs from
  * __fdiv_rn; mode 0 = raw bit patterns, 1 = activation / scale ranges.  Must stay 0. */

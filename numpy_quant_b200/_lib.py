@@ -66,6 +66,7 @@ _SIGNATURES = {
     "nq_softmax_quantize_f32": [vp, i64, i64, i64, C.c_int, f32, C.c_int, f32, C.c_int, i64, vp, i64, vp, vp],
     "nq_gelu_quantize_f32": [vp, i64, i64, i64, f32, f32, f32, C.c_int, f32, C.c_int, i64, vp, i64, vp, vp],
     "nq_reduce_rows_f32": [C.c_int, vp, i64, i64, vp, vp],
+    "nq_memset_async": [vp, C.c_int, i64, vp],
     "nq_selftest_division": [i64, C.c_int, C.c_int, vp, vp],
     "nq_copy_4d": [vp, C.c_int, C.POINTER(i64), C.POINTER(i64), vp, C.POINTER(i64), vp],
 }

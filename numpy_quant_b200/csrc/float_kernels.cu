@@ -1,7 +1,8 @@
 // K7-K9: float32 glue of the fake-quant path (LayerNorm, Softmax, GELU-erf chain,
-// broadcasting elementwise ops, strided copies) and K6 im2col.  Every arithmetic step is
-// an explicitly rounded IEEE op (__fadd_rn/__fmul_rn/__fdiv_rn): no FMA contraction, so the
-// elementwise chains reproduce NumPy's float32 ufunc results op for op.
+// broadcasting elementwise ops, strided copies) and K6 im2col.  Every Add / Mul / Div / Sqrt step
+// is an explicitly rounded IEEE op (__fadd_rn/__fmul_rn, exact division): no FMA contraction,
+// so those chains reproduce NumPy's float32 ufunc results op for op.  exp (Softmax, Erf) and the
+// reciprocal inside Erf run on the MUFU with ~3e-7 relative error (contract: 1e-5).
 #include "common.cuh"
 
 namespace nq {
@@ -12,13 +13,13 @@ __device__ __forceinline__ float erf_as(float x) {
     const float ax = fabsf(x);
     const float a1 = 0.254829592f, a2 = -0.284496736f, a3 = 1.421413741f, a4 = -1.453152027f, a5 = 1.061405429f;
     const float p = 0.3275911f;
-    const float t = __frcp_rn(__fadd_rn(1.0f, __fmul_rn(p, ax)));           // 1 / y, correctly rounded
+    const float t = rcp_fast(__fadd_rn(1.0f, __fmul_rn(p, ax)));
     float y = __fadd_rn(__fmul_rn(a5, t), a4);
     y = __fadd_rn(__fmul_rn(y, t), a3);
     y = __fadd_rn(__fmul_rn(y, t), a2);
     y = __fadd_rn(__fmul_rn(y, t), a1);
     y = __fmul_rn(y, t);
-    const float e = expf(-__fmul_rn(ax, ax));
+    const float e = exp_fast(-__fmul_rn(ax, ax));
     y = __fadd_rn(1.0f, -__fmul_rn(y, e));
     return __fmul_rn(sgn, y);
 }
@@ -298,7 +299,7 @@ __global__ void __launch_bounds__(256) softmax_kernel(const float* __restrict__ 
         for (int j = 0; j < NV; ++j) {
             const int c = lane + j * 32;
             if (c < cols) {
-                v[j] = expf(__fadd_rn(v[j], -m));
+                v[j] = exp_fast(__fadd_rn(v[j], -m));
                 s = __fadd_rn(s, v[j]);
             }
         }

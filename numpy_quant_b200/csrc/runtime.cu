@@ -43,3 +43,10 @@ extern "C" int nq_device_info(int* props_host) {
     props_host[3] = (int)prop.sharedMemPerBlockOptin;
     return NQ_OK;
 }
+
+extern "C" int nq_memset_async(void* ptr, int value, int64_t bytes, void* stream) {
+    if (bytes <= 0) return NQ_OK;
+    cudaError_t e = cudaMemsetAsync(ptr, value, (size_t)bytes, (cudaStream_t)stream);
+    if (e != cudaSuccess) return nq::cuda_fail(e, "nq_memset_async");
+    return NQ_OK;
+}

@@ -334,9 +334,9 @@ def qgemm_to_operand(a: Operand, b: Operand, scale: float, azp: AccZeroPoint, bi
     for i in range(6):
         ep.q_off[i], ep.q_rs[i] = off[i], rs[i]
     if want_rowsum:
-        res.rowsum = torch.zeros((n_rs,), dtype=torch.int32, device=dev).view(res.batch, res.rows)
+        res.rowsum = torch.empty((n_rs,), dtype=torch.int32, device=dev).view(res.batch, res.rows)
+        call("nq_memset_async", res.rowsum.data_ptr(), 0, 4 * n_rs, _stream())
         ep.q_rowsum = res.rowsum.data_ptr()
-        _count()
     sa = 0 if (a.batch == 1 and batch > 1) else M * a.ld
     sb = 0 if (b.batch == 1 and batch > 1) else N * b.ld
     timer = GEMM_TIMER
