@@ -115,6 +115,9 @@ int nq_rowsum_s8(const int8_t* q, int64_t rows, int64_t C, int64_t ld, int32_t* 
 #define NQ_EPI_RAW 0
 #define NQ_EPI_DEQUANT 1
 #define NQ_EPI_REQUANT 2
+#define NQ_EPI_SOFTMAX_QUANT 4   /* attention scores: softmax(dequant / sm_div) over each row (N <= 224), quantized
+                                    with out_scale/out_zp/out_bits; C is the int8 operand [batch, M, ldc] of the
+                                    following P.V MatMul, q_rowsum (caller-zeroed) receives the code sums */
 #define NQ_EPI_QUANT 3   /* float result (dequant + bias) quantized for, and scattered into the K-major int8
                             operand of, the NEXT MatMul -- removes the float32 round trip (see q_* fields) */
 
@@ -146,6 +149,8 @@ typedef struct nq_epilogue {
     int64_t q_rows_per_image, q_cols_per_head;
     int64_t q_off[6], q_rs[6];
     int32_t* q_rowsum;
+    int sm_has_div;                /* NQ_EPI_SOFTMAX_QUANT: divide the scores by sm_div first (graph Div node) */
+    float sm_div;
 } nq_epilogue;
 
 int nq_qgemm_s8(const int8_t* A, const int8_t* B, void* C,

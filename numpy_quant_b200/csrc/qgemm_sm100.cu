@@ -59,6 +59,9 @@ struct GemmParams {
     int64_t q_off[6];                // byte offset  = bo*[0] + bi*[1] + mb*[2] + ms*[3] + nh*[4] + nd*[5]
     int64_t q_rs[6];                 // row-sum slot = same decomposition
     int32_t* q_rowsum;
+    // SOFTMAX epilogue: softmax(dequant / sm_div) over the (single) N tile, quantized with qargs
+    int sm_has_div;
+    float sm_div;
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -127,6 +130,15 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t* r) 
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ void tmem_ld_32x32b_x8(uint32_t taddr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // Read-only global loads as volatile asm: the compiler keeps them where they are written (ahead of the
 // accumulator wait), so their latency overlaps the main loop instead of being sunk to the first use.
@@ -173,7 +185,8 @@ __device__ __forceinline__ int64_t tile_zp(const AccZp& z, int64_t rowterm, int6
     return v;
 }
 
-constexpr int EM_RAW = 0, EM_DEQ_FAST = 1, EM_DEQ_GENERAL = 2, EM_REQUANT = 3, EM_QUANT_SYM = 4, EM_QUANT_ASYM = 5;
+constexpr int EM_RAW = 0, EM_DEQ_FAST = 1, EM_DEQ_GENERAL = 2, EM_REQUANT = 3, EM_QUANT_SYM = 4, EM_QUANT_ASYM = 5,
+              EM_SOFTMAX_SYM = 6, EM_SOFTMAX_ASYM = 7;
 
 template <int BN, int EMODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -361,6 +374,102 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
             const int64_t crow_base = (p.c_inner > 1) ? (b / p.c_inner) * p.stride_c + (b % p.c_inner) * p.stride_c_inner
                                                       : b * p.stride_c;
             const int rows_left = (int)((p.M - mrow0) < 32 ? ((p.M - mrow0) > 0 ? (p.M - mrow0) : 0) : 32);
+            if (EMODE == EM_SOFTMAX_SYM || EMODE == EM_SOFTMAX_ASYM) {
+                // ---- attention scores: dequantize -> (/ c) -> softmax over the row -> quantize, all in
+                // registers.  N <= 224 fits one tile; the 4 warps of a lane quarter split the columns
+                // (56 contiguous columns each) and exchange row max / row sum through shared memory.
+                constexpr int QS = (EMODE == EM_SOFTMAX_ASYM) ? 1 : 0;
+                constexpr int NSUB = 7;                                    // 7 x 8 columns per warp
+                const int col0 = h * (NSUB * 8);
+                float* red = reinterpret_cast<float*>(epi);                // [2][4][128] max / sum exchange
+                const int rloc = q * 32 + lane;
+                const int ncols_w = (int)(p.N - col0 < NSUB * 8 ? (p.N - col0 > 0 ? p.N - col0 : 0) : NSUB * 8);
+                float y[NSUB * 8];
+                float lmax = __int_as_float(0xff800000);
+                const int rm = 0x4B400000 - (int32_t)rowterm;
+                const FastDiv dc = make_fastdiv(p.sm_has_div ? p.sm_div : 1.0f);
+                const bool warp_rows = rows_left > 0;                       // tcgen05.ld is warp-collective: uniform guard
+                if (warp_rows) {
+#pragma unroll
+                    for (int j = 0; j < NSUB; ++j) {
+                        if (j * 8 < ncols_w) {                            // warp-uniform
+                            uint32_t a8[8];
+                            tmem_ld_32x32b_x8(t_row + (uint32_t)(col0 + j * 8), a8);
+                            // column terms: same address for every lane (broadcast loads, L2 resident)
+                            int c8[8];
+#pragma unroll
+                            for (int k = 0; k < 8; ++k)
+                                c8[k] = (cs_b && col0 + j * 8 + k < p.N) ? __ldg(cs_b + col0 + j * 8 + k) * zpa : 0;
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) {
+                                const int x = (int)a8[k] + rm - c8[k];
+                                float f = (((uint32_t)(x ^ 0x4B000000) & 0xFF800000u) == 0)
+                                              ? __fmul_rn(__fadd_rn(__int_as_float(x), -12582912.0f), p.scale)
+                                              : deq_slow(x - 0x4B400000, p.scale);
+                                if (p.sm_has_div) f = div_rn(f, dc);
+                                const bool cv = j * 8 + k < ncols_w;
+                                y[j * 8 + k] = cv ? f : __int_as_float(0xff800000);
+                                lmax = cv ? fmaxf(lmax, f) : lmax;
+                            }
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) y[j * 8 + k] = __int_as_float(0xff800000);
+                        }
+                    }
+                }
+                red[h * 128 + rloc] = lmax;
+                named_bar_sync(1 + q, 128);
+                const float gmax = fmaxf(fmaxf(red[rloc], red[128 + rloc]), fmaxf(red[256 + rloc], red[384 + rloc]));
+                float lsum = 0.f;
+                if (warp_rows) {
+#pragma unroll
+                    for (int i = 0; i < NSUB * 8; ++i) {
+                        if (i < ncols_w) {
+                            y[i] = exp_fast(__fadd_rn(y[i], -gmax));
+                            lsum = __fadd_rn(lsum, y[i]);
+                        }
+                    }
+                }
+                red[512 + h * 128 + rloc] = lsum;
+                named_bar_sync(1 + q, 128);
+                // fixed combination order -> deterministic row sum
+                const float gsum = __fadd_rn(__fadd_rn(red[512 + rloc], red[640 + rloc]),
+                                             __fadd_rn(red[768 + rloc], red[896 + rloc]));
+                if (row_ok && ncols_w > 0) {
+                    const FastDiv ds = make_fastdiv(gsum);
+                    int8_t* dst = reinterpret_cast<int8_t*>(p.C) + b * p.stride_c + m * p.ldc + col0;
+                    int qsum = 0;
+#pragma unroll
+                    for (int j = 0; j < NSUB; ++j) {
+                        if (j * 8 < ncols_w) {
+                            int c[8];
+#pragma unroll
+                            for (int k = 0; k < 8; ++k)
+                                c[k] = (j * 8 + k < ncols_w) ? qz.code<QS>(div_rn(y[j * 8 + k], ds)) : 0;
+                            const int w0 = pack4_codes(c[0], c[1], c[2], c[3]), w1 = pack4_codes(c[4], c[5], c[6], c[7]);
+                            qsum = __dp4a(w0, 0x01010101, __dp4a(w1, 0x01010101, qsum));
+                            if (col0 + j * 8 + 8 <= p.ldc) {               // ldc is a multiple of 16: 8-byte aligned store
+                                *reinterpret_cast<int2*>(dst + j * 8) = make_int2(w0, w1);
+                            } else {
+                                for (int k = 0; k < 8 && col0 + j * 8 + k < p.ldc; ++k)
+                                    dst[j * 8 + k] = (int8_t)((k < 4 ? w0 : w1) >> ((k & 3) * 8));
+                            }
+                        }
+                    }
+                    if (p.q_rowsum) atomicAdd(p.q_rowsum + b * p.M + m, qsum);
+                }
+                // red[] is reused by the next tile: everyone of this quarter must have read it
+                named_bar_sync(1 + q, 128);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(tempty_bar + acc));
+                if (++acc == 2) {
+                    acc = 0;
+                    acc_phase ^= 1;
+                }
+                continue;
+            }
             // QUANT: image / row-in-image of this lane's first read-back row, batch part of the offsets
             uint32_t q_mb0 = 0, q_ms0 = 0;
             int64_t q_base = 0, q_rsbase = 0;
@@ -664,6 +773,14 @@ template <int BN>
 static int launch_qgemm_mode(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t s) {
     if (p.mode == NQ_EPI_RAW) return launch_qgemm<BN, EM_RAW>(ta, tb, p, s);
     if (p.mode == NQ_EPI_REQUANT) return launch_qgemm<BN, EM_REQUANT>(ta, tb, p, s);
+    if (p.mode == NQ_EPI_SOFTMAX_QUANT) {
+        if constexpr (BN == 256)
+            return p.asym_out ? launch_qgemm<BN, EM_SOFTMAX_ASYM>(ta, tb, p, s) : launch_qgemm<BN, EM_SOFTMAX_SYM>(ta, tb, p, s);
+        else {
+            set_error("nq_qgemm_s8: SOFTMAX epilogue is built for the 256-column tile only");
+            return NQ_ERR_UNSUPPORTED;
+        }
+    }
     if (p.mode == NQ_EPI_QUANT)
         return p.asym_out ? launch_qgemm<BN, EM_QUANT_ASYM>(ta, tb, p, s) : launch_qgemm<BN, EM_QUANT_SYM>(ta, tb, p, s);
     return p.fast32 ? launch_qgemm<BN, EM_DEQ_FAST>(ta, tb, p, s) : launch_qgemm<BN, EM_DEQ_GENERAL>(ta, tb, p, s);
@@ -687,7 +804,7 @@ extern "C" int nq_qgemm_s8(const int8_t* A, const int8_t* B, void* Cout, int64_t
     NQ_REQUIRE(ldc >= N, "nq_qgemm_s8: ldc < N");
     NQ_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31) && batch < (1ll << 31), "nq_qgemm_s8: extent too large");
     NQ_REQUIRE(((M + 127) / 128) * ((N + 63) / 64) * batch < (1ll << 31), "nq_qgemm_s8: too many output tiles");
-    NQ_REQUIRE(ep->mode >= NQ_EPI_RAW && ep->mode <= NQ_EPI_QUANT, "nq_qgemm_s8: unknown epilogue mode %d", ep->mode);
+    NQ_REQUIRE(ep->mode >= NQ_EPI_RAW && ep->mode <= NQ_EPI_SOFTMAX_QUANT, "nq_qgemm_s8: unknown epilogue mode %d", ep->mode);
     if (ep->mode != NQ_EPI_RAW)
         if (int rc = check_acc_zp(&ep->zp)) return rc;
 
@@ -703,7 +820,21 @@ extern "C" int nq_qgemm_s8(const int8_t* A, const int8_t* B, void* Cout, int64_t
         // |acc| + |rowsum*zp_b - zp_a*zp_b*K| + |colsum*zp_a| with 8-bit operands (|q| <= 128)
         const long double za = (long double)llabs(p.zp.zp_a), zb = (long double)llabs(p.zp.zp_b);
         const long double bound = 16384.0L * K + 128.0L * K * (za + zb) + za * zb * K;
-        p.fast32 = (ep->mode == NQ_EPI_DEQUANT || ep->mode == NQ_EPI_QUANT) && bound < 2147483000.0L;
+        p.fast32 = (ep->mode == NQ_EPI_DEQUANT || ep->mode == NQ_EPI_QUANT || ep->mode == NQ_EPI_SOFTMAX_QUANT) &&
+                   bound < 2147483000.0L;
+    }
+    if (ep->mode == NQ_EPI_SOFTMAX_QUANT) {
+        NQ_REQUIRE(p.fast32, "nq_qgemm_s8: SOFTMAX epilogue needs the 32-bit zero-point bound");
+        NQ_REQUIRE(N <= 224, "nq_qgemm_s8: SOFTMAX epilogue handles rows of at most 224 columns (N=%lld)", (long long)N);
+        NQ_REQUIRE(ldc % 16 == 0 && ldc >= N, "nq_qgemm_s8: SOFTMAX epilogue writes an int8 operand: ldc %% 16 == 0 required");
+        NQ_REQUIRE(ep->out_bits >= 2 && ep->out_bits <= 8, "nq_qgemm_s8: out_bits %d outside 2..8", ep->out_bits);
+        int qmode;
+        p.qargs = make_qargs(ep->out_bits, ep->out_scale, ep->has_out_zp, ep->out_zp, &qmode);
+        NQ_REQUIRE(qmode != 2, "nq_qgemm_s8: SOFTMAX epilogue needs |out_zp| < 2^20");
+        p.asym_out = ep->has_out_zp;
+        p.q_rowsum = ep->q_rowsum;
+        p.sm_has_div = ep->sm_has_div;
+        p.sm_div = ep->sm_div;
     }
     if (ep->mode == NQ_EPI_QUANT) {
         NQ_REQUIRE(p.fast32, "nq_qgemm_s8: QUANT epilogue needs the 32-bit zero-point bound (K or zero-points too large)");
@@ -743,7 +874,7 @@ extern "C" int nq_qgemm_s8(const int8_t* A, const int8_t* B, void* Cout, int64_t
         p.hi = ldexpf(1.f, ep->out_bits - 1) - 1.f;
     }
 
-    const int bn = (N <= 64) ? 64 : (N <= 128) ? 128 : 256;
+    const int bn = (ep->mode == NQ_EPI_SOFTMAX_QUANT) ? 256 : (N <= 64) ? 64 : (N <= 128) ? 128 : 256;
     CUtensorMap ta, tb;
     if (int rc = make_operand_map(&ta, A, K, M, p.a_batched ? batch : 1, lda, stride_a, BM)) return rc;
     if (int rc = make_operand_map(&tb, B, K, N, p.b_batched ? batch : 1, ldb, stride_b, bn)) return rc;

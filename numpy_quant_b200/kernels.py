@@ -352,6 +352,44 @@ def qgemm_to_operand(a: Operand, b: Operand, scale: float, azp: AccZeroPoint, bi
     return res
 
 
+def qgemm_softmax_to_operand(a: Operand, b: Operand, scale: float, azp: AccZeroPoint, div_c, bits: int,
+                             out_scale, out_zp, want_rowsum: bool) -> Operand:
+    """Attention scores GEMM whose epilogue applies [Div ->] Softmax -> quantize and writes the int8
+    left operand [batch, M, round_up(N, 16)] of the following P.V MatMul (NQ_EPI_SOFTMAX_QUANT)."""
+    assert a.k == b.k
+    batch = max(a.batch, b.batch)
+    M, N, Kd = a.rows, b.rows, a.k
+    dev = a.data.device
+    ld = round_up(N, 16)
+    out = torch.empty((batch, M, ld), dtype=torch.int8, device=dev)
+    lead = a.batch_shape if a.batch == batch else b.batch_shape
+    res = Operand(out, tuple(lead), M, N, ld, None)
+    ep = Epilogue()
+    ep.mode = _lib.EPI_SOFTMAX_QUANT
+    ep.scale = float(scale)
+    ep.zp = azp.c_struct(N)
+    ep.out_bits, ep.out_scale = bits, float(out_scale)
+    ep.has_out_zp, ep.out_zp = int(out_zp is not None), 0 if out_zp is None else int(out_zp)
+    ep.sm_has_div, ep.sm_div = int(div_c is not None), 1.0 if div_c is None else float(div_c)
+    if want_rowsum:
+        res.rowsum = torch.empty((batch, M), dtype=torch.int32, device=dev)
+        call("nq_memset_async", res.rowsum.data_ptr(), 0, 4 * batch * M, _stream())
+        ep.q_rowsum = res.rowsum.data_ptr()
+    sa = 0 if (a.batch == 1 and batch > 1) else M * a.ld
+    sb = 0 if (b.batch == 1 and batch > 1) else N * b.ld
+    timer = GEMM_TIMER
+    if timer is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    call("nq_qgemm_s8", a.data.data_ptr(), b.data.data_ptr(), out.data_ptr(), M, N, Kd, batch, a.ld, b.ld, ld,
+         sa, sb, M * ld, C.byref(ep), _stream())
+    if timer is not None:
+        e1.record()
+        timer.append((2 * batch * M * N * Kd, e0, e1))
+    _count()
+    return res
+
+
 # --------------------------------------------------------------------------- K10 / K11
 def minmax_slots(n_slots: int, device) -> torch.Tensor:
     mm = torch.empty((n_slots, 2), dtype=torch.float32, device=device)

@@ -424,6 +424,23 @@ class QTensor:
             return None
         return qtensor_from_operand(op, role, logical_shape, bit_width, scale, zero_point)
 
+    def softmax_into_operand(self, div_c, bit_width: int, scale, zero_point, want_rowsum: bool):
+        """dequantize -> [/ c] -> softmax(last axis) -> quantize for the next MatMul (as its left operand),
+        all inside the epilogue of the pending attention-score GEMM.  None when not applicable."""
+        L = self._lazy
+        zo = _as_opt_int(zero_point)
+        if not self._pending() or L.get("bias_q") is not None or (zo is not None and abs(zo) >= (1 << 20)):
+            return None
+        if L["N"] > 224 or L["a"].batch != int(np.prod(L["batch_shape"] or (1,))) or L["a"].rows != L["M"]:
+            return None
+        try:
+            op = K.qgemm_softmax_to_operand(L["a"], L["b"], float(self.scale), self._zp, div_c, bit_width,
+                                            float(scale), zo, want_rowsum)
+        except _lib.NqError:
+            return None
+        op.batch_shape = tuple(L["batch_shape"])
+        return qtensor_from_operand(op, "A", tuple(L["batch_shape"]) + (L["M"], L["N"]), bit_width, scale, zero_point)
+
     def dequantize(self, bias: Optional[FTensor] = None, residual: Optional[FTensor] = None) -> FTensor:
         """tensor.py:189-193. `bias` (float32 [N]) and `residual` (float32, result shape) optionally
         fuse the bias Add / residual Add that follow in the graph: (bias + dequant) + residual."""

@@ -325,6 +325,32 @@ def test_qgemm_quantize_into_next_operand(zp_out):
     assert torch.equal(got.data.view(-1), ref.data.view(-1)) and torch.equal(got.rowsum.view(-1), ref.rowsum.view(-1))
 
 
+@pytest.mark.parametrize("N,div", [(197, 8.0), (64, None), (224, 2.5), (5, 8.0)])
+def test_qgemm_softmax_epilogue(N, div):
+    """NQ_EPI_SOFTMAX_QUANT vs the separate route (GEMM -> dequant -> Div -> Softmax -> quantize): the float
+    probabilities agree to 1e-5 (row sums are added in a different order), so codes may differ by one step
+    only where p / scale sits on a rounding boundary; row sums must match the emitted codes exactly."""
+    rng = np.random.default_rng(N)
+    bt, M, Kd = 7, 197, 64
+    a = rng.integers(-128, 128, size=(bt, M, Kd)).astype(np.int8)
+    b = rng.integers(-128, 128, size=(bt, Kd, N)).astype(np.int8)
+    oa, ob = K.operand_from_codes(dev(a), "A", True), K.operand_from_codes(dev(b), "B", True)
+    azp = K.AccZeroPoint(3, -4, Kd, oa.rowsum, ob.rowsum, False)
+    sc = 2.0e-4
+    f = K.qgemm(oa, ob, _lib.EPI_DEQUANT, sc, azp)
+    pf = K.softmax_div_lastdim(f, div) if div else K.softmax_lastdim(f)
+    for zp in (-128, None):
+        ref = K.quantize_operand(pf, "A", 8, 1 / 255, zp, True)
+        got = K.qgemm_softmax_to_operand(oa, ob, sc, azp, div, 8, 1 / 255, zp, True)
+        assert got.ld == K.round_up(N, 16) and got.data.shape == ref.data.shape
+        gc, rc = host(got.data)[:, :, :N].astype(np.int64), host(ref.data)[:, :, :N].astype(np.int64)
+        assert np.abs(gc - rc).max() <= 1 and np.mean(gc != rc) < 2e-3, (np.abs(gc - rc).max(), np.mean(gc != rc))
+        np.testing.assert_array_equal(host(got.rowsum).astype(np.int64), gc.sum(-1))
+        # dequantized probabilities still sum to ~1
+        sp = (gc - (zp or 0)).sum(-1) / 255.0
+        assert np.abs(sp - 1).max() < 0.6
+
+
 def test_qgemm_rejects_bad_arguments():
     a = torch.zeros((1, 4, 8), dtype=torch.int8, device=DEV)
     ep = _lib.Epilogue()
