@@ -363,6 +363,17 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                 }
             };
             if (FASTF) fetch_cols(h);
+            if (EMODE == EM_SOFTMAX_SYM || EMODE == EM_SOFTMAX_ASYM) {
+                // this warp's 56 column terms (colsum * zp_a) -> its private smem strip, fetched while the
+                // MMA is still running; read back as broadcast LDS in the softmax loop
+                int* ctw = reinterpret_cast<int*>(epi) + 1024 + ew * 64;
+                const int cbase0 = h * 56;
+                __syncwarp();
+                const int c0i = cbase0 + lane, c1i = cbase0 + 32 + lane;
+                ctw[lane] = (cs_b && c0i < p.N) ? ldg_s32(cs_b + c0i) * zpa : 0;
+                ctw[32 + lane] = (cs_b && lane < 24 && c1i < p.N) ? ldg_s32(cs_b + c1i) * zpa : 0;
+                __syncwarp();
+            }
             mbar_wait(smem_u32(tfull_bar + acc), acc_phase);
             tc_fence_after();
             if (FASTF) {
@@ -395,11 +406,10 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                         if (j * 8 < ncols_w) {                            // warp-uniform
                             uint32_t a8[8];
                             tmem_ld_32x32b_x8(t_row + (uint32_t)(col0 + j * 8), a8);
-                            // column terms: same address for every lane (broadcast loads, L2 resident)
-                            int c8[8];
-#pragma unroll
-                            for (int k = 0; k < 8; ++k)
-                                c8[k] = (cs_b && col0 + j * 8 + k < p.N) ? __ldg(cs_b + col0 + j * 8 + k) * zpa : 0;
+                            // column terms staged by this warp before the accumulator wait (broadcast LDS)
+                            const int* ctw = reinterpret_cast<const int*>(epi) + 1024 + ew * 64 + j * 8;
+                            const int4 ca = *reinterpret_cast<const int4*>(ctw), cb = *reinterpret_cast<const int4*>(ctw + 4);
+                            const int c8[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
                             tmem_ld_wait();
 #pragma unroll
                             for (int k = 0; k < 8; ++k) {
