@@ -97,6 +97,34 @@ def main():
             ops = 2.0 * bt * M * N * Kd
             emit(case=f"qgemm {lab}", M=M, N=N, K=Kd, batch=bt, epilogue="dequant_f32", ms_median=med, tops=ops / med / 1e9,
                  hbm_gbs_implied=(bt * (M * Kd + N * Kd) + bt * M * N * 4) / med / 1e6)
+    if not args.quick:
+        # epilogue-fused attention pieces at ViT-B b256 shapes
+        g = torch.Generator(device="cuda").manual_seed(1)
+        bt, S, D = 3072, 197, 64
+        q8 = torch.randint(-128, 128, (bt, S, D), generator=g, device=DEV, dtype=torch.int8)
+        k8 = torch.randint(-128, 128, (bt, D, S), generator=g, device=DEV, dtype=torch.int8)
+        oq, ok_ = K.operand_from_codes(q8, "A", True), K.operand_from_codes(k8, "B", True)
+        azp = K.AccZeroPoint(3, -4, D, oq.rowsum, ok_.rowsum, False)
+        med, _ = timed(lambda: K.qgemm_softmax_to_operand(oq, ok_, 1e-4, azp, 8.0, 8, 1 / 255, -128, True))
+        emit(case="qgemm ViT QK^T + softmax + quantize (epilogue)", M=S, N=S, K=D, batch=bt, ms_median=med,
+             tops=2.0 * bt * S * S * D / med / 1e9)
+        f = K.qgemm(oq, ok_, _lib.EPI_DEQUANT, 1e-4, azp)
+        med2, _ = timed(lambda: K.softmax_quantize(f, 8.0, 8, 1 / 255, -128, True))
+        emit(case="softmax+quantize kernel on stored scores", ms_median=med2)
+        a8 = torch.randint(-128, 128, (1, 50432, 768), generator=g, device=DEV, dtype=torch.int8)
+        w8 = torch.randint(-128, 128, (1, 768, 768), generator=g, device=DEV, dtype=torch.int8)
+        oa, ow = K.operand_from_codes(a8, "A", False), K.operand_from_codes(w8, "B", True)
+        azw = K.AccZeroPoint(3, None, 768, None, ow.rowsum, True)
+        bias = torch.randn(768, device=DEV)
+        for kind in ("split_rows", "split_cols"):
+            med, _ = timed(lambda: K.qgemm_to_operand(oa, ow, 1e-4, azw, bias, 8, 0.05, -3, kind, 12, 197, True))
+            emit(case=f"qgemm ViT qkv -> int8 operand ({kind})", ms_median=med, tops=2.0 * 50432 * 768 * 768 / med / 1e9)
+        p8 = torch.randint(-128, 128, (bt, S, S), generator=g, device=DEV, dtype=torch.int8)
+        v8 = torch.randint(-128, 128, (bt, S, D), generator=g, device=DEV, dtype=torch.int8)
+        op_, ov_ = K.operand_from_codes(p8, "A", True), K.operand_from_codes(v8, "B", True)
+        azp2 = K.AccZeroPoint(-128, 9, S, op_.rowsum, ov_.rowsum, False)
+        med, _ = timed(lambda: K.qgemm_to_operand(op_, ov_, 1e-4, azp2, None, 8, 0.05, -3, "merge_heads", 12, S, False))
+        emit(case="qgemm ViT PV -> int8 operand (merge_heads)", ms_median=med, tops=2.0 * bt * S * S * D / med / 1e9)
     if args.gemm_only:
         return
     # HBM-bound kernels: algorithmic bytes per element as fixed in SURVEY.md §8(d)

@@ -30,6 +30,35 @@ for case in cases:
         azp = K.AccZeroPoint(3, -4, Kd, oa.rowsum, ob.rowsum, False)
         for _ in range(2):
             out = K.qgemm(oa, ob, _lib.EPI_DEQUANT, 1e-4, azp)
+    elif case in ("qkv_quant", "v_quant", "o_res"):
+        M, N, Kd = 50432, 768, 768
+        a = torch.randint(-128, 128, (1, M, Kd), generator=g, device=DEV, dtype=torch.int8)
+        b = torch.randint(-128, 128, (1, Kd, N), generator=g, device=DEV, dtype=torch.int8)
+        oa, ob = K.operand_from_codes(a, "A", False), K.operand_from_codes(b, "B", True)
+        azp = K.AccZeroPoint(3, None, Kd, None, ob.rowsum, True)
+        bias = torch.randn(N, device=DEV)
+        res = torch.randn(M, N, device=DEV)
+        for _ in range(2):
+            if case == "o_res":
+                out = K.qgemm(oa, ob, _lib.EPI_DEQUANT, 1e-4, azp, bias_f32=bias, residual=res)
+            else:
+                out = K.qgemm_to_operand(oa, ob, 1e-4, azp, bias, 8, 0.05, -3,
+                                         "split_rows" if case == "qkv_quant" else "split_cols", 12, 197, True).data
+    elif case in ("qk_softmax", "pv_merge"):
+        bt, S, D = 3072, 197, 64
+        if case == "qk_softmax":
+            a = torch.randint(-128, 128, (bt, S, D), generator=g, device=DEV, dtype=torch.int8)
+            b = torch.randint(-128, 128, (bt, D, S), generator=g, device=DEV, dtype=torch.int8)
+        else:
+            a = torch.randint(-128, 128, (bt, S, S), generator=g, device=DEV, dtype=torch.int8)
+            b = torch.randint(-128, 128, (bt, S, D), generator=g, device=DEV, dtype=torch.int8)
+        oa, ob = K.operand_from_codes(a, "A", True), K.operand_from_codes(b, "B", True)
+        azp = K.AccZeroPoint(3, -4, a.shape[-1], oa.rowsum, ob.rowsum, False)
+        for _ in range(2):
+            if case == "qk_softmax":
+                out = K.qgemm_softmax_to_operand(oa, ob, 1e-4, azp, 8.0, 8, 1 / 255, -128, True).data
+            else:
+                out = K.qgemm_to_operand(oa, ob, 1e-4, azp, None, 8, 0.05, -3, "merge_heads", 12, S, False).data
     else:
         a = torch.randint(-128, 128, (1, 4096, 4096), generator=g, device=DEV, dtype=torch.int8)
         oa, ob = K.operand_from_codes(a, "A", False), K.operand_from_codes(a, "B", False)

@@ -13,6 +13,8 @@
 // main loop of tile i+1.
 #include <cuda.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace nq {
@@ -60,8 +62,7 @@ struct GemmParams {
     int64_t q_rs[6];                 // row-sum slot = same decomposition
     int32_t* q_rowsum;
     // SOFTMAX epilogue: softmax(dequant / sm_div) over the (single) N tile, quantized with qargs
-    int sm_has_div;
-    float sm_div;
+    int fast22;                      // SOFTMAX: |acc - zero-point terms| < 2^22 proved on the host (magic int->float route)
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -280,11 +281,15 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                     tc_fence_after();
                     const uint64_t adesc = make_smem_desc(smem_u32(smem_a + stage * C::A_BYTES));
                     const uint64_t bdesc = make_smem_desc(smem_u32(smem_b + stage * C::B_BYTES));
+                    // K tail: only the 32-byte steps that hold real data (TMA zero-filled the rest of the box)
+                    const uint32_t krem = (uint32_t)p.K - kb * BK;
+                    const int ksteps = krem >= (uint32_t)BK ? BK / UMMA_K : (int)((krem + UMMA_K - 1) / UMMA_K);
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         // advance 32 bytes along K inside the swizzle atom: +2 in 16-byte units
-                        mma_i8(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
-                               (kb > 0 || k > 0) ? 1u : 0u);
+                        if (k < ksteps)
+                            mma_i8(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
+                                   (kb > 0 || k > 0) ? 1u : 0u);
                     }
                     tc_commit(smem_u32(empty_bar + stage));               // smem slot free once MMAs retire
                     if (++stage == C::STAGES) {
@@ -386,77 +391,107 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                                                       : b * p.stride_c;
             const int rows_left = (int)((p.M - mrow0) < 32 ? ((p.M - mrow0) > 0 ? (p.M - mrow0) : 0) : 32);
             if (EMODE == EM_SOFTMAX_SYM || EMODE == EM_SOFTMAX_ASYM) {
-                // ---- attention scores: dequantize -> (/ c) -> softmax over the row -> quantize, all in
-                // registers.  N <= 224 fits one tile; the 4 warps of a lane quarter split the columns
-                // (56 contiguous columns each) and exchange row max / row sum through shared memory.
+                // ---- attention scores: dequantize (/ c folded into the scale) -> softmax over the row ->
+                // quantize, all in registers.  N <= 224 fits one tile; the 4 warps of a lane quarter split
+                // the columns (56 contiguous columns each) and exchange row max / row sum / code sum
+                // through shared memory.  Float glue under the 1e-5 contract: the
+                // probabilities are e_i * RN(1 / (sum * s_out)) with e_i = ex2(fma(y_i, log2 e, -max*log2 e));
+                // the codes are the exact round-half-even of that quotient and the row sums are the exact
+                // integer sums of the emitted codes.
                 constexpr int QS = (EMODE == EM_SOFTMAX_ASYM) ? 1 : 0;
                 constexpr int NSUB = 7;                                    // 7 x 8 columns per warp
+                constexpr float kMasked = -1.0e30f;                        // exp() of it is exactly 0, no inf - inf
                 const int col0 = h * (NSUB * 8);
                 float* red = reinterpret_cast<float*>(epi);                // [2][4][128] max / sum exchange
+                int* redq = reinterpret_cast<int*>(epi) + 2048;            // [4][128] code sums
                 const int rloc = q * 32 + lane;
                 const int ncols_w = (int)(p.N - col0 < NSUB * 8 ? (p.N - col0 > 0 ? p.N - col0 : 0) : NSUB * 8);
                 float y[NSUB * 8];
-                float lmax = __int_as_float(0xff800000);
-                const int rm = 0x4B400000 - (int32_t)rowterm;
-                const FastDiv dc = make_fastdiv(p.sm_has_div ? p.sm_div : 1.0f);
+                float lmax = kMasked;
                 const bool warp_rows = rows_left > 0;                       // tcgen05.ld is warp-collective: uniform guard
-                if (warp_rows) {
+                const int* ctw = reinterpret_cast<const int*>(epi) + 1024 + ew * 64;
+                auto pass1 = [&](auto magic_tag) {
+                    constexpr bool MAGIC = decltype(magic_tag)::value;
+                    // MAGIC: |d| < 2^22 proved on the host -> x is the bit pattern of 1.5*2^23 + d
+                    const int rm = (MAGIC ? 0x4B400000 : 0) - (int32_t)rowterm;
 #pragma unroll
                     for (int j = 0; j < NSUB; ++j) {
                         if (j * 8 < ncols_w) {                            // warp-uniform
                             uint32_t a8[8];
                             tmem_ld_32x32b_x8(t_row + (uint32_t)(col0 + j * 8), a8);
                             // column terms staged by this warp before the accumulator wait (broadcast LDS)
-                            const int* ctw = reinterpret_cast<const int*>(epi) + 1024 + ew * 64 + j * 8;
-                            const int4 ca = *reinterpret_cast<const int4*>(ctw), cb = *reinterpret_cast<const int4*>(ctw + 4);
+                            const int4 ca = *reinterpret_cast<const int4*>(ctw + j * 8);
+                            const int4 cb = *reinterpret_cast<const int4*>(ctw + j * 8 + 4);
                             const int c8[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
                             tmem_ld_wait();
+                            const bool ragged = j * 8 + 8 > ncols_w;      // warp-uniform: only the last group
 #pragma unroll
                             for (int k = 0; k < 8; ++k) {
                                 const int x = (int)a8[k] + rm - c8[k];
-                                float f = (((uint32_t)(x ^ 0x4B000000) & 0xFF800000u) == 0)
-                                              ? __fmul_rn(__fadd_rn(__int_as_float(x), -12582912.0f), p.scale)
-                                              : deq_slow(x - 0x4B400000, p.scale);
-                                if (p.sm_has_div) f = div_rn(f, dc);
-                                const bool cv = j * 8 + k < ncols_w;
-                                y[j * 8 + k] = cv ? f : __int_as_float(0xff800000);
-                                lmax = cv ? fmaxf(lmax, f) : lmax;
+                                float f = MAGIC ? __fmul_rn(__fadd_rn(__int_as_float(x), -12582912.0f), p.scale)
+                                                : __fmul_rn(__int2float_rn(x), p.scale);
+                                if (ragged) f = (j * 8 + k < ncols_w) ? f : kMasked;
+                                y[j * 8 + k] = f;
+                                lmax = fmaxf(lmax, f);
                             }
                         } else {
 #pragma unroll
-                            for (int k = 0; k < 8; ++k) y[j * 8 + k] = __int_as_float(0xff800000);
+                            for (int k = 0; k < 8; ++k) y[j * 8 + k] = kMasked;
                         }
                     }
+                };
+                if (warp_rows) {
+                    if (p.fast22) pass1(std::true_type{});
+                    else pass1(std::false_type{});
                 }
+                // the scores now live in registers: hand the accumulator buffer back to the MMA warp
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(tempty_bar + acc));
                 red[h * 128 + rloc] = lmax;
                 named_bar_sync(1 + q, 128);
                 const float gmax = fmaxf(fmaxf(red[rloc], red[128 + rloc]), fmaxf(red[256 + rloc], red[384 + rloc]));
                 float lsum = 0.f;
                 if (warp_rows) {
+                    const float l2e = 1.44269502162933349609375f;
+                    const float m2 = __fmul_rn(gmax, l2e);               // its rounding error scales every e_i alike
+                    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;        // fixed order -> deterministic
 #pragma unroll
-                    for (int i = 0; i < NSUB * 8; ++i) {
-                        if (i < ncols_w) {
-                            y[i] = exp_fast(__fadd_rn(y[i], -gmax));
-                            lsum = __fadd_rn(lsum, y[i]);
+                    for (int j = 0; j < NSUB; ++j) {
+                        if (j * 8 < ncols_w) {
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) {
+                                float e;
+                                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(__fmaf_rn(y[j * 8 + k], l2e, -m2)));
+                                y[j * 8 + k] = e;
+                                if ((k & 3) == 0) s0 = __fadd_rn(s0, e);
+                                else if ((k & 3) == 1) s1 = __fadd_rn(s1, e);
+                                else if ((k & 3) == 2) s2 = __fadd_rn(s2, e);
+                                else s3 = __fadd_rn(s3, e);
+                            }
                         }
                     }
+                    lsum = __fadd_rn(__fadd_rn(s0, s1), __fadd_rn(s2, s3));
                 }
                 red[512 + h * 128 + rloc] = lsum;
                 named_bar_sync(1 + q, 128);
                 // fixed combination order -> deterministic row sum
                 const float gsum = __fadd_rn(__fadd_rn(red[512 + rloc], red[640 + rloc]),
                                              __fadd_rn(red[768 + rloc], red[896 + rloc]));
+                int qsum = 0;
                 if (row_ok && ncols_w > 0) {
-                    const FastDiv ds = make_fastdiv(gsum);
+                    const float kr = __frcp_rn(__fmul_rn(gsum, p.qargs.scale));   // 1 / (row sum * output scale)
                     int8_t* dst = reinterpret_cast<int8_t*>(p.C) + b * p.stride_c + m * p.ldc + col0;
-                    int qsum = 0;
 #pragma unroll
                     for (int j = 0; j < NSUB; ++j) {
                         if (j * 8 < ncols_w) {
+                            const bool ragged = j * 8 + 8 > ncols_w;
                             int c[8];
 #pragma unroll
-                            for (int k = 0; k < 8; ++k)
-                                c[k] = (j * 8 + k < ncols_w) ? qz.code<QS>(div_rn(y[j * 8 + k], ds)) : 0;
+                            for (int k = 0; k < 8; ++k) {
+                                c[k] = qz.template code_of_quotient<QS>(__fmul_rn(y[j * 8 + k], kr));
+                                if (ragged) c[k] = (j * 8 + k < ncols_w) ? c[k] : 0;
+                            }
                             const int w0 = pack4_codes(c[0], c[1], c[2], c[3]), w1 = pack4_codes(c[4], c[5], c[6], c[7]);
                             qsum = __dp4a(w0, 0x01010101, __dp4a(w1, 0x01010101, qsum));
                             if (col0 + j * 8 + 8 <= p.ldc) {               // ldc is a multiple of 16: 8-byte aligned store
@@ -467,13 +502,16 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                             }
                         }
                     }
-                    if (p.q_rowsum) atomicAdd(p.q_rowsum + b * p.M + m, qsum);
                 }
-                // red[] is reused by the next tile: everyone of this quarter must have read it
-                named_bar_sync(1 + q, 128);
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(smem_u32(tempty_bar + acc));
+                if (p.q_rowsum) {
+                    // code sums of the 4 column groups meet in shared memory: plain store, no memset / atomics
+                    redq[h * 128 + rloc] = qsum;
+                    named_bar_sync(1 + q, 128);
+                    if (h == 0 && row_ok)
+                        p.q_rowsum[b * p.M + m] = (redq[rloc] + redq[128 + rloc]) + (redq[256 + rloc] + redq[384 + rloc]);
+                }
+                // red[] / redq[] reuse by the next tile is ordered by that tile's own barriers (each slot is
+                // rewritten only after a barrier that every reader of the previous tile has passed)
                 if (++acc == 2) {
                     acc = 0;
                     acc_phase ^= 1;
@@ -843,8 +881,20 @@ extern "C" int nq_qgemm_s8(const int8_t* A, const int8_t* B, void* Cout, int64_t
         NQ_REQUIRE(qmode != 2, "nq_qgemm_s8: SOFTMAX epilogue needs |out_zp| < 2^20");
         p.asym_out = ep->has_out_zp;
         p.q_rowsum = ep->q_rowsum;
-        p.sm_has_div = ep->sm_has_div;
-        p.sm_div = ep->sm_div;
+        // the Div constant folds into the dequantization scale: exact for a power of two, otherwise one
+        // common relative error of 2^-24 on every score of the row (float glue, 1e-5 contract)
+        if (ep->sm_has_div) {
+            NQ_REQUIRE(ep->sm_div > 0.f && isfinite(ep->sm_div), "nq_qgemm_s8: SOFTMAX divisor must be positive and finite");
+            p.scale = ep->scale / ep->sm_div;
+        }
+        NQ_REQUIRE(p.scale > 1e-30f && p.scale < 1e30f, "nq_qgemm_s8: SOFTMAX epilogue: scale/divisor out of range");
+        {
+            // exact range of sum_k (a - zp_a)(b - zp_b) over 8-bit codes
+            const long double za = (long double)p.zp.zp_a, zb = (long double)p.zp.zp_b;
+            const long double ra = fmaxl(fabsl(-128.0L - za), fabsl(127.0L - za));
+            const long double rb = fmaxl(fabsl(-128.0L - zb), fabsl(127.0L - zb));
+            p.fast22 = (ra * rb * (long double)K) < 4194304.0L;
+        }
     }
     if (ep->mode == NQ_EPI_QUANT) {
         NQ_REQUIRE(p.fast32, "nq_qgemm_s8: QUANT epilogue needs the 32-bit zero-point bound (K or zero-points too large)");
