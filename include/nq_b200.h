@@ -117,7 +117,10 @@ int nq_rowsum_s8(const int8_t* q, int64_t rows, int64_t C, int64_t ld, int32_t* 
 #define NQ_EPI_REQUANT 2
 #define NQ_EPI_SOFTMAX_QUANT 4   /* attention scores: softmax(dequant / sm_div) over each row (N <= 224), quantized
                                     with out_scale/out_zp/out_bits; C is the int8 operand [batch, M, ldc] of the
-                                    following P.V MatMul, q_rowsum (caller-zeroed) receives the code sums */
+                                    following P.V MatMul, q_rowsum[batch * M] receives the code sums (plain stores) */
+#define NQ_EPI_GELU_QUANT 5   /* NQ_EPI_QUANT with the GELU chain (model.py:65-213 Div/Erf/Add/Mul/Mul nodes, erf of
+                                 numpy_helper.py:95-112) applied to bias + dequant before the quantization: the
+                                 first MLP GEMM writes the second one's int8 operand (row layout only) */
 #define NQ_EPI_QUANT 3   /* float result (dequant + bias) quantized for, and scattered into the K-major int8
                             operand of, the NEXT MatMul -- removes the float32 round trip (see q_* fields) */
 
@@ -144,13 +147,17 @@ typedef struct nq_epilogue {
      * applied to the float value the graph would have produced); C is the int8 destination.  With
      * m = mb*q_rows_per_image + ms, n = nh*q_cols_per_head + nd and batch b = bo*c_batch_inner + bi, the
      * code goes to byte C[bo*q_off[0] + bi*q_off[1] + mb*q_off[2] + ms*q_off[3] + nh*q_off[4] + nd*q_off[5]]
-     * and, if q_rowsum != NULL, is added to q_rowsum[same decomposition with q_rs[]] (int32, caller-zeroed):
+     * and, if q_rowsum != NULL, is added to q_rowsum[same decomposition with q_rs[]] (int32; see q_rowsum_count):
      * q_rs[5] == 0 accumulates along n (row sums), q_rs[3] == 0 along m (column sums). */
     int64_t q_rows_per_image, q_cols_per_head;
     int64_t q_off[6], q_rs[6];
     int32_t* q_rowsum;
     int sm_has_div;                /* NQ_EPI_SOFTMAX_QUANT: divide the scores by sm_div first (graph Div node) */
     float sm_div;
+    int64_t q_rowsum_count;        /* number of int32 slots behind q_rowsum (NQ_EPI_QUANT / NQ_EPI_GELU_QUANT): the
+                                      library zeroes them itself when partial sums have to meet through atomics */
+    float gelu_div, gelu_add, gelu_mul;   /* NQ_EPI_GELU_QUANT: constants c1, c2, c3 of the graph's
+                                             Div(x, c1) -> Erf -> Add(., c2) -> Mul(x, .) -> Mul(., c3) chain */
 } nq_epilogue;
 
 int nq_qgemm_s8(const int8_t* A, const int8_t* B, void* C,

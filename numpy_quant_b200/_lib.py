@@ -28,10 +28,11 @@ class Epilogue(C.Structure):
                 ("residual", vp), ("ld_residual", i64), ("stride_residual", i64),
                 ("c_batch_inner", i64), ("stride_c_inner", i64),
                 ("q_rows_per_image", i64), ("q_cols_per_head", i64), ("q_off", i64 * 6), ("q_rs", i64 * 6),
-                ("q_rowsum", vp), ("sm_has_div", C.c_int), ("sm_div", f32)]
+                ("q_rowsum", vp), ("sm_has_div", C.c_int), ("sm_div", f32),
+                ("q_rowsum_count", i64), ("gelu_div", f32), ("gelu_add", f32), ("gelu_mul", f32)]
 
 
-EPI_RAW, EPI_DEQUANT, EPI_REQUANT, EPI_QUANT, EPI_SOFTMAX_QUANT = 0, 1, 2, 3, 4
+EPI_RAW, EPI_DEQUANT, EPI_REQUANT, EPI_QUANT, EPI_SOFTMAX_QUANT, EPI_GELU_QUANT = 0, 1, 2, 3, 4, 5
 UN = dict(neg=0, exp=1, erf=2, tanh=3, sigmoid=4, relu=5, sqrt=6, inv=7, copy=8)
 BIN = dict(add=0, mul=1, div=2)
 

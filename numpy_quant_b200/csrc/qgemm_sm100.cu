@@ -62,6 +62,8 @@ struct GemmParams {
     int64_t q_rs[6];                 // row-sum slot = same decomposition
     int32_t* q_rowsum;
     // SOFTMAX epilogue: softmax(dequant / sm_div) over the (single) N tile, quantized with qargs
+    int q_rs_exclusive;              // Q8 ROWS: every (row, head) row-sum slot is written by exactly one warp: plain store
+    float g_rdiv, g_add, g_mul;      // GELU_QUANT: 1 / c1, c2, c3 of the Div -> Erf -> Add -> Mul -> Mul chain
     int fast22;                      // SOFTMAX: |acc - zero-point terms| < 2^22 proved on the host (magic int->float route)
 };
 
@@ -186,8 +188,29 @@ __device__ __forceinline__ int64_t tile_zp(const AccZp& z, int64_t rowterm, int6
     return v;
 }
 
-constexpr int EM_RAW = 0, EM_DEQ_FAST = 1, EM_DEQ_GENERAL = 2, EM_REQUANT = 3, EM_QUANT_SYM = 4, EM_QUANT_ASYM = 5,
-              EM_SOFTMAX_SYM = 6, EM_SOFTMAX_ASYM = 7;
+// GELU chain Div(x, c1) -> Erf -> Add(c2) -> Mul(x, .) -> Mul(., c3) for the fused epilogue: float glue under the
+// 1e-5 contract.  Same Abramowitz & Stegun 7.1.26 erf as numpy_helper.py:95-112 with the
+// polynomial as fused multiply-adds, 1/(1 + p|u|) and exp(-u^2) on the MUFU: 16 instructions + 2 MUFU per element
+// (the standalone kernels keep one IEEE rounding per ONNX node).
+__device__ __forceinline__ float gelu_fast(float x, float rdiv, float c_add, float c_mul) {
+    const float a1 = 0.254829592f, a2 = -0.284496736f, a3 = 1.421413741f, a4 = -1.453152027f, a5 = 1.061405429f;
+    const float u = __fmul_rn(x, rdiv);
+    const float ax = fabsf(u);
+    float t, e;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(__fmaf_rn(0.3275911f, ax, 1.0f)));
+    float y = __fmaf_rn(a5, t, a4);
+    y = __fmaf_rn(y, t, a3);
+    y = __fmaf_rn(y, t, a2);
+    y = __fmaf_rn(y, t, a1);
+    y = __fmul_rn(y, t);
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(__fmul_rn(__fmul_rn(ax, ax), -1.44269502162933349609375f)));
+    y = __fmaf_rn(-y, e, 1.0f);
+    const float erf_u = __int_as_float(__float_as_int(y) ^ (__float_as_int(u) & 0x80000000));   // sign(u) * y
+    return __fmul_rn(__fmul_rn(x, __fadd_rn(erf_u, c_add)), c_mul);
+}
+
+constexpr int EM_RAW = 0, EM_DEQ_FAST = 1, EM_DEQ_GENERAL = 2, EM_REQUANT = 3, EM_Q8_ROWS = 4, EM_Q8_COLS = 5,
+              EM_SOFTMAX_SYM = 6, EM_SOFTMAX_ASYM = 7, EM_Q8_GELU = 8;
 
 template <int BN, int EMODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -331,9 +354,8 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
         const bool res_vec = p.residual && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0) && ((p.ldr & 3) == 0) &&
                              ((p.stride_r & 3) == 0);
         const int zpa = (int)z.zp_a;
-        constexpr bool QUANT = (EMODE == EM_QUANT_SYM || EMODE == EM_QUANT_ASYM);
-        constexpr bool FASTF = (EMODE == EM_DEQ_FAST) || QUANT;          // float result via the 32-bit fast path
-        constexpr int QM = (EMODE == EM_QUANT_ASYM) ? 1 : 0;
+        constexpr bool FASTF = (EMODE == EM_DEQ_FAST);                   // float result via the 32-bit fast path
+        constexpr bool Q8 = (EMODE == EM_Q8_ROWS || EMODE == EM_Q8_COLS || EMODE == EM_Q8_GELU);
         const Quantizer qz(p.qargs);
         for (uint32_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
             const int64_t b = t / tiles_per_batch;
@@ -345,6 +367,141 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
             const int32_t* cs_b = z.use_col ? z.colsum_b + b * z.cs_stride : nullptr;
             int64_t rowterm = -z.kterm;
             if (z.use_row && row_ok) rowterm += (int64_t)ldg_s32(z.rowsum_a + b * p.M + m) * z.zp_b;
+            if constexpr (Q8) {
+                // ---- int8 operand outputs (NQ_EPI_QUANT / NQ_EPI_GELU_QUANT): thread = accumulator row.
+                // The float value the graph would have produced (bias + dequant [-> GELU]) is quantized with
+                // the consumer's parameters and written straight into the consumer's K-major operand: no
+                // smem transpose, the row part of every address is formed once per tile, column terms and
+                // bias are staged per warp in shared memory and read back as broadcast LDS.128.
+                //   ROWS / GELU: 16 consecutive n are 16 consecutive bytes (one 16-byte store per row)
+                //   COLS       : consecutive m are consecutive bytes (transposing scatter, V operand)
+                constexpr int CPW = BN / 64;                              // 16-column chunks per warp, contiguous
+                constexpr int WCOLS = CPW * 16;
+                const int wcol0 = h * WCOLS;
+                int* ctw = reinterpret_cast<int*>(epi) + ew * 128;        // [64] colsum * zp_a
+                float* bsw = reinterpret_cast<float*>(ctw + 64);          // [64] bias
+                __syncwarp();
+                for (int i = lane; i < WCOLS; i += 32) {
+                    const int64_t n = n0 + wcol0 + i;
+                    const bool ok = n < p.N;
+                    ctw[i] = (cs_b && ok) ? ldg_s32(cs_b + n) * zpa : 0;
+                    bsw[i] = (p.bias_f32 && ok) ? __int_as_float(ldg_s32(p.bias_f32 + n)) : 0.f;
+                }
+                // row part of the scatter offsets (m = mb * S + ms, batch = bo * inner + bi)
+                const uint32_t mu = (uint32_t)(row_ok ? m : p.M - 1);
+                const uint32_t mb = mu / p.q_S, ms = mu - mb * p.q_S;
+                const uint32_t bu = (uint32_t)b, bo = bu / (uint32_t)p.c_inner, bi = bu - bo * (uint32_t)p.c_inner;
+                const int64_t row_off = (int64_t)bo * p.q_off[0] + (int64_t)bi * p.q_off[1] + (int64_t)mb * p.q_off[2] +
+                                        (int64_t)ms * p.q_off[3];
+                const int64_t row_rs = (int64_t)bo * p.q_rs[0] + (int64_t)bi * p.q_rs[1] + (int64_t)mb * p.q_rs[2] +
+                                       (int64_t)ms * p.q_rs[3];
+                __syncwarp();
+                mbar_wait(smem_u32(tfull_bar + acc), acc_phase);
+                tc_fence_after();
+                const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+                const int rm = 0x4B400000 - (int32_t)rowterm;             // int -> float magic folded into the row term
+                int rs_acc = 0;                                           // ROWS: code sum of the current head
+                uint32_t rs_nh = 0xffffffffu;
+                auto flush_rowsum = [&]() {
+                    if (rs_nh != 0xffffffffu && row_ok) {
+                        int32_t* slot = p.q_rowsum + row_rs + (int64_t)rs_nh * p.q_rs[4];
+                        if (p.q_rs_exclusive) *slot = rs_acc;
+                        else atomicAdd(slot, rs_acc);
+                    }
+                };
+#pragma unroll 1
+                for (int i = 0; i < CPW; ++i) {
+                    const int cw = wcol0 + i * 16;
+                    const int64_t nc = n0 + cw;
+                    if (nc >= p.N) break;                                 // warp-uniform (N % 16 == 0)
+                    uint32_t v[16];
+                    tmem_ld_32x32b_x16(t_row + (uint32_t)cw, v);
+                    int ct[16];
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        const int4 c4 = *reinterpret_cast<const int4*>(ctw + i * 16 + g * 4);
+                        ct[4 * g] = c4.x; ct[4 * g + 1] = c4.y; ct[4 * g + 2] = c4.z; ct[4 * g + 3] = c4.w;
+                    }
+                    tmem_ld_wait();
+                    int x[16];
+                    uint32_t bad = 0;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        x[j] = (int)v[j] + rm - ct[j];
+                        bad |= (uint32_t)(x[j] ^ 0x4B000000);
+                    }
+                    float f[16];
+                    if (__builtin_expect((bad & 0xFF800000u) != 0, 0)) {  // some |d| >= 2^22: exact slow route
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) f[j] = deq_slow(x[j] - 0x4B400000, p.scale);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) f[j] = __fmul_rn(__fadd_rn(__int_as_float(x[j]), -12582912.0f), p.scale);
+                    }
+                    int w[4];
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        const float4 b4 = *reinterpret_cast<const float4*>(bsw + i * 16 + g * 4);
+                        float y0 = __fadd_rn(b4.x, f[4 * g]), y1 = __fadd_rn(b4.y, f[4 * g + 1]);
+                        float y2 = __fadd_rn(b4.z, f[4 * g + 2]), y3 = __fadd_rn(b4.w, f[4 * g + 3]);
+                        if constexpr (EMODE == EM_Q8_GELU) {
+                            y0 = gelu_fast(y0, p.g_rdiv, p.g_add, p.g_mul); y1 = gelu_fast(y1, p.g_rdiv, p.g_add, p.g_mul);
+                            y2 = gelu_fast(y2, p.g_rdiv, p.g_add, p.g_mul); y3 = gelu_fast(y3, p.g_rdiv, p.g_add, p.g_mul);
+                        }
+                        w[g] = pack4_codes(qz.template code<1>(y0), qz.template code<1>(y1), qz.template code<1>(y2),
+                                           qz.template code<1>(y3));
+                    }
+                    const uint32_t nu = (uint32_t)nc, nh = nu / p.q_D, nd = nu - nh * p.q_D;
+                    if constexpr (EMODE == EM_Q8_COLS) {
+                        // out[.., nd + j, ms]: consecutive lanes are consecutive bytes
+                        int8_t* dst = reinterpret_cast<int8_t*>(p.C) + row_off + (int64_t)nh * p.q_off[4] + (int64_t)nd * p.q_off[5];
+                        if (row_ok) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) dst[(int64_t)j * p.q_off[5]] = (int8_t)(w[j >> 2] >> ((j & 3) * 8));
+                        }
+                        if (p.q_rowsum) {
+                            // code sums over the rows of each image present in this warp's 32 rows
+                            const uint32_t mb_first = __shfl_sync(0xffffffffu, mb, 0), mb_last = __shfl_sync(0xffffffffu, mb, 31);
+                            for (uint32_t img = mb_first; img <= mb_last; ++img) {
+                                const bool mine_img = row_ok && mb == img;
+                                int keep = 0;
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) {
+                                    const int c = mine_img ? (int)(int8_t)(w[j >> 2] >> ((j & 3) * 8)) : 0;
+                                    const int tot = __reduce_add_sync(0xffffffffu, c);
+                                    keep = (lane == j) ? tot : keep;
+                                }
+                                if (lane < 16) {
+                                    const int64_t slot = (int64_t)bo * p.q_rs[0] + (int64_t)bi * p.q_rs[1] + (int64_t)img * p.q_rs[2] +
+                                                         (int64_t)nh * p.q_rs[4] + (int64_t)(nd + lane) * p.q_rs[5];
+                                    atomicAdd(p.q_rowsum + slot, keep);
+                                }
+                            }
+                        }
+                    } else {
+                        if (row_ok)
+                            *reinterpret_cast<int4*>(reinterpret_cast<int8_t*>(p.C) + row_off + (int64_t)nh * p.q_off[4] + nd) =
+                                make_int4(w[0], w[1], w[2], w[3]);
+                        if (p.q_rowsum) {
+                            if (nh != rs_nh) {
+                                flush_rowsum();
+                                rs_acc = 0;
+                                rs_nh = nh;
+                            }
+                            rs_acc = __dp4a(w[0], 0x01010101, __dp4a(w[1], 0x01010101, __dp4a(w[2], 0x01010101, __dp4a(w[3], 0x01010101, rs_acc))));
+                        }
+                    }
+                }
+                if (EMODE != EM_Q8_COLS && p.q_rowsum) flush_rowsum();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(tempty_bar + acc));
+                if (++acc == 2) {
+                    acc = 0;
+                    acc_phase ^= 1;
+                }
+                continue;
+            }
             // Column operands (colsum for the zero-point, bias) of the NEXT sub-chunk are always in flight
             // one step ahead (first one: issued before waiting for the accumulator): with 227 KB of
             // smem there is no L1 to hit, so every one of these loads is an L2 round trip.
@@ -354,7 +511,7 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                 bs_n = make_int4(0, 0, 0, 0);
                 const int64_t nc = n0 + sidx * 16;
                 if (sidx >= BN / 16 || nc >= p.N) return;
-                if (QUANT || (c_aligned && nc + 16 <= p.N)) {
+                if (c_aligned && nc + 16 <= p.N) {
                     if (cs_b) ct_n = cs_vec ? ldg_v4(cs_b + nc + cl * 4)
                                             : make_int4(ldg_s32(cs_b + nc + cl * 4), ldg_s32(cs_b + nc + cl * 4 + 1),
                                                         ldg_s32(cs_b + nc + cl * 4 + 2), ldg_s32(cs_b + nc + cl * 4 + 3));
@@ -518,26 +675,13 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                 }
                 continue;
             }
-            // QUANT: image / row-in-image of this lane's first read-back row, batch part of the offsets
-            uint32_t q_mb0 = 0, q_ms0 = 0;
-            int64_t q_base = 0, q_rsbase = 0;
-            bool q_uniform = false;
-            if (QUANT) {
-                const uint32_t mfirst = (uint32_t)(mrow0 + rsub);
-                q_mb0 = mfirst / p.q_S;
-                q_ms0 = mfirst - q_mb0 * p.q_S;
-                const int64_t bo = b / p.c_inner, bi = b % p.c_inner;
-                q_base = bo * p.q_off[0] + bi * p.q_off[1];
-                q_rsbase = bo * p.q_rs[0] + bi * p.q_rs[1];
-                q_uniform = rows_left == 32 && ((uint32_t)mrow0 / p.q_S) == ((uint32_t)(mrow0 + 31) / p.q_S);
-            }
 #pragma unroll 1
             for (int sidx = h; sidx < BN / 16; sidx += 4) {
                 const int64_t nc = n0 + sidx * 16;
                 if (nc >= p.N) break;                                     // warp-uniform
                 uint32_t v[16];
                 tmem_ld_32x32b_x16(t_row + (uint32_t)(sidx * 16), v);
-                const bool vec_chunk = QUANT || (c_aligned && nc + 16 <= p.N);
+                const bool vec_chunk = c_aligned && nc + 16 <= p.N;
                 int ct[4];
                 float bs[4];
                 if (FASTF) {
@@ -602,16 +746,6 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                     uint32_t* crow = cbase + (mrow0 + rsub) * p.ldc + (cl << 2);
                     const int64_t cstep = 8 * p.ldc;
                     const bool res_on = (EMODE == EM_DEQ_FAST) && p.residual != nullptr;
-                    // QUANT: column part of the scatter offsets for this lane's 4 columns (one head)
-                    uint32_t q_mb = q_mb0, q_ms = q_ms0;
-                    int64_t q_col = 0, q_rscol = 0;
-                    int colacc[4] = {0, 0, 0, 0};
-                    if (QUANT) {
-                        const uint32_t n_l = (uint32_t)(nc + (cl << 2));
-                        const uint32_t nh = n_l / p.q_D, nd = n_l - nh * p.q_D;
-                        q_col = nh * p.q_off[4] + nd * p.q_off[5];
-                        q_rscol = nh * p.q_rs[4] + nd * p.q_rs[5];
-                    }
                     const float* rrow = res_on ? p.residual + b * p.stride_r + (mrow0 + rsub) * p.ldr + nc + (cl << 2) : nullptr;
                     const int64_t rstep = 8 * p.ldr;
                     float4 res[4];
@@ -653,60 +787,10 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                                 f0 = __fadd_rn(f0, res[it].x); f1 = __fadd_rn(f1, res[it].y);
                                 f2 = __fadd_rn(f2, res[it].z); f3 = __fadd_rn(f3, res[it].w);
                             }
-                            if (QUANT) {
-                                // quantize for the consuming MatMul and scatter into its K-major operand
-                                const bool rv = rr < rows_left;
-                                const int w = pack4_codes(qz.code<QM>(f0), qz.code<QM>(f1), qz.code<QM>(f2), qz.code<QM>(f3));
-                                if (rv) {
-                                    int8_t* dst = reinterpret_cast<int8_t*>(p.C) + q_base + (int64_t)q_mb * p.q_off[2] +
-                                                  (int64_t)q_ms * p.q_off[3] + q_col;
-                                    if (p.q_off[5] == 1) {
-                                        *reinterpret_cast<int*>(dst) = w;
-                                    } else {
-                                        dst[0] = (int8_t)w;
-                                        dst[p.q_off[5]] = (int8_t)(w >> 8);
-                                        dst[2 * p.q_off[5]] = (int8_t)(w >> 16);
-                                        dst[3 * p.q_off[5]] = (int8_t)(w >> 24);
-                                    }
-                                }
-                                if (p.q_rowsum) {
-                                    if (p.q_rs[5] == 0) {          // sums along the columns (K axis = n): one slot per row
-                                        int s4 = rv ? __dp4a(w, 0x01010101, 0) : 0;
-                                        s4 += __shfl_xor_sync(0xffffffffu, s4, 1);
-                                        s4 += __shfl_xor_sync(0xffffffffu, s4, 2);
-                                        if (cl == 0 && rv)
-                                            atomicAdd(p.q_rowsum + q_rsbase + (int64_t)q_mb * p.q_rs[2] + (int64_t)q_ms * p.q_rs[3] + q_rscol, s4);
-                                    } else if (q_uniform) {        // sums along the rows (K axis = m): one slot per column
-                                        colacc[0] += (int)(int8_t)w; colacc[1] += (int)(int8_t)(w >> 8);
-                                        colacc[2] += (int)(int8_t)(w >> 16); colacc[3] += (int)(int8_t)(w >> 24);
-                                    } else if (rv) {               // slab straddles two images: per-element atomics
-                                        int32_t* rsp = p.q_rowsum + q_rsbase + (int64_t)q_mb * p.q_rs[2] + (int64_t)q_ms * p.q_rs[3] + q_rscol;
-                                        atomicAdd(rsp, (int)(int8_t)w);
-                                        atomicAdd(rsp + p.q_rs[5], (int)(int8_t)(w >> 8));
-                                        atomicAdd(rsp + 2 * p.q_rs[5], (int)(int8_t)(w >> 16));
-                                        atomicAdd(rsp + 3 * p.q_rs[5], (int)(int8_t)(w >> 24));
-                                    }
-                                }
-                                q_ms += 8;
-                                while (q_ms >= p.q_S) { q_ms -= p.q_S; ++q_mb; }
-                                continue;
-                            }
                             val = make_uint4(__float_as_uint(f0), __float_as_uint(f1), __float_as_uint(f2), __float_as_uint(f3));
                         }
                         if (rr < rows_left) *reinterpret_cast<uint4*>(crow) = val;
                         crow += cstep;
-                    }
-                    if (QUANT && p.q_rowsum && p.q_rs[5] != 0 && q_uniform) {
-                        // column sums of the whole 32-row slab: reduce over the 8 lanes that share `cl`
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            int v2 = colacc[k];
-                            v2 += __shfl_xor_sync(0xffffffffu, v2, 4);
-                            v2 += __shfl_xor_sync(0xffffffffu, v2, 8);
-                            v2 += __shfl_xor_sync(0xffffffffu, v2, 16);
-                            if (rsub == 0)
-                                atomicAdd(p.q_rowsum + q_rsbase + (int64_t)q_mb0 * p.q_rs[2] + q_rscol + k * p.q_rs[5], v2);
-                        }
                     }
                 } else {
                     // ragged / unaligned: one column per lane (16 columns x 2 rows per instruction)
@@ -830,7 +914,8 @@ static int launch_qgemm_mode(const CUtensorMap& ta, const CUtensorMap& tb, const
         }
     }
     if (p.mode == NQ_EPI_QUANT)
-        return p.asym_out ? launch_qgemm<BN, EM_QUANT_ASYM>(ta, tb, p, s) : launch_qgemm<BN, EM_QUANT_SYM>(ta, tb, p, s);
+        return p.q_off[5] == 1 ? launch_qgemm<BN, EM_Q8_ROWS>(ta, tb, p, s) : launch_qgemm<BN, EM_Q8_COLS>(ta, tb, p, s);
+    if (p.mode == NQ_EPI_GELU_QUANT) return launch_qgemm<BN, EM_Q8_GELU>(ta, tb, p, s);
     return p.fast32 ? launch_qgemm<BN, EM_DEQ_FAST>(ta, tb, p, s) : launch_qgemm<BN, EM_DEQ_GENERAL>(ta, tb, p, s);
 }
 
@@ -852,7 +937,7 @@ extern "C" int nq_qgemm_s8(const int8_t* A, const int8_t* B, void* Cout, int64_t
     NQ_REQUIRE(ldc >= N, "nq_qgemm_s8: ldc < N");
     NQ_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31) && batch < (1ll << 31), "nq_qgemm_s8: extent too large");
     NQ_REQUIRE(((M + 127) / 128) * ((N + 63) / 64) * batch < (1ll << 31), "nq_qgemm_s8: too many output tiles");
-    NQ_REQUIRE(ep->mode >= NQ_EPI_RAW && ep->mode <= NQ_EPI_SOFTMAX_QUANT, "nq_qgemm_s8: unknown epilogue mode %d", ep->mode);
+    NQ_REQUIRE(ep->mode >= NQ_EPI_RAW && ep->mode <= NQ_EPI_GELU_QUANT, "nq_qgemm_s8: unknown epilogue mode %d", ep->mode);
     if (ep->mode != NQ_EPI_RAW)
         if (int rc = check_acc_zp(&ep->zp)) return rc;
 
@@ -868,7 +953,8 @@ extern "C" int nq_qgemm_s8(const int8_t* A, const int8_t* B, void* Cout, int64_t
         // |acc| + |rowsum*zp_b - zp_a*zp_b*K| + |colsum*zp_a| with 8-bit operands (|q| <= 128)
         const long double za = (long double)llabs(p.zp.zp_a), zb = (long double)llabs(p.zp.zp_b);
         const long double bound = 16384.0L * K + 128.0L * K * (za + zb) + za * zb * K;
-        p.fast32 = (ep->mode == NQ_EPI_DEQUANT || ep->mode == NQ_EPI_QUANT || ep->mode == NQ_EPI_SOFTMAX_QUANT) &&
+        p.fast32 = (ep->mode == NQ_EPI_DEQUANT || ep->mode == NQ_EPI_QUANT || ep->mode == NQ_EPI_SOFTMAX_QUANT ||
+                    ep->mode == NQ_EPI_GELU_QUANT) &&
                    bound < 2147483000.0L;
     }
     if (ep->mode == NQ_EPI_SOFTMAX_QUANT) {
@@ -896,7 +982,9 @@ extern "C" int nq_qgemm_s8(const int8_t* A, const int8_t* B, void* Cout, int64_t
             p.fast22 = (ra * rb * (long double)K) < 4194304.0L;
         }
     }
-    if (ep->mode == NQ_EPI_QUANT) {
+    const bool q8 = ep->mode == NQ_EPI_QUANT || ep->mode == NQ_EPI_GELU_QUANT;
+    const int bn = (ep->mode == NQ_EPI_SOFTMAX_QUANT) ? 256 : (N <= 64) ? 64 : (N <= 128) ? 128 : 256;
+    if (q8) {
         NQ_REQUIRE(p.fast32, "nq_qgemm_s8: QUANT epilogue needs the 32-bit zero-point bound (K or zero-points too large)");
         NQ_REQUIRE(N % 16 == 0 && ep->q_cols_per_head > 0 && ep->q_cols_per_head % 16 == 0 && ep->q_rows_per_image > 0,
                    "nq_qgemm_s8: QUANT epilogue needs N and cols_per_head multiples of 16");
@@ -912,12 +1000,39 @@ extern "C" int nq_qgemm_s8(const int8_t* A, const int8_t* B, void* Cout, int64_t
             p.q_rs[i] = ep->q_rs[i];
         }
         p.q_rowsum = ep->q_rowsum;
+        if (ep->q_off[5] == 1) {
+            // ROWS: 16 consecutive n are one aligned 16-byte store
+            for (int i = 0; i < 5; ++i)
+                NQ_REQUIRE(ep->q_off[i] % 16 == 0, "nq_qgemm_s8: QUANT row layout needs q_off[0..4] multiples of 16 bytes");
+            NQ_REQUIRE(((uintptr_t)Cout & 15) == 0, "nq_qgemm_s8: QUANT destination must be 16-byte aligned");
+            NQ_REQUIRE(!ep->q_rowsum || ep->q_rs[5] == 0, "nq_qgemm_s8: QUANT row layout sums codes along n (q_rs[5] == 0)");
+            // one warp owns bn/4 consecutive columns of a row: a (row, head) slot has a single writer when
+            // the heads tile that span and the slot does not depend on the batch-inner / other tiles
+            const int wcols = bn / 4;
+            p.q_rs_exclusive = (wcols % ep->q_cols_per_head == 0) && ep->q_rs[4] != 0 && ep->q_rs[3] != 0 &&
+                               (ep->c_batch_inner <= 1 || ep->q_rs[1] != 0);
+        } else {
+            NQ_REQUIRE(ep->mode == NQ_EPI_QUANT && ep->q_off[3] == 1,
+                       "nq_qgemm_s8: QUANT column layout needs q_off[3] == 1 (consecutive m are consecutive bytes)");
+            NQ_REQUIRE(!ep->q_rowsum || ep->q_rs[3] == 0, "nq_qgemm_s8: QUANT column layout sums codes along m (q_rs[3] == 0)");
+        }
+        if (ep->q_rowsum && !p.q_rs_exclusive) {
+            // partial sums meet through atomics: the library clears the slots itself (stream-ordered)
+            NQ_REQUIRE(ep->q_rowsum_count > 0, "nq_qgemm_s8: q_rowsum_count (number of int32 slots) is required with q_rowsum");
+            cudaError_t e = cudaMemsetAsync(ep->q_rowsum, 0, sizeof(int32_t) * (size_t)ep->q_rowsum_count, (cudaStream_t)stream);
+            if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(q_rowsum)");
+        }
+        if (ep->mode == NQ_EPI_GELU_QUANT) {
+            NQ_REQUIRE(ep->gelu_div != 0.f && isfinite(ep->gelu_div), "nq_qgemm_s8: GELU divisor must be finite and non-zero");
+            p.g_rdiv = 1.0f / ep->gelu_div;
+            p.g_add = ep->gelu_add;
+            p.g_mul = ep->gelu_mul;
+        }
     }
     p.bias_f32 = ep->bias_f32;
     p.bias_q = ep->bias_q;
     p.c_inner = ep->c_batch_inner > 1 ? ep->c_batch_inner : 1;
     p.stride_c_inner = ep->c_batch_inner > 1 ? ep->stride_c_inner : 0;
-    if (ep->mode == NQ_EPI_QUANT) p.c_inner = ep->c_batch_inner > 1 ? ep->c_batch_inner : 1;
     NQ_REQUIRE(p.c_inner == 1 || (batch % p.c_inner == 0 && ep->mode != NQ_EPI_REQUANT),
                "nq_qgemm_s8: c_batch_inner must divide batch (and is not available with REQUANT)");
     p.residual = (ep->mode == NQ_EPI_DEQUANT) ? ep->residual : nullptr;
@@ -934,7 +1049,6 @@ extern "C" int nq_qgemm_s8(const int8_t* A, const int8_t* B, void* Cout, int64_t
         p.hi = ldexpf(1.f, ep->out_bits - 1) - 1.f;
     }
 
-    const int bn = (ep->mode == NQ_EPI_SOFTMAX_QUANT) ? 256 : (N <= 64) ? 64 : (N <= 128) ? 128 : 256;
     CUtensorMap ta, tb;
     if (int rc = make_operand_map(&ta, A, K, M, p.a_batched ? batch : 1, lda, stride_a, BM)) return rc;
     if (int rc = make_operand_map(&tb, B, K, N, p.b_batched ? batch : 1, ldb, stride_b, bn)) return rc;

@@ -280,9 +280,13 @@ def qgemm(a: Operand, b: Operand, mode: int = _lib.EPI_RAW, scale: float = 1.0,
 
 
 def qgemm_to_operand(a: Operand, b: Operand, scale: float, azp: AccZeroPoint, bias_f32: Optional[torch.Tensor],
-                     bits: int, out_scale, out_zp, kind: str, heads: int, seq: int, want_rowsum: bool) -> Operand:
+                     bits: int, out_scale, out_zp, kind: str, heads: int, seq: int, want_rowsum: bool,
+                     gelu: Optional[tuple] = None) -> Operand:
     """GEMM whose epilogue quantizes the float result (bias + dequant) with the consumer's parameters
     and scatters the codes straight into the K-major operand of the NEXT MatMul (NQ_EPI_QUANT).
+    gelu=(c1, c2, c3) applies the graph's Div/Erf/Add/Mul/Mul chain first (NQ_EPI_GELU_QUANT, kind 'rows').
+
+      kind 'rows'        GEMM [batch, M, N] -> operand [batch, M, N] (plain left operand)
 
       kind 'split_rows'  GEMM [B*S, H*D] -> operand [B*H, S, D]      (attention Q as A, K^T as B)
       kind 'split_cols'  GEMM [B*S, H*D] -> operand [B*H, D, S]      (attention V as B)
@@ -329,14 +333,27 @@ def qgemm_to_operand(a: Operand, b: Operand, scale: float, azp: AccZeroPoint, bi
         n_rs = B * S
         ep.q_rows_per_image, ep.q_cols_per_head = S, D
         ep.c_batch_inner = H
+    elif kind == "rows":
+        # plain [batch, M, N] row-major operand (left operand of the next MatMul contracting over N)
+        ld = round_up(N, 16)
+        assert ld == N
+        out = torch.empty((batch, M, ld), dtype=torch.int8, device=dev)
+        lead = a.batch_shape if a.batch == batch else b.batch_shape
+        res = Operand(out, tuple(lead), M, N, ld, None)
+        off = [M * ld, 0, 0, ld, 0, 1]
+        rs = [M, 0, 0, 1, 0, 0]
+        n_rs = batch * M
+        ep.q_rows_per_image, ep.q_cols_per_head = M, N
     else:
         raise ValueError(kind)
     for i in range(6):
         ep.q_off[i], ep.q_rs[i] = off[i], rs[i]
+    if gelu is not None:
+        ep.mode = _lib.EPI_GELU_QUANT
+        ep.gelu_div, ep.gelu_add, ep.gelu_mul = (float(c) for c in gelu)
     if want_rowsum:
         res.rowsum = torch.empty((n_rs,), dtype=torch.int32, device=dev).view(res.batch, res.rows)
-        call("nq_memset_async", res.rowsum.data_ptr(), 0, 4 * n_rs, _stream())
-        ep.q_rowsum = res.rowsum.data_ptr()
+        ep.q_rowsum, ep.q_rowsum_count = res.rowsum.data_ptr(), n_rs     # the library clears them when it needs to
     sa = 0 if (a.batch == 1 and batch > 1) else M * a.ld
     sb = 0 if (b.batch == 1 and batch > 1) else N * b.ld
     timer = GEMM_TIMER
@@ -372,8 +389,7 @@ def qgemm_softmax_to_operand(a: Operand, b: Operand, scale: float, azp: AccZeroP
     ep.has_out_zp, ep.out_zp = int(out_zp is not None), 0 if out_zp is None else int(out_zp)
     ep.sm_has_div, ep.sm_div = int(div_c is not None), 1.0 if div_c is None else float(div_c)
     if want_rowsum:
-        res.rowsum = torch.empty((batch, M), dtype=torch.int32, device=dev)
-        call("nq_memset_async", res.rowsum.data_ptr(), 0, 4 * batch * M, _stream())
+        res.rowsum = torch.empty((batch, M), dtype=torch.int32, device=dev)      # plain stores: no clearing needed
         ep.q_rowsum = res.rowsum.data_ptr()
     sa = 0 if (a.batch == 1 and batch > 1) else M * a.ld
     sb = 0 if (b.batch == 1 and batch > 1) else N * b.ld

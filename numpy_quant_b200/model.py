@@ -432,6 +432,7 @@ class QModel(Model):
         # probability within ~1e-7 of a rounding boundary may quantize to the neighbouring code.  Set to
         # False to keep retain=False bit-identical to the node-by-node run.
         self.fuse_softmax_epilogue = True
+        self.fuse_gelu_epilogue = True
         self._graphs: dict = {}
         self._graph_launches: dict = {}
 
@@ -479,7 +480,7 @@ class QModel(Model):
         producers = {o.name: n for n in self.nodes for o in n.outputs}
         by_name = {n.name: n for n in self.nodes}
         plan = dict(gelu=find_gelu_chains(self.nodes), softmax={}, skip=set(), emit={}, quantize_out=set(), node=by_name,
-                    residual={}, to_operand={}, merge_heads={})
+                    residual={}, to_operand={}, merge_heads={}, gelu_in={})
         for first, spec in plan["gelu"].items():
             plan["skip"].update(spec[4])
             plan["emit"][spec[5]] = first
@@ -550,6 +551,17 @@ class QModel(Model):
         for name, out in emitters.items():
             if self._feeds_only_matmul_lhs(out):
                 plan["quantize_out"].add(name)
+        # bias Add whose value is consumed only by a GELU chain that feeds MatMul left operands: the GEMM
+        # producing the Add's accumulator can run bias + GELU + quantize in its epilogue
+        for first, spec in plan["gelu"].items():
+            x, last = spec[0], spec[5]
+            if last not in plan["quantize_out"] or not isinstance(x, Variable) or not x.inputs:
+                continue
+            add = x.inputs[0]
+            chain = {first, *spec[4], last}
+            if add.op == "Add" and all(c.name in chain for c in x.outputs) and not any(x is o for o in self.outputs) \
+                    and add.name not in plan["residual"] and add.name not in plan["to_operand"]:
+                plan["gelu_in"][add.name] = first
         return plan
 
     # ------------------------------------------------------------------------------
@@ -601,7 +613,7 @@ class QModel(Model):
         replay it: ~200 kernel launches become one graph launch, so the host interpreter loop
         (Python + ctypes per node) disappears from the steady state.  Quantization parameters are
         static after calibration, so the launch sequence depends on shapes only."""
-        key = tuple((tuple(a.shape), str(a.dtype)) for a in inputs) + (self.fuse_softmax_epilogue,)
+        key = tuple((tuple(a.shape), str(a.dtype)) for a in inputs) + (self.fuse_softmax_epilogue, self.fuse_gelu_epilogue)
         entry = self._graphs.get(key)
         dev = torch.device("cuda", torch.cuda.current_device())
         if entry is None:
@@ -651,7 +663,7 @@ class QModel(Model):
             if profile:
                 raise ValueError("profile=True needs the eager interpreter (graph=False)")
             if not torch.cuda.is_current_stream_capturing():
-                key = tuple((tuple(a.shape), str(a.dtype)) for a in inputs) + (self.fuse_softmax_epilogue,)
+                key = tuple((tuple(a.shape), str(a.dtype)) for a in inputs) + (self.fuse_softmax_epilogue, self.fuse_gelu_epilogue)
                 if key not in self._graphs:
                     before = K.LAUNCHES
                     out = self._graph_call(inputs, device_outputs)
@@ -687,7 +699,7 @@ class QModel(Model):
         if fused and self._plan is None:
             self._plan = self._build_plan()
         plan = self._plan if fused else dict(gelu={}, softmax={}, skip=set(), emit={}, quantize_out=set(), node={},
-                                             residual={}, to_operand={}, merge_heads={})
+                                             residual={}, to_operand={}, merge_heads={}, gelu_in={})
         dyn_skip: set = set()
         qcache: dict = {}
         stash: dict = {}
@@ -703,7 +715,9 @@ class QModel(Model):
         for node in self.nodes:
             name = node.name
             out0 = node.outputs[0] if node.outputs else None
-            if name in plan["gelu"]:
+            if name in dyn_skip:
+                outputs_data = [None]
+            elif name in plan["gelu"]:
                 # ---- GELU chain in one kernel (optionally emitting the next MatMul's int8 operand)
                 x, c1, c2, c3, _, last = plan["gelu"][name]
                 xin = as_float(x)
@@ -798,6 +812,23 @@ class QModel(Model):
                         o.data = tensor
                     self._release_inputs(node, remaining, keep, qcache)
                     continue
+                gspec = plan["gelu_in"].get(name) if self.fuse_gelu_epilogue else None
+                if gspec is not None:
+                    # bias Add -> GELU chain -> MatMul left operand: all in this GEMM's epilogue
+                    first, (_, c1, c2, c3, _, last) = gspec, plan["gelu"][gspec]
+                    lastv = plan["node"][last].outputs[0]
+                    qp = self.quant_params[lastv.name]
+                    qg = acc.data.gelu_into_operand(b, (c1, c2, c3), bits, qp.scale, qp.zero_point, self._rowsum_needed(lastv))
+                    if qg is not None:
+                        qcache[(lastv.name, "A")] = qg
+                        stash[last] = None
+                        dyn_skip.add(first)
+                        outputs_data = [None]
+                        tock(node.op, t0)
+                        for o, tensor in zip(node.outputs, outputs_data):
+                            o.data = tensor
+                        self._release_inputs(node, remaining, keep, qcache)
+                        continue
                 res_spec = plan["residual"].get(name)
                 resid = res_spec[0].data if res_spec else None
                 if isinstance(resid, FTensor) and tuple(resid.device_tensor.shape) == tuple(acc.data.shape):

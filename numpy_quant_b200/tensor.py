@@ -424,6 +424,34 @@ class QTensor:
             return None
         return qtensor_from_operand(op, role, logical_shape, bit_width, scale, zero_point)
 
+    def gelu_into_operand(self, bias: Optional[FTensor], consts: tuple, bit_width: int, scale, zero_point,
+                          want_rowsum: bool):
+        """dequantize (+ bias) -> Div/Erf/Add/Mul/Mul (GELU) -> quantize for the next MatMul's left operand, all
+        inside the epilogue of the pending GEMM (NQ_EPI_GELU_QUANT).  Float glue under the 1e-5 contract, so the
+        codes may differ from the node-by-node route where the float value sits on a rounding boundary.
+        Returns None when this accumulator does not qualify."""
+        L = self._lazy
+        zo = _as_opt_int(zero_point)
+        if not self._pending() or L.get("bias_q") is not None or (zo is not None and abs(zo) >= (1 << 20)):
+            return None
+        nb = int(np.prod(L["batch_shape"] or (1,)))
+        flat = L["a"].batch == 1 and L["b"].batch == 1 and nb > 1          # shared-weight GEMM run as one flat batch
+        if L["N"] % 16 or L["a"].rows != (nb * L["M"] if flat else L["M"]):
+            return None
+        try:
+            op = K.qgemm_to_operand(L["a"], L["b"], float(self.scale), self._zp,
+                                    None if bias is None else bias.device_tensor.contiguous(), bit_width,
+                                    float(scale), zo, "rows", 1, L["a"].rows, want_rowsum,
+                                    gelu=tuple(float(c) for c in consts))
+        except _lib.NqError:
+            return None
+        if flat:
+            rs = None if op.rowsum is None else op.rowsum.view(nb, L["M"])
+            op = K.Operand(op.data.view(nb, L["M"], op.ld), tuple(L["batch_shape"]), L["M"], op.k, op.ld, rs)
+        else:
+            op.batch_shape = tuple(L["batch_shape"])
+        return qtensor_from_operand(op, "A", tuple(L["batch_shape"]) + (L["M"], L["N"]), bit_width, scale, zero_point)
+
     def softmax_into_operand(self, div_c, bit_width: int, scale, zero_point, want_rowsum: bool):
         """dequantize -> [/ c] -> softmax(last axis) -> quantize for the next MatMul (as its left operand),
         all inside the epilogue of the pending attention-score GEMM.  None when not applicable."""

@@ -351,6 +351,38 @@ def test_qgemm_softmax_epilogue(N, div):
             assert np.abs((gc - zp).sum(-1) / 255.0 - 1).max() < 0.6
 
 
+@pytest.mark.parametrize("zp", [None, -7, 12])
+def test_qgemm_gelu_epilogue(zp):
+    """NQ_EPI_GELU_QUANT vs the separate route (GEMM -> dequant + bias -> GELU chain -> quantize).  The fused
+    GELU is float glue under the 1e-5 contract: every code must be the round-half-even of a value within
+    1e-5 (relative, plus 1e-6 of the tensor's range) of the reference float GELU / scale + zp; row sums
+    must match the emitted codes exactly."""
+    rng = np.random.default_rng(11)
+    M, N, Kd = 300, 192, 96
+    a = rng.integers(-128, 128, size=(1, M, Kd)).astype(np.int8)
+    w = rng.integers(-128, 128, size=(1, Kd, N)).astype(np.int8)
+    bias = dev(rng.normal(size=N).astype(np.float32))
+    oa, ob = K.operand_from_codes(dev(a), "A", False), K.operand_from_codes(dev(w), "B", True)
+    azp = K.AccZeroPoint(5, None, Kd, None, ob.rowsum, True)
+    sc, so = 2.0e-5, 0.03
+    c = (1.4142135381698608, 1.0, 0.5)
+    f = K.qgemm(oa, ob, _lib.EPI_DEQUANT, sc, azp, bias_f32=bias)
+    ref = K.gelu_quantize(f, *c, 8, so, zp, True)
+    got = K.qgemm_to_operand(oa, ob, sc, azp, bias, 8, so, zp, "rows", 1, M, True, gelu=c)
+    gc, rc = host(got.data).astype(np.int64), host(ref.data).astype(np.int64)
+    assert gc.shape == rc.shape == (1, M, N)
+    assert np.abs(gc - rc).max() <= 1 and np.mean(gc != rc) < 5e-3, (np.abs(gc - rc).max(), np.mean(gc != rc))
+    np.testing.assert_array_equal(host(got.rowsum).astype(np.int64).reshape(1, M), gc.sum(-1))
+    # contract check against the float64 evaluation of the reference chain on the same float32 inputs
+    x = host(f).astype(np.float64)
+    g = rq.erf_poly(x / c[0])
+    g = (g + c[1]) * x * c[2]
+    t = g / so + (0 if zp is None else zp)
+    tol = 0.5 + (1e-5 * np.abs(g) + 1e-6 * np.abs(g).max()) / so + 1e-9
+    t = np.clip(t, -128, 127)
+    assert (np.abs(gc - t) <= tol).all(), float((np.abs(gc - t) - tol).max())
+
+
 def test_qgemm_rejects_bad_arguments():
     a = torch.zeros((1, 4, 8), dtype=torch.int8, device=DEV)
     ep = _lib.Epilogue()
