@@ -23,7 +23,7 @@ constexpr int BM = 128;          // rows of A per tile == TMEM lanes
 constexpr int BK = 128;          // int8 elements per stage along K == one 128-byte swizzle row
 constexpr int UMMA_K = 32;       // K per tcgen05.mma for 8-bit operands
 constexpr int NUM_EPI_WARPS = 16;
-constexpr int NUM_THREADS = 128 + 32 * NUM_EPI_WARPS;
+constexpr int NUM_THREADS = 128 + 32 * NUM_EPI_WARPS;  // 640 threads; registers re-balanced with setmaxnreg (56 / 104)
 
 template <int BN> struct Cfg {
     static constexpr int STAGES = (BN == 256) ? 4 : 6;
@@ -63,7 +63,7 @@ struct GemmParams {
     int32_t* q_rowsum;
     // SOFTMAX epilogue: softmax(dequant / sm_div) over the (single) N tile, quantized with qargs
     int q_rs_exclusive;              // Q8 ROWS: every (row, head) row-sum slot is written by exactly one warp: plain store
-    float g_rdiv, g_add, g_mul;      // GELU_QUANT: 1 / c1, c2, c3 of the Div -> Erf -> Add -> Mul -> Mul chain
+    float g_prdiv, g_nl2e, g_add, g_out;   // GELU_QUANT: 0.3275911 / c1, -log2(e) / c1^2, c2, c3 / s_out
     int fast22;                      // SOFTMAX: |acc - zero-point terms| < 2^22 proved on the host (magic int->float route)
 };
 
@@ -79,18 +79,27 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-// Bounded wait: a protocol bug traps (launch fails with an error) instead of hanging the GPU.
+// Bounded wait: a protocol bug traps (launch fails with an error) instead of hanging the GPU: the wall-clock
+// bound (4 s on %globaltimer, checked every 256 polls) holds whether or not the hardware honours the suspend
+// hint.  The hint (20 us) lets the hardware park the thread until the phase completes instead of re-polling --
+// poll instructions of waiting warps compete with the epilogue warps for issue slots.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
-    for (uint32_t spin = 0; !done; ++spin) {
+    uint64_t t0 = 0;
+    for (uint32_t spin = 1; !done; ++spin) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done)
-            : "r"(bar), "r"(parity)
+            : "r"(bar), "r"(parity), "r"(20000u)
             : "memory");
-        if (!done && spin > (1u << 26)) __trap();
+        if (!done && (spin & 255u) == 0) {
+            uint64_t now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 4000000000ull) __trap();
+        }
     }
 }
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
@@ -192,21 +201,20 @@ __device__ __forceinline__ int64_t tile_zp(const AccZp& z, int64_t rowterm, int6
 // 1e-5 contract.  Same Abramowitz & Stegun 7.1.26 erf as numpy_helper.py:95-112 with the
 // polynomial as fused multiply-adds, 1/(1 + p|u|) and exp(-u^2) on the MUFU: 16 instructions + 2 MUFU per element
 // (the standalone kernels keep one IEEE rounding per ONNX node).
-__device__ __forceinline__ float gelu_fast(float x, float rdiv, float c_add, float c_mul) {
+__device__ __forceinline__ float gelu_fast(float x, float p_rdiv, float nl2e_rdiv2, float c_add, float c_out) {
+    // u = x / c1 enters only as |u| (p_rdiv = 0.3275911 / c1), u^2 (nl2e_rdiv2 = -log2(e) / c1^2) and its sign
     const float a1 = 0.254829592f, a2 = -0.284496736f, a3 = 1.421413741f, a4 = -1.453152027f, a5 = 1.061405429f;
-    const float u = __fmul_rn(x, rdiv);
-    const float ax = fabsf(u);
     float t, e;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(__fmaf_rn(0.3275911f, ax, 1.0f)));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(__fmaf_rn(p_rdiv, fabsf(x), 1.0f)));
     float y = __fmaf_rn(a5, t, a4);
     y = __fmaf_rn(y, t, a3);
     y = __fmaf_rn(y, t, a2);
     y = __fmaf_rn(y, t, a1);
     y = __fmul_rn(y, t);
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(__fmul_rn(__fmul_rn(ax, ax), -1.44269502162933349609375f)));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(__fmul_rn(__fmul_rn(x, x), nl2e_rdiv2)));
     y = __fmaf_rn(-y, e, 1.0f);
-    const float erf_u = __int_as_float(__float_as_int(y) ^ (__float_as_int(u) & 0x80000000));   // sign(u) * y
-    return __fmul_rn(__fmul_rn(x, __fadd_rn(erf_u, c_add)), c_mul);
+    const float erf_u = __int_as_float(__float_as_int(y) ^ (__float_as_int(x) & 0x80000000));   // sign(u) * y, c1 > 0
+    return __fmul_rn(__fmul_rn(x, __fadd_rn(erf_u, c_add)), c_out);      // c_out = c3 / s_out: the quotient to round
 }
 
 constexpr int EM_RAW = 0, EM_DEQ_FAST = 1, EM_DEQ_GENERAL = 2, EM_REQUANT = 3, EM_Q8_ROWS = 4, EM_Q8_COLS = 5,
@@ -264,6 +272,11 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // Register re-balancing between the warpgroups.  The pool is what the CTA got at launch (640 threads x 96 =
+    // 61440 registers): the producer / MMA / allocator warpgroup shrinks to 56 per thread, the four epilogue
+    // warpgroups grow to 104 (128 * 56 + 512 * 104 = 60416 <= 61440; an over-subscribed .inc would block forever).
+    if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
@@ -328,7 +341,9 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
             }
         }
         __syncwarp();
-    } else if (warp >= 4) {
+    }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
         // ===================== epilogue (16 warps) =====================
         // The epilogue is a long dependent instruction stream per element, so it is throughput-
         // bound by how many warps each SM sub-partition can interleave: 16 warps (4 per scheduler),
@@ -409,6 +424,7 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                         else atomicAdd(slot, rs_acc);
                     }
                 };
+                uint32_t nh = (uint32_t)(n0 + wcol0) / p.q_D, nd = (uint32_t)(n0 + wcol0) - nh * p.q_D;
 #pragma unroll 1
                 for (int i = 0; i < CPW; ++i) {
                     const int cw = wcol0 + i * 16;
@@ -434,24 +450,39 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                     if (__builtin_expect((bad & 0xFF800000u) != 0, 0)) {  // some |d| >= 2^22: exact slow route
 #pragma unroll
                         for (int j = 0; j < 16; ++j) f[j] = deq_slow(x[j] - 0x4B400000, p.scale);
-                    } else {
+                    } else if constexpr (EMODE != EM_Q8_GELU) {
 #pragma unroll
                         for (int j = 0; j < 16; ++j) f[j] = __fmul_rn(__fadd_rn(__int_as_float(x[j]), -12582912.0f), p.scale);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) f[j] = __fadd_rn(__int_as_float(x[j]), -12582912.0f);   // scaled below
                     }
+                    const bool gelu_scaled = (bad & 0xFF800000u) != 0;    // warp-divergent only on the rare slow route
                     int w[4];
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
                         const float4 b4 = *reinterpret_cast<const float4*>(bsw + i * 16 + g * 4);
-                        float y0 = __fadd_rn(b4.x, f[4 * g]), y1 = __fadd_rn(b4.y, f[4 * g + 1]);
-                        float y2 = __fadd_rn(b4.z, f[4 * g + 2]), y3 = __fadd_rn(b4.w, f[4 * g + 3]);
                         if constexpr (EMODE == EM_Q8_GELU) {
-                            y0 = gelu_fast(y0, p.g_rdiv, p.g_add, p.g_mul); y1 = gelu_fast(y1, p.g_rdiv, p.g_add, p.g_mul);
-                            y2 = gelu_fast(y2, p.g_rdiv, p.g_add, p.g_mul); y3 = gelu_fast(y3, p.g_rdiv, p.g_add, p.g_mul);
+                            // float glue (1e-5 contract): dequant * scale + bias as one FMA, GELU, and the
+                            // quantizer's division folded into the chain's last constant
+                            const float sc = gelu_scaled ? 1.0f : p.scale;
+                            const float y0 = gelu_fast(__fmaf_rn(f[4 * g], sc, b4.x), p.g_prdiv, p.g_nl2e, p.g_add, p.g_out);
+                            const float y1 = gelu_fast(__fmaf_rn(f[4 * g + 1], sc, b4.y), p.g_prdiv, p.g_nl2e, p.g_add, p.g_out);
+                            const float y2 = gelu_fast(__fmaf_rn(f[4 * g + 2], sc, b4.z), p.g_prdiv, p.g_nl2e, p.g_add, p.g_out);
+                            const float y3 = gelu_fast(__fmaf_rn(f[4 * g + 3], sc, b4.w), p.g_prdiv, p.g_nl2e, p.g_add, p.g_out);
+                            w[g] = pack4_codes(qz.template code_of_quotient<1>(y0), qz.template code_of_quotient<1>(y1),
+                                               qz.template code_of_quotient<1>(y2), qz.template code_of_quotient<1>(y3));
+                        } else {
+                            const float y0 = __fadd_rn(b4.x, f[4 * g]), y1 = __fadd_rn(b4.y, f[4 * g + 1]);
+                            const float y2 = __fadd_rn(b4.z, f[4 * g + 2]), y3 = __fadd_rn(b4.w, f[4 * g + 3]);
+                            w[g] = pack4_codes(qz.template code<1>(y0), qz.template code<1>(y1), qz.template code<1>(y2),
+                                               qz.template code<1>(y3));
                         }
-                        w[g] = pack4_codes(qz.template code<1>(y0), qz.template code<1>(y1), qz.template code<1>(y2),
-                                           qz.template code<1>(y3));
                     }
-                    const uint32_t nu = (uint32_t)nc, nh = nu / p.q_D, nd = nu - nh * p.q_D;
+                    if (i > 0) {                                          // next 16 columns: step (head, column in head)
+                        nd += 16;
+                        if (nd >= p.q_D) { nd = 0; ++nh; }
+                    }
                     if constexpr (EMODE == EM_Q8_COLS) {
                         // out[.., nd + j, ms]: consecutive lanes are consecutive bytes
                         int8_t* dst = reinterpret_cast<int8_t*>(p.C) + row_off + (int64_t)nh * p.q_off[4] + (int64_t)nd * p.q_off[5];
@@ -571,29 +602,38 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                     constexpr bool MAGIC = decltype(magic_tag)::value;
                     // MAGIC: |d| < 2^22 proved on the host -> x is the bit pattern of 1.5*2^23 + d
                     const int rm = (MAGIC ? 0x4B400000 : 0) - (int32_t)rowterm;
+                    // accumulator columns in steps of 16 (8 for the odd last group): half as many TMEM round trips
 #pragma unroll
-                    for (int j = 0; j < NSUB; ++j) {
-                        if (j * 8 < ncols_w) {                            // warp-uniform
-                            uint32_t a8[8];
-                            tmem_ld_32x32b_x8(t_row + (uint32_t)(col0 + j * 8), a8);
+                    for (int j2 = 0; j2 < NSUB; j2 += 2) {
+                        if (j2 * 8 < ncols_w) {                           // warp-uniform
+                            uint32_t a16[16];
+                            const bool two = (j2 + 1 < NSUB) && ((j2 + 1) * 8 < ncols_w);
+                            if (two) tmem_ld_32x32b_x16(t_row + (uint32_t)(col0 + j2 * 8), a16);
+                            else tmem_ld_32x32b_x8(t_row + (uint32_t)(col0 + j2 * 8), a16);
                             // column terms staged by this warp before the accumulator wait (broadcast LDS)
-                            const int4 ca = *reinterpret_cast<const int4*>(ctw + j * 8);
-                            const int4 cb = *reinterpret_cast<const int4*>(ctw + j * 8 + 4);
-                            const int c8[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
-                            tmem_ld_wait();
-                            const bool ragged = j * 8 + 8 > ncols_w;      // warp-uniform: only the last group
+                            int c16[16];
 #pragma unroll
-                            for (int k = 0; k < 8; ++k) {
-                                const int x = (int)a8[k] + rm - c8[k];
+                            for (int g = 0; g < 4; ++g) {
+                                const int4 c4 = *reinterpret_cast<const int4*>(ctw + j2 * 8 + g * 4);
+                                c16[4 * g] = c4.x; c16[4 * g + 1] = c4.y; c16[4 * g + 2] = c4.z; c16[4 * g + 3] = c4.w;
+                            }
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int k = 0; k < 16; ++k) {
+                                if (j2 * 8 + k >= NSUB * 8) break;        // compile time: the 7th group is 8 wide
+                                const bool live = k < 8 || two;           // warp-uniform
+                                const bool ragged = j2 * 8 + (k < 8 ? 8 : 16) > ncols_w;
+                                const int x = (int)a16[k] + rm - c16[k];
                                 float f = MAGIC ? __fmul_rn(__fadd_rn(__int_as_float(x), -12582912.0f), p.scale)
                                                 : __fmul_rn(__int2float_rn(x), p.scale);
-                                if (ragged) f = (j * 8 + k < ncols_w) ? f : kMasked;
-                                y[j * 8 + k] = f;
+                                if (!live || (ragged && j2 * 8 + k >= ncols_w)) f = kMasked;
+                                y[j2 * 8 + k] = f;
                                 lmax = fmaxf(lmax, f);
                             }
                         } else {
 #pragma unroll
-                            for (int k = 0; k < 8; ++k) y[j * 8 + k] = kMasked;
+                            for (int k = 0; k < 16; ++k)
+                                if (j2 * 8 + k < NSUB * 8) y[j2 * 8 + k] = kMasked;
                         }
                     }
                 };
@@ -1024,9 +1064,11 @@ extern "C" int nq_qgemm_s8(const int8_t* A, const int8_t* B, void* Cout, int64_t
         }
         if (ep->mode == NQ_EPI_GELU_QUANT) {
             NQ_REQUIRE(ep->gelu_div != 0.f && isfinite(ep->gelu_div), "nq_qgemm_s8: GELU divisor must be finite and non-zero");
-            p.g_rdiv = 1.0f / ep->gelu_div;
+            NQ_REQUIRE(ep->gelu_div > 0.f, "nq_qgemm_s8: GELU epilogue needs a positive divisor (sign(x / c1) = sign(x))");
+            p.g_prdiv = (float)(0.3275911 / (double)ep->gelu_div);
+            p.g_nl2e = (float)(-1.4426950408889634 / ((double)ep->gelu_div * (double)ep->gelu_div));
             p.g_add = ep->gelu_add;
-            p.g_mul = ep->gelu_mul;
+            p.g_out = (float)((double)ep->gelu_mul / (double)ep->out_scale);
         }
     }
     p.bias_f32 = ep->bias_f32;
