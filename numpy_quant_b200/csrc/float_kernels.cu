@@ -103,8 +103,9 @@ struct Dims4 {
     int64_t d[4], sa[4], sb[4];
 };
 
-// MODE 0: generic strided; 1: a,b,out contiguous same shape (float4); 2: a contiguous, b a
-// row vector over the last dim (bias) (float4); 3: a contiguous, b a scalar.
+// MODE 0: generic strided; 1: a,b,out contiguous same shape (float4); 2: a contiguous, b a contiguous
+// trailing block broadcast over the leading dims (bias row, position embeddings; float4, block length passed
+// in g.sa[0]); 3: a contiguous, b a scalar.
 template <int OP, int MODE>
 __global__ void __launch_bounds__(256) binary_kernel(const float* __restrict__ a, const float* __restrict__ b,
                                                     Dims4 g, int64_t n, float* __restrict__ out) {
@@ -127,7 +128,7 @@ __global__ void __launch_bounds__(256) binary_kernel(const float* __restrict__ a
         const int64_t n4 = n >> 2;
         const float4* a4 = reinterpret_cast<const float4*>(a);
         float4* o4 = reinterpret_cast<float4*>(out);
-        const int64_t c4 = g.d[3] >> 2;
+        const int64_t c4 = g.sa[0] >> 2;                              // MODE 2: float4s in b's contiguous trailing block (host)
         float sb = (MODE == 3) ? b[0] : 0.f;
         if (MODE == 3 && OP == NQ_BIN_DIV) {
             const FastDiv dv = make_fastdiv(sb);
@@ -183,16 +184,33 @@ __global__ void __launch_bounds__(256) layernorm_vec_kernel(const float* __restr
     const int c4 = cols >> 2;
     const float fn = (float)cols;
     const Quantizer qz(qa);
-    for (int64_t row = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); row < rows; row += warps) {
-        const float4* src = reinterpret_cast<const float4*>(x + row * ldx);
-        float4 v[NV];
-        float s = 0.f;
+    // Rows are software-pipelined (NV <= 8): the next row of this warp is already in flight while the current
+    // one is reduced, normalised and stored -- one row per warp at a time leaves HBM latency exposed.
+    constexpr bool PIPE = NV <= 8;
+    auto load_row = [&](int64_t r, float4* dstv) {
+        const float4* src = reinterpret_cast<const float4*>(x + r * ldx);
 #pragma unroll
         for (int j = 0; j < NV; ++j) {
             const int c = lane + j * 32;
-            v[j] = (c < c4) ? __ldcs(src + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-            s = __fadd_rn(s, __fadd_rn(__fadd_rn(v[j].x, v[j].y), __fadd_rn(v[j].z, v[j].w)));
+            dstv[j] = (c < c4 && r < rows) ? __ldcs(src + c) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
+    };
+    const int64_t row0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    float4 nx[PIPE ? NV : 1];
+    if (PIPE) load_row(row0, nx);
+    for (int64_t row = row0; row < rows; row += warps) {
+        float4 v[NV];
+        if (PIPE) {
+#pragma unroll
+            for (int j = 0; j < NV; ++j) v[j] = nx[j];
+            load_row(row + warps, nx);
+        } else {
+            load_row(row, v);
+        }
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < NV; ++j)
+            s = __fadd_rn(s, __fadd_rn(__fadd_rn(v[j].x, v[j].y), __fadd_rn(v[j].z, v[j].w)));
         const float mean = __fdiv_rn(warp_sum(s), fn);
         float ss = 0.f;
 #pragma unroll
@@ -452,6 +470,73 @@ __global__ void __launch_bounds__(256) im2col_kernel(const T* __restrict__ x, in
     }
 }
 
+// One CTA per (b, oh): the kh input rows of every channel are read once, coalesced along w, into shared
+// memory [c][ii][w]; the OW patch rows (each ldo elements, contiguous in the output) are written from there,
+// one warp per patch row.  A per-CTA table maps an output column (ii, j, c) to its tile offset, so the inner
+// loops carry no integer division.  int8 (VEC4): 4 bytes per thread on both sides.
+template <typename T, bool VEC4>
+__global__ void __launch_bounds__(256) im2col_strip_kernel(const T* __restrict__ x, int C, int H, int W, int kh, int kw,
+                                                          int ph0, int pw0, int sh, int sw, int OH, int OW, T pad,
+                                                          T* __restrict__ out, int ldo) {
+    extern __shared__ __align__(16) unsigned char im_smem[];
+    const int kcols = kh * kw * C;
+    uint32_t* lut = reinterpret_cast<uint32_t*>(im_smem);                 // [kcols]: (j << 24) | (c * kh + ii) * W
+    T* tile = reinterpret_cast<T*>(im_smem + (((size_t)kcols * 4 + 15) & ~(size_t)15));
+    const int oh = blockIdx.x % OH;
+    const int64_t b = blockIdx.x / OH;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    for (int col = threadIdx.x; col < kcols; col += blockDim.x) {
+        const int c = col % C, ij = col / C, j = ij % kw, ii = ij / kw;
+        lut[col] = ((uint32_t)j << 24) | (uint32_t)((c * kh + ii) * W);
+    }
+    for (int ci = warp; ci < C * kh; ci += nwarps) {                       // one input row per warp iteration
+        const int c = ci / kh, ii = ci - c * kh;
+        const int h = oh * sh + ii - ph0;
+        const bool in = h >= 0 && h < H;
+        const T* src = x + ((b * C + c) * H + (in ? h : 0)) * (int64_t)W;
+        if (VEC4) {
+            const int* src4 = reinterpret_cast<const int*>(src);
+            int* dst4 = reinterpret_cast<int*>(tile + ci * W);
+            const int pad4 = (int)(uint8_t)pad * 0x01010101;
+            for (int w4 = lane; w4 < (W >> 2); w4 += 32) dst4[w4] = in ? __ldg(src4 + w4) : pad4;
+        } else {
+            for (int w = lane; w < W; w += 32) tile[ci * W + w] = in ? src[w] : pad;
+        }
+    }
+    __syncthreads();
+    for (int ow = warp; ow < OW; ow += nwarps) {                           // one patch row per warp iteration
+        T* dst = out + ((b * OH + oh) * (int64_t)OW + ow) * ldo;
+        const int wbase = ow * sw - pw0;
+        if (VEC4) {
+            for (int c4 = lane * 4; c4 < ldo; c4 += 128) {
+                uint32_t word = 0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int col = c4 + k;
+                    uint32_t v = 0;
+                    if (col < kcols) {
+                        const uint32_t e = lut[col];
+                        const int w = wbase + (int)(e >> 24);
+                        v = (uint8_t)((w >= 0 && w < W) ? tile[(e & 0xffffffu) + w] : pad);
+                    }
+                    word |= v << (8 * k);
+                }
+                *reinterpret_cast<uint32_t*>(dst + c4) = word;
+            }
+        } else {
+            for (int col = lane; col < ldo; col += 32) {
+                T v = (T)0;
+                if (col < kcols) {
+                    const uint32_t e = lut[col];
+                    const int w = wbase + (int)(e >> 24);
+                    v = (w >= 0 && w < W) ? tile[(e & 0xffffffu) + w] : pad;
+                }
+                dst[col] = v;
+            }
+        }
+    }
+}
+
 // counts inputs where the hoisted-reciprocal division differs from __fdiv_rn (must be 0)
 __global__ void selftest_division_kernel(uint64_t n, uint32_t seed, int mode, unsigned long long* mismatches) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
@@ -539,11 +624,27 @@ static void launch_binary(const float* a, const float* b, const Dims4& g, int64_
     };
     const bool a_c = contig(g.sa), al = aligned16(a) && aligned16(out) && (n % 4 == 0);
     const bool b_scalar = [&] { for (int i = 0; i < 4; ++i) if (g.d[i] != 1 && g.sb[i] != 0) return false; return true; }();
-    const bool b_row = (g.sb[3] == 1 || g.d[3] == 1) && [&] { for (int i = 0; i < 3; ++i) if (g.d[i] != 1 && g.sb[i] != 0) return false; return true; }();
+    // b spans the last k dims contiguously and is broadcast (stride 0 / extent 1) over the leading ones
+    int64_t b_block = 0;
+    for (int k = 1; k <= 3 && !b_block; ++k) {
+        bool ok = true;
+        int64_t e = 1;
+        for (int i = 3; i >= 4 - k; --i) {
+            if (g.d[i] != 1 && g.sb[i] != e) ok = false;
+            e *= g.d[i];
+        }
+        for (int i = 0; i < 4 - k; ++i)
+            if (g.d[i] != 1 && g.sb[i] != 0) ok = false;
+        if (ok) b_block = e;
+    }
     const int grid4 = stream_grid((n + 3) / 4, 256), grid1 = stream_grid(n, 256);
     if (a_c && al && contig(g.sb) && aligned16(b)) binary_kernel<OP, 1><<<grid4, 256, 0, s>>>(a, b, g, n, out);
     else if (a_c && al && b_scalar) binary_kernel<OP, 3><<<grid4, 256, 0, s>>>(a, b, g, n, out);
-    else if (a_c && al && b_row && (g.d[3] % 4 == 0) && aligned16(b)) binary_kernel<OP, 2><<<grid4, 256, 0, s>>>(a, b, g, n, out);
+    else if (a_c && al && b_block > 0 && (b_block % 4 == 0) && aligned16(b)) {
+        Dims4 g2 = g;
+        g2.sa[0] = b_block;
+        binary_kernel<OP, 2><<<grid4, 256, 0, s>>>(a, b, g2, n, out);
+    }
     else binary_kernel<OP, 0><<<grid1, 256, 0, s>>>(a, b, g, n, out);
 }
 
@@ -573,14 +674,20 @@ static int launch_layernorm(const float* x, int64_t rows, int64_t cols, int64_t 
     const int grid = stream_grid(rows * 32, 256);
     const bool vec = (cols % 4 == 0) && (ldx % 4 == 0) && aligned16(x) && aligned16(gamma) && aligned16(beta) &&
                      (qmode >= 0 ? ((ldo & 3) == 0) : aligned16(out));
+#define NQ_LN_Q(NV, QM)                                                                                                 \
+    do {                                                                                                                \
+        const int g_ = resident_grid(layernorm_vec_kernel<NV, QM>, rows * 32, 256);                                     \
+        layernorm_vec_kernel<NV, QM><<<g_, 256, 0, s>>>(x, rows, (int)cols, ldx, gamma, beta, eps, out, qa, qout, ldo, rowsum); \
+    } while (0)
 #define NQ_LN(NV)                                                                                                       \
     do {                                                                                                                \
-        if (qmode < 0) layernorm_vec_kernel<NV, -1><<<grid, 256, 0, s>>>(x, rows, (int)cols, ldx, gamma, beta, eps, out, qa, qout, ldo, rowsum); \
-        else if (qmode == 0) layernorm_vec_kernel<NV, 0><<<grid, 256, 0, s>>>(x, rows, (int)cols, ldx, gamma, beta, eps, out, qa, qout, ldo, rowsum); \
-        else if (qmode == 1) layernorm_vec_kernel<NV, 1><<<grid, 256, 0, s>>>(x, rows, (int)cols, ldx, gamma, beta, eps, out, qa, qout, ldo, rowsum); \
-        else layernorm_vec_kernel<NV, 2><<<grid, 256, 0, s>>>(x, rows, (int)cols, ldx, gamma, beta, eps, out, qa, qout, ldo, rowsum); \
+        if (qmode < 0) NQ_LN_Q(NV, -1);                                                                                 \
+        else if (qmode == 0) NQ_LN_Q(NV, 0);                                                                            \
+        else if (qmode == 1) NQ_LN_Q(NV, 1);                                                                            \
+        else NQ_LN_Q(NV, 2);                                                                                            \
     } while (0)
     if (vec && cols <= 512) NQ_LN(4);
+    else if (vec && cols <= 768) NQ_LN(6);
     else if (vec && cols <= 1024) NQ_LN(8);
     else if (vec && cols <= 4096 && qmode < 0) NQ_LN(32);
     else if (qmode < 0) layernorm_generic_kernel<<<grid, 256, 0, s>>>(x, rows, cols, ldx, gamma, beta, eps, out);
@@ -722,6 +829,31 @@ extern "C" int nq_im2col(const void* x, int elem_bytes, int64_t B, int64_t C, in
     const int64_t total = B * OH * OW * ldo;
     const int grid = stream_grid(total, 256);
     cudaStream_t s = (cudaStream_t)stream;
+    const int64_t lut_bytes = (((int64_t)kh * kw * C * 4 + 15) / 16) * 16;
+    const int64_t strip_bytes = lut_bytes + C * kh * W * elem_bytes;
+    if (strip_bytes <= 48 * 1024 && B * OH < (1ll << 31) && OW * ldo < (1ll << 31) && kw < 256 && C * kh * W < (1 << 24) &&
+        (elem_bytes == 1 || elem_bytes == 4)) {
+        const unsigned nb = (unsigned)(B * OH);
+        if (elem_bytes == 1) {
+            const bool vec4 = (W % 4 == 0) && (ldo % 4 == 0) && (((uintptr_t)x | (uintptr_t)out) % 4 == 0);
+            if (vec4)
+                im2col_strip_kernel<int8_t, true><<<nb, 256, (size_t)strip_bytes, s>>>((const int8_t*)x, (int)C, (int)H, (int)W, kh, kw,
+                                                                                       ph0, pw0, sh, sw, (int)OH, (int)OW,
+                                                                                       (int8_t)pad_value, (int8_t*)out, (int)ldo);
+            else
+                im2col_strip_kernel<int8_t, false><<<nb, 256, (size_t)strip_bytes, s>>>((const int8_t*)x, (int)C, (int)H, (int)W, kh, kw,
+                                                                                        ph0, pw0, sh, sw, (int)OH, (int)OW,
+                                                                                        (int8_t)pad_value, (int8_t*)out, (int)ldo);
+        } else {
+            float padf;
+            memcpy(&padf, &pad_value, 4);
+            im2col_strip_kernel<float, false><<<nb, 256, (size_t)strip_bytes, s>>>((const float*)x, (int)C, (int)H, (int)W, kh, kw, ph0,
+                                                                                   pw0, sh, sw, (int)OH, (int)OW, padf, (float*)out,
+                                                                                   (int)ldo);
+        }
+        NQ_CHECK_LAUNCH("nq_im2col");
+        return NQ_OK;
+    }
     if (elem_bytes == 1) {
         im2col_kernel<int8_t><<<grid, 256, 0, s>>>((const int8_t*)x, B, (int)C, (int)H, (int)W, kh, kw, ph0, pw0, sh, sw,
                                                    (int)OH, (int)OW, (int8_t)pad_value, (int8_t*)out, ldo);

@@ -25,13 +25,21 @@ constexpr int UMMA_K = 32;       // K per tcgen05.mma for 8-bit operands
 constexpr int NUM_EPI_WARPS = 16;
 constexpr int NUM_THREADS = 128 + 32 * NUM_EPI_WARPS;  // 640 threads; registers re-balanced with setmaxnreg (56 / 104)
 
-template <int BN> struct Cfg {
-    static constexpr int STAGES = (BN == 256) ? 4 : 6;
+template <int BN, bool WIDE = false> struct Cfg {
+    // WIDE (NQ_EPI_DEQUANT on aligned outputs): 32-column staging slabs, so every float32 row segment that a warp
+    // loads (residual) or stores is a full 128-byte line; paid for with one pipeline stage.
+    static constexpr int STAGES = WIDE ? ((BN == 256) ? 3 : (BN == 128) ? 4 : 6) : ((BN == 256) ? 4 : 6);
     static constexpr int A_BYTES = BM * BK;
     static constexpr int B_BYTES = BN * BK;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-    static constexpr int EPI_BYTES = NUM_EPI_WARPS * (32 * 16 * 4 + 32 * 4);   // staging slabs + row terms
+    // Narrow tiles are drained by GROUPS independent sets of epilogue warps, each on its own tile, so that several
+    // small tiles are in flight per CTA (their per-tile latency chain, not the math, bounds e.g. the P.V GEMM):
+    // BN = 256: 1 group of 16 warps, 2 accumulator buffers; 128: 2 groups of 8, 4 buffers; 64: 4 groups of 4, 8.
+    static constexpr int GROUPS = 256 / BN;
+    static constexpr int NACC = 2 * GROUPS;
+    static constexpr int TMEM_COLS = 512;                                  // NACC * BN
+    static constexpr int SLAB_WORDS = WIDE ? 32 * 32 : 32 * 16;            // per-warp staging slab (32 rows)
+    static constexpr int EPI_BYTES = NUM_EPI_WARPS * (SLAB_WORDS * 4 + 32 * 4);   // staging slabs + row terms
     static constexpr int BAR_BYTES = 256;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES;
     static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB opt-in shared memory of sm_100");
@@ -64,6 +72,7 @@ struct GemmParams {
     // SOFTMAX epilogue: softmax(dequant / sm_div) over the (single) N tile, quantized with qargs
     int q_rs_exclusive;              // Q8 ROWS: every (row, head) row-sum slot is written by exactly one warp: plain store
     float g_prdiv, g_nl2e, g_add, g_out;   // GELU_QUANT: 0.3275911 / c1, -log2(e) / c1^2, c2, c3 / s_out
+    int deq_wide;                    // DEQUANT: alignment / extent conditions of the 32-column epilogue hold (host-checked)
     int fast22;                      // SOFTMAX: |acc - zero-point terms| < 2^22 proved on the host (magic int->float route)
 };
 
@@ -217,13 +226,37 @@ __device__ __forceinline__ float gelu_fast(float x, float p_rdiv, float nl2e_rdi
     return __fmul_rn(__fmul_rn(x, __fadd_rn(erf_u, c_add)), c_out);      // c_out = c3 / s_out: the quotient to round
 }
 
+// Exact re-evaluation of one lane's share of a 32 x 32 step of the wide dequant epilogue (rare: some value left the
+// 2^22 window of the magic-constant int->float conversion).  Same slab / row-term layout as the hot loop.
+__device__ __noinline__ void deq_wide_fix(const uint32_t* slab, const uint32_t* stg_row, int lane, int ct0, int ct1, int ct2,
+                                          int ct3, float b0, float b1, float b2, float b3, bool has_bias, const float* rbase,
+                                          int64_t ldr, float* crow, int64_t ldc, int rows_left, float scale) {
+    const int cj = lane & 7, rq = lane >> 3;
+    const int ct[4] = {ct0, ct1, ct2, ct3};
+    const float bs[4] = {b0, b1, b2, b3};
+    for (int it = 0; it < 8; ++it) {
+        const int rr = it * 4 + rq;
+        if (rr >= rows_left) continue;
+        const uint32_t* src = slab + rr * 32 + ((cj ^ (rr & 7)) << 2);
+        const int rm = (int)stg_row[rr];
+        float f[4];
+        for (int k = 0; k < 4; ++k) {
+            const int d = (int)src[k] + rm - ct[k] - 0x4B400000;          // acc - zero-point terms (int32: host bound)
+            f[k] = (d >= -16777216 && d <= 16777216) ? __fmul_rn((float)d, scale) : (float)((double)d * (double)scale);
+            if (has_bias) f[k] = __fadd_rn(bs[k], f[k]);
+            if (rbase) f[k] = __fadd_rn(f[k], rbase[(int64_t)rr * ldr + k]);
+        }
+        *reinterpret_cast<float4*>(crow + (int64_t)it * 4 * ldc) = make_float4(f[0], f[1], f[2], f[3]);
+    }
+}
+
 constexpr int EM_RAW = 0, EM_DEQ_FAST = 1, EM_DEQ_GENERAL = 2, EM_REQUANT = 3, EM_Q8_ROWS = 4, EM_Q8_COLS = 5,
-              EM_SOFTMAX_SYM = 6, EM_SOFTMAX_ASYM = 7, EM_Q8_GELU = 8;
+              EM_SOFTMAX_SYM = 6, EM_SOFTMAX_ASYM = 7, EM_Q8_GELU = 8, EM_DEQ_WIDE = 9, EM_DEQ_WIDE_RES = 10;
 
 template <int BN, int EMODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
-    using C = Cfg<BN>;
+    using C = Cfg<BN, (EMODE == EM_DEQ_WIDE || EMODE == EM_DEQ_WIDE_RES)>;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 128B swizzle atoms need 1024-byte aligned tiles
     uint8_t* smem = smem_raw;
@@ -235,8 +268,8 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
     uint64_t* full_bar = bars;
     uint64_t* empty_bar = bars + C::STAGES;
     uint64_t* tfull_bar = bars + 2 * C::STAGES;
-    uint64_t* tempty_bar = bars + 2 * C::STAGES + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
+    uint64_t* tempty_bar = bars + 2 * C::STAGES + 8;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 16);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -255,9 +288,9 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
             mbar_init(smem_u32(full_bar + i), 1);
             mbar_init(smem_u32(empty_bar + i), 1);
         }
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < C::NACC; ++i) {
             mbar_init(smem_u32(tfull_bar + i), 1);
-            mbar_init(smem_u32(tempty_bar + i), NUM_EPI_WARPS);  // one arrival per epilogue warp
+            mbar_init(smem_u32(tempty_bar + i), NUM_EPI_WARPS / C::GROUPS);  // one arrival per epilogue warp of the group
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -334,7 +367,7 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                     }
                 }
                 tc_commit(smem_u32(tfull_bar + acc));                     // accumulator ready
-                if (++acc == 2) {
+                if (++acc == C::NACC) {
                     acc = 0;
                     acc_phase ^= 1;
                 }
@@ -356,9 +389,9 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
         const int h = (warp - 4) >> 2;                                    // 0..3
         const int ew = warp - 4;
         uint32_t* stg = epi + ew * (32 * 16);                             // 32 rows x 16 words
-        uint32_t* stg_row = epi + NUM_EPI_WARPS * 32 * 16 + ew * 32;
-        int acc = 0;
-        uint32_t acc_phase = 0;
+        uint32_t* stg_row = epi + NUM_EPI_WARPS * C::SLAB_WORDS + ew * 32;
+        constexpr int HPG = 4 / C::GROUPS;                                // column slots (values of h) per group
+        const int grp = h / HPG, hc = h % HPG;                            // tile group, 64-column slot in the tile
         const AccZp z = p.zp;
         const bool c_aligned = ((p.ldc & 3) == 0) && ((p.stride_c & 3) == 0) && ((p.stride_c_inner & 3) == 0) &&
                                ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
@@ -372,7 +405,39 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
         constexpr bool FASTF = (EMODE == EM_DEQ_FAST);                   // float result via the 32-bit fast path
         constexpr bool Q8 = (EMODE == EM_Q8_ROWS || EMODE == EM_Q8_COLS || EMODE == EM_Q8_GELU);
         const Quantizer qz(p.qargs);
-        for (uint32_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        constexpr bool SOFTMAX = (EMODE == EM_SOFTMAX_SYM || EMODE == EM_SOFTMAX_ASYM);
+        // Per-tile operands of the zero-point correction (this row's rowsum(A), this warp's colsum(B) and bias
+        // columns) are fetched ONE TILE AHEAD: with 227 KB of smem there is no L1 to hit, so each of these
+        // loads is an L2 round trip that would otherwise sit at the head of every tile's critical path.
+        struct TilePre { int rowsum, c0, c1, b0, b1; };
+        auto prefetch_tile = [&](uint32_t tt, TilePre& o) {
+            o.rowsum = o.c0 = o.c1 = o.b0 = o.b1 = 0;
+            if (tt >= total_tiles) return;
+            const uint32_t pb = tt / tiles_per_batch, pr = tt - pb * tiles_per_batch;
+            const uint32_t pm0 = (pr / n_tiles) * BM, pn0 = (pr % n_tiles) * BN;
+            const int64_t pm = (int64_t)pm0 + q * 32 + lane;
+            if (z.use_row && pm < p.M) o.rowsum = ldg_s32(z.rowsum_a + (int64_t)pb * p.M + pm);
+            if constexpr (Q8) {
+                constexpr int W = 64;                                     // columns owned by this warp
+                const int64_t c0i = (int64_t)pn0 + hc * W + lane, c1i = c0i + 32;
+                const int32_t* pcs = z.use_col ? z.colsum_b + (int64_t)pb * z.cs_stride : nullptr;
+                if (lane < W && c0i < p.N) {
+                    if (pcs) o.c0 = ldg_s32(pcs + c0i);
+                    if (Q8 && p.bias_f32) o.b0 = ldg_s32(p.bias_f32 + c0i);
+                }
+                if (lane + 32 < W && c1i < p.N) {
+                    if (pcs) o.c1 = ldg_s32(pcs + c1i);
+                    if (Q8 && p.bias_f32) o.b1 = ldg_s32(p.bias_f32 + c1i);
+                }
+            }
+        };
+        TilePre nxt;
+        prefetch_tile(blockIdx.x + grp * gridDim.x, nxt);
+        // this CTA's i-th tile is t = blockIdx.x + i * gridDim.x, lives in accumulator buffer i % NACC and is
+        // drained by group i % GROUPS
+        for (uint32_t li = grp, t = blockIdx.x + grp * gridDim.x; t < total_tiles; li += C::GROUPS, t += C::GROUPS * gridDim.x) {
+            const int acc = (int)(li % C::NACC);
+            const uint32_t acc_phase = (li / C::NACC) & 1u;
             const int64_t b = t / tiles_per_batch;
             const uint32_t r = t % tiles_per_batch;
             const int64_t m0 = (int64_t)(r / n_tiles) * BM, n0 = (int64_t)(r % n_tiles) * BN;
@@ -380,8 +445,10 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
             const int64_t m = mrow0 + lane;                               // this thread's accumulator row
             const bool row_ok = m < p.M;
             const int32_t* cs_b = z.use_col ? z.colsum_b + b * z.cs_stride : nullptr;
+            const TilePre cur = nxt;
+            prefetch_tile(t + C::GROUPS * gridDim.x, nxt);
             int64_t rowterm = -z.kterm;
-            if (z.use_row && row_ok) rowterm += (int64_t)ldg_s32(z.rowsum_a + b * p.M + m) * z.zp_b;
+            if (z.use_row && row_ok) rowterm += (int64_t)cur.rowsum * z.zp_b;
             if constexpr (Q8) {
                 // ---- int8 operand outputs (NQ_EPI_QUANT / NQ_EPI_GELU_QUANT): thread = accumulator row.
                 // The float value the graph would have produced (bias + dequant [-> GELU]) is quantized with
@@ -390,17 +457,19 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                 // bias are staged per warp in shared memory and read back as broadcast LDS.128.
                 //   ROWS / GELU: 16 consecutive n are 16 consecutive bytes (one 16-byte store per row)
                 //   COLS       : consecutive m are consecutive bytes (transposing scatter, V operand)
-                constexpr int CPW = BN / 64;                              // 16-column chunks per warp, contiguous
+                constexpr int CPW = 4;                                    // 16-column chunks per warp, contiguous
                 constexpr int WCOLS = CPW * 16;
-                const int wcol0 = h * WCOLS;
+                const int wcol0 = hc * WCOLS;
                 int* ctw = reinterpret_cast<int*>(epi) + ew * 128;        // [64] colsum * zp_a
                 float* bsw = reinterpret_cast<float*>(ctw + 64);          // [64] bias
                 __syncwarp();
-                for (int i = lane; i < WCOLS; i += 32) {
-                    const int64_t n = n0 + wcol0 + i;
-                    const bool ok = n < p.N;
-                    ctw[i] = (cs_b && ok) ? ldg_s32(cs_b + n) * zpa : 0;
-                    bsw[i] = (p.bias_f32 && ok) ? __int_as_float(ldg_s32(p.bias_f32 + n)) : 0.f;
+                if (lane < WCOLS) {
+                    ctw[lane] = cur.c0 * zpa;
+                    bsw[lane] = __int_as_float(cur.b0);
+                }
+                if (lane + 32 < WCOLS) {
+                    ctw[lane + 32] = cur.c1 * zpa;
+                    bsw[lane + 32] = __int_as_float(cur.b1);
                 }
                 // row part of the scatter offsets (m = mb * S + ms, batch = bo * inner + bi)
                 const uint32_t mu = (uint32_t)(row_ok ? m : p.M - 1);
@@ -527,10 +596,99 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(smem_u32(tempty_bar + acc));
-                if (++acc == 2) {
-                    acc = 0;
-                    acc_phase ^= 1;
+                continue;
+            }
+            if constexpr (EMODE == EM_DEQ_WIDE || EMODE == EM_DEQ_WIDE_RES) {
+                // ---- float32 output (dequant + bias + residual), host-checked alignment, N % 32 == 0.
+                // 32 rows x 32 columns per step: tcgen05.ld x32 -> XOR-swizzled 4 KB slab (rows of 128 B, 16-byte
+                // chunk ^ (row & 7): conflict-free both ways) -> read-back where one warp instruction covers 4 rows
+                // x 128 B, so the residual LDG.128 and the result STG.128 move whole 128-byte lines.
+                uint32_t* slab = epi + ew * C::SLAB_WORDS;
+                const int cj = lane & 7, rq = lane >> 3;                   // read-back: 16-byte chunk, row within 4
+                constexpr bool has_res = (EMODE == EM_DEQ_WIDE_RES);
+                int4 ct_n = make_int4(0, 0, 0, 0), bs_n = make_int4(0, 0, 0, 0);
+                auto fetch32 = [&](int sidx) {
+                    const int64_t nc = n0 + sidx * 32;
+                    if (sidx >= BN / 32 || nc >= p.N) return;
+                    ct_n = cs_b ? ldg_v4(cs_b + nc + cj * 4) : make_int4(0, 0, 0, 0);
+                    bs_n = p.bias_f32 ? ldg_v4(p.bias_f32 + nc + cj * 4) : make_int4(0, 0, 0, 0);
+                };
+                fetch32(hc);
+                mbar_wait(smem_u32(tfull_bar + acc), acc_phase);
+                tc_fence_after();
+                __syncwarp();
+                stg_row[lane] = (uint32_t)(0x4B400000 - (int32_t)rowterm);   // row term + int->float magic
+                const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+                const int64_t crow_base = (p.c_inner > 1) ? (b / p.c_inner) * p.stride_c + (b % p.c_inner) * p.stride_c_inner
+                                                          : b * p.stride_c;
+                const int rows_left = (int)((p.M - mrow0) < 32 ? ((p.M - mrow0) > 0 ? (p.M - mrow0) : 0) : 32);
+#pragma unroll 1
+                for (int sidx = hc; sidx < BN / 32; sidx += HPG) {
+                    const int64_t nc = n0 + sidx * 32;
+                    if (nc >= p.N || rows_left == 0) break;               // warp-uniform
+                    uint32_t v[32];
+                    tmem_ld_32x32b_x32(t_row + (uint32_t)(sidx * 32), v);
+                    const int ct0 = ct_n.x * zpa, ct1 = ct_n.y * zpa, ct2 = ct_n.z * zpa, ct3 = ct_n.w * zpa;
+                    const float b0 = __int_as_float(bs_n.x), b1 = __int_as_float(bs_n.y);
+                    const float b2 = __int_as_float(bs_n.z), b3 = __int_as_float(bs_n.w);
+                    fetch32(sidx + HPG);
+                    tmem_ld_wait();
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        *reinterpret_cast<uint4*>(slab + lane * 32 + ((j ^ (lane & 7)) << 2)) =
+                            make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    __syncwarp();
+                    uint32_t bad_any = 0;
+                    float* crow = reinterpret_cast<float*>(p.C) + crow_base + (mrow0 + rq) * p.ldc + nc + cj * 4;
+                    const float* rbase = has_res ? p.residual + b * p.stride_r + mrow0 * p.ldr + nc + cj * 4 : nullptr;
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        // residual rows of this half (16 rows): in flight together, then consumed in order
+                        float4 res[4];
+                        if constexpr (has_res) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                // rows past M are clamped to the last valid one (loaded, never stored)
+                                const int rr = (half * 4 + k) * 4 + rq;
+                                const int rc = rr < rows_left ? rr : rows_left - 1;
+                                res[k] = __ldcs(reinterpret_cast<const float4*>(rbase + (int64_t)rc * p.ldr));
+                            }
+                        }
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const int it = half * 4 + k;
+                            const int rr = it * 4 + rq;
+                            const uint4 val = *reinterpret_cast<const uint4*>(slab + rr * 32 + ((cj ^ (rr & 7)) << 2));
+                            const int rm = (int)stg_row[rr];
+                            const int x0 = (int)val.x + rm - ct0, x1 = (int)val.y + rm - ct1;
+                            const int x2 = (int)val.z + rm - ct2, x3 = (int)val.w + rm - ct3;
+                            bad_any |= (uint32_t)(x0 ^ 0x4B000000) | (uint32_t)(x1 ^ 0x4B000000) |
+                                       (uint32_t)(x2 ^ 0x4B000000) | (uint32_t)(x3 ^ 0x4B000000);
+                            float f0 = __fmul_rn(__fadd_rn(__int_as_float(x0), -12582912.0f), p.scale);
+                            float f1 = __fmul_rn(__fadd_rn(__int_as_float(x1), -12582912.0f), p.scale);
+                            float f2 = __fmul_rn(__fadd_rn(__int_as_float(x2), -12582912.0f), p.scale);
+                            float f3 = __fmul_rn(__fadd_rn(__int_as_float(x3), -12582912.0f), p.scale);
+                            if (p.bias_f32) {
+                                f0 = __fadd_rn(b0, f0); f1 = __fadd_rn(b1, f1); f2 = __fadd_rn(b2, f2); f3 = __fadd_rn(b3, f3);
+                            }
+                            if constexpr (has_res) {
+                                f0 = __fadd_rn(f0, res[k].x); f1 = __fadd_rn(f1, res[k].y);
+                                f2 = __fadd_rn(f2, res[k].z); f3 = __fadd_rn(f3, res[k].w);
+                            }
+                            if (rr < rows_left)
+                                *reinterpret_cast<float4*>(crow + (int64_t)it * 4 * p.ldc) = make_float4(f0, f1, f2, f3);
+                        }
+                    }
+                    // some |acc - zero-point terms| >= 2^22 (outside the magic-constant conversion): this lane's part
+                    // of the step is recomputed on the exact general route, out of line and off the hot path
+                    if (__builtin_expect((bad_any & 0xFF800000u) != 0, 0))
+                        deq_wide_fix(slab, stg_row, lane, ct0, ct1, ct2, ct3, b0, b1, b2, b3, p.bias_f32 != nullptr, rbase,
+                                     p.ldr, crow, p.ldc, rows_left, p.scale);
                 }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(tempty_bar + acc));
                 continue;
             }
             // Column operands (colsum for the zero-point, bias) of the NEXT sub-chunk are always in flight
@@ -555,8 +713,8 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                     if (p.bias_f32) bs_n.x = ldg_s32(p.bias_f32 + nc + sc_col);
                 }
             };
-            if (FASTF) fetch_cols(h);
-            if (EMODE == EM_SOFTMAX_SYM || EMODE == EM_SOFTMAX_ASYM) {
+            if (FASTF) fetch_cols(hc);
+            if (SOFTMAX) {
                 // this warp's 56 column terms (colsum * zp_a) -> its private smem strip, fetched while the
                 // MMA is still running; read back as broadcast LDS in the softmax loop
                 int* ctw = reinterpret_cast<int*>(epi) + 1024 + ew * 64;
@@ -709,14 +867,10 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                 }
                 // red[] / redq[] reuse by the next tile is ordered by that tile's own barriers (each slot is
                 // rewritten only after a barrier that every reader of the previous tile has passed)
-                if (++acc == 2) {
-                    acc = 0;
-                    acc_phase ^= 1;
-                }
                 continue;
             }
 #pragma unroll 1
-            for (int sidx = h; sidx < BN / 16; sidx += 4) {
+            for (int sidx = hc; sidx < BN / 16; sidx += HPG) {
                 const int64_t nc = n0 + sidx * 16;
                 if (nc >= p.N) break;                                     // warp-uniform
                 uint32_t v[16];
@@ -728,7 +882,7 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                     ct[0] = ct_n.x * zpa; ct[1] = ct_n.y * zpa; ct[2] = ct_n.z * zpa; ct[3] = ct_n.w * zpa;
                     bs[0] = __int_as_float(bs_n.x); bs[1] = __int_as_float(bs_n.y);
                     bs[2] = __int_as_float(bs_n.z); bs[3] = __int_as_float(bs_n.w);
-                    fetch_cols(sidx + 4);
+                    fetch_cols(sidx + HPG);
                 }
                 tmem_ld_wait();
                 if (EMODE == EM_REQUANT) {
@@ -860,10 +1014,6 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(tempty_bar + acc));
-            if (++acc == 2) {
-                acc = 0;
-                acc_phase ^= 1;
-            }
         }
     }
 
@@ -930,13 +1080,13 @@ static int launch_qgemm(const CUtensorMap& ta, const CUtensorMap& tb, const Gemm
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(qgemm_kernel<BN, EMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             Cfg<BN>::SMEM_BYTES);
+                                             Cfg<BN, (EMODE == EM_DEQ_WIDE || EMODE == EM_DEQ_WIDE_RES)>::SMEM_BYTES);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(qgemm)");
         configured = true;
     }
     const int64_t tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN) * p.batch;
     const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
-    qgemm_kernel<BN, EMODE><<<grid, NUM_THREADS, Cfg<BN>::SMEM_BYTES, s>>>(ta, tb, p);
+    qgemm_kernel<BN, EMODE><<<grid, NUM_THREADS, Cfg<BN, (EMODE == EM_DEQ_WIDE || EMODE == EM_DEQ_WIDE_RES)>::SMEM_BYTES, s>>>(ta, tb, p);
     NQ_CHECK_LAUNCH("nq_qgemm_s8");
     return NQ_OK;
 }
@@ -956,6 +1106,8 @@ static int launch_qgemm_mode(const CUtensorMap& ta, const CUtensorMap& tb, const
     if (p.mode == NQ_EPI_QUANT)
         return p.q_off[5] == 1 ? launch_qgemm<BN, EM_Q8_ROWS>(ta, tb, p, s) : launch_qgemm<BN, EM_Q8_COLS>(ta, tb, p, s);
     if (p.mode == NQ_EPI_GELU_QUANT) return launch_qgemm<BN, EM_Q8_GELU>(ta, tb, p, s);
+    if (p.fast32 && p.deq_wide)
+        return p.residual ? launch_qgemm<BN, EM_DEQ_WIDE_RES>(ta, tb, p, s) : launch_qgemm<BN, EM_DEQ_WIDE>(ta, tb, p, s);
     return p.fast32 ? launch_qgemm<BN, EM_DEQ_FAST>(ta, tb, p, s) : launch_qgemm<BN, EM_DEQ_GENERAL>(ta, tb, p, s);
 }
 
@@ -1046,9 +1198,9 @@ extern "C" int nq_qgemm_s8(const int8_t* A, const int8_t* B, void* Cout, int64_t
                 NQ_REQUIRE(ep->q_off[i] % 16 == 0, "nq_qgemm_s8: QUANT row layout needs q_off[0..4] multiples of 16 bytes");
             NQ_REQUIRE(((uintptr_t)Cout & 15) == 0, "nq_qgemm_s8: QUANT destination must be 16-byte aligned");
             NQ_REQUIRE(!ep->q_rowsum || ep->q_rs[5] == 0, "nq_qgemm_s8: QUANT row layout sums codes along n (q_rs[5] == 0)");
-            // one warp owns bn/4 consecutive columns of a row: a (row, head) slot has a single writer when
+            // one warp owns 64 consecutive columns of a row: a (row, head) slot has a single writer when
             // the heads tile that span and the slot does not depend on the batch-inner / other tiles
-            const int wcols = bn / 4;
+            const int wcols = 64;
             p.q_rs_exclusive = (wcols % ep->q_cols_per_head == 0) && ep->q_rs[4] != 0 && ep->q_rs[3] != 0 &&
                                (ep->c_batch_inner <= 1 || ep->q_rs[1] != 0);
         } else {
@@ -1082,6 +1234,13 @@ extern "C" int nq_qgemm_s8(const int8_t* A, const int8_t* B, void* Cout, int64_t
     p.stride_r = ep->stride_residual;
     NQ_REQUIRE(!p.residual || p.ldr >= N, "nq_qgemm_s8: ld_residual < N");
     p.C = Cout;
+    if (ep->mode == NQ_EPI_DEQUANT) {
+        auto al16 = [](const void* q) { return ((uintptr_t)q & 15) == 0; };
+        static const bool no_wide = getenv("NQ_NO_WIDE_EPILOGUE") != nullptr;   // A/B switch for measurements
+        p.deq_wide = !no_wide && N % 32 == 0 && ldc % 4 == 0 && stride_c % 4 == 0 && p.stride_c_inner % 4 == 0 && al16(Cout) &&
+                     (!p.zp.use_col || (al16(p.zp.colsum_b) && p.zp.cs_stride % 4 == 0)) && (!p.bias_f32 || al16(p.bias_f32)) &&
+                     (!p.residual || (al16(p.residual) && p.ldr % 4 == 0 && p.stride_r % 4 == 0));
+    }
     if (ep->mode == NQ_EPI_REQUANT) {
         NQ_REQUIRE(ep->out_bits >= 2 && ep->out_bits <= 8, "nq_qgemm_s8: out_bits %d outside 2..8", ep->out_bits);
         p.inv_out_scale = 1.0f / ep->out_scale;
