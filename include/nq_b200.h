@@ -238,7 +238,10 @@ int nq_softmax_div_f32(const float* x, int64_t rows, int64_t cols, int64_t ldx, 
  * Same float32 roundings as running the two kernels back to back. */
 int nq_layernorm_quantize_f32(const float* x, int64_t rows, int64_t cols, int64_t ldx, const float* gamma,
                               const float* beta, float eps, int bit_width, float scale, int has_zp, int64_t zp,
-                              int8_t* out, int64_t ldo, int32_t* rowsum, void* stream);
+                              int8_t* out, int64_t ldo, int32_t* rowsum, int float_glue, void* stream);
+/* float_glue != 0: the normalised value is float glue under the 1e-5 contract (one FMA for gamma/beta, division
+ * by the scale through its reciprocal); rounding, clamp and row sums stay exact.  0: the same float32 roundings as
+ * nq_layernorm_f32 followed by nq_quantize_f32. */
 int nq_softmax_quantize_f32(const float* x, int64_t rows, int64_t cols, int64_t ldx, int has_div, float div_const,
                             int bit_width, float scale, int has_zp, int64_t zp,
                             int8_t* out, int64_t ldo, int32_t* rowsum, void* stream);

@@ -63,7 +63,7 @@ _SIGNATURES = {
     "nq_layernorm_f32": [vp, i64, i64, i64, vp, vp, f32, vp, vp],
     "nq_softmax_f32": [vp, i64, i64, i64, vp, vp],
     "nq_softmax_div_f32": [vp, i64, i64, i64, f32, vp, vp],
-    "nq_layernorm_quantize_f32": [vp, i64, i64, i64, vp, vp, f32, C.c_int, f32, C.c_int, i64, vp, i64, vp, vp],
+    "nq_layernorm_quantize_f32": [vp, i64, i64, i64, vp, vp, f32, C.c_int, f32, C.c_int, i64, vp, i64, vp, C.c_int, vp],
     "nq_softmax_quantize_f32": [vp, i64, i64, i64, C.c_int, f32, C.c_int, f32, C.c_int, i64, vp, i64, vp, vp],
     "nq_gelu_quantize_f32": [vp, i64, i64, i64, f32, f32, f32, C.c_int, f32, C.c_int, i64, vp, i64, vp, vp],
     "nq_reduce_rows_f32": [C.c_int, vp, i64, i64, vp, vp],

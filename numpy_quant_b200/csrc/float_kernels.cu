@@ -184,6 +184,7 @@ __global__ void __launch_bounds__(256) layernorm_vec_kernel(const float* __restr
     const int c4 = cols >> 2;
     const float fn = (float)cols;
     const Quantizer qz(qa);
+    const float rscale = __frcp_rn(qa.scale);
     // Rows are software-pipelined (NV <= 8): the next row of this warp is already in flight while the current
     // one is reduced, normalised and stored -- one row per warp at a time leaves HBM latency exposed.
     constexpr bool PIPE = NV <= 8;
@@ -236,15 +237,28 @@ __global__ void __launch_bounds__(256) layernorm_vec_kernel(const float* __restr
             if (c < c4) {
                 const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + c);
                 const float4 bt = __ldg(reinterpret_cast<const float4*>(beta) + c);
-                float4 o;
+                float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (QMODE != 3) {
                 o.x = __fadd_rn(__fmul_rn(__fmul_rn(v[j].x, inv), gm.x), bt.x);
                 o.y = __fadd_rn(__fmul_rn(__fmul_rn(v[j].y, inv), gm.y), bt.y);
                 o.z = __fadd_rn(__fmul_rn(__fmul_rn(v[j].z, inv), gm.z), bt.z);
                 o.w = __fadd_rn(__fmul_rn(__fmul_rn(v[j].w, inv), gm.w), bt.w);
+                }
                 if (QMODE < 0) {
                     __stcs(dst + c, o);
+                } else if (QMODE == 3) {
+                    // float glue (1e-5 contract): normalise with one FMA, divide by the scale through its reciprocal;
+                    // the rounding of the quotient, the clamp and the row sum stay exact
+                    const float4 n4 = make_float4(__fmul_rn(v[j].x, inv), __fmul_rn(v[j].y, inv), __fmul_rn(v[j].z, inv),
+                                                  __fmul_rn(v[j].w, inv));
+                    const int w = pack4_codes(qz.code_of_quotient<1>(__fmul_rn(__fmaf_rn(n4.x, gm.x, bt.x), rscale)),
+                                              qz.code_of_quotient<1>(__fmul_rn(__fmaf_rn(n4.y, gm.y, bt.y), rscale)),
+                                              qz.code_of_quotient<1>(__fmul_rn(__fmaf_rn(n4.z, gm.z, bt.z), rscale)),
+                                              qz.code_of_quotient<1>(__fmul_rn(__fmaf_rn(n4.w, gm.w, bt.w), rscale)));
+                    qsum = __dp4a(w, 0x01010101, qsum);
+                    qdst[c] = w;
                 } else {
-                    constexpr int QM = QMODE < 0 ? 0 : QMODE;
+                    constexpr int QM = (QMODE < 0 || QMODE == 3) ? 0 : QMODE;
                     const int w = pack4_codes(qz.code<QM>(o.x), qz.code<QM>(o.y), qz.code<QM>(o.z), qz.code<QM>(o.w));
                     qsum = __dp4a(w, 0x01010101, qsum);
                     qdst[c] = w;
@@ -684,6 +698,7 @@ static int launch_layernorm(const float* x, int64_t rows, int64_t cols, int64_t 
         if (qmode < 0) NQ_LN_Q(NV, -1);                                                                                 \
         else if (qmode == 0) NQ_LN_Q(NV, 0);                                                                            \
         else if (qmode == 1) NQ_LN_Q(NV, 1);                                                                            \
+        else if (qmode == 3) NQ_LN_Q(NV, 3);                                                                            \
         else NQ_LN_Q(NV, 2);                                                                                            \
     } while (0)
     if (vec && cols <= 512) NQ_LN(4);
@@ -710,12 +725,14 @@ extern "C" int nq_layernorm_f32(const float* x, int64_t rows, int64_t cols, int6
 
 extern "C" int nq_layernorm_quantize_f32(const float* x, int64_t rows, int64_t cols, int64_t ldx, const float* gamma,
                                          const float* beta, float eps, int bit_width, float scale, int has_zp,
-                                         int64_t zp, int8_t* out, int64_t ldo, int32_t* rowsum, void* stream) {
+                                         int64_t zp, int8_t* out, int64_t ldo, int32_t* rowsum, int float_glue,
+                                         void* stream) {
     NQ_REQUIRE(bit_width >= 2 && bit_width <= 8, "nq_layernorm_quantize_f32: bit_width %d outside 2..8", bit_width);
     NQ_REQUIRE(ldo >= cols, "nq_layernorm_quantize_f32: ldo < cols");
     if (rows <= 0 || cols <= 0) return NQ_OK;
     int qmode;
     const QArgs qa = make_qargs(bit_width, scale, has_zp, zp, &qmode);
+    if (float_glue && qmode != 2) qmode = 3;
     if (int rc = launch_layernorm(x, rows, cols, ldx, gamma, beta, eps, nullptr, qmode, qa, out, ldo, rowsum, (cudaStream_t)stream)) return rc;
     NQ_CHECK_LAUNCH("nq_layernorm_quantize_f32");
     return NQ_OK;

@@ -226,6 +226,30 @@ __device__ __forceinline__ float gelu_fast(float x, float p_rdiv, float nl2e_rdi
     return __fmul_rn(__fmul_rn(x, __fadd_rn(erf_u, c_add)), c_out);      // c_out = c3 / s_out: the quotient to round
 }
 
+// Two elements per instruction: Blackwell's packed FFMA2 (fma.rn.f32x2) halves the issue slots of the float chain --
+// every epilogue here is bound by instruction issue.  Same arithmetic as gelu_fast(); the packed multiply / add
+// intrinsics may contract into FFMA2 (float glue, 1e-5 contract).  np1..np5 are the NEGATED A&S coefficients.
+__device__ __forceinline__ float2 gelu_fast2(float2 x, float p_rdiv, float nl2e_rdiv2, float c_add, float c_out) {
+    const float2 ax = make_float2(fabsf(x.x), fabsf(x.y));
+    const float2 den = __ffma2_rn(make_float2(p_rdiv, p_rdiv), ax, make_float2(1.0f, 1.0f));
+    float2 t, e;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.x) : "f"(den.x));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.y) : "f"(den.y));
+    float2 y = __ffma2_rn(make_float2(-1.061405429f, -1.061405429f), t, make_float2(1.453152027f, 1.453152027f));
+    y = __ffma2_rn(y, t, make_float2(-1.421413741f, -1.421413741f));
+    y = __ffma2_rn(y, t, make_float2(0.284496736f, 0.284496736f));
+    y = __ffma2_rn(y, t, make_float2(-0.254829592f, -0.254829592f));
+    y = __fmul2_rn(y, t);                                                 // -poly(t)
+    const float2 z = __fmul2_rn(__fmul2_rn(x, x), make_float2(nl2e_rdiv2, nl2e_rdiv2));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(z.x));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(z.y));
+    y = __ffma2_rn(y, e, make_float2(1.0f, 1.0f));                        // 1 - poly(t) * exp(-u^2)
+    const float2 erf_u = make_float2(__int_as_float(__float_as_int(y.x) ^ (__float_as_int(x.x) & 0x80000000)),
+                                     __int_as_float(__float_as_int(y.y) ^ (__float_as_int(x.y) & 0x80000000)));
+    const float2 xc = __fmul2_rn(x, make_float2(c_out, c_out));
+    return __ffma2_rn(erf_u, xc, __fmul2_rn(xc, make_float2(c_add, c_add)));   // (erf + c2) * x * (c3 / s_out)
+}
+
 // Exact re-evaluation of one lane's share of a 32 x 32 step of the wide dequant epilogue (rare: some value left the
 // 2^22 window of the magic-constant int->float conversion).  Same slab / row-term layout as the hot loop.
 __device__ __noinline__ void deq_wide_fix(const uint32_t* slab, const uint32_t* stg_row, int lane, int ct0, int ct1, int ct2,
@@ -533,14 +557,15 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                         const float4 b4 = *reinterpret_cast<const float4*>(bsw + i * 16 + g * 4);
                         if constexpr (EMODE == EM_Q8_GELU) {
                             // float glue (1e-5 contract): dequant * scale + bias as one FMA, GELU, and the
-                            // quantizer's division folded into the chain's last constant
+                            // quantizer's division folded into the chain's last constant; two elements per FFMA2
                             const float sc = gelu_scaled ? 1.0f : p.scale;
-                            const float y0 = gelu_fast(__fmaf_rn(f[4 * g], sc, b4.x), p.g_prdiv, p.g_nl2e, p.g_add, p.g_out);
-                            const float y1 = gelu_fast(__fmaf_rn(f[4 * g + 1], sc, b4.y), p.g_prdiv, p.g_nl2e, p.g_add, p.g_out);
-                            const float y2 = gelu_fast(__fmaf_rn(f[4 * g + 2], sc, b4.z), p.g_prdiv, p.g_nl2e, p.g_add, p.g_out);
-                            const float y3 = gelu_fast(__fmaf_rn(f[4 * g + 3], sc, b4.w), p.g_prdiv, p.g_nl2e, p.g_add, p.g_out);
-                            w[g] = pack4_codes(qz.template code_of_quotient<1>(y0), qz.template code_of_quotient<1>(y1),
-                                               qz.template code_of_quotient<1>(y2), qz.template code_of_quotient<1>(y3));
+                            const float2 sc2 = make_float2(sc, sc);
+                            const float2 ya = gelu_fast2(__ffma2_rn(make_float2(f[4 * g], f[4 * g + 1]), sc2, make_float2(b4.x, b4.y)),
+                                                         p.g_prdiv, p.g_nl2e, p.g_add, p.g_out);
+                            const float2 yb = gelu_fast2(__ffma2_rn(make_float2(f[4 * g + 2], f[4 * g + 3]), sc2, make_float2(b4.z, b4.w)),
+                                                         p.g_prdiv, p.g_nl2e, p.g_add, p.g_out);
+                            w[g] = pack4_codes(qz.template code_of_quotient<1>(ya.x), qz.template code_of_quotient<1>(ya.y),
+                                               qz.template code_of_quotient<1>(yb.x), qz.template code_of_quotient<1>(yb.y));
                         } else {
                             const float y0 = __fadd_rn(b4.x, f[4 * g]), y1 = __fadd_rn(b4.y, f[4 * g + 1]);
                             const float y2 = __fadd_rn(b4.z, f[4 * g + 2]), y3 = __fadd_rn(b4.w, f[4 * g + 3]);

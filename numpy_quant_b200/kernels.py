@@ -554,13 +554,14 @@ def can_fuse_layernorm_quantize(x: torch.Tensor) -> bool:
 
 
 def layernorm_quantize(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, bits: int, scale, zp,
-                       want_rowsum: bool) -> Operand:
-    """LayerNormalization -> quantize (operand A) in one kernel."""
+                       want_rowsum: bool, float_glue: bool = False) -> Operand:
+    """LayerNormalization -> quantize (operand A) in one kernel.  float_glue=False: exactly the codes of
+    layernorm() followed by quantize_operand(); True: the normalised value is float glue (1e-5 contract)."""
     _need_cuda(x, torch.float32)
     op, rows, cols, ld = _rows_operand(x, want_rowsum)
     call("nq_layernorm_quantize_f32", x.data_ptr(), rows, cols, cols, gamma.contiguous().data_ptr(),
          beta.contiguous().data_ptr(), float(eps), bits, float(scale), int(zp is not None), 0 if zp is None else int(zp),
-         op.data.data_ptr(), ld, _ptr(op.rowsum), _stream())
+         op.data.data_ptr(), ld, _ptr(op.rowsum), int(float_glue), _stream())
     _count()
     return op
 

@@ -433,6 +433,7 @@ class QModel(Model):
         # False to keep retain=False bit-identical to the node-by-node run.
         self.fuse_softmax_epilogue = True
         self.fuse_gelu_epilogue = True
+        self.fuse_layernorm_glue = True
         self._graphs: dict = {}
         self._graph_launches: dict = {}
 
@@ -613,7 +614,7 @@ class QModel(Model):
         replay it: ~200 kernel launches become one graph launch, so the host interpreter loop
         (Python + ctypes per node) disappears from the steady state.  Quantization parameters are
         static after calibration, so the launch sequence depends on shapes only."""
-        key = tuple((tuple(a.shape), str(a.dtype)) for a in inputs) + (self.fuse_softmax_epilogue, self.fuse_gelu_epilogue)
+        key = tuple((tuple(a.shape), str(a.dtype)) for a in inputs) + (self.fuse_softmax_epilogue, self.fuse_gelu_epilogue, self.fuse_layernorm_glue)
         entry = self._graphs.get(key)
         dev = torch.device("cuda", torch.cuda.current_device())
         if entry is None:
@@ -663,7 +664,7 @@ class QModel(Model):
             if profile:
                 raise ValueError("profile=True needs the eager interpreter (graph=False)")
             if not torch.cuda.is_current_stream_capturing():
-                key = tuple((tuple(a.shape), str(a.dtype)) for a in inputs) + (self.fuse_softmax_epilogue, self.fuse_gelu_epilogue)
+                key = tuple((tuple(a.shape), str(a.dtype)) for a in inputs) + (self.fuse_softmax_epilogue, self.fuse_gelu_epilogue, self.fuse_layernorm_glue)
                 if key not in self._graphs:
                     before = K.LAUNCHES
                     out = self._graph_call(inputs, device_outputs)
@@ -866,7 +867,8 @@ class QModel(Model):
                 xt = node.inputs[0].data.device_tensor
                 qp = self.quant_params[out0.name]
                 op = K.layernorm_quantize(xt, g.device_tensor, b.device_tensor, node.attrs["epsilon"], bits,
-                                          float(qp.scale), _zp_int(qp.zero_point), self._rowsum_needed(out0))
+                                          float(qp.scale), _zp_int(qp.zero_point), self._rowsum_needed(out0),
+                                          float_glue=self.fuse_layernorm_glue)
                 self._emit_operand(out0, op, tuple(xt.shape), qcache)
                 outputs_data = [None]
                 tock(node.op, t0)

@@ -451,6 +451,12 @@ def test_fused_producer_quantize_kernels_equal_the_two_step_route(zp):
     ref = K.quantize_operand(K.layernorm(xd, gd, bd, 1e-12), "A", 8, 0.03, zp, True)
     got = K.layernorm_quantize(xd, gd, bd, 1e-12, 8, 0.03, zp, True)
     assert torch.equal(got.data, ref.data) and torch.equal(got.rowsum, ref.rowsum)
+    # float-glue variant (one FMA for gamma/beta, reciprocal of the scale): codes within one step on a small
+    # fraction of rounding-boundary cases, row sums exact for the emitted codes
+    glue = K.layernorm_quantize(xd, gd, bd, 1e-12, 8, 0.03, zp, True, float_glue=True)
+    gc, rc = host(glue.data).astype(np.int64), host(ref.data).astype(np.int64)
+    assert np.abs(gc - rc).max() <= 1 and np.mean(gc != rc) < 5e-3, (np.abs(gc - rc).max(), np.mean(gc != rc))
+    np.testing.assert_array_equal(host(glue.rowsum).astype(np.int64).reshape(gc.shape[:-1]), gc.sum(-1))
     s = (rng.normal(size=(2, 4, 197, 197)) * 5).astype(np.float32)
     sd = dev(s)
     for div in (None, 8.0):

@@ -145,7 +145,7 @@ def test_small_vit(gv, bits):
     want = gv[f"{pre}/out0"]
     assert np.abs(out - want).max() <= 4 * out_scale and np.abs(out - want).mean() <= 0.5 * out_scale
     # retain=False (freed intermediates, fused kernels) is bit-identical to the retained run
-    q.fuse_softmax_epilogue = q.fuse_gelu_epilogue = False
+    q.fuse_softmax_epilogue = q.fuse_gelu_epilogue = q.fuse_layernorm_glue = False
     out2 = q([x], retain=False)[0]
     np.testing.assert_array_equal(out2, out)
     assert by[a0 + "/query/MatMul_output_0"].data is None
@@ -175,7 +175,7 @@ def test_fused_executor_is_bit_identical_with_epilogue_quantization(bits):
     plan = rg.calibrate(rg.import_graph(proto, ol), [x], bits)
     inject_oracle_params(q, model, plan)
     ref = q([x])[0]
-    q.fuse_softmax_epilogue = q.fuse_gelu_epilogue = False
+    q.fuse_softmax_epilogue = q.fuse_gelu_epilogue = q.fuse_layernorm_glue = False
     fused = q([x], retain=False)[0]
     np.testing.assert_array_equal(fused, ref)
     np.testing.assert_array_equal(q([x], graph=True)[0], ref)
@@ -186,7 +186,7 @@ def test_fused_executor_is_bit_identical_with_epilogue_quantization(bits):
     # softmax in the score-GEMM epilogue and GELU in the first MLP GEMM's epilogue: float glue under the 1e-5
     # contract (different summation order / fused multiply-adds) -> same contract vs the reference, not
     # necessarily the same bits as the node-by-node run
-    q.fuse_softmax_epilogue = q.fuse_gelu_epilogue = True
+    q.fuse_softmax_epilogue = q.fuse_gelu_epilogue = q.fuse_layernorm_glue = True
     fused2 = q([x], retain=False)[0]
     assert np.abs(fused2 - want).max() <= 4 * step and np.abs(fused2 - ref).max() <= 2 * step
     np.testing.assert_array_equal(q([x], graph=True)[0], fused2)
