@@ -41,7 +41,8 @@ def workload_config(n_gpus: int) -> dict:
     return {"workload": "configs[1]: ViT-B/16 image classifier, int8 QModel, batch 256 per GPU, synthetic 224x224",
             "bit_width": BITS, "batch_per_gpu": BATCH, "global_batch": BATCH * n_gpus, "image": "3x224x224",
             "graph": "zoo.vit_graph (= models/vit/vit_image_classifier_no_weights.onnx topology, 516 nodes)",
-            "execution": "qmodel(inputs, retain=False, graph=True): fused interpreter captured into one CUDA graph",
+            "execution": "qmodel(inputs, retain=False, graph=True): fused interpreter captured into one CUDA graph; e2e: "
+                         "qmodel.submit(host inputs).result(), two submissions in flight (copies overlap kernels)",
             "weights": "synthetic N(0,0.02), default_rng(0)", "parallelism": f"dp{n_gpus} (batch shards, no collective)",
             "l2_policy": "inputs+activations per step (>= 154 MB in, ~4 GB touched) exceed the 126 MB L2"}
 
@@ -204,12 +205,26 @@ def run_own_arm(args) -> None:
     timer, K.GEMM_TIMER = K.GEMM_TIMER, None
     eager_ms = r0.elapsed_time(r1)
     # ---- end to end (host buffers) ---------------------------------------------------------
+    # serving loop: two submissions in flight, so the H2D copy of step k+1 and the D2H copy of step k-1 overlap
+    # the kernels of step k; every step's copies and its host-visible logits are inside the timed region
     for _ in range(min(args.warmup, 3)):
         step_e2e()
+    pending = None
+    for _ in range(2):
+        nxt = qmodel.submit([x_host])
+        if pending is not None:
+            pending.result()
+        pending = nxt
+    pending.result()
     barrier()
     t0 = time.perf_counter()
+    pending = None
     for _ in range(args.steps):
-        logits = step_e2e()
+        nxt = qmodel.submit([x_host])
+        if pending is not None:
+            logits = pending.result()[0]
+        pending = nxt
+    logits = pending.result()[0]
     barrier()
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop()

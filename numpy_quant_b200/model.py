@@ -434,6 +434,7 @@ class QModel(Model):
         self.fuse_softmax_epilogue = True
         self.fuse_gelu_epilogue = True
         self.fuse_layernorm_glue = True
+        self._pipes = {}
         self._graphs: dict = {}
         self._graph_launches: dict = {}
 
@@ -649,6 +650,56 @@ class QModel(Model):
         if device_outputs:
             return list(static_out)
         return [o.cpu().numpy() for o in static_out]
+
+    # ------------------------------------------------------------------ pipelined host <-> device serving
+    def submit(self, inputs: list) -> "PendingOutputs":
+        """Asynchronous graph-replay forward for host inputs: returns at once with a handle whose `.result()`
+        yields the host outputs.  Host->device copies run on their own stream into one of two staging buffers,
+        device->host copies on a third stream into pinned buffers, so with two submissions in flight the
+        copies of step k+1 / k-1 overlap the kernels of step k.  Same results as `self(inputs, graph=True)`."""
+        key = tuple((tuple(a.shape), str(a.dtype)) for a in inputs) + (self.fuse_softmax_epilogue, self.fuse_gelu_epilogue, self.fuse_layernorm_glue)
+        if key not in self._graphs:
+            outs = self(inputs, graph=True)                   # first use: warm-up + capture, synchronous
+            return PendingOutputs(outs, None)
+        graph, static_in, static_out = self._graphs[key]
+        pipe = self._pipes.get(key)
+        if pipe is None:
+            pipe = dict(h2d=torch.cuda.Stream(), d2h=torch.cuda.Stream(), n=0,
+                        stage=[[torch.empty_like(t) for t in static_in] for _ in range(2)],
+                        host=[[torch.empty(tuple(o.shape), dtype=o.dtype, pin_memory=True) for o in static_out] for _ in range(2)],
+                        consumed=[None, None], done=[None, None])
+            self._pipes[key] = pipe
+        slot = pipe["n"] % 2
+        pipe["n"] += 1
+        main = torch.cuda.current_stream()
+        with torch.cuda.stream(pipe["h2d"]):
+            if pipe["consumed"][slot] is not None:
+                pipe["h2d"].wait_event(pipe["consumed"][slot])      # staging buffer free again
+            for dst, a in zip(pipe["stage"][slot], inputs):
+                dst.copy_(a if isinstance(a, torch.Tensor) else torch.from_numpy(a), non_blocking=True)
+            staged = torch.cuda.Event()
+            staged.record(pipe["h2d"])
+        main.wait_event(staged)
+        for s_in, st in zip(static_in, pipe["stage"][slot]):
+            s_in.copy_(st, non_blocking=True)
+        consumed = torch.cuda.Event()
+        consumed.record(main)
+        pipe["consumed"][slot] = consumed
+        other = pipe["done"][1 - slot]
+        if other is not None:
+            main.wait_event(other)                                  # previous outputs have left static_out
+        graph.replay()
+        K._count(self._graph_launches.setdefault(key, 0))
+        computed = torch.cuda.Event()
+        computed.record(main)
+        with torch.cuda.stream(pipe["d2h"]):
+            pipe["d2h"].wait_event(computed)
+            for h, o in zip(pipe["host"][slot], static_out):
+                h.copy_(o, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(pipe["d2h"])
+        pipe["done"][slot] = done
+        return PendingOutputs(pipe["host"][slot], done)
 
     def __call__(self, inputs: List[np.ndarray], profile=False, *, retain: bool = True,
                  device_outputs: bool = False, graph: bool = False):
@@ -981,6 +1032,20 @@ class QModel(Model):
                     and len(bias.data.shape) == 1 and bias.data.shape[0] == acc.data._lazy["N"]:
                 return True
         return False
+
+
+class PendingOutputs:
+    """Handle returned by `QModel.submit`: `.result()` waits for this submission's device->host copies and
+    returns the host arrays (valid until the submission after next reuses the pinned buffers)."""
+
+    def __init__(self, outs, event):
+        self._outs, self._event = outs, event
+
+    def result(self) -> list:
+        if self._event is None:
+            return list(self._outs)
+        self._event.synchronize()
+        return [o.numpy() for o in self._outs]
 
 
 def first_not_in(name: str, table: dict) -> bool:

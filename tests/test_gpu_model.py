@@ -192,6 +192,27 @@ def test_fused_executor_is_bit_identical_with_epilogue_quantization(bits):
     np.testing.assert_array_equal(q([x], graph=True)[0], fused2)
 
 
+def test_pipelined_submit_matches_graph_replay():
+    """QModel.submit keeps two forwards in flight (H2D / kernels / D2H on separate streams): results are the
+    graph-replay results, in submission order, for alternating inputs."""
+    cfg = dict(batch=3, image_size=32, patch_size=16, hidden=64, heads=4, intermediate=128, layers=1, classes=10)
+    proto = zoo.vit_graph(seed=4, **cfg)
+    rng = np.random.default_rng(6)
+    xs = [rng.normal(size=(3, 3, 32, 32)).astype(np.float32) for _ in range(3)]
+    q = Model.from_onnx(proto).quantize([xs[0]], bit_width=8)
+    want = [q([x], graph=True)[0].copy() for x in xs]
+    pinned = [torch.from_numpy(x).pin_memory() for x in xs]
+    got, pending = [], None
+    for i in range(7):
+        nxt = q.submit([pinned[i % 3]])
+        if pending is not None:
+            got.append(pending.result()[0].copy())
+        pending = nxt
+    got.append(pending.result()[0].copy())
+    for i, g in enumerate(got):
+        np.testing.assert_array_equal(g, want[i % 3])
+
+
 def test_quantized_matmul_surface_known_answers():
     """test_quantization.py:40-149 restated on the device tensors, plus KA-1 literals."""
     k = np.load(os.path.join(G, "ka1.npz"))
