@@ -247,6 +247,33 @@ def run_own_arm(args) -> None:
         pass
     bf16 = peaks.get("bf16_tflops_sustained")
     peak_tops = 2.0 * bf16 if bf16 else 2.0 * 1400.0
+    # DRAM traffic per GEMM launch from the committed ncu --set full captures (launch-weighted mean over the
+    # captured shapes of the step); None if the summary file is missing
+    traffic, traffic_note = None, None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_gemm_dram_traffic.json")))
+        n = sum(tr["launches_per_step"].values())
+        traffic = sum(tr["per_launch_bytes"][k] * c for k, c in tr["launches_per_step"].items()) / n
+        traffic_note = (f"mean DRAM bytes per launch over the {n} of {len(timer) // max(args.steps, 1)} GEMM launches per step "
+                        "whose shape has an ncu --set full capture (profiles/r01_gemm_dram_traffic.json)")
+    except Exception:
+        pass
+    # library int8 GEMM on the same tensor pipe (cuBLASLt through torch._int_mm, 8192^3), for reference
+    lib_tops = None
+    try:
+        a8 = torch.randint(-128, 127, (8192, 8192), device=dev, dtype=torch.int8)
+        for _ in range(3):
+            torch._int_mm(a8, a8)
+        l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0.record()
+        for _ in range(10):
+            torch._int_mm(a8, a8)
+        l1.record()
+        torch.cuda.synchronize()
+        lib_tops = 10 * 2.0 * 8192 ** 3 / (l0.elapsed_time(l1) * 1e-3) / 1e12
+        del a8
+    except Exception:
+        pass
     achieved = gemm_ops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
     images = BATCH * ws * args.steps
     value = images / (ms * 1e-3)
@@ -260,7 +287,11 @@ def run_own_arm(args) -> None:
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tops, "unit": "TFLOP/s",
-                     "frac": (achieved / peak_tops) if achieved else None, "traffic": None,
+                     "frac": (achieved / peak_tops) if achieved else None, "traffic": traffic, "traffic_note": traffic_note,
+                     "library_int8_tops_8192": lib_tops,
+                     "bound_note": ("the int8 GEMMs of this graph carry fused epilogues (dequantize / softmax / GELU / quantize for "
+                                    "the next MatMul); ncu shows them bound by CUDA-core instruction issue in the epilogue warps "
+                                    "(issue slots 57-77 % busy), not by the tensor pipe -- profiles/r01_*_ncu_full.md"),
                      "kernel": "nq::qgemm_kernel<BN> (all tcgen05 int8 GEMM launches of the step)",
                      "launches_per_step": len(timer) // max(args.steps, 1),
                      "share_of_step": gemm_ms / eager_ms if eager_ms else None,

@@ -125,6 +125,28 @@ def main():
         azp2 = K.AccZeroPoint(-128, 9, S, op_.rowsum, ov_.rowsum, False)
         med, _ = timed(lambda: K.qgemm_to_operand(op_, ov_, 1e-4, azp2, None, 8, 0.05, -3, "merge_heads", 12, S, False))
         emit(case="qgemm ViT PV -> int8 operand (merge_heads)", ms_median=med, tops=2.0 * bt * S * S * D / med / 1e9)
+    if not args.quick:
+        # BASELINE config 3: Conv2d block as im2col + int8 qGEMM, batch 1024 (test_conv2d geometry scaled up)
+        Bc, Cc, Hc, Wc, Oc, kh, kw = 1024, 64, 57, 58, 128, 3, 2
+        g = torch.Generator(device="cuda").manual_seed(3)
+        xf = torch.randn((Bc, Cc, Hc, Wc), generator=g, device=DEV)
+        w8 = torch.randint(-128, 128, (1, kh * kw * Cc, Oc), generator=g, device=DEV, dtype=torch.int8)
+        ow_ = K.operand_from_codes(w8, "B", True)
+        bias = torch.randn(Oc, device=DEV)
+        med_q, _ = timed(lambda: K.quantize(xf, 8, 0.03, -5), iters=5)
+        xq = K.quantize(xf, 8, 0.03, -5)
+        med_i, _ = timed(lambda: K.im2col(xq, kh, kw, (0, 2, 2, 1), (2, 1), -5), iters=5)
+        cols, oh, ow2 = K.im2col(xq, kh, kw, (0, 2, 2, 1), (2, 1), -5)
+        oa = K.Operand(cols.view(1, cols.shape[0], cols.shape[1]), (), cols.shape[0], kh * kw * Cc, cols.shape[1], None)
+        azc = K.AccZeroPoint(-5, None, kh * kw * Cc, None, ow_.rowsum, True)
+        med_g, _ = timed(lambda: K.qgemm(oa, ow_, _lib.EPI_DEQUANT, 1e-4, azc, bias_f32=bias), iters=5)
+        Mc = cols.shape[0]
+        ops = 2.0 * Mc * Oc * kh * kw * Cc
+        emit(case="conv block (config 3) b1024: quantize + im2col + qGEMM(dequant+bias)", M=Mc, N=Oc, K=kh * kw * Cc,
+             out_hw=[oh, ow2], ms_quantize=med_q, ms_im2col=med_i, ms_qgemm=med_g, ms_total=med_q + med_i + med_g,
+             images_per_s=Bc / ((med_q + med_i + med_g) * 1e-3), tops_qgemm=ops / med_g / 1e9,
+             quantize_gbs=xf.numel() * 5 / med_q / 1e6, im2col_gbs=(xq.numel() + cols.numel()) / med_i / 1e6)
+        del xf, xq, cols, oa
     if args.gemm_only:
         return
     # HBM-bound kernels: algorithmic bytes per element as fixed in SURVEY.md §8(d)

@@ -110,6 +110,30 @@ def test_gemm_matmul_conv_graphs(gv):
     np.testing.assert_allclose(q([x])[0], gv["conv/b8/out0"], rtol=1e-5, atol=2e-5)
 
 
+def test_conv_block_config3_geometry_vs_oracle():
+    """BASELINE config 3 (Conv2d block, test_conv2d geometry scaled up: asymmetric pads (0,2,2,1), strides (2,1),
+    kernel (3,2), 64 -> 128 channels, 57x58 inputs) at a batch the oracle finishes in seconds: the integer
+    im2col qGEMM path equals the reference's fake-quant float conv within float32 summation rounding, and the
+    calibrated quantization parameters are the oracle's."""
+    proto = zoo.conv_graph(4, 64, (57, 58), 128, (3, 2), (0, 2, 2, 1), (2, 1), seed=0)
+    x = np.random.default_rng(0).normal(size=(4, 64, 57, 58)).astype(np.float32)
+    m = Model.from_onnx(proto)
+    plan = rg.calibrate(rg.import_graph(proto, ol), [x], 8)
+    fref = rg.run_float(rg.import_graph(proto, ol), [x])[0] if hasattr(rg, "run_float") else None
+    fout = m([x])[0]
+    assert fout.shape == (4, 128, 29, 60)
+    if fref is not None:
+        np.testing.assert_allclose(fout, fref, rtol=1e-4, atol=1e-3)
+    q = m.quantize([x], 8)
+    check_qparams_close(q, plan, rtol=1e-4)
+    inject_oracle_params(q, m, plan)
+    want = rg.run_quant(plan, [x])[0]
+    got = q([x])[0]
+    # K = 384 products of magnitude ~1e2 in float32 (reference) vs exact integers (here): summation rounding only
+    np.testing.assert_allclose(got, want, rtol=1e-5, atol=2e-3)
+    np.testing.assert_array_equal(q([x], retain=False)[0], got)
+
+
 VIT_CFG = dict(batch=2, image_size=32, patch_size=16, hidden=32, heads=4, intermediate=64, layers=2, classes=10)
 
 
