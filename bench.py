@@ -282,8 +282,8 @@ def run_own_arm(args) -> None:
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "int8 x int8 -> int32 (tcgen05 kind::i8), f32 glue", "data": "synthetic",
         "config": workload_config(ws),
-        "e2e": {"value": images / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(x_host.numel() * 4),
-                "d2h_bytes_per_step": int(np.asarray(logits).nbytes), "ms_per_step": e2e_ms / args.steps},
+        "e2e": {"value": images / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(x_host.numel() * 4) * ws,
+                "d2h_bytes_per_step": int(np.asarray(logits).nbytes) * ws, "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tops, "unit": "TFLOP/s",

@@ -25,12 +25,13 @@ constexpr int UMMA_K = 32;       // K per tcgen05.mma for 8-bit operands
 constexpr int NUM_EPI_WARPS = 16;
 constexpr int NUM_THREADS = 128 + 32 * NUM_EPI_WARPS;  // 640 threads; registers re-balanced with setmaxnreg (56 / 104)
 
-template <int BN, bool WIDE = false> struct Cfg {
+template <int BN, bool WIDE = false, bool TWO = false> struct Cfg {
     // WIDE (NQ_EPI_DEQUANT on aligned outputs): 32-column staging slabs, so every float32 row segment that a warp
-    // loads (residual) or stores is a full 128-byte line; paid for with one pipeline stage.
-    static constexpr int STAGES = WIDE ? ((BN == 256) ? 3 : (BN == 128) ? 4 : 6) : ((BN == 256) ? 4 : 6);
+    // loads (residual) or stores is a full 128-byte line; paid for with pipeline stages.
+    // TWO: CTA pair (cta_group::2): the pair computes a 256 x BN tile, each CTA stages its 128 rows of A and its half
+    // (BN / 2 rows) of B -- per-SM operand traffic per MMA halves, which is what the 1-CTA main loop is bound by.
     static constexpr int A_BYTES = BM * BK;
-    static constexpr int B_BYTES = BN * BK;
+    static constexpr int B_BYTES = (TWO ? BN / 2 : BN) * BK;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     // Narrow tiles are drained by GROUPS independent sets of epilogue warps, each on its own tile, so that several
     // small tiles are in flight per CTA (their per-tile latency chain, not the math, bounds e.g. the P.V GEMM):
@@ -41,8 +42,11 @@ template <int BN, bool WIDE = false> struct Cfg {
     static constexpr int SLAB_WORDS = WIDE ? 32 * 32 : 32 * 16;            // per-warp staging slab (32 rows)
     static constexpr int EPI_BYTES = NUM_EPI_WARPS * (SLAB_WORDS * 4 + 32 * 4);   // staging slabs + row terms
     static constexpr int BAR_BYTES = 256;
+    static constexpr int FIT = (232448 - EPI_BYTES - BAR_BYTES) / STAGE_BYTES;
+    static constexpr int STAGES = FIT > 6 ? 6 : FIT;                       // 3-6 (full / empty barriers: 2 x 6 slots)
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES;
-    static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB opt-in shared memory of sm_100");
+    static_assert(STAGES >= 3 && SMEM_BYTES <= 232448, "exceeds the 227 KB opt-in shared memory of sm_100");
+    static_assert(!TWO || BN == 256, "CTA pairs are built for the 256-column tile only");
 };
 
 struct GemmParams {
@@ -72,6 +76,7 @@ struct GemmParams {
     // SOFTMAX epilogue: softmax(dequant / sm_div) over the (single) N tile, quantized with qargs
     int q_rs_exclusive;              // Q8 ROWS: every (row, head) row-sum slot is written by exactly one warp: plain store
     float g_prdiv, g_nl2e, g_add, g_out;   // GELU_QUANT: 0.3275911 / c1, -log2(e) / c1^2, c2, c3 / s_out
+    int two_cta;                     // CTA-pair kernel (256-row tiles, cta_group::2)
     int deq_wide;                    // DEQUANT: alignment / extent conditions of the 32-column epilogue hold (host-checked)
     int fast22;                      // SOFTMAX: |acc - zero-point terms| < 2^22 proved on the host (magic int->float route)
 };
@@ -116,6 +121,42 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
         "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
         ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
         : "memory");
+}
+// ---- CTA-pair (cta_group::2) variants: TMA signals the leader CTA's barrier, commits arrive in both CTAs ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_3d_pair(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
+    // executed by both CTAs; the peer bit of the barrier address is cleared so the bytes land on CTA 0's barrier
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar & 0xFEFFFFFFu)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+__device__ __forceinline__ void mma_i8_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
+// arrive on the barrier at the same offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t rank) {
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(bar), "r"(rank));
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -187,8 +228,8 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 }
 
 // kind::i8 instruction descriptor: D=s32, A=B=signed int8, both K-major, N>>3, M>>4.
-__host__ __device__ constexpr uint32_t make_idesc(int bn) {
-    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+__host__ __device__ constexpr uint32_t make_idesc(int bn, int m = BM) {
+    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 // ------------------------------------------------------------------ epilogue math
@@ -277,10 +318,13 @@ __device__ __noinline__ void deq_wide_fix(const uint32_t* slab, const uint32_t* 
 constexpr int EM_RAW = 0, EM_DEQ_FAST = 1, EM_DEQ_GENERAL = 2, EM_REQUANT = 3, EM_Q8_ROWS = 4, EM_Q8_COLS = 5,
               EM_SOFTMAX_SYM = 6, EM_SOFTMAX_ASYM = 7, EM_Q8_GELU = 8, EM_DEQ_WIDE = 9, EM_DEQ_WIDE_RES = 10;
 
-template <int BN, int EMODE>
+template <int BN, int EMODE, bool TWO = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
-    using C = Cfg<BN, (EMODE == EM_DEQ_WIDE || EMODE == EM_DEQ_WIDE_RES)>;
+    using C = Cfg<BN, (EMODE == EM_DEQ_WIDE || EMODE == EM_DEQ_WIDE_RES), TWO>;
+    constexpr int BMT = TWO ? 2 * BM : BM;                                // rows of the (pair's) tile
+    const uint32_t cta_rank = TWO ? cluster_ctarank() : 0u;               // 0 = leader (issues the MMAs)
+    const uint32_t tile_first = TWO ? (blockIdx.x >> 1) : blockIdx.x, tile_step = TWO ? (gridDim.x >> 1) : gridDim.x;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 128B swizzle atoms need 1024-byte aligned tiles
     uint8_t* smem = smem_raw;
@@ -299,7 +343,7 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
 
     // tile bookkeeping in 32 bits (host guarantees total_tiles < 2^31): 64-bit divides are long
     // emulated sequences that would otherwise sit in every role's tile loop
-    const uint32_t m_tiles = (uint32_t)((p.M + BM - 1) / BM), n_tiles = (uint32_t)((p.N + BN - 1) / BN);
+    const uint32_t m_tiles = (uint32_t)((p.M + BMT - 1) / BMT), n_tiles = (uint32_t)((p.N + BN - 1) / BN);
     const uint32_t tiles_per_batch = m_tiles * n_tiles, total_tiles = tiles_per_batch * (uint32_t)p.batch;
     const uint32_t k_blocks = (uint32_t)((p.K + BK - 1) / BK);
 
@@ -314,18 +358,27 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
         }
         for (int i = 0; i < C::NACC; ++i) {
             mbar_init(smem_u32(tfull_bar + i), 1);
-            mbar_init(smem_u32(tempty_bar + i), NUM_EPI_WARPS / C::GROUPS);  // one arrival per epilogue warp of the group
+            // one arrival per epilogue warp of the group (pair: the warps of both CTAs arrive on the leader's barrier)
+            mbar_init(smem_u32(tempty_bar + i), (TWO ? 2 : 1) * NUM_EPI_WARPS / C::GROUPS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                     "n"(C::TMEM_COLS)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if constexpr (TWO) {                                              // same warp, same slot address in both CTAs
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                         "n"(C::TMEM_COLS)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                         "n"(C::TMEM_COLS)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (TWO) cluster_sync_all();                                // peer barriers initialised, both TMEM halves allocated
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -339,16 +392,24 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (uint32_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            for (uint32_t t = tile_first; t < total_tiles; t += tile_step) {
                 const uint32_t b = t / tiles_per_batch, r = t % tiles_per_batch;
-                const int m0 = (int)(r / n_tiles) * BM, n0 = (int)(r % n_tiles) * BN;
+                // pair: this CTA stages its own 128 rows of A and its half of the B rows
+                const int m0 = (int)(r / n_tiles) * BMT + (int)cta_rank * BM;
+                const int n0 = (int)(r % n_tiles) * BN + (TWO ? (int)cta_rank * (BN / 2) : 0);
                 const int ba = p.a_batched ? (int)b : 0, bb = p.b_batched ? (int)b : 0;
                 for (uint32_t kb = 0; kb < k_blocks; ++kb) {
                     mbar_wait(smem_u32(empty_bar + stage), phase ^ 1);
                     const uint32_t fb = smem_u32(full_bar + stage);
-                    mbar_expect_tx(fb, C::STAGE_BYTES);
-                    tma_load_3d(smem_u32(smem_a + stage * C::A_BYTES), &tmap_a, (int)(kb * BK), m0, ba, fb);
-                    tma_load_3d(smem_u32(smem_b + stage * C::B_BYTES), &tmap_b, (int)(kb * BK), n0, bb, fb);
+                    if constexpr (TWO) {
+                        if (cta_rank == 0) mbar_expect_tx(fb, 2 * C::STAGE_BYTES);   // bytes of both CTAs land here
+                        tma_load_3d_pair(smem_u32(smem_a + stage * C::A_BYTES), &tmap_a, (int)(kb * BK), m0, ba, fb);
+                        tma_load_3d_pair(smem_u32(smem_b + stage * C::B_BYTES), &tmap_b, (int)(kb * BK), n0, bb, fb);
+                    } else {
+                        mbar_expect_tx(fb, C::STAGE_BYTES);
+                        tma_load_3d(smem_u32(smem_a + stage * C::A_BYTES), &tmap_a, (int)(kb * BK), m0, ba, fb);
+                        tma_load_3d(smem_u32(smem_b + stage * C::B_BYTES), &tmap_b, (int)(kb * BK), n0, bb, fb);
+                    }
                     if (++stage == C::STAGES) {
                         stage = 0;
                         phase ^= 1;
@@ -359,13 +420,13 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
         __syncwarp();
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(BN);
+        if (lane == 0 && cta_rank == 0) {                                // pair: the leader CTA issues for both
+            constexpr uint32_t idesc = make_idesc(BN, BMT);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (uint32_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            for (uint32_t t = tile_first; t < total_tiles; t += tile_step) {
                 mbar_wait(smem_u32(tempty_bar + acc), acc_phase ^ 1);     // epilogue drained this buffer
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
@@ -380,17 +441,24 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         // advance 32 bytes along K inside the swizzle atom: +2 in 16-byte units
-                        if (k < ksteps)
-                            mma_i8(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
-                                   (kb > 0 || k > 0) ? 1u : 0u);
+                        if (k < ksteps) {
+                            if constexpr (TWO)
+                                mma_i8_pair(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
+                                            (kb > 0 || k > 0) ? 1u : 0u);
+                            else
+                                mma_i8(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
+                                       (kb > 0 || k > 0) ? 1u : 0u);
+                        }
                     }
-                    tc_commit(smem_u32(empty_bar + stage));               // smem slot free once MMAs retire
+                    if constexpr (TWO) tc_commit_pair(smem_u32(empty_bar + stage));   // frees the slot in both CTAs
+                    else tc_commit(smem_u32(empty_bar + stage));          // smem slot free once MMAs retire
                     if (++stage == C::STAGES) {
                         stage = 0;
                         phase ^= 1;
                     }
                 }
-                tc_commit(smem_u32(tfull_bar + acc));                     // accumulator ready
+                if constexpr (TWO) tc_commit_pair(smem_u32(tfull_bar + acc));   // both CTAs' epilogues
+                else tc_commit(smem_u32(tfull_bar + acc));                // accumulator ready
                 if (++acc == C::NACC) {
                     acc = 0;
                     acc_phase ^= 1;
@@ -438,7 +506,7 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
             o.rowsum = o.c0 = o.c1 = o.b0 = o.b1 = 0;
             if (tt >= total_tiles) return;
             const uint32_t pb = tt / tiles_per_batch, pr = tt - pb * tiles_per_batch;
-            const uint32_t pm0 = (pr / n_tiles) * BM, pn0 = (pr % n_tiles) * BN;
+            const uint32_t pm0 = (pr / n_tiles) * BMT + cta_rank * BM, pn0 = (pr % n_tiles) * BN;
             const int64_t pm = (int64_t)pm0 + q * 32 + lane;
             if (z.use_row && pm < p.M) o.rowsum = ldg_s32(z.rowsum_a + (int64_t)pb * p.M + pm);
             if constexpr (Q8) {
@@ -456,21 +524,21 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
             }
         };
         TilePre nxt;
-        prefetch_tile(blockIdx.x + grp * gridDim.x, nxt);
-        // this CTA's i-th tile is t = blockIdx.x + i * gridDim.x, lives in accumulator buffer i % NACC and is
+        prefetch_tile(tile_first + grp * tile_step, nxt);
+        // this CTA's (pair's) i-th tile is t = tile_first + i * tile_step, lives in accumulator buffer i % NACC and is
         // drained by group i % GROUPS
-        for (uint32_t li = grp, t = blockIdx.x + grp * gridDim.x; t < total_tiles; li += C::GROUPS, t += C::GROUPS * gridDim.x) {
+        for (uint32_t li = grp, t = tile_first + grp * tile_step; t < total_tiles; li += C::GROUPS, t += C::GROUPS * tile_step) {
             const int acc = (int)(li % C::NACC);
             const uint32_t acc_phase = (li / C::NACC) & 1u;
             const int64_t b = t / tiles_per_batch;
             const uint32_t r = t % tiles_per_batch;
-            const int64_t m0 = (int64_t)(r / n_tiles) * BM, n0 = (int64_t)(r % n_tiles) * BN;
+            const int64_t m0 = (int64_t)(r / n_tiles) * BMT + cta_rank * BM, n0 = (int64_t)(r % n_tiles) * BN;
             const int64_t mrow0 = m0 + q * 32;
             const int64_t m = mrow0 + lane;                               // this thread's accumulator row
             const bool row_ok = m < p.M;
             const int32_t* cs_b = z.use_col ? z.colsum_b + b * z.cs_stride : nullptr;
             const TilePre cur = nxt;
-            prefetch_tile(t + C::GROUPS * gridDim.x, nxt);
+            prefetch_tile(t + C::GROUPS * tile_step, nxt);
             int64_t rowterm = -z.kterm;
             if (z.use_row && row_ok) rowterm += (int64_t)cur.rowsum * z.zp_b;
             if constexpr (Q8) {
@@ -620,7 +688,7 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                 if (EMODE != EM_Q8_COLS && p.q_rowsum) flush_rowsum();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(smem_u32(tempty_bar + acc));
+                if (lane == 0) { if constexpr (TWO) mbar_arrive_cluster(smem_u32(tempty_bar + acc), 0); else mbar_arrive(smem_u32(tempty_bar + acc)); }
                 continue;
             }
             if constexpr (EMODE == EM_DEQ_WIDE || EMODE == EM_DEQ_WIDE_RES) {
@@ -713,7 +781,7 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(smem_u32(tempty_bar + acc));
+                if (lane == 0) { if constexpr (TWO) mbar_arrive_cluster(smem_u32(tempty_bar + acc), 0); else mbar_arrive(smem_u32(tempty_bar + acc)); }
                 continue;
             }
             // Column operands (colsum for the zero-point, bias) of the NEXT sub-chunk are always in flight
@@ -827,7 +895,7 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                 // the scores now live in registers: hand the accumulator buffer back to the MMA warp
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(smem_u32(tempty_bar + acc));
+                if (lane == 0) { if constexpr (TWO) mbar_arrive_cluster(smem_u32(tempty_bar + acc), 0); else mbar_arrive(smem_u32(tempty_bar + acc)); }
                 red[h * 128 + rloc] = lmax;
                 named_bar_sync(1 + q, 128);
                 const float gmax = fmaxf(fmaxf(red[rloc], red[128 + rloc]), fmaxf(red[256 + rloc], red[384 + rloc]));
@@ -1038,15 +1106,19 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
             // all TMEM reads of this buffer have completed (wait::ld above)
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(tempty_bar + acc));
+            if (lane == 0) { if constexpr (TWO) mbar_arrive_cluster(smem_u32(tempty_bar + acc), 0); else mbar_arrive(smem_u32(tempty_bar + acc)); }
         }
     }
 
     tc_fence_before();
-    __syncthreads();
+    if constexpr (TWO) cluster_sync_all();                                // neither CTA leaves while the other still uses it
+    else __syncthreads();
     if (warp == 2) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM_COLS) : "memory");
+        if constexpr (TWO)
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM_COLS) : "memory");
+        else
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM_COLS) : "memory");
     }
 }
 
@@ -1100,20 +1172,49 @@ static int make_operand_map(CUtensorMap* map, const int8_t* base, int64_t K, int
     return NQ_OK;
 }
 
-template <int BN, int EMODE>
-static int launch_qgemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t s) {
+template <int BN, int EMODE, bool TWO>
+static int launch_qgemm_impl(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t s) {
+    using C = Cfg<BN, (EMODE == EM_DEQ_WIDE || EMODE == EM_DEQ_WIDE_RES), TWO>;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(qgemm_kernel<BN, EMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             Cfg<BN, (EMODE == EM_DEQ_WIDE || EMODE == EM_DEQ_WIDE_RES)>::SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(qgemm_kernel<BN, EMODE, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(qgemm)");
         configured = true;
     }
-    const int64_t tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN) * p.batch;
-    const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
-    qgemm_kernel<BN, EMODE><<<grid, NUM_THREADS, Cfg<BN, (EMODE == EM_DEQ_WIDE || EMODE == EM_DEQ_WIDE_RES)>::SMEM_BYTES, s>>>(ta, tb, p);
+    constexpr int BMT = TWO ? 2 * BM : BM;
+    const int64_t tiles = ((p.M + BMT - 1) / BMT) * ((p.N + BN - 1) / BN) * p.batch;
+    if constexpr (TWO) {
+        // one cluster of 2 CTAs (a TPC's SM pair) per 256 x BN tile slot
+        const int64_t pairs_max = sm_count() / 2;
+        const int pairs = (int)(tiles < pairs_max ? tiles : pairs_max);
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(2 * pairs, 1, 1);
+        cfg.blockDim = dim3(NUM_THREADS, 1, 1);
+        cfg.dynamicSmemBytes = C::SMEM_BYTES;
+        cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, qgemm_kernel<BN, EMODE, true>, ta, tb, p);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(qgemm, cluster 2)");
+    } else {
+        const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
+        qgemm_kernel<BN, EMODE, false><<<grid, NUM_THREADS, C::SMEM_BYTES, s>>>(ta, tb, p);
+    }
     NQ_CHECK_LAUNCH("nq_qgemm_s8");
     return NQ_OK;
+}
+
+template <int BN, int EMODE>
+static int launch_qgemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t s) {
+    if constexpr (BN == 256 && EMODE != EM_SOFTMAX_SYM && EMODE != EM_SOFTMAX_ASYM) {
+        if (p.two_cta) return launch_qgemm_impl<BN, EMODE, true>(ta, tb, p, s);
+    }
+    return launch_qgemm_impl<BN, EMODE, false>(ta, tb, p, s);
 }
 
 template <int BN>
@@ -1275,9 +1376,16 @@ extern "C" int nq_qgemm_s8(const int8_t* A, const int8_t* B, void* Cout, int64_t
         p.hi = ldexpf(1.f, ep->out_bits - 1) - 1.f;
     }
 
+    {
+        static const bool no_pair = getenv("NQ_NO_2CTA") != nullptr;             // A/B switch for measurements
+        // The pair halves the per-SM operand traffic of the main loop; measured (microbench A/B): +10..20 % where the
+        // main loop dominates (K >= 1024: 4096^3, 8192^3, the K = 3072 MLP GEMM), -5..10 % for K = 768 tiles whose time
+        // is the epilogue (the leader's next MMA has to wait for both CTAs' epilogues).
+        p.two_cta = !no_pair && bn == 256 && ep->mode != NQ_EPI_SOFTMAX_QUANT && M >= 256 && K >= 1024;
+    }
     CUtensorMap ta, tb;
     if (int rc = make_operand_map(&ta, A, K, M, p.a_batched ? batch : 1, lda, stride_a, BM)) return rc;
-    if (int rc = make_operand_map(&tb, B, K, N, p.b_batched ? batch : 1, ldb, stride_b, bn)) return rc;
+    if (int rc = make_operand_map(&tb, B, K, N, p.b_batched ? batch : 1, ldb, stride_b, p.two_cta ? bn / 2 : bn)) return rc;
     cudaStream_t s = (cudaStream_t)stream;
     if (bn == 64) return launch_qgemm_mode<64>(ta, tb, p, s);
     if (bn == 128) return launch_qgemm_mode<128>(ta, tb, p, s);
