@@ -78,6 +78,7 @@ struct GemmParams {
     float g_prdiv, g_nl2e, g_add, g_out;   // GELU_QUANT: 0.3275911 / c1, -log2(e) / c1^2, c2, c3 / s_out
     int two_cta;                     // CTA-pair kernel (256-row tiles, cta_group::2)
     int deq_wide;                    // DEQUANT: alignment / extent conditions of the 32-column epilogue hold (host-checked)
+    int sm_noclamp;                  // SOFTMAX: p / s_out + zp stays inside [lo, hi] for every p in [0, 1]
     int fast22;                      // SOFTMAX: |acc - zero-point terms| < 2^22 proved on the host (magic int->float route)
 };
 
@@ -937,7 +938,10 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                             int c[8];
 #pragma unroll
                             for (int k = 0; k < 8; ++k) {
-                                c[k] = qz.template code_of_quotient<QS>(__fmul_rn(y[j * 8 + k], kr));
+                                // probabilities lie in [0, 1]: when [0, 1 / s_out] maps inside the code range (host
+                                // check) the quotient needs no clamp and rounds straight out of the FMA
+                                c[k] = p.sm_noclamp ? __float_as_int(__fmaf_rn(y[j * 8 + k], kr, qz.magic))
+                                                    : qz.template code_of_quotient<QS>(__fmul_rn(y[j * 8 + k], kr));
                                 if (ragged) c[k] = (j * 8 + k < ncols_w) ? c[k] : 0;
                             }
                             const int w0 = pack4_codes(c[0], c[1], c[2], c[3]), w1 = pack4_codes(c[4], c[5], c[6], c[7]);
@@ -1298,6 +1302,12 @@ extern "C" int nq_qgemm_s8(const int8_t* A, const int8_t* B, void* Cout, int64_t
             const long double ra = fmaxl(fabsl(-128.0L - za), fabsl(127.0L - za));
             const long double rb = fmaxl(fabsl(-128.0L - zb), fabsl(127.0L - zb));
             p.fast22 = (ra * rb * (long double)K) < 4194304.0L;
+        }
+        {
+            // p in [0, 1] (up to a few ulp): p / s_out + zp in [zp, zp + 1 / s_out]; no clamp needed when that
+            // interval, widened by the rounding slack, lies inside [lo - 0.5, hi + 0.5)
+            const double top = (double)p.qargs.zpf + 1.0 / (double)p.qargs.scale * (1.0 + 1e-6);
+            p.sm_noclamp = ((double)p.qargs.zpf >= (double)p.qargs.lo) && (top < (double)p.qargs.hi + 0.49);
         }
     }
     const bool q8 = ep->mode == NQ_EPI_QUANT || ep->mode == NQ_EPI_GELU_QUANT;
