@@ -458,6 +458,22 @@ __global__ void __launch_bounds__(256) copy4d_kernel(const T* __restrict__ x, Co
     }
 }
 
+// innermost dim contiguous on both sides and 16-byte aligned rows: one 16-byte chunk per thread iteration
+__global__ void __launch_bounds__(256) copy4d_rows16_kernel(const uint4* __restrict__ x, Copy4 g, int64_t chunks_per_row,
+                                                           int64_t n_chunks, uint4* __restrict__ out) {
+    // g.sx / g.so of dims 0..2 are in units of 16-byte chunks here (host-converted)
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_chunks; i += stride) {
+        const int64_t c = i % chunks_per_row;
+        int64_t r = i / chunks_per_row;
+        const int64_t i2 = r % g.d[2];
+        r /= g.d[2];
+        const int64_t i1 = r % g.d[1];
+        const int64_t i0 = r / g.d[1];
+        out[i0 * g.so[0] + i1 * g.so[1] + i2 * g.so[2] + c] = __ldcs(x + i0 * g.sx[0] + i1 * g.sx[1] + i2 * g.sx[2] + c);
+    }
+}
+
 // ---- K6 im2col: x[B,C,H,W] -> rows (b, oh, ow), cols (i, j, c) ------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256) im2col_kernel(const T* __restrict__ x, int64_t B, int C, int H, int W, int kh,
@@ -827,6 +843,25 @@ extern "C" int nq_copy_4d(const void* x, int elem_bytes, const int64_t* dims_hos
     if (n <= 0) return NQ_OK;
     cudaStream_t s = (cudaStream_t)stream;
     const int grid = stream_grid(n, 256);
+    {
+        // rows contiguous along the last dim on both sides, everything a multiple of 16 bytes: vector row copy
+        const int64_t eb = elem_bytes, row_bytes = g.d[3] * eb;
+        bool ok = (g.d[3] == 1 || (g.sx[3] == 1 && g.so[3] == 1)) && row_bytes % 16 == 0 &&
+                  (reinterpret_cast<uintptr_t>(x) % 16 == 0) && (reinterpret_cast<uintptr_t>(out) % 16 == 0);
+        for (int i = 0; i < 3 && ok; ++i)
+            if (g.d[i] != 1 && ((g.sx[i] * eb) % 16 != 0 || (g.so[i] * eb) % 16 != 0)) ok = false;
+        if (ok) {
+            Copy4 gc = g;
+            for (int i = 0; i < 3; ++i) {
+                gc.sx[i] = g.sx[i] * eb / 16;
+                gc.so[i] = g.so[i] * eb / 16;
+            }
+            const int64_t cpr = row_bytes / 16, n_chunks = g.d[0] * g.d[1] * g.d[2] * cpr;
+            copy4d_rows16_kernel<<<stream_grid(n_chunks, 256), 256, 0, s>>>((const uint4*)x, gc, cpr, n_chunks, (uint4*)out);
+            NQ_CHECK_LAUNCH("nq_copy_4d");
+            return NQ_OK;
+        }
+    }
     if (elem_bytes == 1) copy4d_kernel<int8_t><<<grid, 256, 0, s>>>((const int8_t*)x, g, n, (int8_t*)out);
     else if (elem_bytes == 4) copy4d_kernel<int32_t><<<grid, 256, 0, s>>>((const int32_t*)x, g, n, (int32_t*)out);
     else if (elem_bytes == 8) copy4d_kernel<int64_t><<<grid, 256, 0, s>>>((const int64_t*)x, g, n, (int64_t*)out);
