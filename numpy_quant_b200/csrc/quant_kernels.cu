@@ -214,6 +214,50 @@ __global__ void __launch_bounds__(256) acc_post_kernel(const int32_t* __restrict
     }
 }
 
+// Vector variant: N % 4 == 0, 16-byte aligned rows.  One thread per 4 consecutive n of a row: one int4 load, the
+// row term once, the 4 column terms as one int4 load, float4 / packed-int8 store.  Same arithmetic as above;
+// the asymmetric requantize tail rint(zp + t) runs through the quantizer's single-add rounding (|zp| < 2^20:
+// exactly round-half-even of zp + t, see common.cuh) instead of float64.
+template <int MODE, bool F64>   // MODE 1 dequant -> f32, 2 requant -> s8; F64: float64 requantize tail (huge zp)
+__global__ void __launch_bounds__(256) acc_post_vec_kernel(const int32_t* __restrict__ acc, int64_t rows, int64_t M,
+                                                          int N4, int64_t ldacc, float scale, AccZp z,
+                                                          const int64_t* __restrict__ bias_q, float inv_out_scale,
+                                                          int has_out_zp, double out_zp, float lo, float hi,
+                                                          void* __restrict__ out) {
+    const int64_t total = rows * N4;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const float zpf = (float)out_zp, tlo = lo - zpf, thi = hi - zpf, magic = kMagic + zpf;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int64_t row = i / N4;
+        const int c4 = (int)(i - row * N4);
+        const int4 a4 = __ldcs(reinterpret_cast<const int4*>(acc + row * ldacc) + c4);
+        int64_t rowterm = -z.kterm;
+        if (z.use_row) rowterm += (int64_t)__ldg(z.rowsum_a + row) * z.zp_b;
+        int4 cs = make_int4(0, 0, 0, 0);
+        if (z.use_col) cs = __ldg(reinterpret_cast<const int4*>(z.colsum_b + (row / M) * z.cs_stride) + c4);
+        const int av[4] = {a4.x, a4.y, a4.z, a4.w}, cv[4] = {cs.x, cs.y, cs.z, cs.w};
+        float d[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            int64_t a = av[k];
+            if (MODE == 2 && bias_q) a += __ldg(bias_q + c4 * 4 + k);
+            d[k] = dequantize_one(a - rowterm - (int64_t)cv[k] * z.zp_a, scale);
+        }
+        if (MODE == 1) {
+            __stcs(reinterpret_cast<float4*>(out) + i, make_float4(d[0], d[1], d[2], d[3]));
+        } else {
+            int c[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (F64) c[k] = has_out_zp ? requantize_one<true>(d[k], inv_out_scale, out_zp, lo, hi)
+                                           : requantize_one<false>(d[k], inv_out_scale, 0.0, lo, hi);
+                else c[k] = __float_as_int(__fadd_rn(fminf(fmaxf(__fmul_rn(inv_out_scale, d[k]), tlo), thi), magic));
+            }
+            __stcs(reinterpret_cast<int*>(out) + i, pack4_codes(c[0], c[1], c[2], c[3]));
+        }
+    }
+}
+
 // requantize tail on an already dequantized tensor: clip(rint(zp + (1/s) * d))
 template <bool ASYM>
 __global__ void __launch_bounds__(256) requantize_f32_kernel(const float* __restrict__ d, int64_t n, float inv,
@@ -361,6 +405,68 @@ __global__ void __launch_bounds__(256) unpack_kernel(const uint8_t* __restrict__
     }
 }
 
+// 32 codes per thread: two 16-byte loads -> BITS 32-bit words of the same bitstream (4 groups of 8 codes), all
+// shifts compile-time constants.  The (< 32 code) tail runs through the byte-granular kernel above.
+template <int BITS>
+__global__ void __launch_bounds__(256) pack32_kernel(const int4* __restrict__ q, int64_t chunks, uint32_t* __restrict__ packed) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    constexpr unsigned mask = (1u << BITS) - 1u;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < chunks; t += stride) {
+        const int4 a = __ldcs(q + 2 * t), b = __ldcs(q + 2 * t + 1);
+        const unsigned w[8] = {(unsigned)a.x, (unsigned)a.y, (unsigned)a.z, (unsigned)a.w,
+                               (unsigned)b.x, (unsigned)b.y, (unsigned)b.z, (unsigned)b.w};
+        uint32_t out[BITS];
+#pragma unroll
+        for (int j = 0; j < BITS; ++j) out[j] = 0;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            const unsigned v = (w[i >> 2] >> ((i & 3) * 8)) & mask;
+            const int bit = i * BITS, j = bit >> 5, sh = bit & 31;
+            out[j] |= v << sh;
+            if (sh + BITS > 32) out[j + 1] |= v >> (32 - sh);
+        }
+#pragma unroll
+        for (int j = 0; j < BITS; ++j) __stcs(packed + t * BITS + j, out[j]);
+    }
+}
+
+template <int BITS>
+__global__ void __launch_bounds__(256) unpack32_kernel(const uint32_t* __restrict__ packed, int64_t chunks, int4* __restrict__ q) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    constexpr unsigned mask = (1u << BITS) - 1u;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < chunks; t += stride) {
+        uint32_t in[BITS + 1];
+#pragma unroll
+        for (int j = 0; j < BITS; ++j) in[j] = __ldcs(packed + t * BITS + j);
+        in[BITS] = 0;
+        unsigned w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            const int bit = i * BITS, j = bit >> 5, sh = bit & 31;
+            unsigned v = in[j] >> sh;
+            if (sh + BITS > 32) v |= in[j + 1] << (32 - sh);
+            int f = (int)(v & mask);
+            f = (f << (32 - BITS)) >> (32 - BITS);                          // sign-extend the field
+            w[i >> 2] |= ((unsigned)f & 0xffu) << ((i & 3) * 8);
+        }
+        __stcs(q + 2 * t, make_int4((int)w[0], (int)w[1], (int)w[2], (int)w[3]));
+        __stcs(q + 2 * t + 1, make_int4((int)w[4], (int)w[5], (int)w[6], (int)w[7]));
+    }
+}
+
+#define NQ_DISPATCH_BITS(bits, KERNEL, ...)                  \
+    do {                                                     \
+        switch (bits) {                                      \
+            case 2: KERNEL<2> __VA_ARGS__; break;            \
+            case 3: KERNEL<3> __VA_ARGS__; break;            \
+            case 4: KERNEL<4> __VA_ARGS__; break;            \
+            case 5: KERNEL<5> __VA_ARGS__; break;            \
+            case 6: KERNEL<6> __VA_ARGS__; break;            \
+            case 7: KERNEL<7> __VA_ARGS__; break;            \
+            default: KERNEL<8> __VA_ARGS__; break;           \
+        }                                                    \
+    } while (0)
+
 }  // namespace nq
 
 using namespace nq;
@@ -456,8 +562,15 @@ extern "C" int nq_dequantize_acc(const int32_t* acc, int64_t batch, int64_t M, i
                                  float scale, const nq_acc_zp* zp, float* out, void* stream) {
     if (batch * M * N <= 0) return NQ_OK;
     if (int rc = check_acc_zp(zp)) return rc;
-    acc_post_kernel<1, false><<<stream_grid(batch * M * N, 256), 256, 0, (cudaStream_t)stream>>>(
-        acc, batch, M, N, ldacc, scale, make_acc_zp(zp), nullptr, 0.f, 0.0, 0.f, 0.f, out);
+    const AccZp z = make_acc_zp(zp);
+    const bool vec = N % 4 == 0 && ldacc % 4 == 0 && ((uintptr_t)acc % 16 == 0) && ((uintptr_t)out % 16 == 0) && N / 4 < (1ll << 31) &&
+                     (!z.use_col || (((uintptr_t)z.colsum_b % 16 == 0) && z.cs_stride % 4 == 0));
+    if (vec)
+        acc_post_vec_kernel<1, false><<<stream_grid(batch * M * (N / 4), 256), 256, 0, (cudaStream_t)stream>>>(
+            acc, batch * M, M, (int)(N / 4), ldacc, scale, z, nullptr, 0.f, 0, 0.0, 0.f, 0.f, out);
+    else
+        acc_post_kernel<1, false><<<stream_grid(batch * M * N, 256), 256, 0, (cudaStream_t)stream>>>(
+            acc, batch, M, N, ldacc, scale, z, nullptr, 0.f, 0.0, 0.f, 0.f, out);
     NQ_CHECK_LAUNCH("nq_dequantize_acc");
     return NQ_OK;
 }
@@ -473,6 +586,23 @@ extern "C" int nq_requantize_acc(const int32_t* acc, int64_t batch, int64_t M, i
     const float inv = 1.0f / out_scale;            // float32(1) / float32 scale, IEEE division (host)
     const int grid = stream_grid(batch * M * N, 256);
     cudaStream_t s = (cudaStream_t)stream;
+    {
+        const AccZp z = make_acc_zp(zp);
+        const bool vec = N % 4 == 0 && ldacc % 4 == 0 && ((uintptr_t)acc % 16 == 0) && ((uintptr_t)out % 4 == 0) && N / 4 < (1ll << 31) &&
+                         (!z.use_col || (((uintptr_t)z.colsum_b % 16 == 0) && z.cs_stride % 4 == 0));
+        if (vec) {
+            const int g4 = stream_grid(batch * M * (N / 4), 256);
+            const bool f64 = has_out_zp && !(out_zp > -(1 << 20) && out_zp < (1 << 20));
+            if (f64)
+                acc_post_vec_kernel<2, true><<<g4, 256, 0, s>>>(acc, batch * M, M, (int)(N / 4), ldacc, scale, z, bias_q, inv,
+                                                                has_out_zp, (double)out_zp, lo, hi, out);
+            else
+                acc_post_vec_kernel<2, false><<<g4, 256, 0, s>>>(acc, batch * M, M, (int)(N / 4), ldacc, scale, z, bias_q, inv,
+                                                                 has_out_zp, has_out_zp ? (double)out_zp : 0.0, lo, hi, out);
+            NQ_CHECK_LAUNCH("nq_requantize_acc");
+            return NQ_OK;
+        }
+    }
     if (has_out_zp)
         acc_post_kernel<2, true><<<grid, 256, 0, s>>>(acc, batch, M, N, ldacc, scale, make_acc_zp(zp), bias_q, inv, (double)out_zp, lo, hi, out);
     else
@@ -520,7 +650,16 @@ extern "C" int nq_minmax_f32(const float* x, int64_t n, float* minmax, int64_t s
 extern "C" int nq_pack_s8(const int8_t* q, int64_t n, int bit_width, uint8_t* packed, void* stream) {
     NQ_REQUIRE(bit_width >= 2 && bit_width <= 8, "nq_pack_s8: bit_width %d outside 2..8", bit_width);
     if (n <= 0) return NQ_OK;
-    pack_kernel<<<stream_grid((n + 7) / 8, 256), 256, 0, (cudaStream_t)stream>>>(q, n, bit_width, packed);
+    cudaStream_t s = (cudaStream_t)stream;
+    int64_t done = 0;
+    if (((uintptr_t)q % 16 == 0) && ((uintptr_t)packed % 4 == 0) && n >= 32) {
+        const int64_t chunks = n / 32;
+        NQ_DISPATCH_BITS(bit_width, pack32_kernel, <<<stream_grid(chunks, 256), 256, 0, s>>>((const int4*)q, chunks, (uint32_t*)packed));
+        done = chunks * 32;
+    }
+    if (done < n)                                      // tail (or unaligned buffers): byte-granular kernel
+        pack_kernel<<<stream_grid((n - done + 7) / 8, 256), 256, 0, s>>>(q + done, n - done, bit_width,
+                                                                        packed + done / 8 * bit_width);
     NQ_CHECK_LAUNCH("nq_pack_s8");
     return NQ_OK;
 }
@@ -528,7 +667,16 @@ extern "C" int nq_pack_s8(const int8_t* q, int64_t n, int bit_width, uint8_t* pa
 extern "C" int nq_unpack_s8(const uint8_t* packed, int64_t n, int bit_width, int8_t* q, void* stream) {
     NQ_REQUIRE(bit_width >= 2 && bit_width <= 8, "nq_unpack_s8: bit_width %d outside 2..8", bit_width);
     if (n <= 0) return NQ_OK;
-    unpack_kernel<<<stream_grid((n + 7) / 8, 256), 256, 0, (cudaStream_t)stream>>>(packed, n, bit_width, q);
+    cudaStream_t s = (cudaStream_t)stream;
+    int64_t done = 0;
+    if (((uintptr_t)q % 16 == 0) && ((uintptr_t)packed % 4 == 0) && n >= 32) {
+        const int64_t chunks = n / 32;
+        NQ_DISPATCH_BITS(bit_width, unpack32_kernel, <<<stream_grid(chunks, 256), 256, 0, s>>>((const uint32_t*)packed, chunks, (int4*)q));
+        done = chunks * 32;
+    }
+    if (done < n)
+        unpack_kernel<<<stream_grid((n - done + 7) / 8, 256), 256, 0, s>>>(packed + done / 8 * bit_width, n - done, bit_width,
+                                                                          q + done);
     NQ_CHECK_LAUNCH("nq_unpack_s8");
     return NQ_OK;
 }
