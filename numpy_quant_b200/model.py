@@ -651,6 +651,29 @@ class QModel(Model):
             return list(static_out)
         return [o.cpu().numpy() for o in static_out]
 
+    # ------------------------------------------------------------------ sub-byte weight storage
+    def pack_weights(self) -> dict:
+        """Store every quantized MatMul / Gemm weight (right operand, a Constant) as a bit_width-bit packed
+        bitstream (BASELINE config 4: int4 / 2-bit sweeps with sub-byte packing); each forward unpacks a weight
+        into a transient int8 operand right before its GEMM.  Results are unchanged.  Returns the byte counts."""
+        packed = dense = 0
+        for n in self.nodes:
+            if n.op not in ("MatMul", "Gemm") or len(n.inputs) < 2:
+                continue
+            wv = n.inputs[1]
+            if not isinstance(wv, Constant) or not isinstance(wv.data, QTensor) or wv.data.bit_width > 8:
+                continue
+            # Gemm(transB=1) consumes the transposed view of the stored [N, K] matrix: its K-major form is role "A"
+            role = "A" if (n.op == "Gemm" and n.attrs.get("transB")) else "B"
+            q = wv.data
+            if len(q.shape) != 2:
+                continue
+            dense += int(np.prod(q.shape))
+            packed += q.pack_storage(role)
+        self._graphs.clear()                                 # captured graphs hold the old operand buffers
+        self._pipes.clear()
+        return {"int8_bytes": dense, "resident_bytes": packed, "bit_width": self.bit_width}
+
     # ------------------------------------------------------------------ pipelined host <-> device serving
     def submit(self, inputs: list) -> "PendingOutputs":
         """Asynchronous graph-replay forward for host inputs: returns at once with a handle whose `.result()`

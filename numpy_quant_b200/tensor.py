@@ -264,12 +264,16 @@ class QTensor:
       _oplayout (Operand, role, logical shape): codes that so far exist only in the K-major
                 operand layout of the GEMM (written there directly by quantize_tensor)
       _lazy     pending GEMM of a matmul result (operands + optional int bias)
+      _packed   (role, packed bitstream, operand geometry, row sums): sub-byte storage of a weight -- the K-major
+                operand buffer packed to bit_width bits per code (nq_pack_s8); unpacked into a transient int8
+                operand right before each GEMM (the tensor pipe has no int4 / int2 kind)
     """
 
     def __init__(self, data, bit_width: int, scale, zero_point=None):
         self._lazy = None
         self._oplayout = None
         self._ops: dict = {}           # cached K-major GEMM operands by role
+        self._packed = None
         self._src = None               # base QTensor when this is the 2-D transpose of it
         self._host = None
         self._deq = None
@@ -326,6 +330,8 @@ class QTensor:
             return tuple(self._q.shape)
         if self._oplayout is not None:
             return tuple(self._oplayout[2])
+        if self._packed is not None:
+            return tuple(self._packed["logical"])
         L = self._lazy
         return tuple(L["batch_shape"]) + (L["M"], L["N"])
 
@@ -335,6 +341,13 @@ class QTensor:
     def _codes(self) -> torch.Tensor:
         """Integer codes in logical layout (un-pads an operand / runs the pending GEMM raw)."""
         if self._q is None:
+            if self._packed is not None and self._oplayout is None:
+                P = self._packed                                # observability only: the GEMM path never comes here
+                op = self._unpacked_operand()
+                v = op.data[:, :, : op.k]
+                if P["role"] == "B":
+                    v = v.transpose(1, 2)
+                return K.materialize(v).view(P["logical"])      # not cached: storage stays packed
             if self._oplayout is not None:
                 op, role, shape = self._oplayout
                 v = op.data[:, :, : op.k]
@@ -519,9 +532,34 @@ class QTensor:
         return self._host
 
     # -- K4 / K5 -----------------------------------------------------------------------
+    # -- sub-byte storage ---------------------------------------------------------------
+    def pack_storage(self, role: str = "B") -> int:
+        """Keep only the bit_width-bit packed form of this tensor's GEMM operand (plus its row sums); returns the
+        bytes now resident.  `.data` still works (unpacks on demand)."""
+        if self._src is not None:
+            return self._src.pack_storage("A" if role == "B" else "B")
+        if self._packed is not None:
+            return int(self._packed["data"].numel())
+        op = self._operand(role, True)
+        logical = tuple(self.shape)
+        packed = K.pack(op.data.reshape(-1), self.bit_width)
+        self._packed = dict(role=role, data=packed, n=int(op.data.numel()), dshape=tuple(op.data.shape),
+                            batch_shape=tuple(op.batch_shape), rows=op.rows, k=op.k, ld=op.ld, rowsum=op.rowsum,
+                            logical=logical)
+        self._q, self._oplayout, self._deq, self._host = None, None, None, None
+        self._ops.clear()
+        return int(packed.numel())
+
+    def _unpacked_operand(self) -> K.Operand:
+        P = self._packed
+        data = K.unpack(P["data"], P["n"], self.bit_width).view(P["dshape"])
+        return K.Operand(data, P["batch_shape"], P["rows"], P["k"], P["ld"], P["rowsum"])
+
     def _operand(self, role: str, want_rowsum: bool) -> K.Operand:
         if self._src is not None:                       # transposed 2-D view: roles swap, cache on the base
             return self._src._operand("A" if role == "B" else "B", want_rowsum)
+        if self._packed is not None and self._packed["role"] == role:
+            return self._unpacked_operand()             # transient int8 operand, freed after the GEMM
         op = self._ops.get(role)
         if op is None:
             q = self._codes()

@@ -216,6 +216,36 @@ def test_fused_executor_is_bit_identical_with_epilogue_quantization(bits):
     np.testing.assert_array_equal(q([x], graph=True)[0], fused2)
 
 
+@pytest.mark.parametrize("bits", [4, 2])
+def test_packed_weight_storage_config4(bits):
+    """BASELINE config 4 (ViT int4 / 2-bit with sub-byte packing): weights kept as bit_width-bit bitstreams and
+    unpacked into transient int8 operands per GEMM give bit-identical outputs, `.data` of a packed weight still
+    returns the reference's int64 codes, and the resident bytes shrink by 8 / bit_width (up to row padding)."""
+    cfg = dict(batch=2, image_size=32, patch_size=16, hidden=64, heads=4, intermediate=128, layers=2, classes=10)
+    proto = zoo.vit_graph(seed=7, **cfg)
+    x = np.random.default_rng(8).normal(size=(2, 3, 32, 32)).astype(np.float32)
+    model = Model.from_onnx(proto)
+    q = model.quantize([x], bit_width=bits)
+    plan = rg.calibrate(rg.import_graph(proto, ol), [x], bits)
+    inject_oracle_params(q, model, plan)
+    ref = q([x])[0]
+    ref_fused = q([x], retain=False)[0]
+    wname = next(n.inputs[1].name for n in q.nodes if n.op == "MatMul" and isinstance(n.inputs[1].data, QTensor)
+                 and len(n.inputs[1].data.shape) == 2)
+    wq = {v.name: v for v in q.values}[wname].data
+    codes_before = wq.data.copy()
+    info = q.pack_weights()
+    assert info["resident_bytes"] <= info["int8_bytes"] * bits / 8 * 1.35 + 64, info
+    np.testing.assert_array_equal(wq.data, codes_before)
+    assert wq.data.dtype == np.int64 and np.abs(codes_before).max() <= 2 ** (bits - 1)
+    np.testing.assert_array_equal(q([x])[0], ref)
+    np.testing.assert_array_equal(q([x], retain=False)[0], ref_fused)
+    np.testing.assert_array_equal(q([x], graph=True)[0], ref_fused)
+    want = rg.run_quant(plan, [x])[0]
+    step = float(plan.qparams["logits"][0])
+    assert np.abs(ref - want).max() <= 4 * step
+
+
 def test_pipelined_submit_matches_graph_replay():
     """QModel.submit keeps two forwards in flight (H2D / kernels / D2H on separate streams): results are the
     graph-replay results, in submission order, for alternating inputs."""
