@@ -246,6 +246,52 @@ def test_packed_weight_storage_config4(bits):
     assert np.abs(ref - want).max() <= 4 * step
 
 
+def test_vit_b16_full_size_batch_invariance_and_replay():
+    """BASELINE config 2 at its full size (ViT-B/16, batch 256, synthetic 224x224), through size-independent
+    properties: quantization parameters are per-tensor and static, every kernel works row by row, and row sums are
+    exact integer sums, so (a) the logits of an image do not depend on what else is in the batch -- with the batch
+    made of 32 copies of the same 8 images, every copy equals a batch-8 forward with the same parameters
+    bit for bit -- and (b) for 256 distinct images eager fused execution, CUDA-graph replay and the pipelined submit
+    path agree bit for bit."""
+    vit = dict(image_size=224, patch_size=16, hidden=768, heads=12, intermediate=3072, layers=12, classes=1000)
+    rng = np.random.default_rng(1)
+    x8 = torch.from_numpy(rng.normal(size=(8, 3, 224, 224)).astype(np.float32)).cuda()
+    x_rep = x8.repeat(32, 1, 1, 1).contiguous()
+    big = Model.from_onnx(zoo.vit_graph(batch=256, seed=0, **vit))
+    qbig = big.quantize([x_rep], bit_width=8)
+    big.release()
+    small = Model.from_onnx(zoo.vit_graph(batch=8, seed=0, **vit))
+    qsmall = small.quantize([x8], bit_width=8)
+    small.release()
+    # The float calibration pass runs fp32 cuBLAS GEMMs whose summation order depends on the batch size, so min / max
+    # can differ by an ulp between the two graphs: give the batch-8 model the batch-256 model's parameters and
+    # quantized constants ("identical inputs and scales").
+    checked = 0
+    for name, qp in qbig.quant_params.items():
+        other = qsmall.quant_params[name]
+        if any(k in name for k in ("MatMul", "LayerNorm", "Softmax", "bias", "weight")):
+            np.testing.assert_allclose(np.float64(qp.scale), np.float64(other.scale), rtol=1e-5, err_msg=name)
+            checked += 1
+        qsmall.quant_params[name] = qp
+    assert checked > 200
+    big_consts = {v.name: v for v in qbig.values if isinstance(v, Constant)}
+    for v in qsmall.values:
+        if isinstance(v, Constant) and isinstance(v.data, QTensor):
+            v.data = big_consts[v.name].data
+    qsmall._const_deq.clear()
+    out8 = qsmall([x8], retain=False, device_outputs=True)[0].clone()
+    out_rep = qbig([x_rep], retain=False, device_outputs=True)[0].clone()
+    assert tuple(out_rep.shape) == (256, 1000) and bool(torch.isfinite(out_rep).all())
+    assert torch.equal(out_rep.view(32, 8, 1000), out8.unsqueeze(0).expand(32, 8, 1000))
+    x = torch.from_numpy(rng.normal(size=(256, 3, 224, 224)).astype(np.float32)).cuda()
+    out256 = qbig([x], retain=False, device_outputs=True)[0].clone()
+    replay = qbig([x], retain=False, device_outputs=True, graph=True)[0]
+    assert torch.equal(replay, out256)
+    host = qbig.submit([x.cpu().pin_memory()]).result()[0]
+    np.testing.assert_array_equal(host, out256.cpu().numpy())
+    assert len(set(out256.argmax(-1).cpu().tolist())) > 4      # not degenerate
+
+
 def test_pipelined_submit_matches_graph_replay():
     """QModel.submit keeps two forwards in flight (H2D / kernels / D2H on separate streams): results are the
     graph-replay results, in submission order, for alternating inputs."""
