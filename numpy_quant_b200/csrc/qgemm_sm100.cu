@@ -870,17 +870,29 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                                 c16[4 * g] = c4.x; c16[4 * g + 1] = c4.y; c16[4 * g + 2] = c4.z; c16[4 * g + 3] = c4.w;
                             }
                             tmem_ld_wait();
+                            // columns past N only in the last (ragged) pair of groups: warp-uniform fast path
+                            const bool clean = j2 * 8 + 16 <= ncols_w || (j2 + 1 >= NSUB && j2 * 8 + 8 <= ncols_w);
+                            if (clean) {
 #pragma unroll
-                            for (int k = 0; k < 16; ++k) {
-                                if (j2 * 8 + k >= NSUB * 8) break;        // compile time: the 7th group is 8 wide
-                                const bool live = k < 8 || two;           // warp-uniform
-                                const bool ragged = j2 * 8 + (k < 8 ? 8 : 16) > ncols_w;
-                                const int x = (int)a16[k] + rm - c16[k];
-                                float f = MAGIC ? __fmul_rn(__fadd_rn(__int_as_float(x), -12582912.0f), p.scale)
-                                                : __fmul_rn(__int2float_rn(x), p.scale);
-                                if (!live || (ragged && j2 * 8 + k >= ncols_w)) f = kMasked;
-                                y[j2 * 8 + k] = f;
-                                lmax = fmaxf(lmax, f);
+                                for (int k = 0; k < 16; ++k) {
+                                    if (j2 * 8 + k >= NSUB * 8) break;    // compile time: the 7th group is 8 wide
+                                    const int x = (int)a16[k] + rm - c16[k];
+                                    const float f = MAGIC ? __fmul_rn(__fadd_rn(__int_as_float(x), -12582912.0f), p.scale)
+                                                          : __fmul_rn(__int2float_rn(x), p.scale);
+                                    y[j2 * 8 + k] = f;
+                                    lmax = fmaxf(lmax, f);
+                                }
+                            } else {
+#pragma unroll
+                                for (int k = 0; k < 16; ++k) {
+                                    if (j2 * 8 + k >= NSUB * 8) break;
+                                    const int x = (int)a16[k] + rm - c16[k];
+                                    float f = MAGIC ? __fmul_rn(__fadd_rn(__int_as_float(x), -12582912.0f), p.scale)
+                                                    : __fmul_rn(__int2float_rn(x), p.scale);
+                                    if (j2 * 8 + k >= ncols_w) f = kMasked;  // also covers the unloaded upper half
+                                    y[j2 * 8 + k] = f;
+                                    lmax = fmaxf(lmax, f);
+                                }
                             }
                         } else {
 #pragma unroll
@@ -931,28 +943,29 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                 if (row_ok && ncols_w > 0) {
                     const float kr = __frcp_rn(__fmul_rn(gsum, p.qargs.scale));   // 1 / (row sum * output scale)
                     int8_t* dst = reinterpret_cast<int8_t*>(p.C) + b * p.stride_c + m * p.ldc + col0;
+                    // full groups of 8 columns carry no masking at all; the (at most one) ragged group is separate.
+                    // A group that holds a valid column always lies inside the row (ldc = round_up(N, 16)), so every
+                    // store is one aligned 8-byte store.
+                    const int nfull = ncols_w >> 3, nrem = ncols_w & 7;
+                    auto emit_group = [&](int j, auto ragged_tag) {
+                        constexpr bool RAGGED = decltype(ragged_tag)::value;
+                        int c[8];
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            // probabilities lie in [0, 1]: when [0, 1 / s_out] maps inside the code range (host
+                            // check) the quotient needs no clamp and rounds straight out of the FMA
+                            c[k] = p.sm_noclamp ? __float_as_int(__fmaf_rn(y[j * 8 + k], kr, qz.magic))
+                                                : qz.template code_of_quotient<QS>(__fmul_rn(y[j * 8 + k], kr));
+                            if (RAGGED) c[k] = (k < nrem) ? c[k] : 0;
+                        }
+                        const int w0 = pack4_codes(c[0], c[1], c[2], c[3]), w1 = pack4_codes(c[4], c[5], c[6], c[7]);
+                        qsum = __dp4a(w0, 0x01010101, __dp4a(w1, 0x01010101, qsum));
+                        *reinterpret_cast<int2*>(dst + j * 8) = make_int2(w0, w1);
+                    };
 #pragma unroll
                     for (int j = 0; j < NSUB; ++j) {
-                        if (j * 8 < ncols_w) {
-                            const bool ragged = j * 8 + 8 > ncols_w;
-                            int c[8];
-#pragma unroll
-                            for (int k = 0; k < 8; ++k) {
-                                // probabilities lie in [0, 1]: when [0, 1 / s_out] maps inside the code range (host
-                                // check) the quotient needs no clamp and rounds straight out of the FMA
-                                c[k] = p.sm_noclamp ? __float_as_int(__fmaf_rn(y[j * 8 + k], kr, qz.magic))
-                                                    : qz.template code_of_quotient<QS>(__fmul_rn(y[j * 8 + k], kr));
-                                if (ragged) c[k] = (j * 8 + k < ncols_w) ? c[k] : 0;
-                            }
-                            const int w0 = pack4_codes(c[0], c[1], c[2], c[3]), w1 = pack4_codes(c[4], c[5], c[6], c[7]);
-                            qsum = __dp4a(w0, 0x01010101, __dp4a(w1, 0x01010101, qsum));
-                            if (col0 + j * 8 + 8 <= p.ldc) {               // ldc is a multiple of 16: 8-byte aligned store
-                                *reinterpret_cast<int2*>(dst + j * 8) = make_int2(w0, w1);
-                            } else {
-                                for (int k = 0; k < 8 && col0 + j * 8 + k < p.ldc; ++k)
-                                    dst[j * 8 + k] = (int8_t)((k < 4 ? w0 : w1) >> ((k & 3) * 8));
-                            }
-                        }
+                        if (j < nfull) emit_group(j, std::false_type{});
+                        else if (j == nfull && nrem > 0) emit_group(j, std::true_type{});
                     }
                 }
                 if (p.q_rowsum) {
