@@ -510,8 +510,8 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
             const uint32_t pm0 = (pr / n_tiles) * BMT + cta_rank * BM, pn0 = (pr % n_tiles) * BN;
             const int64_t pm = (int64_t)pm0 + q * 32 + lane;
             if (z.use_row && pm < p.M) o.rowsum = ldg_s32(z.rowsum_a + (int64_t)pb * p.M + pm);
-            if constexpr (Q8) {
-                constexpr int W = 64;                                     // columns owned by this warp
+            if constexpr (SOFTMAX || Q8) {
+                constexpr int W = SOFTMAX ? 56 : 64;                      // columns owned by this warp
                 const int64_t c0i = (int64_t)pn0 + hc * W + lane, c1i = c0i + 32;
                 const int32_t* pcs = z.use_col ? z.colsum_b + (int64_t)pb * z.cs_stride : nullptr;
                 if (lane < W && c0i < p.N) {
@@ -809,14 +809,12 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
             };
             if (FASTF) fetch_cols(hc);
             if (SOFTMAX) {
-                // this warp's 56 column terms (colsum * zp_a) -> its private smem strip, fetched while the
-                // MMA is still running; read back as broadcast LDS in the softmax loop
+                // this warp's 56 column terms (colsum * zp_a, fetched one tile ahead) -> its private smem strip,
+                // read back as broadcast LDS in the softmax loop
                 int* ctw = reinterpret_cast<int*>(epi) + 1024 + ew * 64;
-                const int cbase0 = h * 56;
                 __syncwarp();
-                const int c0i = cbase0 + lane, c1i = cbase0 + 32 + lane;
-                ctw[lane] = (cs_b && c0i < p.N) ? ldg_s32(cs_b + c0i) * zpa : 0;
-                ctw[32 + lane] = (cs_b && lane < 24 && c1i < p.N) ? ldg_s32(cs_b + c1i) * zpa : 0;
+                ctw[lane] = cur.c0 * zpa;
+                ctw[32 + lane] = cur.c1 * zpa;
                 __syncwarp();
             }
             mbar_wait(smem_u32(tfull_bar + acc), acc_phase);
