@@ -21,7 +21,7 @@ from . import kernels as K
 from . import onnx_lite
 from .numpy_quantization import quant_parameters
 from .tensor import (FTensor, ITensor, QTensor, Tensor, concat, fconv2d, qconv2d, qtensor_from_operand,
-                     quantize_tensor, where)
+                     quantize_tensor, where, _to_device)
 
 
 class Constant:
@@ -650,6 +650,129 @@ class QModel(Model):
         if device_outputs:
             return list(static_out)
         return [o.cpu().numpy() for o in static_out]
+
+    # ------------------------------------------------------------------ persistence
+    def save(self, path: str) -> None:
+        """Write the quantized model -- graph, quantization parameters and the quantized constants with their
+        bit_width-bit codes packed (nq_pack_s8) -- as one `.npz`; `QModel.load` restores it without the float
+        weights or a calibration pass.  (The reference has no persistence of `QModel`.)"""
+        import json
+        arrays: dict = {}
+
+        def enc_attr(v):
+            if isinstance(v, np.ndarray):
+                key = f"attr{len(arrays)}"
+                arrays[key] = v
+                return {"t": "array", "k": key}
+            if isinstance(v, (bytes, bytearray)):
+                return {"t": "bytes", "v": v.decode("latin1")}
+            if isinstance(v, (list, tuple)):
+                return {"t": "list", "v": [enc_attr(x) for x in v]}
+            if isinstance(v, (np.integer, int)):
+                return {"t": "int", "v": int(v)}
+            if isinstance(v, (np.floating, float)):
+                return {"t": "float", "v": float(v)}
+            if isinstance(v, str):
+                return {"t": "str", "v": v}
+            raise ValueError(f"cannot serialise attribute of type {type(v)}")
+
+        def enc_zp(z):
+            return None if z is None else int(np.asarray(z).reshape(-1)[0])
+
+        values = []
+        for i, v in enumerate(self.values):
+            rec = {"name": v.name, "kind": "const" if isinstance(v, Constant) else "var"}
+            d = v.data if isinstance(v, Constant) else None
+            if isinstance(d, QTensor):
+                codes = np.ascontiguousarray(d.data)                       # int64, reference layout
+                rec.update(tensor="q", bits=int(d.bit_width), scale=float(np.float32(d.scale)), zp=enc_zp(d.zero_point),
+                           shape=list(codes.shape))
+                key = f"const{i}"
+                if d.bit_width <= 8 and codes.size:
+                    packed = K.pack(_to_device(codes.astype(np.int8)).reshape(-1), int(d.bit_width))
+                    arrays[key] = packed.cpu().numpy()
+                    rec["packed"] = True
+                else:
+                    arrays[key] = codes
+                    rec["packed"] = False
+                rec["k"] = key
+            elif isinstance(d, ITensor):
+                key = f"const{i}"
+                arrays[key] = np.asarray(d.data)
+                rec.update(tensor="i", k=key)
+            elif isinstance(d, FTensor):
+                key = f"const{i}"
+                arrays[key] = np.asarray(d.data)
+                rec.update(tensor="f", k=key)
+            values.append(rec)
+        meta = {
+            "format": "numpy_quant_b200.qmodel/1", "bit_width": int(self.bit_width),
+            "nodes": [{"name": n.name, "op": n.op, "attrs": {k: enc_attr(a) for k, a in n.attrs.items()},
+                       "inputs": [i.name for i in n.inputs], "outputs": [o.name for o in n.outputs]} for n in self.nodes],
+            "values": values, "inputs": [v.name for v in self.inputs], "outputs": [v.name for v in self.outputs],
+            "qparams": {name: [float(np.float32(qp.scale)), enc_zp(qp.zero_point)] for name, qp in self.quant_params.items()},
+        }
+        arrays["meta"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
+        np.savez(path, **arrays)
+
+    @classmethod
+    def load(cls, path: str) -> "QModel":
+        """Restore a model written by `save` (codes unpacked on the device)."""
+        import json
+        with np.load(path if str(path).endswith(".npz") else str(path) + ".npz") as z:
+            meta = json.loads(bytes(z["meta"]).decode())
+            if meta.get("format") != "numpy_quant_b200.qmodel/1":
+                raise ValueError("not a numpy_quant_b200 quantized-model file")
+            arrays = {k: z[k] for k in z.files if k != "meta"}
+
+        def dec_attr(e):
+            t = e["t"]
+            if t == "array":
+                return arrays[e["k"]]
+            if t == "bytes":
+                return e["v"].encode("latin1")
+            if t == "list":
+                return [dec_attr(x) for x in e["v"]]
+            return e["v"]
+
+        def dec_zp(zv):
+            return None if zv is None else np.int64(zv)
+
+        vals: dict = {}
+        for rec in meta["values"]:
+            if rec["kind"] == "var":
+                vals[rec["name"]] = Variable(rec["name"], [], [], None)
+                continue
+            kind = rec.get("tensor")
+            if kind == "q":
+                shape = tuple(rec["shape"])
+                if rec["packed"]:
+                    n = int(np.prod(shape))
+                    codes = K.unpack(_to_device(arrays[rec["k"]]), n, int(rec["bits"])).view(shape)
+                    data = QTensor(codes, int(rec["bits"]), np.float32(rec["scale"]), dec_zp(rec["zp"]))
+                else:
+                    data = QTensor(arrays[rec["k"]].astype(np.int64).reshape(shape), int(rec["bits"]), np.float32(rec["scale"]),
+                                   dec_zp(rec["zp"]))
+            elif kind == "i":
+                data = ITensor(arrays[rec["k"]])
+            elif kind == "f":
+                data = FTensor(arrays[rec["k"]])
+            else:
+                data = None
+            vals[rec["name"]] = Constant(rec["name"], [], data)
+        nodes = []
+        for nrec in meta["nodes"]:
+            node = Node(nrec["name"], nrec["op"], {k: dec_attr(a) for k, a in nrec["attrs"].items()},
+                        [vals[i] for i in nrec["inputs"]], [vals[o] for o in nrec["outputs"]])
+            nodes.append(node)
+            for v in node.inputs:
+                v.outputs.append(node)
+            for v in node.outputs:
+                if isinstance(v, Variable):
+                    v.inputs.append(node)
+        qparams = {name: QuantizationParams(np.float32(sv), dec_zp(zv)) for name, (sv, zv) in meta["qparams"].items()}
+        return cls(nodes, [vals[r["name"]] for r in meta["values"]], [vals[n] for n in meta["inputs"]],
+                   [vals[n] for n in meta["outputs"]], int(meta["bit_width"]), qparams)
 
     # ------------------------------------------------------------------ sub-byte weight storage
     def pack_weights(self) -> dict:

@@ -292,6 +292,32 @@ def test_vit_b16_full_size_batch_invariance_and_replay():
     assert len(set(out256.argmax(-1).cpu().tolist())) > 4      # not degenerate
 
 
+@pytest.mark.parametrize("bits", [8, 4])
+def test_qmodel_save_load_roundtrip(tmp_path, bits):
+    """a quantized model written with packed codes reloads without float weights or calibration
+    and reproduces every output bit for bit (node-by-node, fused and graph replay); MLP (Gemm/int64 biases) and ViT."""
+    proto = ol.load(os.path.join(G, "mlp.onnx"))
+    xm = np.random.default_rng(2).normal(size=(16, 2)).astype(np.float32)
+    qm = Model.from_onnx(proto).quantize([xm], bit_width=bits)
+    qm.save(str(tmp_path / "mlp.npz"))
+    qm2 = QModel.load(str(tmp_path / "mlp.npz"))
+    np.testing.assert_array_equal(qm2([xm])[0], qm([xm])[0])
+    cfg = dict(batch=2, image_size=32, patch_size=16, hidden=64, heads=4, intermediate=128, layers=2, classes=10)
+    x = np.random.default_rng(3).normal(size=(2, 3, 32, 32)).astype(np.float32)
+    q = Model.from_onnx(zoo.vit_graph(seed=5, **cfg)).quantize([x], bit_width=bits)
+    path = str(tmp_path / "vit.npz")
+    q.save(path)
+    q2 = QModel.load(path)
+    assert q2.bit_width == bits and set(q2.quant_params) == set(q.quant_params)
+    np.testing.assert_array_equal(q2([x])[0], q([x])[0])
+    np.testing.assert_array_equal(q2([x], retain=False)[0], q([x], retain=False)[0])
+    np.testing.assert_array_equal(q2([x], graph=True)[0], q([x], graph=True)[0])
+    # packed codes: the file is much smaller than int8 weights would be at 4 bit
+    wbytes = sum(int(np.prod(v.data.shape)) for v in q.values if isinstance(v, Constant) and isinstance(v.data, QTensor)
+                 and v.data.bit_width <= 8)
+    assert os.path.getsize(path) < wbytes * bits / 8 * 1.6 + 200000
+
+
 def test_pipelined_submit_matches_graph_replay():
     """QModel.submit keeps two forwards in flight (H2D / kernels / D2H on separate streams): results are the
     graph-replay results, in submission order, for alternating inputs."""
