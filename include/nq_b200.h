@@ -160,6 +160,42 @@ typedef struct nq_epilogue {
                                              Div(x, c1) -> Erf -> Add(., c2) -> Mul(x, .) -> Mul(., c3) chain */
 } nq_epilogue;
 
+/* ---- fused quantized attention (one kernel per layer; replaces, for every image and head, the chain
+ * MatMul(Q, K^T) -> dequantize -> Div -> Softmax -> quantize -> MatMul(P, V) -> dequantize -> Transpose(0,2,1,3) ->
+ * Reshape -> quantize of the reference's interpreter, model.py:486-565 with tensor.py:139-146 / 205-210).
+ * Q  [BH, S, ld_q]  int8 K-major (row = query, contraction D)          -- left operand of the score MatMul
+ * Kt [BH, S, ld_k]  int8 K-major (row = key,   contraction D)          -- right operand (K^T), stored transposed
+ * Vt [BH, D, ld_v]  int8 K-major (row = head-dim column, contraction S) -- right operand of P.V, stored transposed
+ * out [B, S, H*D] int8: the left operand of the output projection; out_rowsum [B*S] int32 or NULL.
+ * Scores, probabilities and the context accumulator stay in TMEM / shared memory.  Same codes as
+ * NQ_EPI_SOFTMAX_QUANT followed by NQ_EPI_QUANT.  Limits: S <= 208, D <= 64, D % 16 == 0. */
+typedef struct nq_attention {
+    float scale_qk;                /* float32(s_q * s_k)                                  */
+    int has_div;                   /* graph Div node in front of the Softmax              */
+    float div;
+    int has_zq, has_zk;
+    int64_t zq, zk;
+    const int32_t* rowsum_q;       /* [BH, S] sums of Q rows   (needed when has_zk)       */
+    const int32_t* colsum_k;       /* [BH, S] sums of Kt rows  (needed when has_zq)       */
+    int p_bits;                    /* quantization of the probabilities                   */
+    float p_scale;
+    int has_p_zp;
+    int64_t p_zp;
+    float scale_pv;                /* float32(s_p * s_v)                                  */
+    int has_zv;
+    int64_t zv;
+    const int32_t* colsum_v;       /* [BH, D] sums of Vt rows  (needed when has_p_zp)     */
+    int out_bits;                  /* quantization of the context (next MatMul's operand) */
+    float out_scale;
+    int has_out_zp;
+    int64_t out_zp;
+    int8_t* out;
+    int32_t* out_rowsum;           /* cleared by the library                              */
+} nq_attention;
+
+int nq_attention_s8(const int8_t* Q, const int8_t* Kt, const int8_t* Vt, int64_t BH, int64_t H, int64_t S, int64_t D,
+                    int64_t ld_q, int64_t ld_k, int64_t ld_v, const nq_attention* a, void* stream);
+
 int nq_qgemm_s8(const int8_t* A, const int8_t* B, void* C,
                 int64_t M, int64_t N, int64_t K, int64_t batch,
                 int64_t lda, int64_t ldb, int64_t ldc,

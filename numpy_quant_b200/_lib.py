@@ -32,6 +32,16 @@ class Epilogue(C.Structure):
                 ("q_rowsum_count", i64), ("gelu_div", f32), ("gelu_add", f32), ("gelu_mul", f32)]
 
 
+class Attention(C.Structure):
+    """struct nq_attention"""
+    _fields_ = [("scale_qk", f32), ("has_div", C.c_int), ("div", f32), ("has_zq", C.c_int), ("has_zk", C.c_int),
+                ("zq", i64), ("zk", i64), ("rowsum_q", vp), ("colsum_k", vp),
+                ("p_bits", C.c_int), ("p_scale", f32), ("has_p_zp", C.c_int), ("p_zp", i64),
+                ("scale_pv", f32), ("has_zv", C.c_int), ("zv", i64), ("colsum_v", vp),
+                ("out_bits", C.c_int), ("out_scale", f32), ("has_out_zp", C.c_int), ("out_zp", i64),
+                ("out", vp), ("out_rowsum", vp)]
+
+
 EPI_RAW, EPI_DEQUANT, EPI_REQUANT, EPI_QUANT, EPI_SOFTMAX_QUANT, EPI_GELU_QUANT = 0, 1, 2, 3, 4, 5
 UN = dict(neg=0, exp=1, erf=2, tanh=3, sigmoid=4, relu=5, sqrt=6, inv=7, copy=8)
 BIN = dict(add=0, mul=1, div=2)
@@ -50,6 +60,7 @@ _SIGNATURES = {
     "nq_requantize_f32": [vp, i64, C.c_int, f32, C.c_int, i64, vp, vp],
     "nq_rowsum_s8": [vp, i64, i64, i64, vp, vp],
     "nq_qgemm_s8": [vp, vp, vp, i64, i64, i64, i64, i64, i64, i64, i64, i64, i64, C.POINTER(Epilogue), vp],
+    "nq_attention_s8": [vp, vp, vp, i64, i64, i64, i64, i64, i64, i64, C.POINTER(Attention), vp],
     "nq_qgemm_s8_simt": [vp, vp, vp, i64, i64, i64, i64, i64, i64, i64, i64, i64, i64, vp],
     "nq_im2col": [vp, C.c_int, i64, i64, i64, i64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                   C.c_int, i32, vp, i64, vp],

@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libnq_b200.so")
-SOURCES = ["runtime.cu", "quant_kernels.cu", "float_kernels.cu", "qgemm_sm100.cu"]
+SOURCES = ["runtime.cu", "quant_kernels.cu", "float_kernels.cu", "qgemm_sm100.cu", "attn_sm100.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "--fmad=false",                     # explicit IEEE ops; never contract the float glue
               "-Xcompiler", "-fPIC", "-cudart", "static"]

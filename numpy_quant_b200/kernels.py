@@ -406,6 +406,62 @@ def qgemm_softmax_to_operand(a: Operand, b: Operand, scale: float, azp: AccZeroP
     return res
 
 
+def can_fuse_attention(q: Operand, k: Operand, v: Operand) -> bool:
+    """Geometry the fused attention kernel is built for: per (image, head) Q [S, D], K^T [S, D], V^T [D, S]."""
+    return (q.batch == k.batch == v.batch and q.rows == k.rows == v.k and q.k == k.k == v.rows and q.rows <= 208
+            and q.k <= 64 and q.k % 16 == 0 and len(q.batch_shape) == 2)
+
+
+def attention(q: Operand, k: Operand, v: Operand, scale_qk: float, zq, zk, div_c, p_bits: int, p_scale, p_zp,
+              scale_pv: float, zv, out_bits: int, out_scale, out_zp, want_rowsum: bool) -> Operand:
+    """softmax(Q.K^T / c) . V for every (image, head) in one kernel (nq_attention_s8); returns the int8 left
+    operand [1, B*S, H*D] of the output projection (merge heads), plus its row sums on request."""
+    assert can_fuse_attention(q, k, v)
+    B, H = (int(x) for x in q.batch_shape)
+    S, D = q.rows, q.k
+    dev = q.data.device
+    out = torch.empty((1, B * S, H * D), dtype=torch.int8, device=dev)
+    res = Operand(out, (), B * S, H * D, H * D, None)
+    a = _lib.Attention()
+    a.scale_qk = float(scale_qk)
+    a.has_div, a.div = int(div_c is not None), 1.0 if div_c is None else float(div_c)
+    a.has_zq, a.zq = int(zq is not None), 0 if zq is None else int(zq)
+    a.has_zk, a.zk = int(zk is not None), 0 if zk is None else int(zk)
+    if zk is not None:
+        if q.rowsum is None:
+            q.rowsum = rowsum(q)
+        a.rowsum_q = q.rowsum.data_ptr()
+    if zq is not None:
+        if k.rowsum is None:
+            k.rowsum = rowsum(k)
+        a.colsum_k = k.rowsum.data_ptr()
+    a.p_bits, a.p_scale = int(p_bits), float(p_scale)
+    a.has_p_zp, a.p_zp = int(p_zp is not None), 0 if p_zp is None else int(p_zp)
+    a.scale_pv = float(scale_pv)
+    a.has_zv, a.zv = int(zv is not None), 0 if zv is None else int(zv)
+    if p_zp is not None:
+        if v.rowsum is None:
+            v.rowsum = rowsum(v)
+        a.colsum_v = v.rowsum.data_ptr()
+    a.out_bits, a.out_scale = int(out_bits), float(out_scale)
+    a.has_out_zp, a.out_zp = int(out_zp is not None), 0 if out_zp is None else int(out_zp)
+    a.out = out.data_ptr()
+    if want_rowsum:
+        res.rowsum = torch.empty((1, B * S), dtype=torch.int32, device=dev)
+        a.out_rowsum = res.rowsum.data_ptr()
+    timer = GEMM_TIMER
+    if timer is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    call("nq_attention_s8", q.data.data_ptr(), k.data.data_ptr(), v.data.data_ptr(), B * H, H, S, D, q.ld, k.ld, v.ld,
+         C.byref(a), _stream())
+    if timer is not None:
+        e1.record()
+        timer.append((4 * B * H * S * S * D, e0, e1))
+    _count()
+    return res
+
+
 # --------------------------------------------------------------------------- K10 / K11
 def minmax_slots(n_slots: int, device) -> torch.Tensor:
     mm = torch.empty((n_slots, 2), dtype=torch.float32, device=device)

@@ -383,6 +383,32 @@ def test_qgemm_gelu_epilogue(zp):
     assert (np.abs(gc - t) <= tol).all(), float((np.abs(gc - t) - tol).max())
 
 
+@pytest.mark.parametrize("S,D,zq,zk,zv", [(197, 64, 3, -4, 9), (197, 64, None, None, None), (50, 32, -7, 2, -1), (208, 16, 1, None, 5)])
+def test_fused_attention_equals_the_two_gemm_route(S, D, zq, zk, zv):
+    """nq_attention_s8 (QK^T -> softmax -> quantize -> P.V -> quantize, merge heads, one kernel) emits exactly the codes
+    and row sums of NQ_EPI_SOFTMAX_QUANT followed by NQ_EPI_QUANT(merge_heads): same arithmetic, exact integer MMAs."""
+    rng = np.random.default_rng(S * 7 + D)
+    B, H = 3, 4
+    q8 = rng.integers(-128, 128, size=(B * H, S, D)).astype(np.int8)
+    k8 = rng.integers(-128, 128, size=(B * H, D, S)).astype(np.int8)            # logical K^T [D, S]
+    v8 = rng.integers(-128, 128, size=(B * H, S, D)).astype(np.int8)
+    oq, ok, ov = (K.operand_from_codes(dev(q8), "A", True), K.operand_from_codes(dev(k8), "B", True),
+                  K.operand_from_codes(dev(v8), "B", True))
+    for o in (oq, ok, ov):
+        o.batch_shape = (B, H)
+    s1, s_p, s_v, s_o = 2.0e-4, 1 / 255, 0.02, 0.011
+    for p_zp, o_zp in ((-128, -6), (None, None)):
+        azp1 = K.AccZeroPoint(zq, zk, D, oq.rowsum, ok.rowsum, False)
+        P = K.qgemm_softmax_to_operand(oq, ok, s1, azp1, 8.0, 8, s_p, p_zp, True)
+        azp2 = K.AccZeroPoint(p_zp, zv, S, P.rowsum, ov.rowsum, False)
+        P.batch_shape = (B, H)
+        ref = K.qgemm_to_operand(P, ov, np.float32(s_p) * np.float32(s_v), azp2, None, 8, s_o, o_zp, "merge_heads", H, S, True)
+        got = K.attention(oq, ok, ov, s1, zq, zk, 8.0, 8, s_p, p_zp, float(np.float32(s_p) * np.float32(s_v)), zv, 8, s_o, o_zp, True)
+        assert got.data.shape == ref.data.shape
+        assert torch.equal(got.data, ref.data), float((got.data != ref.data).float().mean())
+        assert torch.equal(got.rowsum.view(-1), ref.rowsum.view(-1))
+
+
 def test_qgemm_rejects_bad_arguments():
     a = torch.zeros((1, 4, 8), dtype=torch.int8, device=DEV)
     ep = _lib.Epilogue()
