@@ -119,6 +119,15 @@ def main():
         for kind in ("split_rows", "split_cols"):
             med, _ = timed(lambda: K.qgemm_to_operand(oa, ow, 1e-4, azw, bias, 8, 0.05, -3, kind, 12, 197, True))
             emit(case=f"qgemm ViT qkv -> int8 operand ({kind})", ms_median=med, tops=2.0 * 50432 * 768 * 768 / med / 1e9)
+        # fused attention kernel at the same shapes (B = 256, H = 12)
+        kt8 = torch.randint(-128, 128, (bt, D, S), generator=g, device=DEV, dtype=torch.int8)
+        vv8 = torch.randint(-128, 128, (bt, S, D), generator=g, device=DEV, dtype=torch.int8)
+        fq, fk, fv = K.operand_from_codes(q8, "A", True), K.operand_from_codes(kt8, "B", True), K.operand_from_codes(vv8, "B", True)
+        for o in (fq, fk, fv):
+            o.batch_shape = (bt // 12, 12)
+        med, _ = timed(lambda: K.attention(fq, fk, fv, 1e-4, 3, -4, 8.0, 8, 1 / 255, -128, 1e-4, 9, 8, 0.05, -3, False))
+        emit(case="fused attention ViT-B b256 (QK^T + softmax + P.V + merge heads, one kernel)", batch=bt, S=S, D=D, ms_median=med,
+             tops=4.0 * bt * S * S * D / med / 1e9)
         p8 = torch.randint(-128, 128, (bt, S, S), generator=g, device=DEV, dtype=torch.int8)
         v8 = torch.randint(-128, 128, (bt, S, D), generator=g, device=DEV, dtype=torch.int8)
         op_, ov_ = K.operand_from_codes(p8, "A", True), K.operand_from_codes(v8, "B", True)

@@ -22,7 +22,7 @@ from numpy_quant_b200 import kernels as K, zoo  # noqa: E402
 from numpy_quant_b200.model import Model  # noqa: E402
 
 VIT = dict(image_size=224, patch_size=16, hidden=768, heads=12, intermediate=3072, layers=12, classes=1000)
-MODES = {0: "raw", 1: "dequant", 2: "requant", 3: "quant", 4: "softmax_quant", 5: "gelu_quant"}
+MODES = {0: "raw", 1: "dequant", 2: "requant", 3: "quant", 4: "softmax_quant", 5: "gelu_quant"}  # nq_attention_s8 is listed by name
 
 
 def main():

@@ -194,6 +194,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
         float* red = reinterpret_cast<float*>(epi);                        // [2][4][128] max / sum exchange
         int* redq = reinterpret_cast<int*>(epi) + 1024;                    // [4][128] code sums
         int* ctw = reinterpret_cast<int*>(epi) + 2048 + ew * 64;           // this warp's 56 score column terms
+        int* ctv = reinterpret_cast<int*>(epi) + 3072 + ew * 16;           // this warp's 16 context column terms
         constexpr int NSUB = 7;
         constexpr float kMasked = -1.0e30f;
         const int col0 = h * (NSUB * 8);
@@ -226,12 +227,11 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
             tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(O_COL + h * 16), v);
             int rowterm = (int)-p.kterm2;
             if (p.use_row2) rowterm += rowsum_p * p.zv;
-            int ct[16];
+            int ct[16];                                                    // staged by this warp one phase earlier
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
-                int4 c4 = make_int4(0, 0, 0, 0);
-                if (p.use_col2) c4 = ldg_v4(p.colsum_v + (int64_t)bh * p.D + h * 16 + g * 4);
-                ct[4 * g] = c4.x * p.zp_p; ct[4 * g + 1] = c4.y * p.zp_p; ct[4 * g + 2] = c4.z * p.zp_p; ct[4 * g + 3] = c4.w * p.zp_p;
+                const int4 c4 = *reinterpret_cast<const int4*>(ctv + g * 4);
+                ct[4 * g] = c4.x; ct[4 * g + 1] = c4.y; ct[4 * g + 2] = c4.z; ct[4 * g + 3] = c4.w;
             }
             tmem_ld_wait();
             int w[4];
@@ -269,9 +269,14 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
             prefetch(t + gridDim.x, nxt);
             int rowterm = (int)-p.kterm1;
             if (p.use_row1 && row_ok) rowterm += cur.rowsum * p.zk;
+            // context column terms of the previous tile (colsum(V) * zp_p): loaded here, consumed after pass 3
+            int cv = 0;
+            if (li > 0 && p.use_col2 && lane < 16 && h * 16 + lane < p.D)
+                cv = ldg_s32(p.colsum_v + (int64_t)(t_prev / m_tiles) * p.D + h * 16 + lane);
             __syncwarp();
             ctw[lane] = cur.c0 * p.zq;
             ctw[32 + lane] = cur.c1 * p.zq;
+            if (lane < 16) ctv[lane] = cv * p.zp_p;
             __syncwarp();
             const int sb = (int)(li & 1);
             mbar_wait(smem_u32(sfull_bar + sb), (li >> 1) & 1u);
@@ -414,6 +419,12 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
             rowsum_prev = rowsum_p;
         }
         if (li > 0) {
+            int cv = 0;
+            if (p.use_col2 && lane < 16 && h * 16 + lane < p.D)
+                cv = ldg_s32(p.colsum_v + (int64_t)(t_prev / m_tiles) * p.D + h * 16 + lane);
+            __syncwarp();
+            if (lane < 16) ctv[lane] = cv * p.zp_p;
+            __syncwarp();
             mbar_wait(smem_u32(ofull_bar), (li - 1) & 1u);
             tc_fence_after();
             context_epilogue(t_prev, rowsum_prev);

@@ -412,6 +412,12 @@ def can_fuse_attention(q: Operand, k: Operand, v: Operand) -> bool:
             and q.k <= 64 and q.k % 16 == 0 and len(q.batch_shape) == 2)
 
 
+def can_fuse_attention_qk(q: Operand, k: Operand) -> bool:
+    """The part of `can_fuse_attention` that is known at the score MatMul (V has the same S and D)."""
+    return (q.batch == k.batch and q.rows == k.rows and q.k == k.k and q.rows <= 208 and q.k <= 64 and q.k % 16 == 0
+            and len(q.batch_shape) == 2)
+
+
 def attention(q: Operand, k: Operand, v: Operand, scale_qk: float, zq, zk, div_c, p_bits: int, p_scale, p_zp,
               scale_pv: float, zv, out_bits: int, out_scale, out_zp, want_rowsum: bool) -> Operand:
     """softmax(Q.K^T / c) . V for every (image, head) in one kernel (nq_attention_s8); returns the int8 left

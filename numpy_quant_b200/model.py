@@ -434,6 +434,7 @@ class QModel(Model):
         self.fuse_softmax_epilogue = True
         self.fuse_gelu_epilogue = True
         self.fuse_layernorm_glue = True
+        self.fuse_attention = True
         self._pipes = {}
         self._graphs: dict = {}
         self._graph_launches: dict = {}
@@ -482,7 +483,7 @@ class QModel(Model):
         producers = {o.name: n for n in self.nodes for o in n.outputs}
         by_name = {n.name: n for n in self.nodes}
         plan = dict(gelu=find_gelu_chains(self.nodes), softmax={}, skip=set(), emit={}, quantize_out=set(), node=by_name,
-                    residual={}, to_operand={}, merge_heads={}, gelu_in={})
+                    residual={}, to_operand={}, merge_heads={}, gelu_in={}, attention={}, attention_pv={}, attention_tr={})
         for first, spec in plan["gelu"].items():
             plan["skip"].update(spec[4])
             plan["emit"][spec[5]] = first
@@ -544,6 +545,20 @@ class QModel(Model):
                 continue
             if self._feeds_only_matmul_lhs(rs.outputs[0]):
                 plan["merge_heads"][n.name] = dict(reshape=rs)
+        # Div -> Softmax -> MatMul(P, V) -> Transpose(0,2,1,3) -> Reshape -> MatMul left operand: one attention kernel
+        for dname, (xv, c, sm_name) in plan["softmax"].items():
+            smv = by_name[sm_name].outputs[0]
+            if not single(smv):
+                continue
+            pv = smv.outputs[0]
+            if pv.op != "MatMul" or pv.inputs[0] is not smv or pv.inputs[1] is smv or not single(pv.outputs[0]):
+                continue
+            tr = pv.outputs[0].outputs[0]
+            if tr.name in plan["merge_heads"] and tr.inputs[0] is pv.outputs[0]:
+                plan["attention"][dname] = dict(softmax=sm_name, pv=pv.name, transpose=tr.name,
+                                                reshape=plan["merge_heads"][tr.name]["reshape"].name)
+                plan["attention_pv"][pv.name] = dname
+                plan["attention_tr"][tr.name] = dname
         emitters = {}
         for n in self.nodes:
             if n.op == "LayerNormalization" or (n.op == "Softmax" and n.attrs.get("axis", -1) == -1):
@@ -615,7 +630,7 @@ class QModel(Model):
         replay it: ~200 kernel launches become one graph launch, so the host interpreter loop
         (Python + ctypes per node) disappears from the steady state.  Quantization parameters are
         static after calibration, so the launch sequence depends on shapes only."""
-        key = tuple((tuple(a.shape), str(a.dtype)) for a in inputs) + (self.fuse_softmax_epilogue, self.fuse_gelu_epilogue, self.fuse_layernorm_glue)
+        key = tuple((tuple(a.shape), str(a.dtype)) for a in inputs) + (self.fuse_softmax_epilogue, self.fuse_gelu_epilogue, self.fuse_layernorm_glue, self.fuse_attention)
         entry = self._graphs.get(key)
         dev = torch.device("cuda", torch.cuda.current_device())
         if entry is None:
@@ -803,7 +818,7 @@ class QModel(Model):
         yields the host outputs.  Host->device copies run on their own stream into one of two staging buffers,
         device->host copies on a third stream into pinned buffers, so with two submissions in flight the
         copies of step k+1 / k-1 overlap the kernels of step k.  Same results as `self(inputs, graph=True)`."""
-        key = tuple((tuple(a.shape), str(a.dtype)) for a in inputs) + (self.fuse_softmax_epilogue, self.fuse_gelu_epilogue, self.fuse_layernorm_glue)
+        key = tuple((tuple(a.shape), str(a.dtype)) for a in inputs) + (self.fuse_softmax_epilogue, self.fuse_gelu_epilogue, self.fuse_layernorm_glue, self.fuse_attention)
         if key not in self._graphs:
             outs = self(inputs, graph=True)                   # first use: warm-up + capture, synchronous
             return PendingOutputs(outs, None)
@@ -861,7 +876,7 @@ class QModel(Model):
             if profile:
                 raise ValueError("profile=True needs the eager interpreter (graph=False)")
             if not torch.cuda.is_current_stream_capturing():
-                key = tuple((tuple(a.shape), str(a.dtype)) for a in inputs) + (self.fuse_softmax_epilogue, self.fuse_gelu_epilogue, self.fuse_layernorm_glue)
+                key = tuple((tuple(a.shape), str(a.dtype)) for a in inputs) + (self.fuse_softmax_epilogue, self.fuse_gelu_epilogue, self.fuse_layernorm_glue, self.fuse_attention)
                 if key not in self._graphs:
                     before = K.LAUNCHES
                     out = self._graph_call(inputs, device_outputs)
@@ -897,8 +912,9 @@ class QModel(Model):
         if fused and self._plan is None:
             self._plan = self._build_plan()
         plan = self._plan if fused else dict(gelu={}, softmax={}, skip=set(), emit={}, quantize_out=set(), node={},
-                                             residual={}, to_operand={}, merge_heads={}, gelu_in={})
+                                             residual={}, to_operand={}, merge_heads={}, gelu_in={}, attention={}, attention_pv={}, attention_tr={})
         dyn_skip: set = set()
+        attn_pending: dict = {}
         qcache: dict = {}
         stash: dict = {}
         remaining = None
@@ -935,6 +951,18 @@ class QModel(Model):
                 # ---- Div + Softmax (+ quantize) in one kernel
                 x, c, sm_name = plan["softmax"][name]
                 smv = plan["node"][sm_name].outputs[0]
+                aspec = plan["attention"].get(name) if (self.fuse_attention and self.fuse_softmax_epilogue) else None
+                if aspec is not None and isinstance(x.data, QTensor) and x.data._pending():
+                    # whole attention in one kernel: remember the pending score GEMM, launch at the merge-heads node
+                    L = x.data._lazy
+                    if L.get("bias_q") is None and L["a"].batch == int(np.prod(L["batch_shape"] or (1,))) \
+                            and K.can_fuse_attention_qk(L["a"], L["b"]):
+                        attn_pending[name] = dict(scores=x.data, c=c, spec=aspec)
+                        stash[sm_name] = None
+                        for o in node.outputs:
+                            o.data = None
+                        self._release_inputs(node, remaining, keep, qcache)
+                        continue
                 if self.fuse_softmax_epilogue and sm_name in plan["quantize_out"] and isinstance(x.data, QTensor) \
                         and x.data._pending():
                     # scores never leave the GEMM: softmax + quantize run in its epilogue
@@ -965,6 +993,34 @@ class QModel(Model):
                 outputs_data = [None]
             elif name in plan["emit"] or name in stash:
                 outputs_data = [stash.pop(name)]
+            elif name in plan["attention_pv"] and plan["attention_pv"][name] in attn_pending:
+                # P.V of a fused attention: only collect the V operand (already in its K-major layout)
+                rec = attn_pending[plan["attention_pv"][name]]
+                vval = node.inputs[1]
+                vq = qcache.get((vval.name, "B"))
+                if vq is None or isinstance(vval.data, QTensor):
+                    if isinstance(vval.data, FTensor):
+                        t0 = tick()
+                        vq = self._quantized_operand(vval, "B", node.inputs[0], qcache)
+                        tock("TinyqQuant", t0)
+                    else:
+                        vq = vval.data
+                rec["v"] = vq
+                outputs_data = [None]
+            elif name in plan["attention_tr"] and plan["attention_tr"][name] in attn_pending:
+                # Transpose(0,2,1,3) of the context: launch the attention kernel, emit the output projection's operand
+                rec = attn_pending.pop(plan["attention_tr"][name])
+                spec = rec["spec"]
+                smv = plan["node"][spec["softmax"]].outputs[0]
+                outv = plan["node"][spec["reshape"]].outputs[0]
+                qp_p, qp_o = self.quant_params[smv.name], self.quant_params[outv.name]
+                t0 = tick()
+                qctx = rec["scores"].attention_into_operand(rec["c"], rec["v"], bits, qp_p.scale, qp_p.zero_point, qp_o.scale,
+                                                            qp_o.zero_point, self._rowsum_needed(outv))
+                tock("MatMul", t0)
+                qcache[(outv.name, "A")] = qctx
+                dyn_skip.add(spec["reshape"])
+                outputs_data = [None]
             elif node.op == "Constant" and out0.data is not None:
                 outputs_data = [out0.data]                      # immutable: uploaded once, reused
             elif node.op in ("MatMul", "Gemm"):

@@ -465,6 +465,25 @@ class QTensor:
             op.batch_shape = tuple(L["batch_shape"])
         return qtensor_from_operand(op, "A", tuple(L["batch_shape"]) + (L["M"], L["N"]), bit_width, scale, zero_point)
 
+    def attention_into_operand(self, div_c, v: "QTensor", bit_width: int, p_scale, p_zero_point, out_scale, out_zero_point,
+                               want_rowsum: bool):
+        """self = pending Q.K^T scores [B, H, S, S]; v = quantized V [B, H, S, D].  dequantize -> [/ c] -> softmax ->
+        quantize(p) -> MatMul(., V) -> dequantize -> Transpose(0,2,1,3) -> Reshape -> quantize(out): the whole
+        attention of the graph in one kernel (nq_attention_s8); returns the [B, S, H*D] left operand of the output
+        projection.  Same codes as softmax_into_operand + quantize_into_operand(merge_heads)."""
+        L = self._lazy
+        qa, kb = L["a"], L["b"]
+        vb = v._operand("B", True)
+        if not K.can_fuse_attention(qa, kb, vb):
+            raise ValueError("attention_into_operand: geometry not supported by the fused kernel")
+        za, zk = _as_opt_int(self._zp.zp_a), _as_opt_int(self._zp.zp_b)
+        zp_p, zv = _as_opt_int(p_zero_point), _as_opt_int(v._scalar_zp())
+        scale_pv = np.float32(p_scale) * np.float32(v.scale)
+        op = K.attention(qa, kb, vb, float(self.scale), za, zk, div_c, bit_width, float(p_scale), zp_p, float(scale_pv), zv,
+                         bit_width, float(out_scale), _as_opt_int(out_zero_point), want_rowsum)
+        B, H = (int(x) for x in qa.batch_shape)
+        return qtensor_from_operand(op, "A", (B, qa.rows, H * qa.k), bit_width, out_scale, out_zero_point)
+
     def softmax_into_operand(self, div_c, bit_width: int, scale, zero_point, want_rowsum: bool):
         """dequantize -> [/ c] -> softmax(last axis) -> quantize for the next MatMul (as its left operand),
         all inside the epilogue of the pending attention-score GEMM.  None when not applicable."""
