@@ -12,7 +12,10 @@
 //   warp 0      TMA producer: Q tile [128 x D], K tile [208 x D], V^T tile [64 x S] per stage (3 stages)
 //   warp 1      MMA issuer:   S(i) one tile ahead of the softmax, O(i-1) as soon as P(i-1) is in shared memory
 //   warp 2      TMEM allocator (2 x 208 columns for S, 64 for O)
-//   warps 4-19  softmax of tile i (as in qgemm_sm100.cu), then the context epilogue of tile i-1, then P(i) -> smem
+//   warps 4-19  softmax of tile i (as in qgemm_sm100.cu), P(i) -> smem
+//   warps 20-23 context epilogue of tile i (dequantize O, quantize, merge heads) -- concurrent with the softmax of
+//               tile i+1, so its latencies fill the softmax warps' idle issue slots
+// Registers (launch 768 x 80 = 61440): setmaxnreg 48 / 96 / 48.
 #include <cuda.h>
 
 #include <type_traits>
@@ -28,7 +31,8 @@ int make_operand_map(CUtensorMap* map, const int8_t* base, int64_t K, int64_t ro
 namespace attn {
 
 constexpr int NUM_EPI_WARPS = 16;
-constexpr int NUM_THREADS = 128 + 32 * NUM_EPI_WARPS;
+constexpr int NUM_CTX_WARPS = 4;                // context epilogue: one warp per TMEM lane quarter
+constexpr int NUM_THREADS = 128 + 32 * NUM_EPI_WARPS + 32 * NUM_CTX_WARPS;   // 768
 constexpr int BN1 = 208;                       // key columns of the score tile (S <= 208)
 constexpr int BN2 = 64;                        // head dim columns of the context tile (D <= 64)
 constexpr int STAGES = 3;
@@ -78,8 +82,11 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
     uint64_t* sempty_bar = sfull_bar + 2;      // [2] scores drained (16 warps)
     uint64_t* pfull_bar = sempty_bar + 2;      // P tile written (16 warps)
     uint64_t* ofull_bar = pfull_bar + 1;       // context accumulator ready
-    uint64_t* oempty_bar = ofull_bar + 1;      // context accumulator drained (16 warps)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(oempty_bar + 1);
+    uint64_t* oempty_bar = ofull_bar + 1;      // context accumulator drained (4 context warps)
+    uint64_t* rs_bar = oempty_bar + 1;         // [2] row sums of P handed to the context warps (one warp per quarter);
+                                               // by tile parity: the softmax may complete tile i + 2 before a context warp
+                                               // polls for tile i + 1, which a single barrier's phase parity cannot tell apart
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rs_bar + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t m_tiles = (uint32_t)((p.S + BM - 1) / BM);
@@ -103,7 +110,9 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
         }
         mbar_init(smem_u32(pfull_bar), NUM_EPI_WARPS);
         mbar_init(smem_u32(ofull_bar), 1);
-        mbar_init(smem_u32(oempty_bar), NUM_EPI_WARPS);
+        mbar_init(smem_u32(oempty_bar), NUM_CTX_WARPS);
+        mbar_init(smem_u32(rs_bar), 4);
+        mbar_init(smem_u32(rs_bar + 1), 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -117,7 +126,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp < 4) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
         if (warp == 0) {
             // ===================== TMA producer =====================
             if (lane == 0) {
@@ -186,15 +195,69 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
             }
             __syncwarp();
         }
+    } else if (warp >= 4 + NUM_EPI_WARPS) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
+        // ===================== context epilogue (4 warps, one per TMEM lane quarter) =====================
+        // O(i) = P(i) . V is drained here while the softmax warps already work on tile i + 1.
+        const int q = warp & 3;
+        const int rloc = q * 32 + lane;
+        const int* rsbuf = reinterpret_cast<const int*>(epi) + 3584;      // [2][128] row sums of P (from the softmax warps)
+        const Quantizer qzo(p.qo);
+        uint32_t li = 0;
+        for (uint32_t t = blockIdx.x; t < total_tiles; t += gridDim.x, ++li) {
+            const uint32_t bh = t / m_tiles, m0 = (t - bh * m_tiles) * BM;
+            const int64_t m = (int64_t)m0 + rloc;
+            const bool row_ok = m < p.S;
+            const bool warp_rows = (int64_t)m0 + q * 32 < p.S;
+            const uint32_t b = bh / (uint32_t)p.H, hh = bh - b * (uint32_t)p.H;
+            mbar_wait(smem_u32(rs_bar + (li & 1)), (li >> 1) & 1u);
+            int rowterm = (int)-p.kterm2;
+            if (p.use_row2) rowterm += rsbuf[(li & 1) * 128 + rloc] * p.zv;
+            mbar_wait(smem_u32(ofull_bar), li & 1u);
+            tc_fence_after();
+            int8_t* dst = p.C + (((int64_t)b * p.S + m) * p.H + hh) * p.D;
+            int rs_out = 0;
+            if (warp_rows) {
+#pragma unroll 1
+                for (int c16 = 0; c16 * 16 < p.D; ++c16) {
+                    uint32_t v[16];
+                    tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(O_COL + c16 * 16), v);
+                    tmem_ld_wait();
+                    int w[4];
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        int4 c4 = make_int4(0, 0, 0, 0);
+                        if (p.use_col2) c4 = ldg_v4(p.colsum_v + (int64_t)bh * p.D + c16 * 16 + g * 4);
+                        const int ct[4] = {c4.x * p.zp_p, c4.y * p.zp_p, c4.z * p.zp_p, c4.w * p.zp_p};
+                        int c[4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            // |acc - zero-point terms| <= S * 255 * 255 < 2^24: exact int -> float, one IEEE multiply
+                            const int d = (int)v[4 * g + k] - rowterm - ct[k];
+                            c[k] = qzo.code<1>(__fmul_rn(__int2float_rn(d), p.scale2));
+                        }
+                        w[g] = pack4_codes(c[0], c[1], c[2], c[3]);
+                    }
+                    if (row_ok) {
+                        *reinterpret_cast<int4*>(dst + c16 * 16) = make_int4(w[0], w[1], w[2], w[3]);
+                        rs_out = __dp4a(w[0], 0x01010101, __dp4a(w[1], 0x01010101, __dp4a(w[2], 0x01010101, __dp4a(w[3], 0x01010101, rs_out))));
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(oempty_bar));
+            if (p.o_rowsum && row_ok && warp_rows) atomicAdd(p.o_rowsum + (int64_t)b * p.S + m, rs_out);
+        }
     } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
-        // ===================== softmax + context epilogue (16 warps) =====================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 96;");
+        // ===================== softmax (16 warps) =====================
         const int q = warp & 3, h = (warp - 4) >> 2, ew = warp - 4;
         const int rloc = q * 32 + lane;
         float* red = reinterpret_cast<float*>(epi);                        // [2][4][128] max / sum exchange
         int* redq = reinterpret_cast<int*>(epi) + 1024;                    // [4][128] code sums
         int* ctw = reinterpret_cast<int*>(epi) + 2048 + ew * 64;           // this warp's 56 score column terms
-        int* ctv = reinterpret_cast<int*>(epi) + 3072 + ew * 16;           // this warp's 16 context column terms
+        int* rsbuf = reinterpret_cast<int*>(epi) + 3584;                   // [2][128] row sums of P for the context warps
         constexpr int NSUB = 7;
         constexpr float kMasked = -1.0e30f;
         const int col0 = h * (NSUB * 8);
@@ -214,51 +277,9 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
                 if (lane < 24 && c1i < p.S) o.c1 = ldg_s32(p.colsum_k + (int64_t)bh * p.S + c1i);
             }
         };
-        // ---- context epilogue of one tile: dequantize O (exact), quantize with the consumer's parameters, scatter
-        auto context_epilogue = [&](uint32_t tt, int rowsum_p) {
-            const uint32_t bh = tt / m_tiles, m0 = (tt - bh * m_tiles) * BM;
-            const int64_t m = (int64_t)m0 + rloc;
-            const bool row_ok = m < p.S;
-            const int rows_left = (int)(p.S - (m0 + q * 32));
-            if (h * 16 >= p.D || rows_left <= 0) return;                   // warp-uniform
-            const Quantizer qzo(p.qo);
-            const uint32_t b = bh / (uint32_t)p.H, hh = bh - b * (uint32_t)p.H;
-            uint32_t v[16];
-            tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(O_COL + h * 16), v);
-            int rowterm = (int)-p.kterm2;
-            if (p.use_row2) rowterm += rowsum_p * p.zv;
-            int ct[16];                                                    // staged by this warp one phase earlier
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-                const int4 c4 = *reinterpret_cast<const int4*>(ctv + g * 4);
-                ct[4 * g] = c4.x; ct[4 * g + 1] = c4.y; ct[4 * g + 2] = c4.z; ct[4 * g + 3] = c4.w;
-            }
-            tmem_ld_wait();
-            int w[4];
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-                int c[4];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    // |acc - zero-point terms| <= S * 255 * 255 < 2^24: exact int -> float, one IEEE multiply
-                    const int d = (int)v[4 * g + k] - rowterm - ct[4 * g + k];
-                    c[k] = qzo.code<1>(__fmul_rn(__int2float_rn(d), p.scale2));
-                }
-                w[g] = pack4_codes(c[0], c[1], c[2], c[3]);
-            }
-            if (row_ok) {
-                int8_t* dst = p.C + (((int64_t)b * p.S + m) * p.H + hh) * p.D + h * 16;
-                *reinterpret_cast<int4*>(dst) = make_int4(w[0], w[1], w[2], w[3]);
-                if (p.o_rowsum)
-                    atomicAdd(p.o_rowsum + (int64_t)b * p.S + m,
-                              __dp4a(w[0], 0x01010101, __dp4a(w[1], 0x01010101, __dp4a(w[2], 0x01010101, __dp4a(w[3], 0x01010101, 0)))));
-            }
-        };
-
         Pre nxt;
         prefetch(blockIdx.x, nxt);
-        uint32_t li = 0, t_prev = 0;
-        int rowsum_prev = 0;
+        uint32_t li = 0;
         for (uint32_t t = blockIdx.x; t < total_tiles; t += gridDim.x, ++li) {
             const uint32_t bh = t / m_tiles, m0 = (t - bh * m_tiles) * BM;
             const int64_t m = (int64_t)m0 + rloc;
@@ -269,14 +290,9 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
             prefetch(t + gridDim.x, nxt);
             int rowterm = (int)-p.kterm1;
             if (p.use_row1 && row_ok) rowterm += cur.rowsum * p.zk;
-            // context column terms of the previous tile (colsum(V) * zp_p): loaded here, consumed after pass 3
-            int cv = 0;
-            if (li > 0 && p.use_col2 && lane < 16 && h * 16 + lane < p.D)
-                cv = ldg_s32(p.colsum_v + (int64_t)(t_prev / m_tiles) * p.D + h * 16 + lane);
             __syncwarp();
             ctw[lane] = cur.c0 * p.zq;
             ctw[32 + lane] = cur.c1 * p.zq;
-            if (lane < 16) ctv[lane] = cv * p.zp_p;
             __syncwarp();
             const int sb = (int)(li & 1);
             mbar_wait(smem_u32(sfull_bar + sb), (li >> 1) & 1u);
@@ -407,28 +423,12 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
             if (lane == 0) mbar_arrive(smem_u32(pfull_bar));
             redq[h * 128 + rloc] = qsum;
             named_bar_sync(1 + q, 128);
-            const int rowsum_p = (redq[rloc] + redq[128 + rloc]) + (redq[256 + rloc] + redq[384 + rloc]);
-            // ---------------- context of the previous tile
-            if (li > 0) {
-                context_epilogue(t_prev, rowsum_prev);
-                tc_fence_before();
+            if (h == 0) {
+                // row sums of P(i) -> the context warps (double-buffered by tile parity)
+                rsbuf[(li & 1) * 128 + rloc] = (redq[rloc] + redq[128 + rloc]) + (redq[256 + rloc] + redq[384 + rloc]);
                 __syncwarp();
-                if (lane == 0) mbar_arrive(smem_u32(oempty_bar));
+                if (lane == 0) mbar_arrive(smem_u32(rs_bar + (li & 1)));
             }
-            t_prev = t;
-            rowsum_prev = rowsum_p;
-        }
-        if (li > 0) {
-            int cv = 0;
-            if (p.use_col2 && lane < 16 && h * 16 + lane < p.D)
-                cv = ldg_s32(p.colsum_v + (int64_t)(t_prev / m_tiles) * p.D + h * 16 + lane);
-            __syncwarp();
-            if (lane < 16) ctv[lane] = cv * p.zp_p;
-            __syncwarp();
-            mbar_wait(smem_u32(ofull_bar), (li - 1) & 1u);
-            tc_fence_after();
-            context_epilogue(t_prev, rowsum_prev);
-            tc_fence_before();
         }
     }
 
