@@ -279,7 +279,7 @@ def run_own_arm(args) -> None:
         tr = json.load(open(os.path.join(ROOT, "profiles", "r01_gemm_dram_traffic.json")))
         n = sum(tr["launches_per_step"].values())
         traffic = sum(tr["per_launch_bytes"][k] * c for k, c in tr["launches_per_step"].items()) / n
-        traffic_note = (f"mean DRAM bytes per launch over the {n} of {len(timer) // max(args.steps, 1)} GEMM launches per step "
+        traffic_note = (f"mean DRAM bytes per launch over the {n} of {len(timer) // max(args.steps, 1)} tensor-core launches (GEMMs + attention) per step "
                         "whose shape has an ncu --set full capture (profiles/r01_gemm_dram_traffic.json)")
     except Exception:
         pass
@@ -317,7 +317,7 @@ def run_own_arm(args) -> None:
                      "bound_note": ("the int8 GEMMs of this graph carry fused epilogues (dequantize / softmax / GELU / quantize for "
                                     "the next MatMul); ncu shows them bound by CUDA-core instruction issue in the epilogue warps "
                                     "(issue slots 57-77 % busy), not by the tensor pipe -- profiles/r01_*_ncu_full.md"),
-                     "kernel": "nq::qgemm_kernel<BN> (all tcgen05 int8 GEMM launches of the step)",
+                     "kernel": "nq::qgemm_kernel<BN> + attn::attn_kernel (all tcgen05 int8 launches of the step)",
                      "launches_per_step": len(timer) // max(args.steps, 1),
                      "share_of_step": gemm_ms / eager_ms if eager_ms else None,
                      "measured_in": "eager pass of the same steps (events cannot be recorded inside a CUDA graph)",

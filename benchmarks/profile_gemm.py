@@ -47,6 +47,16 @@ for case in cases:
             else:
                 out = K.qgemm_to_operand(oa, ob, 1e-4, azp, bias, 8, 0.05, -3,
                                          "split_rows" if case == "qkv_quant" else "split_cols", 12, 197, True).data
+    elif case == "attention":
+        bt, S, D = 3072, 197, 64
+        q8 = torch.randint(-128, 128, (bt, S, D), generator=g, device=DEV, dtype=torch.int8)
+        k8 = torch.randint(-128, 128, (bt, D, S), generator=g, device=DEV, dtype=torch.int8)
+        v8 = torch.randint(-128, 128, (bt, S, D), generator=g, device=DEV, dtype=torch.int8)
+        fq, fk, fv = K.operand_from_codes(q8, "A", True), K.operand_from_codes(k8, "B", True), K.operand_from_codes(v8, "B", True)
+        for o in (fq, fk, fv):
+            o.batch_shape = (bt // 12, 12)
+        for _ in range(2):
+            out = K.attention(fq, fk, fv, 1e-4, 3, -4, 8.0, 8, 1 / 255, -128, 1e-4, 9, 8, 0.05, -3, False).data
     elif case in ("qk_softmax", "pv_merge"):
         bt, S, D = 3072, 197, 64
         if case == "qk_softmax":
