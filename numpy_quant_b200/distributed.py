@@ -32,7 +32,9 @@ def init_from_env(backend: Optional[str] = None) -> tuple[int, int, int]:
             backend = "nccl" if torch.cuda.is_available() else "gloo"
         if backend == "nccl":
             torch.cuda.set_device(local)
-        dist.init_process_group(backend=backend, rank=rank, world_size=ws)
+            dist.init_process_group(backend=backend, rank=rank, world_size=ws, device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group(backend=backend, rank=rank, world_size=ws)
     elif torch.cuda.is_available():
         torch.cuda.set_device(local)
     return rank, local, ws
