@@ -30,6 +30,25 @@ int make_operand_map(CUtensorMap* map, const int8_t* base, int64_t K, int64_t ro
 
 namespace attn {
 
+// Waiters that are off the critical path (TMA producer: 3 stages ahead; context warps: a tile behind) back off with
+// nanosleep: their poll loops otherwise take ~15 % of the issue slots the softmax warps need.
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (uint32_t spin = 1; !done; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (!done) {
+            __nanosleep(256);
+            if (spin > (1u << 24)) __trap();                              // ~4 s: protocol bug -> error instead of a hang
+        }
+    }
+}
+
 constexpr int NUM_EPI_WARPS = 16;
 constexpr int NUM_CTX_WARPS = 4;                // context epilogue: one warp per TMEM lane quarter
 constexpr int NUM_THREADS = 128 + 32 * NUM_EPI_WARPS + 32 * NUM_CTX_WARPS;   // 768
@@ -41,7 +60,7 @@ constexpr int K_BYTES = BN1 * BK;              // 26 KB
 constexpr int V_BYTES = 2 * BN2 * BK;          // 16 KB: two k-blocks of the key axis
 constexpr int STAGE_BYTES = Q_BYTES + K_BYTES + V_BYTES;
 constexpr int P_BYTES = 2 * BM * BK;           // 32 KB: P as the K-major A operand of the second MMA (two k-blocks)
-constexpr int EPI_WORDS = 4096;                // max / sum / code-sum exchange + per-warp column terms
+constexpr int EPI_WORDS = 4864;                // max / sum / code-sum exchange, per-warp column / row terms (cp.async targets)
 constexpr int BAR_BYTES = 256;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + P_BYTES + EPI_WORDS * 4 + BAR_BYTES;
 static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB opt-in shared memory of sm_100");
@@ -134,7 +153,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
                 uint32_t phase = 0;
                 for (uint32_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
                     const int bh = (int)(t / m_tiles), m0 = (int)(t % m_tiles) * BM;
-                    mbar_wait(smem_u32(empty_bar + stage), phase ^ 1);
+                    mbar_wait_relaxed(smem_u32(empty_bar + stage), phase ^ 1);
                     const uint32_t fb = smem_u32(full_bar + stage);
                     uint8_t* st = smem + stage * STAGE_BYTES;
                     mbar_expect_tx(fb, STAGE_BYTES);
@@ -201,7 +220,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
         // O(i) = P(i) . V is drained here while the softmax warps already work on tile i + 1.
         const int q = warp & 3;
         const int rloc = q * 32 + lane;
-        const int* rsbuf = reinterpret_cast<const int*>(epi) + 3584;      // [2][128] row sums of P (from the softmax warps)
+        const int* rsbuf = reinterpret_cast<const int*>(epi) + 4608;      // [2][128] row sums of P (from the softmax warps)
         const Quantizer qzo(p.qo);
         uint32_t li = 0;
         for (uint32_t t = blockIdx.x; t < total_tiles; t += gridDim.x, ++li) {
@@ -210,10 +229,10 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
             const bool row_ok = m < p.S;
             const bool warp_rows = (int64_t)m0 + q * 32 < p.S;
             const uint32_t b = bh / (uint32_t)p.H, hh = bh - b * (uint32_t)p.H;
-            mbar_wait(smem_u32(rs_bar + (li & 1)), (li >> 1) & 1u);
+            mbar_wait_relaxed(smem_u32(rs_bar + (li & 1)), (li >> 1) & 1u);
             int rowterm = (int)-p.kterm2;
             if (p.use_row2) rowterm += rsbuf[(li & 1) * 128 + rloc] * p.zv;
-            mbar_wait(smem_u32(ofull_bar), li & 1u);
+            mbar_wait_relaxed(smem_u32(ofull_bar), li & 1u);
             tc_fence_after();
             int8_t* dst = p.C + (((int64_t)b * p.S + m) * p.H + hh) * p.D;
             int rs_out = 0;
@@ -256,29 +275,33 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
         const int rloc = q * 32 + lane;
         float* red = reinterpret_cast<float*>(epi);                        // [2][4][128] max / sum exchange
         int* redq = reinterpret_cast<int*>(epi) + 1024;                    // [4][128] code sums
-        int* ctw = reinterpret_cast<int*>(epi) + 2048 + ew * 64;           // this warp's 56 score column terms
-        int* rsbuf = reinterpret_cast<int*>(epi) + 3584;                   // [2][128] row sums of P for the context warps
+        int* ctw2 = reinterpret_cast<int*>(epi) + 2048 + ew * 128;         // this warp's 56 score column terms, 2 tile buffers
+        int* rowraw = reinterpret_cast<int*>(epi) + 1536 + ew * 32;        // this warp's rowsum(Q) values of the next tile
+        int* rsbuf = reinterpret_cast<int*>(epi) + 4608;                   // [2][128] row sums of P for the context warps
         constexpr int NSUB = 7;
         constexpr float kMasked = -1.0e30f;
         const int col0 = h * (NSUB * 8);
         const int ncols_w = (int)(p.S - col0 < NSUB * 8 ? (p.S - col0 > 0 ? p.S - col0 : 0) : NSUB * 8);
         const int nfull = ncols_w >> 3, nrem = ncols_w & 7;
-        // per-tile operands fetched one tile ahead (L2 round trips off the critical path)
-        struct Pre { int rowsum, c0, c1; };
-        auto prefetch = [&](uint32_t tt, Pre& o) {
-            o.rowsum = o.c0 = o.c1 = 0;
+        // Per-tile operands of the zero-point correction (rowsum(Q) of this thread's row, colsum(K) of this warp's 56
+        // columns) travel global -> shared memory with cp.async ONE TILE AHEAD: no registers held across the tile, no
+        // L2 round trip at the head of a tile's critical path.
+        auto stage_next = [&](uint32_t tt, int buf) {
             if (tt >= total_tiles) return;
             const uint32_t bh = tt / m_tiles, m0 = (tt - bh * m_tiles) * BM;
             const int64_t m = (int64_t)m0 + rloc;
-            if (p.use_row1 && m < p.S) o.rowsum = ldg_s32(p.rowsum_q + (int64_t)bh * p.S + m);
+            if (p.use_row1 && m < p.S)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(rowraw + lane)), "l"(p.rowsum_q + (int64_t)bh * p.S + m) : "memory");
             if (p.use_col1) {
                 const int64_t c0i = col0 + lane, c1i = c0i + 32;
-                if (c0i < p.S) o.c0 = ldg_s32(p.colsum_k + (int64_t)bh * p.S + c0i);
-                if (lane < 24 && c1i < p.S) o.c1 = ldg_s32(p.colsum_k + (int64_t)bh * p.S + c1i);
+                const int32_t* src = p.colsum_k + (int64_t)bh * p.S;
+                if (c0i < p.S)
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(ctw2 + buf * 64 + lane)), "l"(src + c0i) : "memory");
+                if (lane < 24 && c1i < p.S)
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(ctw2 + buf * 64 + 32 + lane)), "l"(src + c1i) : "memory");
             }
         };
-        Pre nxt;
-        prefetch(blockIdx.x, nxt);
+        stage_next(blockIdx.x, 0);
         uint32_t li = 0;
         for (uint32_t t = blockIdx.x; t < total_tiles; t += gridDim.x, ++li) {
             const uint32_t bh = t / m_tiles, m0 = (t - bh * m_tiles) * BM;
@@ -286,14 +309,22 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
             const bool row_ok = m < p.S;
             const int rows_left = (int)(p.S - (m0 + q * 32));
             const bool warp_rows = rows_left > 0;
-            const Pre cur = nxt;
-            prefetch(t + gridDim.x, nxt);
+            asm volatile("cp.async.wait_all;" ::: "memory");               // this tile's terms (issued one tile ago) have landed
+            __syncwarp();
+            int* ctw = ctw2 + (li & 1) * 64;
             int rowterm = (int)-p.kterm1;
-            if (p.use_row1 && row_ok) rowterm += cur.rowsum * p.zk;
+            if (p.use_row1 && row_ok) rowterm += rowraw[lane] * p.zk;
+            if (p.use_col1) {                                              // raw column sums -> column terms, in place
+                const int v0 = ctw[lane] * p.zq, v1 = ctw[32 + lane] * p.zq;
+                __syncwarp();
+                ctw[lane] = v0;
+                ctw[32 + lane] = v1;
+            } else {
+                ctw[lane] = 0;
+                ctw[32 + lane] = 0;
+            }
             __syncwarp();
-            ctw[lane] = cur.c0 * p.zq;
-            ctw[32 + lane] = cur.c1 * p.zq;
-            __syncwarp();
+            stage_next(t + gridDim.x, (int)((li + 1) & 1));
             const int sb = (int)(li & 1);
             mbar_wait(smem_u32(sfull_bar + sb), (li >> 1) & 1u);
             tc_fence_after();
