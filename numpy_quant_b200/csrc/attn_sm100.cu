@@ -229,6 +229,16 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
             const bool row_ok = m < p.S;
             const bool warp_rows = (int64_t)m0 + q * 32 < p.S;
             const uint32_t b = bh / (uint32_t)p.H, hh = bh - b * (uint32_t)p.H;
+            // column terms of this tile (colsum(V) * zp_p, 64 values, the same for every row): one 16-byte load per
+            // lane into the warp's smem strip before the waits, broadcast LDS.128 in the loop
+            int* ctv = reinterpret_cast<int*>(epi) + 4096 + q * 64;
+            __syncwarp();
+            if (lane < 16) {
+                int4 c4 = make_int4(0, 0, 0, 0);
+                if (p.use_col2 && lane * 4 < p.D) c4 = ldg_v4(p.colsum_v + (int64_t)bh * p.D + lane * 4);
+                *reinterpret_cast<int4*>(ctv + lane * 4) = make_int4(c4.x * p.zp_p, c4.y * p.zp_p, c4.z * p.zp_p, c4.w * p.zp_p);
+            }
+            __syncwarp();
             mbar_wait_relaxed(smem_u32(rs_bar + (li & 1)), (li >> 1) & 1u);
             int rowterm = (int)-p.kterm2;
             if (p.use_row2) rowterm += rsbuf[(li & 1) * 128 + rloc] * p.zv;
@@ -245,9 +255,8 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
                     int w[4];
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
-                        int4 c4 = make_int4(0, 0, 0, 0);
-                        if (p.use_col2) c4 = ldg_v4(p.colsum_v + (int64_t)bh * p.D + c16 * 16 + g * 4);
-                        const int ct[4] = {c4.x * p.zp_p, c4.y * p.zp_p, c4.z * p.zp_p, c4.w * p.zp_p};
+                        const int4 c4 = *reinterpret_cast<const int4*>(ctv + c16 * 16 + g * 4);
+                        const int ct[4] = {c4.x, c4.y, c4.z, c4.w};
                         int c[4];
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
