@@ -1,16 +1,19 @@
 // K4/K5: int8 x int8 -> int32 GEMM on the 5th-gen tensor cores (tcgen05.mma kind::i8),
 // replacing the reference's `np.matmul` on int64 arrays (numpy_quantization.py:44-61).
 //
-// Persistent, warp-specialised, one CTA per SM:
+// Persistent, warp-specialised, one CTA per SM (or a CTA pair per 256-row tile, cta_group::2, when the main loop
+// dominates: K >= 1024):
 //   warp 0      TMA producer   (cp.async.bulk.tensor 3-D, 128B swizzle, K-major tiles)
-//   warp 1      MMA issuer     (one elected thread, tcgen05.mma cta_group::1, M=128, N=BN, K=32)
-//   warp 2      TMEM allocator (2 accumulator buffers of BN int32 columns)
-//   warps 4-19  epilogue       (tcgen05.ld 32x32b -> per-warp swizzled smem transpose ->
-//                               zero-point correction + dequant(+bias) on the row-contiguous
-//                               read-back -> 16-byte coalesced stores; requant -> int8 codes)
-// smem ring of STAGES x (A 128x128 B + B BNx128 B); mbarrier full/empty per stage and
-// tmem_full/tmem_empty per accumulator buffer, so the epilogue of tile i overlaps the
-// main loop of tile i+1.
+//   warp 1      MMA issuer     (one elected thread, tcgen05.mma, M=128 (256 for a pair), N=BN, K=32)
+//   warp 2      TMEM allocator (512 columns: 2 x 256, 4 x 128 or 8 x 64 accumulator buffers)
+//   warps 4-19  epilogue, one template instantiation per mode:
+//                 RAW / DEQUANT (ragged, general) / REQUANT   tcgen05.ld x16 -> swizzled smem transpose -> 16-byte stores
+//                 DEQUANT wide (+bias, +residual)              x32, 4 KB slabs: whole 128-byte lines per row segment
+//                 QUANT rows / cols, GELU_QUANT                thread = row, codes straight into the next operand
+//                 SOFTMAX_QUANT                                4 warps per lane quarter share a row through smem
+//               narrow tiles (BN < 256) are drained by 2 / 4 independent warp groups, one tile each
+// smem ring of STAGES x (A 128x128 B + B BNx128 B); mbarrier full/empty per stage and tmem_full/tmem_empty per
+// accumulator buffer, so the epilogue of tile i overlaps the main loop of tile i+1; setmaxnreg 56 / 104.
 #include <cuda.h>
 
 #include <type_traits>
