@@ -261,8 +261,13 @@ def run_own_arm(args) -> None:
     else:
         e2e_ms = e2e_s * 1e3
 
-    gemm_ops = sum(o for o, _, _ in timer)
-    gemm_ms = sum(a.elapsed_time(b) for _, a, b in timer)
+    # timer entries: (ops, start, end[, tag]); the fused attention kernel is reported next to the GEMM family
+    gemm = [e for e in timer if len(e) == 3]
+    attn = [e for e in timer if len(e) == 4]
+    gemm_ops = sum(e[0] for e in gemm)
+    gemm_ms = sum(e[1].elapsed_time(e[2]) for e in gemm)
+    attn_ops = sum(e[0] for e in attn)
+    attn_ms = sum(e[1].elapsed_time(e[2]) for e in attn)
     if rank != 0:
         return
     peaks = {}
@@ -279,7 +284,7 @@ def run_own_arm(args) -> None:
         tr = json.load(open(os.path.join(ROOT, "profiles", "r01_gemm_dram_traffic.json")))
         n = sum(tr["launches_per_step"].values())
         traffic = sum(tr["per_launch_bytes"][k] * c for k, c in tr["launches_per_step"].items()) / n
-        traffic_note = (f"mean DRAM bytes per launch over the {n} of {len(timer) // max(args.steps, 1)} tensor-core launches (GEMMs + attention) per step "
+        traffic_note = (f"mean DRAM bytes per launch over the {n} of {len(gemm) // max(args.steps, 1)} GEMM launches per step "
                         "whose shape has an ncu --set full capture (profiles/r01_gemm_dram_traffic.json)")
     except Exception:
         pass
@@ -317,9 +322,14 @@ def run_own_arm(args) -> None:
                      "bound_note": ("the int8 GEMMs of this graph carry fused epilogues (dequantize / softmax / GELU / quantize for "
                                     "the next MatMul); ncu shows them bound by CUDA-core instruction issue in the epilogue warps "
                                     "(issue slots 57-77 % busy), not by the tensor pipe -- profiles/r01_*_ncu_full.md"),
-                     "kernel": "nq::qgemm_kernel<BN> + attn::attn_kernel (all tcgen05 int8 launches of the step)",
-                     "launches_per_step": len(timer) // max(args.steps, 1),
+                     "kernel": "nq::qgemm_kernel<BN, epilogue> (all instantiations launched in the step: the int8 GEMMs)",
+                     "launches_per_step": len(gemm) // max(args.steps, 1),
                      "share_of_step": gemm_ms / eager_ms if eager_ms else None,
+                     "attention_kernel": {"kernel": "nq::attn::attn_kernel (QK^T + softmax + P.V + merge heads)",
+                                          "launches_per_step": len(attn) // max(args.steps, 1),
+                                          "share_of_step": attn_ms / eager_ms if eager_ms else None,
+                                          "achieved_tops": (attn_ops / (attn_ms * 1e-3) / 1e12) if attn_ms > 0 else None,
+                                          "note": "softmax-bound (CUDA-core issue), the two MMAs are ~4 % of its time"},
                      "measured_in": "eager pass of the same steps (events cannot be recorded inside a CUDA graph)",
                      "eager_ms_per_step": eager_ms / args.steps,
                      "peak_source": ("2 x MEASURED_PEAKS.json bf16_tflops_sustained (int8 = 2x bf16 on the tensor pipe; "

@@ -463,7 +463,7 @@ def attention(q: Operand, k: Operand, v: Operand, scale_qk: float, zq, zk, div_c
          C.byref(a), _stream())
     if timer is not None:
         e1.record()
-        timer.append((4 * B * H * S * S * D, e0, e1))
+        timer.append((4 * B * H * S * S * D, e0, e1, "attention"))
     _count()
     return res
 
