@@ -739,7 +739,11 @@ def where(condition: ITensor, a: Tensor, b: Tensor):
     assert a.__class__ == b.__class__, f"types {a.__class__} and {b.__class__} do not match"
     if isinstance(a, ITensor):
         return ITensor(np.where(condition.data, a.data, b.data))
-    raise NotImplementedError("where() on device tensors is not part of the quantized hot path")
+    if isinstance(a, FTensor):
+        # off the quantized hot path (shape arithmetic uses ITensor): an elementwise select, plain torch indexing
+        cond = torch.from_numpy(np.ascontiguousarray(np.asarray(condition.data) != 0)).to(a.device_tensor.device)
+        return FTensor(torch.where(cond, a.device_tensor, b.device_tensor))
+    raise ValueError("where() cannot build a QTensor (the reference's tensor.py:251-253 fails for QTensor as well)")
 
 
 def fconv2d(x: FTensor, w: FTensor, b: FTensor, pads, strides):

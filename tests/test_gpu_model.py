@@ -318,6 +318,54 @@ def test_qmodel_save_load_roundtrip(tmp_path, bits):
     assert os.path.getsize(path) < wbytes * bits / 8 * 1.6 + 200000
 
 
+def test_tensor_surface_off_the_hot_path():
+    """the parts of the FTensor / QTensor surface that QModel never reaches on its hot path
+    behave like the reference's NumPy expressions (tensor.py:60-153, 212-221, 245-253)."""
+    from numpy_quant_b200.tensor import ITensor, concat, where
+    rng = np.random.default_rng(4)
+    x = rng.normal(size=(2, 3, 4, 5)).astype(np.float32)
+    f = FTensor(x)
+    np.testing.assert_array_equal(f.T.data, x.T)
+    np.testing.assert_array_equal(f.transpose(0, 2, 1, 3).data, x.transpose(0, 2, 1, 3))
+    np.testing.assert_array_equal(f.reshape(ITensor(np.array([6, 20], np.int64))).data, x.reshape(6, 20))
+    np.testing.assert_array_equal(f.take(ITensor(np.array([2, 0], np.int64)), 1).data, x.take([2, 0], 1))
+    np.testing.assert_array_equal(f[:, 1:3, ::2].data, x[:, 1:3, ::2])
+    np.testing.assert_array_equal(f.copy().data, x)
+    np.testing.assert_array_equal((-f).data, -x)
+    np.testing.assert_array_equal((f + f).data, x + x)
+    np.testing.assert_array_equal((f * f).data, x * x)
+    np.testing.assert_array_equal(f.div(FTensor(np.float32(3.0) + np.abs(x))).data, x / (np.float32(3.0) + np.abs(x)))
+    np.testing.assert_array_equal(f.relu().data, (x > 0) * x)
+    np.testing.assert_array_equal(f.max(axis=-1, keepdims=True).data, x.max(-1, keepdims=True))
+    np.testing.assert_allclose(f.mean(axis=-1, keepdims=False).data, x.mean(-1), rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(f.sum(axis=1, keepdims=True).data, x.sum(1, keepdims=True), rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(f.sigmoid().data, 1 / (1 + np.exp(-x)), rtol=1e-6)
+    np.testing.assert_allclose(f.softmax(axis=-1).data, np.exp(x - x.max(-1, keepdims=True)) / np.exp(x - x.max(-1, keepdims=True)).sum(-1, keepdims=True), rtol=1e-5)
+    e = FTensor(x[:, :1]).expand(ITensor(np.array([2, 3, 4, 5], np.int64)))
+    np.testing.assert_array_equal(e.data, np.broadcast_to(x[:, :1], (2, 3, 4, 5)))
+    np.testing.assert_array_equal(concat([f, f], axis=2).data, np.concatenate([x, x], axis=2))
+    cond = ITensor((rng.random(size=(2, 3, 4, 5)) > 0.5).astype(np.int64))
+    np.testing.assert_array_equal(where(cond, f, -f).data, np.where(cond.data, x, -x))
+    np.testing.assert_array_equal(where(cond, ITensor(np.arange(120).reshape(2, 3, 4, 5)), ITensor(np.zeros((2, 3, 4, 5), np.int64))).data,
+                                  np.where(cond.data, np.arange(120).reshape(2, 3, 4, 5), 0))
+    with pytest.raises(ValueError):
+        FTensor(x.astype(np.float64))
+    with pytest.raises(ValueError):
+        QTensor(np.zeros(3, np.int32), 8, np.float32(1.0))
+    # QTensor.relu: clamp the codes at the zero-point; QTensor.sigmoid: dequantize -> sigmoid -> quantize with own params
+    q = quantize_tensor_min_max(f, 8, True)
+    codes, zp, sc = q.data, int(q.zero_point), np.float32(q.scale)
+    want = codes.copy()
+    want[want < zp] = zp
+    np.testing.assert_array_equal(q.relu().data, want)
+    act = (1 / (1 + np.exp(-rq.dequantize(codes, sc, np.int64(zp))))).astype(np.float32)
+    qs = q.sigmoid()
+    assert np.abs(qs.data - rq.quantize(act, 8, sc, np.int64(zp))).max() <= 1      # exp differs by <= 2 ulp from NumPy's
+    assert qs.bit_width == 8 and np.float32(qs.scale) == sc and int(qs.zero_point) == zp
+    with pytest.raises(AssertionError):
+        q.matmul(quantize_tensor_min_max(FTensor(x.transpose(0, 1, 3, 2).copy()), 4, True))
+
+
 def test_pipelined_submit_matches_graph_replay():
     """QModel.submit keeps two forwards in flight (H2D / kernels / D2H on separate streams): results are the
     graph-replay results, in submission order, for alternating inputs."""
