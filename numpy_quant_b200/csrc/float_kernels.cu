@@ -503,8 +503,9 @@ __global__ void __launch_bounds__(256) im2col_kernel(const T* __restrict__ x, in
 // One CTA per (b, oh): the kh input rows of every channel are read once, coalesced along w, into shared
 // memory [c][ii][w]; the OW patch rows (each ldo elements, contiguous in the output) are written from there,
 // one warp per patch row.  A per-CTA table maps an output column (ii, j, c) to its tile offset, so the inner
-// loops carry no integer division.  int8 (VEC4): 4 bytes per thread on both sides.
-template <typename T, bool VEC4>
+// loops carry no integer division.  int8: 4 bytes per thread on the output side (VEC4: ldo % 4 == 0) and on the
+// input side (VEC_IN: W % 4 == 0), independently.
+template <typename T, bool VEC4, bool VEC_IN>
 __global__ void __launch_bounds__(256) im2col_strip_kernel(const T* __restrict__ x, int C, int H, int W, int kh, int kw,
                                                           int ph0, int pw0, int sh, int sw, int OH, int OW, T pad,
                                                           T* __restrict__ out, int ldo) {
@@ -524,7 +525,7 @@ __global__ void __launch_bounds__(256) im2col_strip_kernel(const T* __restrict__
         const int h = oh * sh + ii - ph0;
         const bool in = h >= 0 && h < H;
         const T* src = x + ((b * C + c) * H + (in ? h : 0)) * (int64_t)W;
-        if (VEC4) {
+        if (VEC_IN) {
             const int* src4 = reinterpret_cast<const int*>(src);
             int* dst4 = reinterpret_cast<int*>(tile + ci * W);
             const int pad4 = (int)(uint8_t)pad * 0x01010101;
@@ -563,6 +564,73 @@ __global__ void __launch_bounds__(256) im2col_strip_kernel(const T* __restrict__
                 }
                 dst[col] = v;
             }
+        }
+    }
+}
+
+// int8, C % 4 == 0 (CNN blocks): the strip is staged CHANNEL-CONTIGUOUS, tile[(ii * W + w) * CP + c] with
+// CP = C + 4 (row stride of 17 words mod 32: the transposing byte stores of the coalesced input rows are conflict
+// free), so every 4 output bytes (4 consecutive channels of one (ii, j) tap) are one 32-bit shared-memory load.
+// A per-CTA table over the output WORDS carries the tap's tile offset and j.
+__global__ void __launch_bounds__(256) im2col_strip_c4_kernel(const int8_t* __restrict__ x, int C, int H, int W, int kh, int kw,
+                                                             int ph0, int pw0, int sh, int sw, int OH, int OW, int8_t pad,
+                                                             int8_t* __restrict__ out, int ldo) {
+    extern __shared__ __align__(16) unsigned char im_smem[];
+    const int kcols = kh * kw * C, kwords = kcols >> 2, CP = C + 4;
+    uint32_t* lut = reinterpret_cast<uint32_t*>(im_smem);                 // [kwords]: (j << 24) | ((ii * W + j) * CP + c0)
+    int8_t* tile = reinterpret_cast<int8_t*>(im_smem + (((size_t)kwords * 4 + 15) & ~(size_t)15));
+    const int oh = blockIdx.x % OH;
+    const int64_t b = blockIdx.x / OH;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    for (int wi = threadIdx.x; wi < kwords; wi += blockDim.x) {
+        const int col = wi << 2, c0 = col % C, ij = col / C, j = ij % kw, ii = ij / kw;
+        lut[wi] = ((uint32_t)j << 24) | (uint32_t)((ii * W + j) * CP + c0);
+    }
+    const int h0 = oh * sh - ph0, strip = kh * W;
+    const bool all_in = h0 >= 0 && h0 + kh <= H;                          // the kh input rows of a channel are contiguous
+    for (int c = warp; c < C; c += nwarps) {                               // one channel per warp iteration
+        const int8_t* base = x + ((b * C + c) * H) * (int64_t)W;
+        if (all_in) {
+            // 8 independent loads per lane in flight before the first store: one load at a time leaves the
+            // kernel bound by load latency
+            const int8_t* src = base + h0 * (int64_t)W;
+            for (int i0 = 0; i0 < strip; i0 += 256) {
+                int8_t v[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int i = i0 + k * 32 + lane;
+                    v[k] = (i < strip) ? src[i] : (int8_t)0;
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int i = i0 + k * 32 + lane;
+                    if (i < strip) tile[i * CP + c] = v[k];
+                }
+            }
+        } else {
+            for (int ii = 0; ii < kh; ++ii) {
+                const int h = h0 + ii;
+                const bool in = h >= 0 && h < H;
+                const int8_t* src = base + (in ? h : 0) * (int64_t)W;
+                int8_t* dst = tile + (ii * W) * CP + c;
+                for (int w = lane; w < W; w += 32) dst[w * CP] = in ? src[w] : pad;
+            }
+        }
+    }
+    __syncthreads();
+    const uint32_t pad4 = (uint32_t)(uint8_t)pad * 0x01010101u;
+    const int ldw = ldo >> 2;
+    for (int ow = warp; ow < OW; ow += nwarps) {                           // one patch row per warp iteration
+        uint32_t* dst = reinterpret_cast<uint32_t*>(out + ((b * OH + oh) * (int64_t)OW + ow) * ldo);
+        const int wbase = ow * sw - pw0;
+        for (int wi = lane; wi < ldw; wi += 32) {
+            uint32_t word = 0;
+            if (wi < kwords) {
+                const uint32_t e = lut[wi];
+                const int w = wbase + (int)(e >> 24);
+                word = (w >= 0 && w < W) ? *reinterpret_cast<const uint32_t*>(tile + (int)(e & 0xffffffu) + wbase * CP) : pad4;
+            }
+            dst[wi] = word;
         }
     }
 }
@@ -886,20 +954,26 @@ extern "C" int nq_im2col(const void* x, int elem_bytes, int64_t B, int64_t C, in
     if (strip_bytes <= 48 * 1024 && B * OH < (1ll << 31) && OW * ldo < (1ll << 31) && kw < 256 && C * kh * W < (1 << 24) &&
         (elem_bytes == 1 || elem_bytes == 4)) {
         const unsigned nb = (unsigned)(B * OH);
-        if (elem_bytes == 1) {
-            const bool vec4 = (W % 4 == 0) && (ldo % 4 == 0) && (((uintptr_t)x | (uintptr_t)out) % 4 == 0);
-            if (vec4)
-                im2col_strip_kernel<int8_t, true><<<nb, 256, (size_t)strip_bytes, s>>>((const int8_t*)x, (int)C, (int)H, (int)W, kh, kw,
-                                                                                       ph0, pw0, sh, sw, (int)OH, (int)OW,
-                                                                                       (int8_t)pad_value, (int8_t*)out, (int)ldo);
-            else
-                im2col_strip_kernel<int8_t, false><<<nb, 256, (size_t)strip_bytes, s>>>((const int8_t*)x, (int)C, (int)H, (int)W, kh, kw,
-                                                                                        ph0, pw0, sh, sw, (int)OH, (int)OW,
-                                                                                        (int8_t)pad_value, (int8_t*)out, (int)ldo);
+        const int64_t c4_bytes = (((int64_t)kh * kw * C + 15) / 16) * 16 + (int64_t)kh * W * (C + 4);
+        if (elem_bytes == 1 && C % 4 == 0 && ldo % 4 == 0 && ((uintptr_t)out % 4 == 0) && c4_bytes <= 48 * 1024 &&
+            kh * W * (C + 4) < (1 << 24)) {
+            im2col_strip_c4_kernel<<<nb, 256, (size_t)c4_bytes, s>>>((const int8_t*)x, (int)C, (int)H, (int)W, kh, kw, ph0, pw0, sh, sw,
+                                                                     (int)OH, (int)OW, (int8_t)pad_value, (int8_t*)out, (int)ldo);
+        } else if (elem_bytes == 1) {
+            const bool vec_out = (ldo % 4 == 0) && ((uintptr_t)out % 4 == 0);
+            const bool vec_in = (W % 4 == 0) && ((uintptr_t)x % 4 == 0);
+#define NQ_IM2COL_S8(VO, VI)                                                                                            \
+    im2col_strip_kernel<int8_t, VO, VI><<<nb, 256, (size_t)strip_bytes, s>>>((const int8_t*)x, (int)C, (int)H, (int)W, kh, kw, ph0, \
+                                                                             pw0, sh, sw, (int)OH, (int)OW, (int8_t)pad_value,       \
+                                                                             (int8_t*)out, (int)ldo)
+            if (vec_out && vec_in) NQ_IM2COL_S8(true, true);
+            else if (vec_out) NQ_IM2COL_S8(true, false);
+            else NQ_IM2COL_S8(false, false);
+#undef NQ_IM2COL_S8
         } else {
             float padf;
             memcpy(&padf, &pad_value, 4);
-            im2col_strip_kernel<float, false><<<nb, 256, (size_t)strip_bytes, s>>>((const float*)x, (int)C, (int)H, (int)W, kh, kw, ph0,
+            im2col_strip_kernel<float, false, false><<<nb, 256, (size_t)strip_bytes, s>>>((const float*)x, (int)C, (int)H, (int)W, kh, kw, ph0,
                                                                                    pw0, sh, sw, (int)OH, (int)OW, padf, (float*)out,
                                                                                    (int)ldo);
         }
