@@ -155,7 +155,21 @@ def main():
              out_hw=[oh, ow2], ms_quantize=med_q, ms_im2col=med_i, ms_qgemm=med_g, ms_total=med_q + med_i + med_g,
              images_per_s=Bc / ((med_q + med_i + med_g) * 1e-3), tops_qgemm=ops / med_g / 1e9,
              quantize_gbs=xf.numel() * 5 / med_q / 1e6, im2col_gbs=(xq.numel() + cols.numel()) / med_i / 1e6)
-        del xf, xq, cols, oa
+        del cols, oa
+        # the same block as an implicit GEMM: NCHW -> padded NHWC relayout (1x1 im2col), then nq_qconv2d_s8
+        pads_c = (0, 2, 2, 1)
+        med_r, _ = timed(lambda: K.nhwc_pad(xq, pads_c, -5), iters=5)
+        med_f, _ = timed(lambda: K.nhwc_pad(xf, pads_c, -5, quant=(8, 0.03, -5)), iters=5)
+        nhwc = K.nhwc_pad(xf, pads_c, -5, quant=(8, 0.03, -5))
+        wk = K.operand_from_codes(w8[0].t().contiguous(), "A", True)
+        azi = K.AccZeroPoint(-5, None, kh * kw * Cc, None, wk.rowsum, True)
+        med_c, _ = timed(lambda: K.qconv2d(nhwc, wk, kh, kw, (2, 1), _lib.EPI_DEQUANT, 1e-4, azi, bias_f32=bias), iters=5)
+        emit(case="conv block (config 3) b1024, implicit GEMM: quantize->NHWC + qconv2d(dequant+bias)", M=Mc, N=Oc,
+             K=kh * kw * Cc, ms_quantize_nhwc=med_f, ms_qconv=med_c, ms_total=med_f + med_c,
+             images_per_s=Bc / ((med_f + med_c) * 1e-3), tops_qconv=ops / med_c / 1e9,
+             quantize_nhwc_gbs=(4 * xf.numel() + nhwc.numel()) / med_f / 1e6,
+             ms_relayout_codes=med_r, relayout_codes_gbs=(xq.numel() + nhwc.numel()) / med_r / 1e6)
+        del xf, xq, nhwc
     if args.gemm_only:
         return
     # HBM-bound kernels: algorithmic bytes per element as fixed in SURVEY.md §8(d)

@@ -202,12 +202,29 @@ int nq_qgemm_s8(const int8_t* A, const int8_t* B, void* C,
                 int64_t stride_a, int64_t stride_b, int64_t stride_c,
                 const nq_epilogue* ep, void* stream);
 
+/* Implicit-GEMM convolution (replaces the im2col + int matmul of the quantized Conv node: numpy_helper.py:18-92
+ * extract_sliding_windows / conv2d, reached from model.py:95-100): the patch matrix is never materialised.
+ * X: padded NHWC image codes [n_img][Hp][Wp][Cin] (pad pixels hold the activation zero-point code), Cin % 64 == 0;
+ * Wm: filter matrix [O][KH*KW*Cin] in (kh, kw, c) order, row stride ldw bytes (% 16), symmetric codes.
+ * out[(n, oh, ow), o] with OH = (Hp - KH) / stride_h + 1, OW = (Wp - KW) / stride_w + 1; the patch rows are read by
+ * im2col-mode TMA straight into the MMA's shared-memory operand.  Epilogues: RAW, DEQUANT (+bias), REQUANT. */
+int nq_qconv2d_s8(const int8_t* X, const int8_t* Wm, void* C, int64_t n_img, int64_t Hp, int64_t Wp, int64_t Cin,
+                  int64_t KH, int64_t KW, int64_t stride_h, int64_t stride_w, int64_t O, int64_t ldw, int64_t ldc,
+                  const nq_epilogue* ep, void* stream);
+
 /* Plain CUDA-core integer GEMM with the same arguments (RAW epilogue only): the
  * on-device cross-check for the tensor-core kernel at sizes the CPU oracle cannot reach. */
 int nq_qgemm_s8_simt(const int8_t* A, const int8_t* B, int32_t* C,
                      int64_t M, int64_t N, int64_t K, int64_t batch,
                      int64_t lda, int64_t ldb, int64_t ldc,
                      int64_t stride_a, int64_t stride_b, int64_t stride_c, void* stream);
+
+/* NCHW -> padded NHWC relayout feeding nq_qconv2d_s8: x[B,C,H,W] int8 codes (elem_bytes 1) or float32 (elem_bytes 4:
+ * quantized on the way with bits / scale / zp exactly like nq_quantize_f32) -> out[B][H+ph0+ph1][W+pw0+pw1][C] int8,
+ * pad pixels = pad_code (the activation zero-point code: the quantized 0.0 of the reference's float padding,
+ * numpy_helper.py:40-47).  C % 4 == 0. */
+int nq_nhwc_pad(const void* x, int elem_bytes, int64_t B, int64_t C, int64_t H, int64_t W, int ph0, int pw0, int ph1, int pw1,
+                int pad_code, int bits, float scale, int has_zp, int64_t zp, int8_t* out, void* stream);
 
 /* ---- K6: im2col for Conv (numpy_helper.py:18-92, tensor.py:256-264) ----------------------
  * x[B,C,H,W] (int8 codes or float32; elem_bytes 1 or 4) -> patches

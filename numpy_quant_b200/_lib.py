@@ -61,7 +61,10 @@ _SIGNATURES = {
     "nq_rowsum_s8": [vp, i64, i64, i64, vp, vp],
     "nq_qgemm_s8": [vp, vp, vp, i64, i64, i64, i64, i64, i64, i64, i64, i64, i64, C.POINTER(Epilogue), vp],
     "nq_attention_s8": [vp, vp, vp, i64, i64, i64, i64, i64, i64, i64, C.POINTER(Attention), vp],
+    "nq_qconv2d_s8": [vp, vp, vp, i64, i64, i64, i64, i64, i64, i64, i64, i64, i64, i64, C.POINTER(Epilogue), vp],
     "nq_qgemm_s8_simt": [vp, vp, vp, i64, i64, i64, i64, i64, i64, i64, i64, i64, i64, vp],
+    "nq_nhwc_pad": [vp, C.c_int, i64, i64, i64, i64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int,
+                    i64, vp, vp],
     "nq_im2col": [vp, C.c_int, i64, i64, i64, i64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                   C.c_int, i32, vp, i64, vp],
     "nq_pack_s8": [vp, i64, C.c_int, vp, vp],

@@ -635,6 +635,66 @@ __global__ void __launch_bounds__(256) im2col_strip_c4_kernel(const int8_t* __re
     }
 }
 
+// NCHW -> padded NHWC relayout for the implicit-GEMM convolution, optionally quantizing on the way (QMODE >= 0:
+// float32 in, codes out; QMODE < 0: int8 codes in).  One CTA per (image, block of HB padded rows): the rows of a
+// channel are one contiguous strip of the input (coalesced reads, 8 in flight per lane), staged channel-contiguous
+// with the conflict-free C + 4 pitch of the im2col kernel above, written back as whole NHWC rows (pad pixels = `pad`).
+template <int QMODE, typename TIn>
+__global__ void __launch_bounds__(256) nhwc_pad_kernel(const TIn* __restrict__ x, int C, int H, int W, int ph0, int pw0, int Hp,
+                                                       int Wp, int HB, int8_t pad, QArgs qa, int8_t* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char im_smem[];
+    int8_t* tile = reinterpret_cast<int8_t*>(im_smem);
+    const int CP = C + 4, hblocks = (Hp + HB - 1) / HB;
+    const int hp0 = (blockIdx.x % hblocks) * HB;
+    const int64_t b = blockIdx.x / hblocks;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const int hlo = max(hp0 - ph0, 0), hhi = min(hp0 + HB - ph0, H);      // input rows of this block
+    const int strip = (hhi - hlo) * W;
+    if (strip > 0) {
+        const Quantizer qz(qa);
+        for (int c = warp; c < C; c += nwarps) {
+            const TIn* src = x + ((b * C + c) * H + hlo) * (int64_t)W;
+            for (int i0 = 0; i0 < strip; i0 += 256) {
+                TIn v[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int i = i0 + k * 32 + lane;
+                    v[k] = (i < strip) ? src[i] : TIn(0);
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int i = i0 + k * 32 + lane;
+                    int8_t code;
+                    if constexpr (QMODE >= 0) code = (int8_t)qz.template code<QMODE>((float)v[k]);
+                    else code = (int8_t)v[k];
+                    if (i < strip) tile[i * CP + c] = code;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    const uint32_t pad4 = (uint32_t)(uint8_t)pad * 0x01010101u;
+    const int cw = C >> 2, row_words = Wp * cw;
+    const int step_pix = blockDim.x / cw, step_wc = blockDim.x % cw;
+    for (int r = 0; r < HB && hp0 + r < Hp; ++r) {
+        const int h = hp0 + r - ph0;
+        const bool row_in = h >= hlo && h < hhi;
+        uint32_t* dst = reinterpret_cast<uint32_t*>(out + ((b * Hp + hp0 + r) * (int64_t)Wp) * C);
+        const int8_t* trow = tile + (int64_t)(h - hlo) * W * CP;
+        int pix = threadIdx.x / cw, wc = threadIdx.x % cw;                // (pixel, word in pixel) of this thread's word
+        for (int wi = threadIdx.x; wi < row_words; wi += blockDim.x) {
+            const int w = pix - pw0;
+            dst[wi] = (row_in && w >= 0 && w < W) ? *reinterpret_cast<const uint32_t*>(trow + w * CP + (wc << 2)) : pad4;
+            pix += step_pix;
+            wc += step_wc;
+            if (wc >= cw) {
+                wc -= cw;
+                ++pix;
+            }
+        }
+    }
+}
+
 // counts inputs where the hoisted-reciprocal division differs from __fdiv_rn (must be 0)
 __global__ void selftest_division_kernel(uint64_t n, uint32_t seed, int mode, unsigned long long* mismatches) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
@@ -935,6 +995,37 @@ extern "C" int nq_copy_4d(const void* x, int elem_bytes, const int64_t* dims_hos
     else if (elem_bytes == 8) copy4d_kernel<int64_t><<<grid, 256, 0, s>>>((const int64_t*)x, g, n, (int64_t*)out);
     else NQ_REQUIRE(false, "nq_copy_4d: elem_bytes %d not in {1,4,8}", elem_bytes);
     NQ_CHECK_LAUNCH("nq_copy_4d");
+    return NQ_OK;
+}
+
+extern "C" int nq_nhwc_pad(const void* x, int elem_bytes, int64_t B, int64_t C, int64_t H, int64_t W, int ph0, int pw0, int ph1,
+                           int pw1, int pad_code, int bits, float scale, int has_zp, int64_t zp, int8_t* out, void* stream) {
+    NQ_REQUIRE(elem_bytes == 1 || elem_bytes == 4, "nq_nhwc_pad: elem_bytes %d not in {1,4}", elem_bytes);
+    NQ_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && ph0 >= 0 && pw0 >= 0 && ph1 >= 0 && pw1 >= 0, "nq_nhwc_pad: bad extents");
+    NQ_REQUIRE(C % 4 == 0 && ((uintptr_t)out % 4 == 0), "nq_nhwc_pad: channels must be a multiple of 4 (C=%lld)", (long long)C);
+    const int64_t Hp = H + ph0 + ph1, Wp = W + pw0 + pw1, row_bytes = W * (C + 4);
+    NQ_REQUIRE(row_bytes <= 48 * 1024, "nq_nhwc_pad: one image row (%lld bytes staged) exceeds 48 KB", (long long)row_bytes);
+    int64_t HB = 32768 / row_bytes;
+    HB = HB < 1 ? 1 : (HB > Hp ? Hp : HB);
+    const int64_t nb = B * ((Hp + HB - 1) / HB);
+    NQ_REQUIRE(nb < (1ll << 31) && Wp * C < (1ll << 31) && H * W < (1ll << 31), "nq_nhwc_pad: extent too large");
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t smem = (size_t)(HB * row_bytes);
+    int qmode = -1;
+    QArgs qa{};
+    if (elem_bytes == 4) {
+        NQ_REQUIRE(bits >= 2 && bits <= 8, "nq_nhwc_pad: bits %d outside 2..8", bits);
+        qa = make_qargs(bits, scale, has_zp, zp, &qmode);
+    }
+#define NQ_NHWC(QM, T)                                                                                                        \
+    nhwc_pad_kernel<QM, T><<<(unsigned)nb, 256, smem, s>>>((const T*)x, (int)C, (int)H, (int)W, ph0, pw0, (int)Hp, (int)Wp, (int)HB, \
+                                                           (int8_t)pad_code, qa, out)
+    if (qmode < 0) NQ_NHWC(-1, int8_t);
+    else if (qmode == 0) NQ_NHWC(0, float);
+    else if (qmode == 1) NQ_NHWC(1, float);
+    else NQ_NHWC(2, float);
+#undef NQ_NHWC
+    NQ_CHECK_LAUNCH("nq_nhwc_pad");
     return NQ_OK;
 }
 

@@ -81,6 +81,10 @@ struct GemmParams {
     int deq_wide;                    // DEQUANT: alignment / extent conditions of the 32-column epilogue hold (host-checked)
     int sm_noclamp;                  // SOFTMAX: p / s_out + zp stays inside [lo, hi] for every p in [0, 1]
     int fast22;                      // SOFTMAX: |acc - zero-point terms| < 2^22 proved on the host (magic int->float route)
+    // implicit-GEMM convolution (nq_qconv2d_s8): A rows are output pixels (n, oh, ow) of a padded NHWC image, read
+    // by im2col-mode TMA; K = (kh, kw, c) in 64-channel slices
+    int conv;
+    uint32_t cv_C, cv_KW, cv_OW, cv_OH, cv_sw, cv_sh;
 };
 
 // ------------------------------------------------------------------ epilogue math
@@ -256,6 +260,20 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                         if (cta_rank == 0) mbar_expect_tx(fb, 2 * C::STAGE_BYTES);   // bytes of both CTAs land here
                         tma_load_3d_pair(smem_u32(smem_a + stage * C::A_BYTES), &tmap_a, (int)(kb * BK), m0, ba, fb);
                         tma_load_3d_pair(smem_u32(smem_b + stage * C::B_BYTES), &tmap_b, (int)(kb * BK), n0, bb, fb);
+                    } else if (p.conv) {
+                        // two 64-byte K slices per stage: (filter tap, 64 channels) of 128 output pixels each,
+                        // 64B-swizzled sub-tiles; the base pixel of row m0 is (ow * sw, oh * sh) of image m0 / (OH * OW)
+                        const uint32_t pix = (uint32_t)m0 % (p.cv_OW * p.cv_OH), img = (uint32_t)m0 / (p.cv_OW * p.cv_OH);
+                        const int w0 = (int)((pix % p.cv_OW) * p.cv_sw), h0 = (int)((pix / p.cv_OW) * p.cv_sh);
+                        const uint32_t nsub = ((uint32_t)p.K - kb * BK) >= (uint32_t)BK ? 2u : 1u;
+                        mbar_expect_tx(fb, nsub * (C::STAGE_BYTES / 2));
+                        for (uint32_t j = 0; j < nsub; ++j) {
+                            const uint32_t k0 = kb * BK + j * 64, tap = k0 / p.cv_C;
+                            tma_load_im2col_4d(smem_u32(smem_a + stage * C::A_BYTES + j * (C::A_BYTES / 2)), &tmap_a,
+                                               (int)(k0 % p.cv_C), w0, h0, (int)img, (uint16_t)(tap % p.cv_KW),
+                                               (uint16_t)(tap / p.cv_KW), fb);
+                            tma_load_3d(smem_u32(smem_b + stage * C::B_BYTES + j * (C::B_BYTES / 2)), &tmap_b, (int)k0, n0, bb, fb);
+                        }
                     } else {
                         mbar_expect_tx(fb, C::STAGE_BYTES);
                         tma_load_3d(smem_u32(smem_a + stage * C::A_BYTES), &tmap_a, (int)(kb * BK), m0, ba, fb);
@@ -289,6 +307,19 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                     // K tail: only the 32-byte steps that hold real data (TMA zero-filled the rest of the box)
                     const uint32_t krem = (uint32_t)p.K - kb * BK;
                     const int ksteps = krem >= (uint32_t)BK ? BK / UMMA_K : (int)((krem + UMMA_K - 1) / UMMA_K);
+                    if (!TWO && p.conv) {
+                        // 64B-swizzled sub-tiles (one per 64-channel slice), two 32-byte K steps each
+#pragma unroll
+                        for (int k = 0; k < BK / UMMA_K; ++k) {
+                            if (k < ksteps) {
+                                const int j = k >> 1;
+                                mma_i8(d_tmem,
+                                       make_smem_desc_sw64(smem_u32(smem_a + stage * C::A_BYTES + j * (C::A_BYTES / 2))) + (uint64_t)((k & 1) * 2),
+                                       make_smem_desc_sw64(smem_u32(smem_b + stage * C::B_BYTES + j * (C::B_BYTES / 2))) + (uint64_t)((k & 1) * 2),
+                                       idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                            }
+                        }
+                    } else
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         // advance 32 bytes along K inside the swizzle atom: +2 in 16-byte units
@@ -1037,6 +1068,56 @@ int make_operand_map(CUtensorMap* map, const int8_t* base, int64_t K, int64_t ro
     return NQ_OK;
 }
 
+// Implicit-GEMM convolution operands.  A: im2col-mode map over the padded NHWC image [n][Hp][Wp][C]: 128 output
+// pixels x 64 channels per load; the bounding box keeps every filter tap of every base pixel inside the (already
+// padded) image, so nothing is zero-filled except rows past the last image.  B: filter matrix [O][KH*KW*C] in
+// 64-byte K slices.  Both 64B-swizzled (make_smem_desc_sw64).
+struct ConvGeom {
+    int64_t n_img, Hp, Wp, C, KH, KW, sh, sw, OH, OW;
+};
+
+using EncodeIm2colFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const int*, const int*, cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int make_conv_maps(CUtensorMap* ta, CUtensorMap* tb, const int8_t* X, const int8_t* Wm, const ConvGeom& g, int64_t O,
+                          int64_t ldw, int bn) {
+    static EncodeIm2colFn enc_i2c = nullptr;
+    if (!enc_i2c) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            enc_i2c = reinterpret_cast<EncodeIm2colFn>(ptr);
+    }
+    EncodeTiledFn enc = get_encode_fn();
+    NQ_REQUIRE(enc && enc_i2c, "cuTensorMapEncodeTiled / cuTensorMapEncodeIm2col not available from the driver");
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)g.C, (cuuint64_t)g.Wp, (cuuint64_t)g.Hp, (cuuint64_t)g.n_img};
+        cuuint64_t strides[3] = {(cuuint64_t)g.C, (cuuint64_t)(g.Wp * g.C), (cuuint64_t)(g.Hp * g.Wp * g.C)};
+        int lower[2] = {0, 0};                                            // {W, H}: base pixels start at the image corner
+        int upper[2] = {-(int)(g.KW - 1), -(int)(g.KH - 1)};              // ... and stop where the last tap still fits
+        cuuint32_t estr[4] = {1, (cuuint32_t)g.sw, (cuuint32_t)g.sh, 1};
+        CUresult r = enc_i2c(ta, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<int8_t*>(X), dims, strides, lower, upper, 64, BM, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        NQ_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeIm2col failed (CUresult %d; C=%lld Wp=%lld Hp=%lld n=%lld)", (int)r,
+                   (long long)g.C, (long long)g.Wp, (long long)g.Hp, (long long)g.n_img);
+    }
+    {
+        const int64_t K = g.KH * g.KW * g.C;
+        cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)O, 1};
+        cuuint64_t strides[2] = {(cuuint64_t)ldw, (cuuint64_t)(O * ldw)};
+        cuuint32_t box[3] = {64, (cuuint32_t)bn, 1};
+        cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = enc(tb, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<int8_t*>(Wm), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        NQ_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (filter matrix) failed (CUresult %d)", (int)r);
+    }
+    return NQ_OK;
+}
+
 template <int BN, int EMODE, bool TWO>
 static int launch_qgemm_impl(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t s) {
     using C = Cfg<BN, (EMODE == EM_DEQ_WIDE || EMODE == EM_DEQ_WIDE_RES), TWO>;
@@ -1106,9 +1187,10 @@ static int launch_qgemm_mode(const CUtensorMap& ta, const CUtensorMap& tb, const
 
 using namespace nq;
 
-extern "C" int nq_qgemm_s8(const int8_t* A, const int8_t* B, void* Cout, int64_t M, int64_t N, int64_t K,
-                           int64_t batch, int64_t lda, int64_t ldb, int64_t ldc, int64_t stride_a, int64_t stride_b,
-                           int64_t stride_c, const nq_epilogue* ep, void* stream) {
+// nq_qgemm_s8 and nq_qconv2d_s8 (cv != nullptr: A is the padded NHWC image, lda = K is nominal)
+static int qgemm_run(const int8_t* A, const int8_t* B, void* Cout, int64_t M, int64_t N, int64_t K, int64_t batch, int64_t lda,
+                     int64_t ldb, int64_t ldc, int64_t stride_a, int64_t stride_b, int64_t stride_c, const nq_epilogue* ep,
+                     void* stream, const ConvGeom* cv) {
     NQ_REQUIRE(ep, "nq_qgemm_s8: epilogue descriptor is NULL");
     NQ_REQUIRE(M > 0 && N > 0 && K > 0 && batch > 0, "nq_qgemm_s8: empty problem M=%lld N=%lld K=%lld batch=%lld",
                (long long)M, (long long)N, (long long)K, (long long)batch);
@@ -1252,15 +1334,46 @@ extern "C" int nq_qgemm_s8(const int8_t* A, const int8_t* B, void* Cout, int64_t
         // The pair halves the per-SM operand traffic of the main loop; measured (microbench A/B): +10..20 % where the
         // main loop dominates (K >= 1024: 4096^3, 8192^3, the K = 3072 MLP GEMM), -5..10 % for K = 768 tiles whose time
         // is the epilogue (the leader's next MMA has to wait for both CTAs' epilogues).
-        p.two_cta = !no_pair && bn == 256 && ep->mode != NQ_EPI_SOFTMAX_QUANT && M >= 256 && K >= 1024;
+        p.two_cta = !no_pair && !cv && bn == 256 && ep->mode != NQ_EPI_SOFTMAX_QUANT && M >= 256 && K >= 1024;
     }
     CUtensorMap ta, tb;
-    if (int rc = make_operand_map(&ta, A, K, M, p.a_batched ? batch : 1, lda, stride_a, BM)) return rc;
-    if (int rc = make_operand_map(&tb, B, K, N, p.b_batched ? batch : 1, ldb, stride_b, p.two_cta ? bn / 2 : bn)) return rc;
+    if (cv) {
+        p.conv = 1;
+        p.cv_C = (uint32_t)cv->C; p.cv_KW = (uint32_t)cv->KW;
+        p.cv_OW = (uint32_t)cv->OW; p.cv_OH = (uint32_t)cv->OH;
+        p.cv_sw = (uint32_t)cv->sw; p.cv_sh = (uint32_t)cv->sh;
+        if (int rc = make_conv_maps(&ta, &tb, A, B, *cv, N, ldb, bn)) return rc;
+    } else {
+        if (int rc = make_operand_map(&ta, A, K, M, p.a_batched ? batch : 1, lda, stride_a, BM)) return rc;
+        if (int rc = make_operand_map(&tb, B, K, N, p.b_batched ? batch : 1, ldb, stride_b, p.two_cta ? bn / 2 : bn)) return rc;
+    }
     cudaStream_t s = (cudaStream_t)stream;
     if (bn == 64) return launch_qgemm_mode<64>(ta, tb, p, s);
     if (bn == 128) return launch_qgemm_mode<128>(ta, tb, p, s);
     return launch_qgemm_mode<256>(ta, tb, p, s);
+}
+
+extern "C" int nq_qgemm_s8(const int8_t* A, const int8_t* B, void* Cout, int64_t M, int64_t N, int64_t K,
+                           int64_t batch, int64_t lda, int64_t ldb, int64_t ldc, int64_t stride_a, int64_t stride_b,
+                           int64_t stride_c, const nq_epilogue* ep, void* stream) {
+    return qgemm_run(A, B, Cout, M, N, K, batch, lda, ldb, ldc, stride_a, stride_b, stride_c, ep, stream, nullptr);
+}
+
+extern "C" int nq_qconv2d_s8(const int8_t* X, const int8_t* Wm, void* Cout, int64_t n_img, int64_t Hp, int64_t Wp, int64_t Cin,
+                             int64_t KH, int64_t KW, int64_t stride_h, int64_t stride_w, int64_t O, int64_t ldw, int64_t ldc,
+                             const nq_epilogue* ep, void* stream) {
+    NQ_REQUIRE(n_img > 0 && Hp > 0 && Wp > 0 && Cin > 0 && KH > 0 && KW > 0 && O > 0, "nq_qconv2d_s8: empty problem");
+    NQ_REQUIRE(Cin % 64 == 0, "nq_qconv2d_s8: channels must be a multiple of 64 (K slices of one filter tap; C=%lld)", (long long)Cin);
+    NQ_REQUIRE(KH <= Hp && KW <= Wp && KH <= 128 && KW <= 128, "nq_qconv2d_s8: filter %lldx%lld does not fit the padded image %lldx%lld",
+               (long long)KH, (long long)KW, (long long)Hp, (long long)Wp);
+    NQ_REQUIRE(stride_h >= 1 && stride_h <= 8 && stride_w >= 1 && stride_w <= 8, "nq_qconv2d_s8: strides must be 1..8 (TMA traversal stride)");
+    NQ_REQUIRE(ep && (ep->mode == NQ_EPI_RAW || ep->mode == NQ_EPI_DEQUANT || ep->mode == NQ_EPI_REQUANT),
+               "nq_qconv2d_s8: epilogue must be RAW, DEQUANT or REQUANT");
+    NQ_REQUIRE(ep->mode == NQ_EPI_RAW || !ep->zp.has_zp_b, "nq_qconv2d_s8: filters must be symmetric (no row sums of the patch matrix exist)");
+    ConvGeom g{n_img, Hp, Wp, Cin, KH, KW, stride_h, stride_w, (Hp - KH) / stride_h + 1, (Wp - KW) / stride_w + 1};
+    const int64_t M = n_img * g.OH * g.OW, K = KH * KW * Cin;
+    NQ_REQUIRE(M < (1ll << 31) && Wp * stride_w < (1ll << 31), "nq_qconv2d_s8: extent too large");
+    return qgemm_run(X, Wm, Cout, M, O, K, 1, K, ldw, ldc, 0, 0, 0, ep, stream, &g);
 }
 
 extern "C" int nq_qgemm_s8_simt(const int8_t* A, const int8_t* B, int32_t* Cm, int64_t M, int64_t N, int64_t K,

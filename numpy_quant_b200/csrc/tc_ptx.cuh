@@ -50,6 +50,17 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
         ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
         : "memory");
 }
+// im2col-mode load of a [pixels x channels] tile of an NHWC tensor: coordinates are the first channel and the base
+// pixel (w, h, n) of the tile's first row, (off_w, off_h) the filter tap added to every base pixel.  The traversal
+// (stride, wrap along W, H, N) and the tile extent live in the tensor map (cuTensorMapEncodeIm2col).
+__device__ __forceinline__ void tma_load_im2col_4d(uint32_t dst, const CUtensorMap* map, int c, int w, int h, int n,
+                                                   uint16_t off_w, uint16_t off_h, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6], "
+        "{%7, %8};" ::"r"(dst),
+        "l"(map), "r"(c), "r"(w), "r"(h), "r"(n), "r"(bar), "h"(off_w), "h"(off_h)
+        : "memory");
+}
 // ---- CTA-pair (cta_group::2) variants: TMA signals the leader CTA's barrier, commits arrive in both CTAs ----
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
@@ -152,6 +163,18 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
     d |= (uint64_t)(1024 >> 4) << 32;               // SBO = 1024 B       bits [32,46)
     d |= (uint64_t)1 << 46;                         // version            bits [46,48)
     d |= (uint64_t)2 << 61;                         // SWIZZLE_128B       bits [61,64)
+    return d;
+}
+
+// K-major, 64-byte-swizzled operand tile: rows of 64 B, 8-row groups 512 B apart (layout 4).  The implicit-GEMM
+// convolution stages K in 64-channel slices (one filter tap of an NHWC pixel), two of them per pipeline stage.
+__device__ __forceinline__ uint64_t make_smem_desc_sw64(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(512 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)4 << 61;                         // SWIZZLE_64B
     return d;
 }
 

@@ -279,6 +279,38 @@ def qgemm(a: Operand, b: Operand, mode: int = _lib.EPI_RAW, scale: float = 1.0,
     return out if (heads or ldn == N) else out[:, :, :N]
 
 
+def qconv2d(x_nhwc: torch.Tensor, w: Operand, kh: int, kw: int, strides, mode: int = _lib.EPI_RAW, scale: float = 1.0,
+            azp: Optional[AccZeroPoint] = None, bias_f32: Optional[torch.Tensor] = None) -> tuple[torch.Tensor, int, int]:
+    """Implicit-GEMM convolution (nq_qconv2d_s8): x_nhwc int8 [n, Hp, Wp, C] already padded (pad pixels = zero-point
+    code), w the filter matrix operand [O, kh*kw*C] in (kh, kw, c) order.  Returns out[n*OH*OW, O], OH, OW."""
+    _need_cuda(x_nhwc)
+    assert x_nhwc.dtype == torch.int8 and x_nhwc.is_contiguous() and x_nhwc.dim() == 4
+    n, Hp, Wp, Cc = (int(v) for v in x_nhwc.shape)
+    sh, sw = (int(v) for v in strides)
+    assert w.batch == 1 and w.k == kh * kw * Cc, f"filter matrix K {w.k} != {kh}*{kw}*{Cc}"
+    OH, OW = (Hp - kh) // sh + 1, (Wp - kw) // sw + 1
+    O = w.rows
+    dtype = {_lib.EPI_RAW: torch.int32, _lib.EPI_DEQUANT: torch.float32}[mode]
+    out = torch.empty((n * OH * OW, O), dtype=dtype, device=x_nhwc.device)
+    ep = Epilogue()
+    ep.mode = mode
+    ep.scale = float(scale)
+    if azp is not None:
+        ep.zp = azp.c_struct(O)
+    ep.bias_f32 = _ptr(bias_f32)
+    timer = GEMM_TIMER
+    if timer is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    call("nq_qconv2d_s8", x_nhwc.data_ptr(), w.data.data_ptr(), out.data_ptr(), n, Hp, Wp, Cc, kh, kw, sh, sw, O, w.ld, O,
+         C.byref(ep), _stream())
+    if timer is not None:
+        e1.record()
+        timer.append((2 * n * OH * OW * O * w.k, e0, e1))
+    _count()
+    return out, OH, OW
+
+
 def qgemm_to_operand(a: Operand, b: Operand, scale: float, azp: AccZeroPoint, bias_f32: Optional[torch.Tensor],
                      bits: int, out_scale, out_zp, kind: str, heads: int, seq: int, want_rowsum: bool,
                      gelu: Optional[tuple] = None) -> Operand:
@@ -683,6 +715,30 @@ def materialize(x: torch.Tensor) -> torch.Tensor:
     so = [d[1] * d[2] * d[3], d[2] * d[3], d[3], 1]
     call("nq_copy_4d", v.data_ptr(), x.element_size(), _lib.i64x4(d), _lib.i64x4(sx), out.data_ptr(),
          _lib.i64x4(so), _stream())
+    _count()
+    return out
+
+
+def can_nhwc_pad(C_: int, W: int) -> bool:
+    return C_ % 4 == 0 and W * (C_ + 4) <= 48 * 1024
+
+
+def nhwc_pad(x: torch.Tensor, pads, pad_code: int, quant: Optional[tuple] = None) -> torch.Tensor:
+    """x[B,C,H,W] int8 codes -- or float32 with quant=(bits, scale, zp|None), quantized on the way -- to the padded
+    NHWC int8 image [B, H+ph0+ph1, W+pw0+pw1, C] that nq_qconv2d_s8 reads (pad pixels = pad_code)."""
+    _need_cuda(x)
+    x = materialize(x)
+    B, Cc, H, W = (int(v) for v in x.shape)
+    ph0, pw0, ph1, pw1 = (int(p) for p in pads)
+    out = torch.empty((B, H + ph0 + ph1, W + pw0 + pw1, Cc), dtype=torch.int8, device=x.device)
+    if quant is None:
+        assert x.dtype == torch.int8
+        call("nq_nhwc_pad", x.data_ptr(), 1, B, Cc, H, W, ph0, pw0, ph1, pw1, int(pad_code), 8, 1.0, 0, 0, out.data_ptr(), _stream())
+    else:
+        assert x.dtype == torch.float32
+        bits, scale, zp = quant
+        call("nq_nhwc_pad", x.data_ptr(), 4, B, Cc, H, W, ph0, pw0, ph1, pw1, int(pad_code), int(bits), float(scale),
+             int(zp is not None), 0 if zp is None else int(zp), out.data_ptr(), _stream())
     _count()
     return out
 

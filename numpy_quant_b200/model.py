@@ -20,7 +20,7 @@ import torch
 from . import kernels as K
 from . import onnx_lite
 from .numpy_quantization import quant_parameters
-from .tensor import (FTensor, ITensor, QTensor, Tensor, concat, fconv2d, qconv2d, qtensor_from_operand,
+from .tensor import (FTensor, ITensor, QTensor, Tensor, concat, fconv2d, qconv2d, qtensor_from_operand, quantize_tensor_nhwc,
                      quantize_tensor, where, _to_device)
 
 
@@ -592,6 +592,24 @@ class QModel(Model):
             return d[1]
         return value.data.dequantize()
 
+    def _conv_input_pads(self, value: Value):
+        """The common `pads` of the Conv nodes consuming `value` as their image, or None if anything else reads it
+        (model outputs included) or the quantized weights are not symmetric 8-bit-or-narrower codes."""
+        if not value.outputs or value in self.outputs:
+            return None
+        pads = None
+        for n in value.outputs:
+            if n.op != "Conv" or n.inputs[0] is not value or value in n.inputs[1:]:
+                return None
+            w = n.inputs[1].data
+            if not isinstance(w, QTensor) or w._zp is not None or w.bit_width > 8:
+                return None
+            p = tuple(int(v) for v in n.attrs["pads"])
+            if pads is not None and p != pads:
+                return None
+            pads = p
+        return pads
+
     def _rowsum_needed(self, value: Value) -> bool:
         """Row sums of a left operand are needed iff some consuming MatMul has an asymmetric right operand."""
         for n in value.outputs:
@@ -887,7 +905,13 @@ class QModel(Model):
         for array, variable in zip(inputs, self.inputs):
             qparams = self.quant_params[variable.name]
             if isinstance(array, torch.Tensor) or array.dtype == np.float32:
-                variable.data = quantize_tensor(FTensor(array), self.bit_width, qparams.scale, qparams.zero_point)
+                pads = self._conv_input_pads(variable)
+                q = None
+                if pads is not None:
+                    # consumed only by Conv nodes: quantized straight into the padded NHWC image their TMA reads
+                    q = quantize_tensor_nhwc(FTensor(array), self.bit_width, qparams.scale, qparams.zero_point, pads)
+                variable.data = q if q is not None else \
+                    quantize_tensor(FTensor(array), self.bit_width, qparams.scale, qparams.zero_point)
             elif array.dtype == np.int64:
                 variable.data = ITensor(array)
             else:

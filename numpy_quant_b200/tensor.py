@@ -263,6 +263,8 @@ class QTensor:
       _q        codes in logical layout (torch int8 / int32 / int64), or None
       _oplayout (Operand, role, logical shape): codes that so far exist only in the K-major
                 operand layout of the GEMM (written there directly by quantize_tensor)
+      _nhwc     (padded NHWC image, pads, logical NCHW shape): codes of a Conv input that so far exist only in
+                the layout nq_qconv2d_s8 reads (written there by quantize_tensor_nhwc)
       _lazy     pending GEMM of a matmul result (operands + optional int bias)
       _packed   (role, packed bitstream, operand geometry, row sums): sub-byte storage of a weight -- the K-major
                 operand buffer packed to bit_width bits per code (nq_pack_s8); unpacked into a transient int8
@@ -272,6 +274,7 @@ class QTensor:
     def __init__(self, data, bit_width: int, scale, zero_point=None):
         self._lazy = None
         self._oplayout = None
+        self._nhwc = None
         self._ops: dict = {}           # cached K-major GEMM operands by role
         self._packed = None
         self._src = None               # base QTensor when this is the 2-D transpose of it
@@ -330,6 +333,8 @@ class QTensor:
             return tuple(self._q.shape)
         if self._oplayout is not None:
             return tuple(self._oplayout[2])
+        if self._nhwc is not None:
+            return tuple(self._nhwc[2])
         if self._packed is not None:
             return tuple(self._packed["logical"])
         L = self._lazy
@@ -354,6 +359,9 @@ class QTensor:
                 if role == "B":
                     v = v.transpose(1, 2)
                 self._q = K.materialize(v).view(shape)
+            elif self._nhwc is not None:
+                img, (ph0, pw0, _, _), shape = self._nhwc
+                self._q = K.materialize(img[:, ph0:ph0 + shape[2], pw0:pw0 + shape[3], :].permute(0, 3, 1, 2))
             else:
                 L = self._lazy
                 acc = K.qgemm(L["a"], L["b"])
@@ -673,6 +681,24 @@ def quantize_tensor(tensor: FTensor, bit_width: int, scale: np.float32, zero_poi
     return qtensor_from_operand(op, role, tuple(t.shape), bit_width, scale, zero_point)
 
 
+def quantize_tensor_nhwc(tensor: FTensor, bit_width: int, scale: np.float32, zero_point, pads) -> Optional[QTensor]:
+    """quantize_tensor for a value consumed only by Conv nodes with these pads: float32 NCHW is quantized straight into
+    the padded NHWC image of the implicit-GEMM convolution (pad pixels = the zero-point code, the quantized 0.0 of the
+    reference's float padding).  None when the geometry is not served by that route."""
+    t = tensor.device_tensor
+    zi = _as_opt_int(zero_point)
+    if t.dim() != 4 or not (2 <= bit_width <= 8) or not IMPLICIT_CONV:
+        return None
+    lo, hi = -(1 << (bit_width - 1)), (1 << (bit_width - 1)) - 1
+    if int(t.shape[1]) % 64 != 0 or not K.can_nhwc_pad(int(t.shape[1]), int(t.shape[3])) or (zi is not None and not lo <= zi <= hi):
+        return None
+    pads = tuple(int(p) for p in pads)
+    img = K.nhwc_pad(t, pads, 0 if zi is None else zi, quant=(bit_width, float(scale), zi))
+    out = QTensor(None, bit_width, scale=scale, zero_point=zero_point)
+    out._nhwc = (img, pads, tuple(int(v) for v in t.shape))
+    return out
+
+
 def qtensor_from_operand(op: K.Operand, role: str, shape: tuple, bit_width: int, scale, zero_point) -> QTensor:
     """Wrap codes that exist only in the K-major GEMM operand layout (`.data` un-pads on demand)."""
     out = QTensor(None, bit_width, scale=scale, zero_point=zero_point)
@@ -746,6 +772,9 @@ def where(condition: ITensor, a: Tensor, b: Tensor):
     raise ValueError("where() cannot build a QTensor (the reference's tensor.py:251-253 fails for QTensor as well)")
 
 
+IMPLICIT_CONV = True     # A/B switch: False materialises the patch matrix (nq_im2col + nq_qgemm_s8)
+
+
 def fconv2d(x: FTensor, w: FTensor, b: FTensor, pads, strides):
     """Float im2col convolution (tensor.py:256-264, numpy_helper.py:18-92): used by the
     float calibration pass; GEMM through the fp32 library matmul."""
@@ -768,11 +797,10 @@ def qconv2d(x: QTensor, w: QTensor, b: FTensor, pads, strides) -> FTensor:
         raise ValueError("qconv2d expects symmetric weights")
     if zx is not None and not (-128 <= zx <= 127):
         return fconv2d(x.dequantize(), w.dequantize(), b, pads, strides)
-    xq, wq = x._codes(), w._codes()
+    wq = w._codes()
     o, c, kh, kw = (int(s) for s in wq.shape)
-    cols, oh, ow = K.im2col(xq, kh, kw, pads, strides, 0 if zx is None else zx)
+    xshape = tuple(int(v) for v in x.shape)
     k = kh * kw * c
-    opa = K.Operand(cols.view(1, cols.shape[0], cols.shape[1]), (), cols.shape[0], k, cols.shape[1], None)
     opb = w._ops.get("conv")
     if opb is None:
         wk = K.materialize(wq.permute(0, 2, 3, 1)).view(o, k)            # [O, kh*kw*c] == K-major B operand
@@ -780,6 +808,24 @@ def qconv2d(x: QTensor, w: QTensor, b: FTensor, pads, strides) -> FTensor:
         w._ops["conv"] = opb
     azp = K.AccZeroPoint(zx, None, k, None, opb.rowsum, True)
     scale = np.float32(x.scale) * np.float32(w.scale)
+    n = xshape[0]
+    sh, sw = (int(s) for s in strides)
+    pads = tuple(int(p) for p in pads)
+    hp, wp = xshape[2] + pads[0] + pads[2], xshape[3] + pads[1] + pads[3]
+    if IMPLICIT_CONV and x.bit_width <= 8 and c % 64 == 0 and sh <= 8 and sw <= 8 and hp >= kh and wp >= kw \
+            and K.can_nhwc_pad(c, xshape[3]):
+        # implicit GEMM: the patch matrix is never written.  The codes live in (or are relaid to) a padded NHWC image
+        # (pad pixels = zp_x, i.e. the quantized zero of the reference's float padding); the GEMM's im2col-mode TMA
+        # reads the (kh, kw) taps of every output pixel straight from it.
+        if x._nhwc is not None and x._nhwc[1] == pads:
+            nhwc = x._nhwc[0]
+        else:
+            nhwc = K.nhwc_pad(x._codes(), pads, 0 if zx is None else zx)
+        y, oh, ow = K.qconv2d(nhwc, opb, kh, kw, (sh, sw), _lib.EPI_DEQUANT, float(scale), azp,
+                              bias_f32=b.device_tensor.contiguous())
+        return FTensor(y.view(n, oh, ow, o).permute(0, 3, 1, 2))
+    xq = x._codes()
+    cols, oh, ow = K.im2col(xq, kh, kw, pads, strides, 0 if zx is None else zx)
+    opa = K.Operand(cols.view(1, cols.shape[0], cols.shape[1]), (), cols.shape[0], k, cols.shape[1], None)
     y = K.qgemm(opa, opb, _lib.EPI_DEQUANT, float(scale), azp, bias_f32=b.device_tensor.contiguous())
-    n = int(xq.shape[0])
     return FTensor(y.view(n, oh, ow, o).permute(0, 3, 1, 2))

@@ -518,6 +518,60 @@ def test_copy_and_im2col(kv):
     np.testing.assert_array_equal(host(qc)[:, :18].reshape(2, oh * ow, 18), ref)
 
 
+@pytest.mark.parametrize("geom", [
+    # (n, C, H, W, O, kh, kw, pads, strides)
+    (3, 64, 9, 10, 32, 3, 2, (0, 2, 2, 1), (2, 1)),          # test_conv2d geometry, one K slice per tap, 3 stages
+    (2, 64, 7, 6, 48, 3, 1, (1, 0, 1, 0), (1, 1)),           # K = 192: last stage holds a single 64-byte slice
+    (5, 128, 12, 11, 130, 2, 2, (1, 1, 0, 0), (3, 2)),       # two slices per tap, N tail, stride 3 x 2
+    (2, 192, 5, 5, 16, 1, 1, (0, 0, 0, 0), (1, 1)),          # pointwise conv
+    (37, 64, 8, 9, 256, 3, 3, (1, 1, 1, 1), (1, 1)),         # many M tiles with a ragged last one
+])
+def test_implicit_gemm_conv_equals_patch_matrix_route(geom):
+    """nq_qconv2d_s8 (im2col-mode TMA, no patch matrix) gives the integer accumulators of the reference's
+    extract_sliding_windows + matmul (numpy_helper.py:18-92) bit for bit, and the same float32 result as
+    nq_im2col + nq_qgemm_s8 with the dequantize + bias epilogue."""
+    n, Cc, H, W, O, kh, kw, pads, strides = geom
+    rng = np.random.default_rng(n * 100 + Cc)
+    zx = -7
+    xq = rng.integers(-128, 128, size=(n, Cc, H, W)).astype(np.int8)
+    wq = rng.integers(-127, 128, size=(O, Cc, kh, kw)).astype(np.int8)
+    bias = rng.normal(size=O).astype(np.float32)
+    ph0, pw0, ph1, pw1 = pads
+    sh, sw = strides
+    xp = np.pad(xq.transpose(0, 2, 3, 1), ((0, 0), (ph0, ph1), (pw0, pw1), (0, 0)), constant_values=zx).astype(np.int64)
+    oh, ow = (xp.shape[1] - kh) // sh + 1, (xp.shape[2] - kw) // sw + 1
+    patches = np.stack([xp[:, i * sh:i * sh + kh, j * sw:j * sw + kw, :].reshape(n, -1)
+                        for i in range(oh) for j in range(ow)], 1).reshape(n * oh * ow, -1)
+    wmat = wq.transpose(0, 2, 3, 1).reshape(O, -1).astype(np.int64)
+    acc = patches @ wmat.T
+
+    xd = dev(xq)
+    opb = K.operand_from_codes(dev(wq.transpose(0, 2, 3, 1).reshape(O, -1).copy()), "A", True)
+    nhwc = K.nhwc_pad(xd, pads, zx)
+    hp, wp = xp.shape[1:3]
+    np.testing.assert_array_equal(host(nhwc), xp)
+    # the same image straight from float32 (quantize fused into the relayout): codes of nq_quantize_f32
+    xf = (rng.normal(size=xq.shape) * 3).astype(np.float32)
+    for bits, sc, zp in ((8, 0.05, zx), (8, 0.04, None), (4, 0.7, 2)):
+        want_codes = host(K.quantize(dev(xf), bits, sc, zp)).transpose(0, 2, 3, 1)
+        pc = 0 if zp is None else zp
+        got = host(K.nhwc_pad(dev(xf), pads, pc, quant=(bits, sc, zp)))
+        np.testing.assert_array_equal(got, np.pad(want_codes, ((0, 0), (ph0, ph1), (pw0, pw1), (0, 0)), constant_values=pc))
+    raw, oh2, ow2 = K.qconv2d(nhwc, opb, kh, kw, strides)
+    assert (oh2, ow2) == (oh, ow)
+    np.testing.assert_array_equal(host(raw), acc)
+
+    k = kh * kw * Cc
+    azp = K.AccZeroPoint(zx, None, k, None, opb.rowsum, True)
+    y, _, _ = K.qconv2d(nhwc, opb, kh, kw, strides, _lib.EPI_DEQUANT, 3e-4, azp, bias_f32=dev(bias))
+    cols, _, _ = K.im2col(xd, kh, kw, pads, strides, zx)
+    opa = K.Operand(cols.view(1, cols.shape[0], cols.shape[1]), (), cols.shape[0], k, cols.shape[1], None)
+    y2 = K.qgemm(opa, opb, _lib.EPI_DEQUANT, 3e-4, azp, bias_f32=dev(bias))
+    assert torch.equal(y, y2.view(y.shape))
+    want = ((acc - zx * wmat.sum(1)[None, :]).astype(np.float64) * np.float64(np.float32(3e-4))).astype(np.float32) + bias
+    np.testing.assert_array_equal(host(y), want)
+
+
 # ----------------------------------------------------------------------------- K10 / K11
 def test_minmax_and_pack_roundtrip():
     rng = np.random.default_rng(2)
