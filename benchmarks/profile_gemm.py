@@ -57,6 +57,17 @@ for case in cases:
             o.batch_shape = (bt // 12, 12)
         for _ in range(2):
             out = K.attention(fq, fk, fv, 1e-4, 3, -4, 8.0, 8, 1 / 255, -128, 1e-4, 9, 8, 0.05, -3, False).data
+    elif case == "conv":
+        # BASELINE config 3 as an implicit GEMM: quantize -> padded NHWC, then nq_qconv2d_s8
+        Bc, Cc, Hc, Wc, Oc, kh, kw = 1024, 64, 57, 58, 128, 3, 2
+        xf = torch.randn((Bc, Cc, Hc, Wc), generator=g, device=DEV)
+        w8 = torch.randint(-128, 128, (Oc, kh * kw * Cc), generator=g, device=DEV, dtype=torch.int8)
+        wk = K.operand_from_codes(w8, "A", True)
+        azp = K.AccZeroPoint(-5, None, kh * kw * Cc, None, wk.rowsum, True)
+        bias = torch.randn(Oc, device=DEV)
+        for _ in range(2):
+            nhwc = K.nhwc_pad(xf, (0, 2, 2, 1), -5, quant=(8, 0.03, -5))
+            out, _, _ = K.qconv2d(nhwc, wk, kh, kw, (2, 1), _lib.EPI_DEQUANT, 1e-4, azp, bias_f32=bias)
     elif case in ("qk_softmax", "pv_merge"):
         bt, S, D = 3072, 197, 64
         if case == "qk_softmax":
