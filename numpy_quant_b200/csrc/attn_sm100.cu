@@ -181,8 +181,8 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
                     if (have) {
                         // ---- scores of tile li (one tile ahead of the softmax warps)
                         const int sb = (int)(li & 1);
-                        mbar_wait(smem_u32(sempty_bar + sb), ((li >> 1) & 1u) ^ 1u);
-                        mbar_wait(smem_u32(full_bar + stage), (li / STAGES) & 1u);
+                        mbar_wait_backoff(smem_u32(sempty_bar + sb), ((li >> 1) & 1u) ^ 1u);
+                        mbar_wait_backoff(smem_u32(full_bar + stage), (li / STAGES) & 1u);
                         tc_fence_after();
                         uint8_t* st = smem + stage * STAGE_BYTES;
                         const uint64_t qd = make_smem_desc(smem_u32(st)), kd = make_smem_desc(smem_u32(st + Q_BYTES));
@@ -193,8 +193,8 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
                     if (li > 0) {
                         // ---- context of tile li - 1: P is in shared memory, the accumulator buffer is free
                         const uint32_t lp = li - 1;
-                        mbar_wait(smem_u32(pfull_bar), lp & 1u);
-                        mbar_wait(smem_u32(oempty_bar), (lp & 1u) ^ 1u);
+                        mbar_wait_backoff(smem_u32(pfull_bar), lp & 1u);
+                        mbar_wait_backoff(smem_u32(oempty_bar), (lp & 1u) ^ 1u);
                         tc_fence_after();
                         uint8_t* st = smem + prev_stage * STAGE_BYTES;
                         const uint64_t vd0 = make_smem_desc(smem_u32(st + Q_BYTES + K_BYTES));
@@ -360,14 +360,19 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
                         tmem_ld_wait();
                         const bool clean = j2 * 8 + 16 <= ncols_w || (j2 + 1 >= NSUB && j2 * 8 + 8 <= ncols_w);
                         if (clean) {
+                            // two columns per instruction (packed add, packed multiply: each lane IEEE-rounded exactly
+                            // like the scalar pair, so the codes stay those of the SOFTMAX_QUANT epilogue)
 #pragma unroll
-                            for (int k = 0; k < 16; ++k) {
+                            for (int k = 0; k < 16; k += 2) {
                                 if (j2 * 8 + k >= NSUB * 8) break;
-                                const int x = (int)a16[k] + rm - c16[k];
-                                const float f = MAGIC ? __fmul_rn(__fadd_rn(__int_as_float(x), -12582912.0f), p.scale1)
-                                                      : __fmul_rn(__int2float_rn(x), p.scale1);
-                                y[j2 * 8 + k] = f;
-                                lmax = fmaxf(lmax, f);
+                                const int x0 = (int)a16[k] + rm - c16[k], x1 = (int)a16[k + 1] + rm - c16[k + 1];
+                                const float2 s2 = make_float2(p.scale1, p.scale1);
+                                const float2 f = MAGIC ? __fmul2_rn(__fadd2_rn(make_float2(__int_as_float(x0), __int_as_float(x1)),
+                                                                               make_float2(-12582912.0f, -12582912.0f)), s2)
+                                                       : __fmul2_rn(make_float2(__int2float_rn(x0), __int2float_rn(x1)), s2);
+                                y[j2 * 8 + k] = f.x;
+                                y[j2 * 8 + k + 1] = f.y;
+                                lmax = fmaxf(lmax, fmaxf(f.x, f.y));
                             }
                         } else {
 #pragma unroll
@@ -403,23 +408,26 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
             if (warp_rows) {
                 const float l2e = 1.44269502162933349609375f;
                 const float m2 = __fmul_rn(gmax, l2e);
-                float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+                // four partial sums (columns k & 3) as two packed accumulators: same additions, same order
+                float2 s01 = make_float2(0.f, 0.f), s23 = make_float2(0.f, 0.f);
+                const float2 l2e2 = make_float2(l2e, l2e), nm2 = make_float2(-m2, -m2);
 #pragma unroll
                 for (int j = 0; j < NSUB; ++j) {
                     if (j * 8 < ncols_w) {
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) {
-                            float e;
-                            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(__fmaf_rn(y[j * 8 + k], l2e, -m2)));
-                            y[j * 8 + k] = e;
-                            if ((k & 3) == 0) s0 = __fadd_rn(s0, e);
-                            else if ((k & 3) == 1) s1 = __fadd_rn(s1, e);
-                            else if ((k & 3) == 2) s2 = __fadd_rn(s2, e);
-                            else s3 = __fadd_rn(s3, e);
+                        for (int k = 0; k < 8; k += 2) {
+                            const float2 a = __ffma2_rn(make_float2(y[j * 8 + k], y[j * 8 + k + 1]), l2e2, nm2);
+                            float2 e;
+                            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(a.x));
+                            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(a.y));
+                            y[j * 8 + k] = e.x;
+                            y[j * 8 + k + 1] = e.y;
+                            if ((k & 3) == 0) s01 = __fadd2_rn(s01, e);
+                            else s23 = __fadd2_rn(s23, e);
                         }
                     }
                 }
-                lsum = __fadd_rn(__fadd_rn(s0, s1), __fadd_rn(s2, s3));
+                lsum = __fadd_rn(__fadd_rn(s01.x, s01.y), __fadd_rn(s23.x, s23.y));
             }
             red[512 + h * 128 + rloc] = lsum;
             named_bar_sync(1 + q, 128);
@@ -439,11 +447,24 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
                 auto emit_group = [&](int j, auto ragged_tag) {
                     constexpr bool RAGGED = decltype(ragged_tag)::value;
                     int c[8];
+                    const float2 kr2 = make_float2(kr, kr), mg2 = make_float2(qzp.magic, qzp.magic);
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        c[k] = p.sm_noclamp ? __float_as_int(__fmaf_rn(y[j * 8 + k], kr, qzp.magic))
-                                            : qzp.code_of_quotient<1>(__fmul_rn(y[j * 8 + k], kr));
-                        if (RAGGED) c[k] = (k < nrem) ? c[k] : 0;
+                    for (int k = 0; k < 8; k += 2) {
+                        const float2 e = make_float2(y[j * 8 + k], y[j * 8 + k + 1]);
+                        if (p.sm_noclamp) {
+                            const float2 r = __ffma2_rn(e, kr2, mg2);
+                            c[k] = __float_as_int(r.x);
+                            c[k + 1] = __float_as_int(r.y);
+                        } else {
+                            const float2 t = __fmul2_rn(e, kr2);
+                            const float2 r = __fadd2_rn(make_float2(fminf(fmaxf(t.x, qzp.tlo), qzp.thi), fminf(fmaxf(t.y, qzp.tlo), qzp.thi)), mg2);
+                            c[k] = __float_as_int(r.x);
+                            c[k + 1] = __float_as_int(r.y);
+                        }
+                        if (RAGGED) {
+                            c[k] = (k < nrem) ? c[k] : 0;
+                            c[k + 1] = (k + 1 < nrem) ? c[k + 1] : 0;
+                        }
                     }
                     int w0 = pack4_codes(c[0], c[1], c[2], c[3]), w1 = pack4_codes(c[4], c[5], c[6], c[7]);
                     if (!row_ok) w0 = w1 = 0;                             // rows past S: zeros (their outputs are never stored)

@@ -254,7 +254,7 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                 const int n0 = (int)(r % n_tiles) * BN + (TWO ? (int)cta_rank * (BN / 2) : 0);
                 const int ba = p.a_batched ? (int)b : 0, bb = p.b_batched ? (int)b : 0;
                 for (uint32_t kb = 0; kb < k_blocks; ++kb) {
-                    mbar_wait(smem_u32(empty_bar + stage), phase ^ 1);
+                    mbar_wait_backoff(smem_u32(empty_bar + stage), phase ^ 1);
                     const uint32_t fb = smem_u32(full_bar + stage);
                     if constexpr (TWO) {
                         if (cta_rank == 0) mbar_expect_tx(fb, 2 * C::STAGE_BYTES);   // bytes of both CTAs land here
@@ -296,11 +296,11 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
             int acc = 0;
             uint32_t acc_phase = 0;
             for (uint32_t t = tile_first; t < total_tiles; t += tile_step) {
-                mbar_wait(smem_u32(tempty_bar + acc), acc_phase ^ 1);     // epilogue drained this buffer
+                mbar_wait_backoff(smem_u32(tempty_bar + acc), acc_phase ^ 1);   // epilogue drained this buffer
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
                 for (uint32_t kb = 0; kb < k_blocks; ++kb) {
-                    mbar_wait(smem_u32(full_bar + stage), phase);
+                    mbar_wait_backoff(smem_u32(full_bar + stage), phase);
                     tc_fence_after();
                     const uint64_t adesc = make_smem_desc(smem_u32(smem_a + stage * C::A_BYTES));
                     const uint64_t bdesc = make_smem_desc(smem_u32(smem_b + stage * C::B_BYTES));
@@ -493,12 +493,18 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                     if (__builtin_expect((bad & 0xFF800000u) != 0, 0)) {  // some |d| >= 2^22: exact slow route
 #pragma unroll
                         for (int j = 0; j < 16; ++j) f[j] = deq_slow(x[j] - 0x4B400000, p.scale);
-                    } else if constexpr (EMODE != EM_Q8_GELU) {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) f[j] = __fmul_rn(__fadd_rn(__int_as_float(x[j]), -12582912.0f), p.scale);
                     } else {
+                        // two columns per instruction: a packed add and a packed multiply round each lane exactly like
+                        // the scalar pair (the bias add below stays scalar: ptxas would contract a packed multiply +
+                        // packed add into one FFMA2, i.e. a single rounding)
+                        const float2 nm = make_float2(-12582912.0f, -12582912.0f), sc2 = make_float2(p.scale, p.scale);
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) f[j] = __fadd_rn(__int_as_float(x[j]), -12582912.0f);   // scaled below
+                        for (int j = 0; j < 16; j += 2) {
+                            float2 t = __fadd2_rn(make_float2(__int_as_float(x[j]), __int_as_float(x[j + 1])), nm);
+                            if constexpr (EMODE != EM_Q8_GELU) t = __fmul2_rn(t, sc2);       // GELU: scaled below
+                            f[j] = t.x;
+                            f[j + 1] = t.y;
+                        }
                     }
                     const bool gelu_scaled = (bad & 0xFF800000u) != 0;    // warp-divergent only on the rare slow route
                     int w[4];
@@ -640,16 +646,19 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                             const int x2 = (int)val.z + rm - ct2, x3 = (int)val.w + rm - ct3;
                             bad_any |= (uint32_t)(x0 ^ 0x4B000000) | (uint32_t)(x1 ^ 0x4B000000) |
                                        (uint32_t)(x2 ^ 0x4B000000) | (uint32_t)(x3 ^ 0x4B000000);
-                            float f0 = __fmul_rn(__fadd_rn(__int_as_float(x0), -12582912.0f), p.scale);
-                            float f1 = __fmul_rn(__fadd_rn(__int_as_float(x1), -12582912.0f), p.scale);
-                            float f2 = __fmul_rn(__fadd_rn(__int_as_float(x2), -12582912.0f), p.scale);
-                            float f3 = __fmul_rn(__fadd_rn(__int_as_float(x3), -12582912.0f), p.scale);
+                            // packed add / packed multiply (each lane rounded like the scalar op); the bias add is
+                            // scalar so that ptxas cannot contract multiply + add into a single-rounding FFMA2
+                            const float2 nm = make_float2(-12582912.0f, -12582912.0f), sc2 = make_float2(p.scale, p.scale);
+                            const float2 fa = __fmul2_rn(__fadd2_rn(make_float2(__int_as_float(x0), __int_as_float(x1)), nm), sc2);
+                            const float2 fb = __fmul2_rn(__fadd2_rn(make_float2(__int_as_float(x2), __int_as_float(x3)), nm), sc2);
+                            float f0 = fa.x, f1 = fa.y, f2 = fb.x, f3 = fb.y;
                             if (p.bias_f32) {
                                 f0 = __fadd_rn(b0, f0); f1 = __fadd_rn(b1, f1); f2 = __fadd_rn(b2, f2); f3 = __fadd_rn(b3, f3);
                             }
                             if constexpr (has_res) {
-                                f0 = __fadd_rn(f0, res[k].x); f1 = __fadd_rn(f1, res[k].y);
-                                f2 = __fadd_rn(f2, res[k].z); f3 = __fadd_rn(f3, res[k].w);
+                                const float2 ra = __fadd2_rn(make_float2(f0, f1), make_float2(res[k].x, res[k].y));
+                                const float2 rb = __fadd2_rn(make_float2(f2, f3), make_float2(res[k].z, res[k].w));
+                                f0 = ra.x; f1 = ra.y; f2 = rb.x; f3 = rb.y;
                             }
                             if (rr < rows_left)
                                 *reinterpret_cast<float4*>(crow + (int64_t)it * 4 * p.ldc) = make_float4(f0, f1, f2, f3);

@@ -44,6 +44,31 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         }
     }
 }
+// Same bound, for the single-thread roles (TMA producer, MMA issuer): a few immediate polls, then nanosleep between
+// polls.  Short waits (main-loop-bound GEMMs) never sleep; long waits (the epilogue is the bottleneck and the role is
+// a tile ahead) stop spending the issue slots of the sub-partition they share with four epilogue warps.
+__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    uint64_t t0 = 0;
+    for (uint32_t spin = 1; !done; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity), "r"(20000u)
+            : "memory");
+        if (!done && spin > 4) {
+            asm volatile("nanosleep.u32 %0;" ::"r"(spin > 32 ? 200u : 60u));
+            if ((spin & 255u) == 0) {
+                uint64_t now;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                if (t0 == 0) t0 = now;
+                else if (now - t0 > 4000000000ull) __trap();
+            }
+        }
+    }
+}
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
