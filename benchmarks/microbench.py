@@ -199,6 +199,11 @@ def main():
         gm = torch.ones(shp[1], device=DEV)
         med, _ = timed(lambda: K.layernorm(x, gm, gm, 1e-12))
         emit(case="layernorm f32", shape=shp, ms=med, gbs=8.0 * n / med / 1e6, frac_hbm=8.0 * n / med / 1e6 / HBM)
+        if shp[1] <= 1024:
+            for glue in (False, True):
+                med, _ = timed(lambda: K.layernorm_quantize(x, gm, gm, 1e-12, 8, 0.03, -5, False, float_glue=glue))
+                emit(case=f"layernorm -> quantize (int8 operand){', float glue' if glue else ''}", shape=shp, ms=med,
+                     gbs=5.0 * n / med / 1e6, frac_hbm=5.0 * n / med / 1e6 / HBM)
         med, _ = timed(lambda: K.binary("add", x, gm))
         emit(case="bias add f32", shape=shp, ms=med, gbs=8.0 * n / med / 1e6, frac_hbm=8.0 * n / med / 1e6 / HBM)
         for bits in (4, 2):

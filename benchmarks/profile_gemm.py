@@ -57,6 +57,11 @@ for case in cases:
             o.batch_shape = (bt // 12, 12)
         for _ in range(2):
             out = K.attention(fq, fk, fv, 1e-4, 3, -4, 8.0, 8, 1 / 255, -128, 1e-4, 9, 8, 0.05, -3, False).data
+    elif case == "ln":
+        x = torch.randn((50432, 768), generator=g, device=DEV)
+        gm, bt = torch.randn(768, device=DEV), torch.randn(768, device=DEV)
+        for _ in range(3):
+            out = K.layernorm_quantize(x, gm, bt, 1e-12, 8, 0.03, -5, False, float_glue=True).data
     elif case == "conv":
         # BASELINE config 3 as an implicit GEMM: quantize -> padded NHWC, then nq_qconv2d_s8
         Bc, Cc, Hc, Wc, Oc, kh, kw = 1024, 64, 57, 58, 128, 3, 2

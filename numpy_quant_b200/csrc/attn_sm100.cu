@@ -74,7 +74,8 @@ struct Params {
     const int32_t* colsum_k;                   // [BH, S]  (used when Q is asymmetric)
     int zq, zk, use_row1, use_col1;
     int64_t kterm1;                            // zq * zk * D
-    int fast22, sm_noclamp;
+    int fast22, sm_noclamp;                    // sm_noclamp: zp_p >= lo, so p / s + zp needs no lower clamp
+    float sm_top;                              // upper clamp in the magic-sum domain (1.5 * 2^23 + hi), or huge when p = 1 fits
     QArgs qp;                                  // P quantizer
     // context
     float scale2;                              // s_p * s_v
@@ -453,8 +454,8 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
                         const float2 e = make_float2(y[j * 8 + k], y[j * 8 + k + 1]);
                         if (p.sm_noclamp) {
                             const float2 r = __ffma2_rn(e, kr2, mg2);
-                            c[k] = __float_as_int(r.x);
-                            c[k + 1] = __float_as_int(r.y);
+                            c[k] = __float_as_int(fminf(r.x, p.sm_top));
+                            c[k + 1] = __float_as_int(fminf(r.y, p.sm_top));
                         } else {
                             const float2 t = __fmul2_rn(e, kr2);
                             const float2 r = __fadd2_rn(make_float2(fminf(fmaxf(t.x, qzp.tlo), qzp.thi), fminf(fmaxf(t.y, qzp.tlo), qzp.thi)), mg2);
@@ -543,8 +544,12 @@ extern "C" int nq_attention_s8(const int8_t* Q, const int8_t* Kt, const int8_t* 
     p.qp = make_qargs(a->p_bits, a->p_scale, a->has_p_zp, a->p_zp, &qmode);
     NQ_REQUIRE(qmode != 2, "nq_attention_s8: |p_zp| must be < 2^20");
     {
+        // probabilities lie in [0, 1]: with zp >= lo the quotient p / s + zp never needs the lower clamp and rounds
+        // straight out of one FMA with the magic constant; the upper clamp is a min in that domain, and vanishes
+        // (huge bound) when even p = 1 maps inside the code range
         const double top = (double)p.qp.zpf + 1.0 / (double)p.qp.scale * (1.0 + 1e-6);
-        p.sm_noclamp = ((double)p.qp.zpf >= (double)p.qp.lo) && (top < (double)p.qp.hi + 0.49);
+        p.sm_noclamp = (double)p.qp.zpf >= (double)p.qp.lo;
+        p.sm_top = (top < (double)p.qp.hi + 0.49) ? 3.0e38f : 12582912.0f + p.qp.hi;
     }
     p.scale2 = a->scale_pv;
     p.colsum_v = a->colsum_v;

@@ -276,6 +276,93 @@ __global__ void __launch_bounds__(256) layernorm_vec_kernel(const float* __restr
     }
 }
 
+// LayerNormalization -> quantize under the float-glue contract (1e-5 on the normalised value; rounding, clamp and
+// row sum of the codes exact): the instruction-lean variant that the fused executor uses.  Same structure as
+// layernorm_vec_kernel (one warp per row, next row in flight), with two elements per instruction (packed f32x2 add /
+// multiply / FMA), gamma / s_out and beta / s_out staged once per CTA in shared memory so the affine step and the
+// division by the output scale are one FMA, and 3 resident CTAs per SM.
+template <int NV>
+__global__ void __launch_bounds__(256, 3) layernorm_glue_kernel(const float* __restrict__ x, int64_t rows, int cols, int64_t ldx,
+                                                               const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                               float eps, QArgs qa, int8_t* __restrict__ qout, int64_t ldo,
+                                                               int32_t* __restrict__ rowsum) {
+    extern __shared__ __align__(16) unsigned char ln_smem[];
+    float4* gs = reinterpret_cast<float4*>(ln_smem);                       // [c4] gamma / s_out
+    float4* bs = gs + (cols >> 2);                                         // [c4] beta / s_out
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int c4 = cols >> 2;
+    const float fn = (float)cols;
+    const Quantizer qz(qa);
+    const float rscale = __frcp_rn(qa.scale);
+    for (int c = threadIdx.x; c < c4; c += blockDim.x) {
+        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c), b = __ldg(reinterpret_cast<const float4*>(beta) + c);
+        gs[c] = make_float4(g.x * rscale, g.y * rscale, g.z * rscale, g.w * rscale);
+        bs[c] = make_float4(b.x * rscale, b.y * rscale, b.z * rscale, b.w * rscale);
+    }
+    __syncthreads();
+    auto load_row = [&](int64_t r, float4* dstv) {
+        r = r < rows ? r : rows - 1;                                       // past the end: a harmless re-read, never used
+        const float4* src = reinterpret_cast<const float4*>(x + r * ldx) + lane;
+#pragma unroll
+        for (int j = 0; j < NV; ++j)
+            dstv[j] = (lane + j * 32 < c4) ? __ldcs(src + j * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    const int64_t row0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    float4 nx[NV];
+    load_row(row0, nx);
+    const float2 mg2 = make_float2(qz.magic, qz.magic);
+    for (int64_t row = row0; row < rows; row += warps) {
+        float2 a[NV], b[NV];                                               // (x, y) and (z, w) halves of the row's float4s
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            a[j] = make_float2(nx[j].x, nx[j].y);
+            b[j] = make_float2(nx[j].z, nx[j].w);
+        }
+        load_row(row + warps, nx);
+        float2 s2 = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < NV; ++j) s2 = __fadd2_rn(s2, __fadd2_rn(a[j], b[j]));       // padding lanes hold zeros
+        const float mean = warp_sum(s2.x + s2.y) / fn;
+        const float2 nm = make_float2(-mean, -mean);
+        float2 q2 = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            if (lane + j * 32 < c4) {
+                a[j] = __fadd2_rn(a[j], nm);
+                b[j] = __fadd2_rn(b[j], nm);
+                q2 = __ffma2_rn(a[j], a[j], q2);
+                q2 = __ffma2_rn(b[j], b[j], q2);
+            }
+        }
+        const float var = warp_sum(q2.x + q2.y) / fn;
+        const float inv = __fdiv_rn(1.0f, __fsqrt_rn(var + eps));
+        const float2 inv2 = make_float2(inv, inv);
+        int* qdst = reinterpret_cast<int*>(qout + row * ldo);
+        int qsum = 0;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            const int c = lane + j * 32;
+            if (c < c4) {
+                const float4 g = gs[c], bt = bs[c];
+                const float2 ta = __ffma2_rn(__fmul2_rn(a[j], inv2), make_float2(g.x, g.y), make_float2(bt.x, bt.y));
+                const float2 tb = __ffma2_rn(__fmul2_rn(b[j], inv2), make_float2(g.z, g.w), make_float2(bt.z, bt.w));
+                const float2 ra = __fadd2_rn(make_float2(fminf(fmaxf(ta.x, qz.tlo), qz.thi), fminf(fmaxf(ta.y, qz.tlo), qz.thi)), mg2);
+                const float2 rb = __fadd2_rn(make_float2(fminf(fmaxf(tb.x, qz.tlo), qz.thi), fminf(fmaxf(tb.y, qz.tlo), qz.thi)), mg2);
+                const int w = pack4_codes(__float_as_int(ra.x), __float_as_int(ra.y), __float_as_int(rb.x), __float_as_int(rb.y));
+                qsum = __dp4a(w, 0x01010101, qsum);
+                qdst[c] = w;
+            }
+        }
+        for (int64_t c = c4 + lane; c < (ldo >> 2); c += 32) qdst[c] = 0;  // zero the K padding
+        if (rowsum) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) qsum += __shfl_xor_sync(0xffffffffu, qsum, o);
+            if (lane == 0) rowsum[row] = qsum;
+        }
+    }
+}
+
 // generic fallback: any cols / alignment, re-reads the row (L1/L2 resident)
 __global__ void __launch_bounds__(256) layernorm_generic_kernel(const float* __restrict__ x, int64_t rows, int64_t cols,
                                                                int64_t ldx, const float* __restrict__ gamma,
@@ -845,7 +932,16 @@ static int launch_layernorm(const float* x, int64_t rows, int64_t cols, int64_t 
         else if (qmode == 3) NQ_LN_Q(NV, 3);                                                                            \
         else NQ_LN_Q(NV, 2);                                                                                            \
     } while (0)
-    if (vec && cols <= 512) NQ_LN(4);
+#define NQ_LN_GLUE(NV)                                                                                                  \
+    do {                                                                                                                \
+        const size_t sm_ = (size_t)cols * 8;                                                                            \
+        const int g_ = resident_grid(layernorm_glue_kernel<NV>, rows * 32, 256, sm_);                                   \
+        layernorm_glue_kernel<NV><<<g_, 256, sm_, s>>>(x, rows, (int)cols, ldx, gamma, beta, eps, qa, qout, ldo, rowsum); \
+    } while (0)
+    if (qmode == 3 && vec && cols <= 512) NQ_LN_GLUE(4);
+    else if (qmode == 3 && vec && cols <= 768) NQ_LN_GLUE(6);
+    else if (qmode == 3 && vec && cols <= 1024) NQ_LN_GLUE(8);
+    else if (vec && cols <= 512) NQ_LN(4);
     else if (vec && cols <= 768) NQ_LN(6);
     else if (vec && cols <= 1024) NQ_LN(8);
     else if (vec && cols <= 4096 && qmode < 0) NQ_LN(32);
@@ -855,6 +951,7 @@ static int launch_layernorm(const float* x, int64_t rows, int64_t cols, int64_t 
         return NQ_ERR_UNSUPPORTED;
     }
 #undef NQ_LN
+#undef NQ_LN_GLUE
     return NQ_OK;
 }
 

@@ -79,7 +79,8 @@ struct GemmParams {
     float g_prdiv, g_nl2e, g_add, g_out;   // GELU_QUANT: 0.3275911 / c1, -log2(e) / c1^2, c2, c3 / s_out
     int two_cta;                     // CTA-pair kernel (256-row tiles, cta_group::2)
     int deq_wide;                    // DEQUANT: alignment / extent conditions of the 32-column epilogue hold (host-checked)
-    int sm_noclamp;                  // SOFTMAX: p / s_out + zp stays inside [lo, hi] for every p in [0, 1]
+    int sm_noclamp;                  // SOFTMAX: out_zp >= lo: p / s_out + zp (p in [0, 1]) needs no lower clamp
+    float sm_top;                    // SOFTMAX: upper clamp in the magic-sum domain (1.5 * 2^23 + hi), huge when p = 1 fits
     int fast22;                      // SOFTMAX: |acc - zero-point terms| < 2^22 proved on the host (magic int->float route)
     // implicit-GEMM convolution (nq_qconv2d_s8): A rows are output pixels (n, oh, ow) of a padded NHWC image, read
     // by im2col-mode TMA; K = (kh, kw, c) in 64-channel slices
@@ -840,9 +841,9 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                         int c[8];
 #pragma unroll
                         for (int k = 0; k < 8; ++k) {
-                            // probabilities lie in [0, 1]: when [0, 1 / s_out] maps inside the code range (host
-                            // check) the quotient needs no clamp and rounds straight out of the FMA
-                            c[k] = p.sm_noclamp ? __float_as_int(__fmaf_rn(y[j * 8 + k], kr, qz.magic))
+                            // probabilities lie in [0, 1]: with zp >= lo (host check) the quotient rounds straight
+                            // out of the FMA; only the upper clamp remains, as a min in the magic-sum domain
+                            c[k] = p.sm_noclamp ? __float_as_int(fminf(__fmaf_rn(y[j * 8 + k], kr, qz.magic), p.sm_top))
                                                 : qz.template code_of_quotient<QS>(__fmul_rn(y[j * 8 + k], kr));
                             if (RAGGED) c[k] = (k < nrem) ? c[k] : 0;
                         }
@@ -1256,10 +1257,12 @@ static int qgemm_run(const int8_t* A, const int8_t* B, void* Cout, int64_t M, in
             p.fast22 = (ra * rb * (long double)K) < 4194304.0L;
         }
         {
-            // p in [0, 1] (up to a few ulp): p / s_out + zp in [zp, zp + 1 / s_out]; no clamp needed when that
-            // interval, widened by the rounding slack, lies inside [lo - 0.5, hi + 0.5)
+            // p in [0, 1] (up to a few ulp): p / s_out + zp in [zp, zp + 1 / s_out].  zp >= lo: no lower clamp, the
+            // quotient rounds straight out of one FMA with the magic constant; the upper clamp is a min in that
+            // domain and vanishes (huge bound) when [.., zp + 1 / s_out], widened by the rounding slack, stays below hi + 0.5
             const double top = (double)p.qargs.zpf + 1.0 / (double)p.qargs.scale * (1.0 + 1e-6);
-            p.sm_noclamp = ((double)p.qargs.zpf >= (double)p.qargs.lo) && (top < (double)p.qargs.hi + 0.49);
+            p.sm_noclamp = (double)p.qargs.zpf >= (double)p.qargs.lo;
+            p.sm_top = (top < (double)p.qargs.hi + 0.49) ? 3.0e38f : 12582912.0f + p.qargs.hi;
         }
     }
     const bool q8 = ep->mode == NQ_EPI_QUANT || ep->mode == NQ_EPI_GELU_QUANT;
