@@ -342,9 +342,41 @@ def load_model_from_string(data: bytes) -> ModelProto:
     return m
 
 
-def load(path) -> ModelProto:
+def load_external_data(m: ModelProto, base_dir) -> ModelProto:
+    """Pull the payload of every EXTERNAL initializer (onnx external-data convention, as written by the reference's
+    exporter `models/vit.py:71-86` with save_as_external_data=True) into `raw_data`: `location` is a path relative
+    to the model file, `offset` / `length` select the byte range (whole file when absent)."""
+    import os
+    cache: dict[str, memoryview] = {}
+    for t in m.graph.initializer:
+        if t.data_location != 1 or t.raw_data:
+            continue
+        loc = t.external_data.get("location")
+        if not loc:
+            raise ValueError(f"tensor {t.name!r} is EXTERNAL but names no location")
+        full = os.path.normpath(os.path.join(str(base_dir), loc))
+        if full not in cache:
+            with open(full, "rb") as fh:
+                cache[full] = memoryview(fh.read())
+        blob = cache[full]
+        off = int(t.external_data.get("offset", "0") or 0)
+        n = t.external_data.get("length")
+        n = int(n) if n not in (None, "") else len(blob) - off
+        if off < 0 or n < 0 or off + n > len(blob):
+            raise ValueError(f"tensor {t.name!r}: external range [{off}, {off + n}) outside {loc} ({len(blob)} bytes)")
+        t.raw_data = bytes(blob[off:off + n])
+        t.data_location = 0
+        t.external_data = {}
+    return m
+
+
+def load(path, load_external: bool = True) -> ModelProto:
+    import os
     with open(path, "rb") as fh:
-        return load_model_from_string(fh.read())
+        m = load_model_from_string(fh.read())
+    if load_external:
+        load_external_data(m, os.path.dirname(os.path.abspath(str(path))))
+    return m
 
 
 # ---- encoder ---------------------------------------------------------------
@@ -376,8 +408,12 @@ def _enc_tensor(t: TensorProto) -> bytes:
         out += _ld(7, b"".join(_varint(v) for v in t.int64_data))
     if t.name:
         out += _ld(8, t.name.encode())
-    if t.raw_data:
+    if t.raw_data and t.data_location != 1:
         out += _ld(9, t.raw_data)
+    if t.data_location == 1:
+        for k, v in t.external_data.items():
+            out += _ld(13, _ld(1, k.encode()) + _ld(2, str(v).encode()))
+        out += _key(14, 0) + _varint(1)
     return out
 
 
@@ -428,6 +464,34 @@ def serialize(m: ModelProto) -> bytes:
     return out
 
 
-def save(m: ModelProto, path) -> None:
+def save(m: ModelProto, path, save_as_external_data: bool = False, location: str | None = None,
+         size_threshold: int = 1024) -> None:
+    """Write the model; with save_as_external_data the raw payload of every initializer of at least `size_threshold`
+    bytes goes to one side file `location` (default: <model file name>.data) next to the model, 64-byte aligned,
+    referenced by location / offset / length entries -- the layout onnx.save(..., save_as_external_data=True) produces."""
+    import copy
+    import os
+    path = str(path)
+    if not save_as_external_data:
+        with open(path, "wb") as fh:
+            fh.write(serialize(m))
+        return
+    location = location or os.path.basename(path) + ".data"
+    out = copy.copy(m)
+    out.graph = copy.copy(m.graph)
+    out.graph.initializer = []
+    blob = bytearray()
+    for t in m.graph.initializer:
+        payload = t.raw_data or to_array(t).astype(np.dtype(_NP_OF[t.data_type]).newbyteorder("<")).tobytes()
+        if len(payload) < size_threshold:
+            out.graph.initializer.append(t)
+            continue
+        blob.extend(b"\0" * (-len(blob) % 64))
+        ext = TensorProto(name=t.name, dims=list(t.dims), data_type=t.data_type, data_location=1,
+                          external_data={"location": location, "offset": str(len(blob)), "length": str(len(payload))})
+        blob.extend(payload)
+        out.graph.initializer.append(ext)
+    with open(os.path.join(os.path.dirname(os.path.abspath(path)), location), "wb") as fh:
+        fh.write(bytes(blob))
     with open(path, "wb") as fh:
-        fh.write(serialize(m))
+        fh.write(serialize(out))

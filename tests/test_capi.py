@@ -38,6 +38,23 @@ def test_argument_validation_needs_no_gpu(lib):
         _lib.call("nq_qgemm_s8", None, None, None, 1, 1, 1, 1, 16, 16, 1, 0, 0, 0, None, None)
 
 
+def test_conv_entry_points_validate_arguments(lib):
+    ep = _lib.Epilogue()
+    with pytest.raises(_lib.NqError, match="multiple of 64"):          # channels: one filter tap = whole 64-byte K slices
+        _lib.call("nq_qconv2d_s8", None, None, None, 1, 8, 8, 3, 3, 3, 1, 1, 16, 32, 16, _lib.C.byref(ep), None)
+    with pytest.raises(_lib.NqError, match="does not fit"):
+        _lib.call("nq_qconv2d_s8", None, None, None, 1, 2, 8, 64, 3, 3, 1, 1, 16, 576, 16, _lib.C.byref(ep), None)
+    with pytest.raises(_lib.NqError, match="strides"):
+        _lib.call("nq_qconv2d_s8", None, None, None, 1, 8, 8, 64, 3, 3, 9, 1, 16, 576, 16, _lib.C.byref(ep), None)
+    ep.mode = _lib.EPI_QUANT
+    with pytest.raises(_lib.NqError, match="RAW, DEQUANT or REQUANT"):
+        _lib.call("nq_qconv2d_s8", None, None, None, 1, 8, 8, 64, 3, 3, 1, 1, 16, 576, 16, _lib.C.byref(ep), None)
+    with pytest.raises(_lib.NqError, match="multiple of 4"):
+        _lib.call("nq_nhwc_pad", None, 1, 1, 3, 8, 8, 0, 0, 0, 0, 0, 8, 1.0, 0, 0, None, None)
+    with pytest.raises(_lib.NqError, match="elem_bytes"):
+        _lib.call("nq_nhwc_pad", None, 2, 1, 64, 8, 8, 0, 0, 0, 0, 0, 8, 1.0, 0, 0, None, None)
+
+
 def test_no_libcuda_link_dependency():
     import subprocess
     out = subprocess.run(["ldd", _lib.LIB_PATH], capture_output=True, text=True).stdout

@@ -47,6 +47,32 @@ def test_onnx_lite_attribute_kinds_roundtrip():
         ol.to_array(ol.TensorProto(name="w", dims=[2], data_location=1, external_data={"location": "w.data"}))
 
 
+def test_onnx_lite_external_data_roundtrip(tmp_path):
+    """The reference's exporter writes ViT weights with save_as_external_data=True (models/vit.py:71-86): initializers
+    whose payload sits in a side file load transparently, and save() can produce the same layout."""
+    m = zoo.vit_graph(batch=1, layers=1, hidden=32, heads=4, intermediate=64, image_size=32, classes=3)
+    path = tmp_path / "vit.onnx"
+    ol.save(m, path, save_as_external_data=True, size_threshold=256)
+    side = tmp_path / "vit.onnx.data"
+    assert side.exists() and side.stat().st_size > 0
+    bare = ol.load(path, load_external=False)
+    ext = [t for t in bare.graph.initializer if t.data_location == 1]
+    small = [t for t in bare.graph.initializer if t.data_location != 1]
+    assert ext and small and all(not t.raw_data for t in ext)
+    assert all(int(t.external_data["offset"]) % 64 == 0 and t.external_data["location"] == "vit.onnx.data" for t in ext)
+    with pytest.raises(ValueError, match="externally"):
+        ol.to_array(ext[0])
+    full = ol.load(path)
+    assert [t.name for t in full.graph.initializer] == [t.name for t in m.graph.initializer]
+    for a, b in zip(m.graph.initializer, full.graph.initializer):
+        assert b.data_location == 0
+        np.testing.assert_array_equal(ol.to_array(a), ol.to_array(b))
+    # a truncated side file is an error, not silent garbage
+    side.write_bytes(side.read_bytes()[:100])
+    with pytest.raises(ValueError, match="outside"):
+        ol.load(path)
+
+
 def test_vit_zoo_census_matches_committed_topology():
     """SURVEY.md §3.5 census of models/vit/vit_image_classifier_no_weights.onnx."""
     from collections import Counter
