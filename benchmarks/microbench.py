@@ -135,6 +135,16 @@ def main():
         med, _ = timed(lambda: K.qgemm_to_operand(op_, ov_, 1e-4, azp2, None, 8, 0.05, -3, "merge_heads", 12, S, False))
         emit(case="qgemm ViT PV -> int8 operand (merge_heads)", ms_median=med, tops=2.0 * bt * S * S * D / med / 1e9)
     if not args.quick:
+        # output projection / MLP-2: dequantize + bias + residual add in the epilogue (float32 residual stream)
+        for name, (M, N, Kd) in (("o-proj", (50432, 768, 768)), ("MLP-2", (50432, 768, 3072))):
+            a = torch.randint(-128, 128, (1, M, Kd), generator=g, device=DEV, dtype=torch.int8)
+            b = torch.randint(-128, 128, (1, Kd, N), generator=g, device=DEV, dtype=torch.int8)
+            oa, ob = K.operand_from_codes(a, "A", False), K.operand_from_codes(b, "B", True)
+            azp = K.AccZeroPoint(3, None, Kd, None, ob.rowsum, True)
+            bias, res = torch.randn(N, device=DEV), torch.randn(M, N, device=DEV)
+            med, _ = timed(lambda: K.qgemm(oa, ob, _lib.EPI_DEQUANT, 1e-4, azp, bias_f32=bias, residual=res))
+            emit(case=f"qgemm ViT {name} + bias + residual (f32 out)", M=M, N=N, K=Kd, ms_median=med, tops=2.0 * M * N * Kd / med / 1e9)
+            del a, b, oa, ob, res
         # BASELINE config 3: Conv2d block as im2col + int8 qGEMM, batch 1024 (test_conv2d geometry scaled up)
         Bc, Cc, Hc, Wc, Oc, kh, kw = 1024, 64, 57, 58, 128, 3, 2
         g = torch.Generator(device="cuda").manual_seed(3)

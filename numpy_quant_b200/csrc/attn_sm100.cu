@@ -395,8 +395,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
                 }
             };
             if (warp_rows) {
-                if (p.fast22) pass1(std::true_type{});
-                else pass1(std::false_type{});
+                pass1(std::true_type{});               // host-checked: |score - zero-point terms| < 2^22
             }
             tc_fence_before();
             __syncwarp();
@@ -539,6 +538,7 @@ extern "C" int nq_attention_s8(const int8_t* Q, const int8_t* Kt, const int8_t* 
         const long double ra = fmaxl(fabsl(-128.0L - zq), fabsl(127.0L - zq)), rb = fmaxl(fabsl(-128.0L - zk), fabsl(127.0L - zk));
         NQ_REQUIRE(ra * rb * (long double)D < 2147483000.0L, "nq_attention_s8: score zero-point terms exceed int32");
         p.fast22 = (ra * rb * (long double)D) < 4194304.0L;
+        NQ_REQUIRE(p.fast22, "nq_attention_s8: max|q - zq| * max|k - zk| * D must stay below 2^22 (zero-points outside the int8 range?)");
     }
     int qmode;
     p.qp = make_qargs(a->p_bits, a->p_scale, a->has_p_zp, a->p_zp, &qmode);

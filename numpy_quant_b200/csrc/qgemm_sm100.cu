@@ -762,14 +762,18 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                             // columns past N only in the last (ragged) pair of groups: warp-uniform fast path
                             const bool clean = j2 * 8 + 16 <= ncols_w || (j2 + 1 >= NSUB && j2 * 8 + 8 <= ncols_w);
                             if (clean) {
+                                // two columns per instruction (packed add / multiply, each lane rounded like the scalar op)
 #pragma unroll
-                                for (int k = 0; k < 16; ++k) {
+                                for (int k = 0; k < 16; k += 2) {
                                     if (j2 * 8 + k >= NSUB * 8) break;    // compile time: the 7th group is 8 wide
-                                    const int x = (int)a16[k] + rm - c16[k];
-                                    const float f = MAGIC ? __fmul_rn(__fadd_rn(__int_as_float(x), -12582912.0f), p.scale)
-                                                          : __fmul_rn(__int2float_rn(x), p.scale);
-                                    y[j2 * 8 + k] = f;
-                                    lmax = fmaxf(lmax, f);
+                                    const int x0 = (int)a16[k] + rm - c16[k], x1 = (int)a16[k + 1] + rm - c16[k + 1];
+                                    const float2 s2 = make_float2(p.scale, p.scale);
+                                    const float2 f = MAGIC ? __fmul2_rn(__fadd2_rn(make_float2(__int_as_float(x0), __int_as_float(x1)),
+                                                                                   make_float2(-12582912.0f, -12582912.0f)), s2)
+                                                           : __fmul2_rn(make_float2(__int2float_rn(x0), __int2float_rn(x1)), s2);
+                                    y[j2 * 8 + k] = f.x;
+                                    y[j2 * 8 + k + 1] = f.y;
+                                    lmax = fmaxf(lmax, fmaxf(f.x, f.y));
                                 }
                             } else {
 #pragma unroll
@@ -805,23 +809,26 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                 if (warp_rows) {
                     const float l2e = 1.44269502162933349609375f;
                     const float m2 = __fmul_rn(gmax, l2e);               // its rounding error scales every e_i alike
-                    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;        // fixed order -> deterministic
+                    // four partial sums (columns k & 3) as two packed accumulators: fixed order -> deterministic
+                    float2 s01 = make_float2(0.f, 0.f), s23 = make_float2(0.f, 0.f);
+                    const float2 l2e2 = make_float2(l2e, l2e), nm2 = make_float2(-m2, -m2);
 #pragma unroll
                     for (int j = 0; j < NSUB; ++j) {
                         if (j * 8 < ncols_w) {
 #pragma unroll
-                            for (int k = 0; k < 8; ++k) {
-                                float e;
-                                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(__fmaf_rn(y[j * 8 + k], l2e, -m2)));
-                                y[j * 8 + k] = e;
-                                if ((k & 3) == 0) s0 = __fadd_rn(s0, e);
-                                else if ((k & 3) == 1) s1 = __fadd_rn(s1, e);
-                                else if ((k & 3) == 2) s2 = __fadd_rn(s2, e);
-                                else s3 = __fadd_rn(s3, e);
+                            for (int k = 0; k < 8; k += 2) {
+                                const float2 a = __ffma2_rn(make_float2(y[j * 8 + k], y[j * 8 + k + 1]), l2e2, nm2);
+                                float2 e;
+                                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(a.x));
+                                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(a.y));
+                                y[j * 8 + k] = e.x;
+                                y[j * 8 + k + 1] = e.y;
+                                if ((k & 3) == 0) s01 = __fadd2_rn(s01, e);
+                                else s23 = __fadd2_rn(s23, e);
                             }
                         }
                     }
-                    lsum = __fadd_rn(__fadd_rn(s0, s1), __fadd_rn(s2, s3));
+                    lsum = __fadd_rn(__fadd_rn(s01.x, s01.y), __fadd_rn(s23.x, s23.y));
                 }
                 red[512 + h * 128 + rloc] = lsum;
                 named_bar_sync(1 + q, 128);

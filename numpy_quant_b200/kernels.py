@@ -444,10 +444,16 @@ def can_fuse_attention(q: Operand, k: Operand, v: Operand) -> bool:
             and q.k <= 64 and q.k % 16 == 0 and len(q.batch_shape) == 2)
 
 
-def can_fuse_attention_qk(q: Operand, k: Operand) -> bool:
-    """The part of `can_fuse_attention` that is known at the score MatMul (V has the same S and D)."""
-    return (q.batch == k.batch and q.rows == k.rows and q.k == k.k and q.rows <= 208 and q.k <= 64 and q.k % 16 == 0
-            and len(q.batch_shape) == 2)
+def can_fuse_attention_qk(q: Operand, k: Operand, zq=None, zk=None) -> bool:
+    """The part of `can_fuse_attention` that is known at the score MatMul (V has the same S and D).  zq / zk: the
+    operands' zero-points -- the kernel converts the corrected scores with the 2^22 magic-constant route, which needs
+    max|q - zq| * max|k - zk| * D < 2^22 (true for any zero-point inside the int8 range at D <= 64)."""
+    if not (q.batch == k.batch and q.rows == k.rows and q.k == k.k and q.rows <= 208 and q.k <= 64 and q.k % 16 == 0
+            and len(q.batch_shape) == 2):
+        return False
+    ra = max(abs(-128 - int(zq or 0)), abs(127 - int(zq or 0)))
+    rb = max(abs(-128 - int(zk or 0)), abs(127 - int(zk or 0)))
+    return ra * rb * q.k < (1 << 22)
 
 
 def attention(q: Operand, k: Operand, v: Operand, scale_qk: float, zq, zk, div_c, p_bits: int, p_scale, p_zp,

@@ -980,7 +980,7 @@ class QModel(Model):
                     # whole attention in one kernel: remember the pending score GEMM, launch at the merge-heads node
                     L = x.data._lazy
                     if L.get("bias_q") is None and L["a"].batch == int(np.prod(L["batch_shape"] or (1,))) \
-                            and K.can_fuse_attention_qk(L["a"], L["b"]):
+                            and K.can_fuse_attention_qk(L["a"], L["b"], getattr(x.data._zp, "zp_a", None), getattr(x.data._zp, "zp_b", None)):
                         attn_pending[name] = dict(scores=x.data, c=c, spec=aspec)
                         stash[sm_name] = None
                         for o in node.outputs:
