@@ -739,22 +739,30 @@ __global__ void __launch_bounds__(256) nhwc_pad_kernel(const TIn* __restrict__ x
     const int strip = (hhi - hlo) * W;
     if (strip > 0) {
         const Quantizer qz(qa);
-        for (int c = warp; c < C; c += nwarps) {
+        // a warp takes 4 channels at a time: lanes run along the (contiguous) strip of each channel, so every load
+        // instruction is one coalesced row segment, and the 4 codes of a pixel leave as one 32-bit shared-memory
+        // store (word stride C/4 + 1 between lanes: conflict free); 2 pixels x 4 channels = 8 loads in flight per lane
+        const int64_t cstride = (int64_t)H * W;
+        for (int c = warp * 4; c < C; c += nwarps * 4) {
             const TIn* src = x + ((b * C + c) * H + hlo) * (int64_t)W;
-            for (int i0 = 0; i0 < strip; i0 += 256) {
-                TIn v[8];
+            for (int i0 = 0; i0 < strip; i0 += 64) {
+                TIn v[2][4];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const int i = i0 + k * 32 + lane;
-                    v[k] = (i < strip) ? src[i] : TIn(0);
+                for (int u = 0; u < 2; ++u) {
+                    const int i = i0 + u * 32 + lane;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) v[u][k] = (i < strip) ? src[k * cstride + i] : TIn(0);
                 }
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const int i = i0 + k * 32 + lane;
-                    int8_t code;
-                    if constexpr (QMODE >= 0) code = (int8_t)qz.template code<QMODE>((float)v[k]);
-                    else code = (int8_t)v[k];
-                    if (i < strip) tile[i * CP + c] = code;
+                for (int u = 0; u < 2; ++u) {
+                    const int i = i0 + u * 32 + lane;
+                    int code[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        if constexpr (QMODE >= 0) code[k] = qz.template code<QMODE>((float)v[u][k]);
+                        else code[k] = (int)v[u][k];
+                    }
+                    if (i < strip) *reinterpret_cast<int*>(tile + i * CP + c) = pack4_codes(code[0], code[1], code[2], code[3]);
                 }
             }
         }
