@@ -135,6 +135,17 @@ def main():
         med, _ = timed(lambda: K.qgemm_to_operand(op_, ov_, 1e-4, azp2, None, 8, 0.05, -3, "merge_heads", 12, S, False))
         emit(case="qgemm ViT PV -> int8 operand (merge_heads)", ms_median=med, tops=2.0 * bt * S * S * D / med / 1e9)
     if not args.quick:
+        # MLP-1: bias + GELU chain + quantize for MLP-2 in the epilogue
+        a = torch.randint(-128, 128, (1, 50432, 768), generator=g, device=DEV, dtype=torch.int8)
+        b = torch.randint(-128, 128, (1, 768, 3072), generator=g, device=DEV, dtype=torch.int8)
+        oa, ob = K.operand_from_codes(a, "A", False), K.operand_from_codes(b, "B", True)
+        azp = K.AccZeroPoint(3, None, 768, None, ob.rowsum, True)
+        bias = torch.randn(3072, device=DEV)
+        med, _ = timed(lambda: K.qgemm_to_operand(oa, ob, 1e-4, azp, bias, 8, 0.05, -3, "rows", 1, 50432, False,
+                                                  gelu=(1.4142135381698608, 1.0, 0.5)))
+        emit(case="qgemm ViT MLP-1 + bias + GELU -> int8 operand", M=50432, N=3072, K=768, ms_median=med,
+             tops=2.0 * 50432 * 3072 * 768 / med / 1e9)
+        del a, b, oa, ob
         # output projection / MLP-2: dequantize + bias + residual add in the epilogue (float32 residual stream)
         for name, (M, N, Kd) in (("o-proj", (50432, 768, 768)), ("MLP-2", (50432, 768, 3072))):
             a = torch.randint(-128, 128, (1, M, Kd), generator=g, device=DEV, dtype=torch.int8)
