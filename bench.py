@@ -29,16 +29,18 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "quantized ViT-B/16 int8 inference throughput"
 UNIT = "images/s"
 BATCH = int(os.environ.get("NQ_BENCH_BATCH", "256"))
-BITS = 8
+BITS = int(os.environ.get("NQ_BENCH_BITS", "8"))   # 4 / 2: BASELINE config 4 (packed sub-byte weights), diagnostic runs only
+METRIC = f"quantized ViT-B/16 int{BITS} inference throughput"
 VIT = dict(image_size=224, patch_size=16, hidden=768, heads=12, intermediate=3072, layers=12, classes=1000)
 GOP_PER_IMAGE = 34.90                      # integer MatMul+Gemm ops per image, 2*MACs
 
 
 def workload_config(n_gpus: int) -> dict:
-    return {"workload": "configs[1]: ViT-B/16 image classifier, int8 QModel, batch 256 per GPU, synthetic 224x224",
+    name = ("configs[1]: ViT-B/16 image classifier, int8 QModel" if BITS == 8 else
+            f"configs[3]: ViT-B/16 image classifier, int{BITS} QModel (codes packed to {BITS} bits in HBM)")
+    return {"workload": f"{name}, batch {BATCH} per GPU, synthetic 224x224",
             "bit_width": BITS, "batch_per_gpu": BATCH, "global_batch": BATCH * n_gpus, "image": "3x224x224",
             "graph": "zoo.vit_graph (= models/vit/vit_image_classifier_no_weights.onnx topology, 516 nodes)",
             "execution": "qmodel(inputs, retain=False, graph=True): fused interpreter captured into one CUDA graph; e2e: "
@@ -178,9 +180,12 @@ def run_own_arm(args) -> None:
     rng = np.random.default_rng(1 + rank)
     x_host = torch.from_numpy(rng.normal(size=(BATCH, 3, 224, 224)).astype(np.float32)).pin_memory()
     x_dev = x_host.to(dev)
-    qmodel = model.quantize([x_dev], bit_width=BITS)          # NCCL all-reduce(min/max) inside when ws > 1
+    # NCCL all-reduce(min/max) inside when ws > 1; activations of the calibration pass are freed as it goes
+    qmodel = model.quantize([x_dev], bit_width=BITS, keep_values=False)
     model.release()
     qmodel.release()
+    if BITS < 8:
+        qmodel.pack_weights()
     torch.cuda.empty_cache()
 
     def barrier():

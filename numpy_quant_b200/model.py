@@ -344,16 +344,69 @@ class Model:
             vmin[v.name], vmax[v.name] = np.mean(flat.min()), np.mean(flat.max())
         return vmin, vmax
 
-    def quantize(self, calibration_inputs: list, bit_width=8, *, group=None):
+    def _calibrate_streaming(self, inputs: list, group=None):
+        """The calibration pass of `quantize(keep_values=False)`: the float forward of `__call__` with the min / max
+        of every float value reduced as soon as it is produced and the activation freed after its last consumer, so
+        the pass holds the live set instead of all 700+ intermediate tensors (at ViT-B batch 512 that is a few GB
+        instead of more than the 180 GB of HBM).  Same statistics, same all-reduce as `_value_min_max`."""
+        for array, variable in zip(inputs, self.inputs):
+            if isinstance(array, torch.Tensor) or array.dtype == np.float32:
+                variable.data = FTensor(array)
+            elif array.dtype == np.int64:
+                variable.data = ITensor(array.copy())
+            else:
+                raise ValueError(f"Array dtype {array.dtype} not supported")
+        slot = {v.name: i for i, v in enumerate(self.values)}
+        dev = next(v.data.device_tensor.device for v in self.values if isinstance(v.data, FTensor))
+        mm = K.minmax_slots(len(self.values), dev)
+        is_float = set()
+
+        def record(v):
+            if isinstance(v.data, FTensor) and v.name not in is_float:
+                K.minmax_into(v.data.device_tensor, mm, slot[v.name])
+                is_float.add(v.name)
+
+        for v in self.values:
+            if v.data is not None:
+                record(v)                                   # constants and inputs
+        keep = {id(v) for v in self.outputs} | {id(v) for v in self.inputs}
+        remaining = {id(v): len({id(n) for n in v.outputs}) for v in self.values}
+        for node in self.nodes:
+            outputs = onnx_operator_implementation(node.op, [i.data for i in node.inputs], node.attrs)
+            for o, tensor in zip(node.outputs, outputs):
+                o.data = tensor
+                record(o)
+            for i in {id(v): v for v in node.inputs}.values():
+                remaining[id(i)] -= 1
+                if remaining[id(i)] == 0 and isinstance(i, Variable) and id(i) not in keep and isinstance(i.data, FTensor):
+                    i.data = None                           # statistics taken, no consumer left
+        from .distributed import allreduce_minmax
+        stats = allreduce_minmax(mm, group).cpu().numpy()
+        vmin, vmax = {}, {}
+        for v in self.values:
+            if v.name in is_float:
+                vmin[v.name], vmax[v.name] = np.float32(stats[slot[v.name], 0]), np.float32(stats[slot[v.name], 1])
+            else:
+                data = v.data.data                          # ITensor (host int64) statistics
+                flat = data.reshape((data.shape[0], -1) if data.shape else (-1,))
+                vmin[v.name], vmax[v.name] = np.mean(flat.min()), np.mean(flat.max())
+        return vmin, vmax
+
+    def quantize(self, calibration_inputs: list, bit_width=8, *, group=None, keep_values: bool = True):
         """Calibrate on `calibration_inputs` and return the quantized model
         (reference model.py:328-442): per-tensor affine, min/max calibrated; constants
-        symmetric `bit_width` bits, activations asymmetric, Gemm / Add biases 4*bit_width bits."""
+        symmetric `bit_width` bits, activations asymmetric, Gemm / Add biases 4*bit_width bits.
+        keep_values=False frees every float activation of the calibration pass after its last use (`Value.data` of
+        intermediates is then not readable afterwards, unlike the reference) -- same parameters, a fraction of the HBM."""
         if not 2 <= int(bit_width) <= 8:
             raise ValueError("bit_width must be in 2..8 on the B200 path (int8 tensor-core operands)")
-        self(calibration_inputs)
         node_dict = {node.name: node for node in self.nodes}
         value_dict = {value.name: value for value in self.values}
-        value_min_dict, value_max_dict = self._value_min_max(group)
+        if keep_values:
+            self(calibration_inputs)
+            value_min_dict, value_max_dict = self._value_min_max(group)
+        else:
+            value_min_dict, value_max_dict = self._calibrate_streaming(calibration_inputs, group)
 
         def get_quantization_params(value: Value, asymmetric: bool):
             scale, zero_point = quant_parameters(value_min_dict[value.name], value_max_dict[value.name],

@@ -137,6 +137,30 @@ def test_conv_block_config3_geometry_vs_oracle():
 VIT_CFG = dict(batch=2, image_size=32, patch_size=16, hidden=32, heads=4, intermediate=64, layers=2, classes=10)
 
 
+def test_streaming_calibration_gives_the_same_parameters():
+    """quantize(keep_values=False) -- statistics reduced on the fly, activations freed after their last consumer --
+    derives bit-identical quantization parameters and the same quantized outputs as the reference-like pass that
+    keeps every `Value.data` readable."""
+    x = np.random.default_rng(5).normal(size=(2, 3, 32, 32)).astype(np.float32)
+    qa = Model.from_onnx(zoo.vit_graph(seed=0, **VIT_CFG)).quantize([x], bit_width=8)
+    mb = Model.from_onnx(zoo.vit_graph(seed=0, **VIT_CFG))
+    qb = mb.quantize([x], bit_width=8, keep_values=False)
+    assert set(qa.quant_params) == set(qb.quant_params)
+    for name, pa in qa.quant_params.items():
+        pb = qb.quant_params[name]
+        assert np.float32(pa.scale) == np.float32(pb.scale), name
+        assert (pa.zero_point is None) == (pb.zero_point is None) and (pa.zero_point is None or int(pa.zero_point) == int(pb.zero_point)), name
+    freed = [v for v in mb.values if v.data is None]
+    assert len(freed) > 50                                    # intermediates were released
+    np.testing.assert_array_equal(qa([x])[0], qb([x])[0])
+    # conv graph (model input feeding a Conv): same thing
+    proto = zoo.conv_graph(2, 64, (9, 10), 16, (3, 2), (0, 2, 2, 1), (2, 1), seed=0)
+    xc = np.random.default_rng(6).normal(size=(2, 64, 9, 10)).astype(np.float32)
+    ya = Model.from_onnx(proto).quantize([xc], 8)([xc])[0]
+    yb = Model.from_onnx(proto).quantize([xc], 8, keep_values=False)([xc])[0]
+    np.testing.assert_array_equal(ya, yb)
+
+
 @pytest.mark.parametrize("bits", [8, 4])
 def test_small_vit(gv, bits):
     proto = zoo.vit_graph(seed=0, **VIT_CFG)
