@@ -224,36 +224,51 @@ __global__ void __launch_bounds__(256) acc_post_vec_kernel(const int32_t* __rest
                                                           const int64_t* __restrict__ bias_q, float inv_out_scale,
                                                           int has_out_zp, double out_zp, float lo, float hi,
                                                           void* __restrict__ out) {
-    const int64_t total = rows * N4;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    // One warp per (row, 128-column segment) unit: the row term is formed once per unit, there is no per-element
+    // index division, and 4 independent 16-byte loads per lane are in flight before the first use.
     const float zpf = (float)out_zp, tlo = lo - zpf, thi = hi - zpf, magic = kMagic + zpf;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-        const int64_t row = i / N4;
-        const int c4 = (int)(i - row * N4);
-        const int4 a4 = __ldcs(reinterpret_cast<const int4*>(acc + row * ldacc) + c4);
-        int64_t rowterm = -z.kterm;
-        if (z.use_row) rowterm += (int64_t)__ldg(z.rowsum_a + row) * z.zp_b;
-        int4 cs = make_int4(0, 0, 0, 0);
-        if (z.use_col) cs = __ldg(reinterpret_cast<const int4*>(z.colsum_b + (row / M) * z.cs_stride) + c4);
-        const int av[4] = {a4.x, a4.y, a4.z, a4.w}, cv[4] = {cs.x, cs.y, cs.z, cs.w};
-        float d[4];
+    const int lane = threadIdx.x & 31;
+    const int segs = (N4 + 127) >> 7;                                     // 128 int4 (512 columns) per unit
+    const int64_t units = rows * segs, warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t u = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; u < units; u += warps) {
+        const int64_t row = u / segs;
+        const int c40 = (int)(u - row * segs) << 7;
+        const int4* arow = reinterpret_cast<const int4*>(acc + row * ldacc);
+        int4 a4[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            int64_t a = av[k];
-            if (MODE == 2 && bias_q) a += __ldg(bias_q + c4 * 4 + k);
-            d[k] = dequantize_one(a - rowterm - (int64_t)cv[k] * z.zp_a, scale);
+            const int c4 = c40 + k * 32 + lane;
+            a4[k] = c4 < N4 ? __ldcs(arow + c4) : make_int4(0, 0, 0, 0);
         }
-        if (MODE == 1) {
-            __stcs(reinterpret_cast<float4*>(out) + i, make_float4(d[0], d[1], d[2], d[3]));
-        } else {
-            int c[4];
+        int64_t rowterm = -z.kterm;
+        if (z.use_row) rowterm += (int64_t)__ldg(z.rowsum_a + row) * z.zp_b;
+        const int4* csrow = z.use_col ? reinterpret_cast<const int4*>(z.colsum_b + (row / M) * z.cs_stride) : nullptr;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                if (F64) c[k] = has_out_zp ? requantize_one<true>(d[k], inv_out_scale, out_zp, lo, hi)
-                                           : requantize_one<false>(d[k], inv_out_scale, 0.0, lo, hi);
-                else c[k] = __float_as_int(__fadd_rn(fminf(fmaxf(__fmul_rn(inv_out_scale, d[k]), tlo), thi), magic));
+        for (int k = 0; k < 4; ++k) {
+            const int c4 = c40 + k * 32 + lane;
+            if (c4 >= N4) continue;
+            const int4 cs = csrow ? __ldg(csrow + c4) : make_int4(0, 0, 0, 0);
+            const int av[4] = {a4[k].x, a4[k].y, a4[k].z, a4[k].w}, cv[4] = {cs.x, cs.y, cs.z, cs.w};
+            float d[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                int64_t a = av[e];
+                if (MODE == 2 && bias_q) a += __ldg(bias_q + c4 * 4 + e);
+                d[e] = dequantize_one(a - rowterm - (int64_t)cv[e] * z.zp_a, scale);
             }
-            __stcs(reinterpret_cast<int*>(out) + i, pack4_codes(c[0], c[1], c[2], c[3]));
+            const int64_t i = row * N4 + c4;
+            if (MODE == 1) {
+                __stcs(reinterpret_cast<float4*>(out) + i, make_float4(d[0], d[1], d[2], d[3]));
+            } else {
+                int c[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    if (F64) c[e] = has_out_zp ? requantize_one<true>(d[e], inv_out_scale, out_zp, lo, hi)
+                                               : requantize_one<false>(d[e], inv_out_scale, 0.0, lo, hi);
+                    else c[e] = __float_as_int(__fadd_rn(fminf(fmaxf(__fmul_rn(inv_out_scale, d[e]), tlo), thi), magic));
+                }
+                __stcs(reinterpret_cast<int*>(out) + i, pack4_codes(c[0], c[1], c[2], c[3]));
+            }
         }
     }
 }
