@@ -150,7 +150,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append([c.strip() for c in out.split(",")])
             except Exception:
                 pass
-            self._halt.wait(0.2)
+            self._halt.wait(0.05)
 
     def stop(self) -> dict:
         self._halt.set()
