@@ -30,8 +30,8 @@ for case in cases:
         azp = K.AccZeroPoint(3, -4, Kd, oa.rowsum, ob.rowsum, False)
         for _ in range(2):
             out = K.qgemm(oa, ob, _lib.EPI_DEQUANT, 1e-4, azp)
-    elif case in ("qkv_quant", "v_quant", "o_res", "fc1_gelu"):
-        M, N, Kd = (50432, 3072, 768) if case == "fc1_gelu" else (50432, 768, 768)
+    elif case in ("qkv_quant", "v_quant", "o_res", "fc2_res", "fc1_gelu"):
+        M, N, Kd = (50432, 3072, 768) if case == "fc1_gelu" else (50432, 768, 3072) if case == "fc2_res" else (50432, 768, 768)
         a = torch.randint(-128, 128, (1, M, Kd), generator=g, device=DEV, dtype=torch.int8)
         b = torch.randint(-128, 128, (1, Kd, N), generator=g, device=DEV, dtype=torch.int8)
         oa, ob = K.operand_from_codes(a, "A", False), K.operand_from_codes(b, "B", True)
@@ -39,7 +39,7 @@ for case in cases:
         bias = torch.randn(N, device=DEV)
         res = torch.randn(M, N, device=DEV)
         for _ in range(2):
-            if case == "o_res":
+            if case in ("o_res", "fc2_res"):
                 out = K.qgemm(oa, ob, _lib.EPI_DEQUANT, 1e-4, azp, bias_f32=bias, residual=res)
             elif case == "fc1_gelu":
                 out = K.qgemm_to_operand(oa, ob, 1e-4, azp, bias, 8, 0.05, -3, "rows", 1, M, False,
