@@ -608,6 +608,21 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                 for (int sidx = hc; sidx < BN / 32; sidx += HPG) {
                     const int64_t nc = n0 + sidx * 32;
                     if (nc >= p.N || rows_left == 0) break;               // warp-uniform
+                    // residual rows of the first half (16 rows) leave for L2 / HBM before the accumulator round trip:
+                    // their latency overlaps the TMEM load and the slab staging; the second half is issued right
+                    // after the staging and overlaps the first half's arithmetic
+                    const float* rbase = has_res ? p.residual + b * p.stride_r + mrow0 * p.ldr + nc + cj * 4 : nullptr;
+                    float4 res0[4], res1[4];
+                    auto load_res = [&](int half, float4* dstv) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            // rows past M are clamped to the last valid one (loaded, never stored)
+                            const int rr = (half * 4 + k) * 4 + rq;
+                            const int rc = rr < rows_left ? rr : rows_left - 1;
+                            dstv[k] = __ldcs(reinterpret_cast<const float4*>(rbase + (int64_t)rc * p.ldr));
+                        }
+                    };
+                    if constexpr (has_res) load_res(0, res0);
                     uint32_t v[32];
                     tmem_ld_32x32b_x32(t_row + (uint32_t)(sidx * 32), v);
                     const int ct0 = ct_n.x * zpa, ct1 = ct_n.y * zpa, ct2 = ct_n.z * zpa, ct3 = ct_n.w * zpa;
@@ -623,20 +638,10 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                     __syncwarp();
                     uint32_t bad_any = 0;
                     float* crow = reinterpret_cast<float*>(p.C) + crow_base + (mrow0 + rq) * p.ldc + nc + cj * 4;
-                    const float* rbase = has_res ? p.residual + b * p.stride_r + mrow0 * p.ldr + nc + cj * 4 : nullptr;
+                    if constexpr (has_res) load_res(1, res1);
 #pragma unroll
                     for (int half = 0; half < 2; ++half) {
-                        // residual rows of this half (16 rows): in flight together, then consumed in order
-                        float4 res[4];
-                        if constexpr (has_res) {
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                // rows past M are clamped to the last valid one (loaded, never stored)
-                                const int rr = (half * 4 + k) * 4 + rq;
-                                const int rc = rr < rows_left ? rr : rows_left - 1;
-                                res[k] = __ldcs(reinterpret_cast<const float4*>(rbase + (int64_t)rc * p.ldr));
-                            }
-                        }
+                        const float4* res = half ? res1 : res0;
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
                             const int it = half * 4 + k;
