@@ -164,6 +164,9 @@ class ClockSampler(threading.Thread):
 
 
 def run_own_arm(args) -> None:
+    # stdout carries exactly one JSON line: NCCL's own banner ("NCCL version ...", printed to stdout when the
+    # environment sets NCCL_DEBUG) goes to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     import torch
     import torch.distributed as dist
     from numpy_quant_b200 import distributed as nqd, kernels as K, zoo
