@@ -127,7 +127,7 @@ def run_reference_arm(args) -> None:
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit_json(line)
 
 
 # ------------------------------------------------------------------------------------------
@@ -164,9 +164,6 @@ class ClockSampler(threading.Thread):
 
 
 def run_own_arm(args) -> None:
-    # stdout carries exactly one JSON line: NCCL's own banner ("NCCL version ...", printed to stdout when the
-    # environment sets NCCL_DEBUG) goes to stderr
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     import torch
     import torch.distributed as dist
     from numpy_quant_b200 import distributed as nqd, kernels as K, zoo
@@ -352,10 +349,29 @@ def run_own_arm(args) -> None:
         cs = CpuSample()
         sec = cs.step()
         line["cpu_baseline"] = {"value": 1.0 / sec, "unit": UNIT, "cores": 1, "kind": "port", "sample": cs.sample}
-    print(json.dumps(line), flush=True)
+    emit_json(line)
+
+
+_JSON_FD = None
+
+
+def emit_json(line: dict) -> None:
+    """The one JSON line of the contract, on the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
 
 
 def main() -> None:
+    # stdout carries exactly one JSON line: everything else that writes to file descriptor 1 (NCCL prints its
+    # "NCCL version ..." banner there) is sent to stderr for the duration of the run
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
