@@ -1278,7 +1278,12 @@ static int qgemm_run(const int8_t* A, const int8_t* B, void* Cout, int64_t M, in
         }
     }
     const bool q8 = ep->mode == NQ_EPI_QUANT || ep->mode == NQ_EPI_GELU_QUANT;
-    const int bn = (ep->mode == NQ_EPI_SOFTMAX_QUANT) ? 256 : (N <= 64) ? 64 : (N <= 128) ? 128 : 256;
+    int bn = (ep->mode == NQ_EPI_SOFTMAX_QUANT) ? 256 : (N <= 64) ? 64 : (N <= 128) ? 128 : 256;
+    {
+        // A/B switch for measurements: narrower tiles for wide N (more A re-reads, two / four tile groups in flight)
+        static const int force_bn = getenv("NQ_FORCE_BN") ? atoi(getenv("NQ_FORCE_BN")) : 0;
+        if ((force_bn == 64 || force_bn == 128) && ep->mode != NQ_EPI_SOFTMAX_QUANT && force_bn < bn) bn = force_bn;
+    }
     if (q8) {
         NQ_REQUIRE(p.fast32, "nq_qgemm_s8: QUANT epilogue needs the 32-bit zero-point bound (K or zero-points too large)");
         NQ_REQUIRE(N % 16 == 0 && ep->q_cols_per_head > 0 && ep->q_cols_per_head % 16 == 0 && ep->q_rows_per_image > 0,
@@ -1358,7 +1363,8 @@ static int qgemm_run(const int8_t* A, const int8_t* B, void* Cout, int64_t M, in
         // The pair halves the per-SM operand traffic of the main loop; measured (microbench A/B): +10..20 % where the
         // main loop dominates (K >= 1024: 4096^3, 8192^3, the K = 3072 MLP GEMM), -5..10 % for K = 768 tiles whose time
         // is the epilogue (the leader's next MMA has to wait for both CTAs' epilogues).
-        p.two_cta = !no_pair && !cv && bn == 256 && ep->mode != NQ_EPI_SOFTMAX_QUANT && M >= 256 && K >= 1024;
+        static const int pair_min_k = getenv("NQ_2CTA_MINK") ? atoi(getenv("NQ_2CTA_MINK")) : 1024;   // A/B switch
+        p.two_cta = !no_pair && !cv && bn == 256 && ep->mode != NQ_EPI_SOFTMAX_QUANT && M >= 256 && K >= pair_min_k;
     }
     CUtensorMap ta, tb;
     if (cv) {
