@@ -167,16 +167,17 @@ typedef struct nq_epilogue {
  * Kt [BH, S, ld_k]  int8 K-major (row = key,   contraction D)          -- right operand (K^T), stored transposed
  * Vt [BH, D, ld_v]  int8 K-major (row = head-dim column, contraction S) -- right operand of P.V, stored transposed
  * out [B, S, H*D] int8: the left operand of the output projection; out_rowsum [B*S] int32 or NULL.
- * Scores, probabilities and the context accumulator stay in TMEM / shared memory.  Same codes as
- * NQ_EPI_SOFTMAX_QUANT followed by NQ_EPI_QUANT.  Limits: S <= 208, D <= 64, D % 16 == 0. */
+ * Scores, probabilities and the context accumulator stay in TMEM / shared memory.  The zero-point terms of both
+ * MatMuls (numpy_quantization.py:49-61) are accumulated by the tensor core itself (constant-operand passes), so no
+ * row / column sums are passed in; softmax is float glue (1e-5 contract); GIVEN the emitted P codes the context
+ * accumulator and the output codes are bit-exact.  Limits: S <= 208, D <= 64, D % 16 == 0, |zq|, |zv| <= 254,
+ * lo_p - zp_p in [-254, 254]; anything else returns NQ_ERR_INVALID (callers use NQ_EPI_SOFTMAX_QUANT + NQ_EPI_QUANT). */
 typedef struct nq_attention {
     float scale_qk;                /* float32(s_q * s_k)                                  */
     int has_div;                   /* graph Div node in front of the Softmax              */
     float div;
     int has_zq, has_zk;
     int64_t zq, zk;
-    const int32_t* rowsum_q;       /* [BH, S] sums of Q rows   (needed when has_zk)       */
-    const int32_t* colsum_k;       /* [BH, S] sums of Kt rows  (needed when has_zq)       */
     int p_bits;                    /* quantization of the probabilities                   */
     float p_scale;
     int has_p_zp;
@@ -184,13 +185,14 @@ typedef struct nq_attention {
     float scale_pv;                /* float32(s_p * s_v)                                  */
     int has_zv;
     int64_t zv;
-    const int32_t* colsum_v;       /* [BH, D] sums of Vt rows  (needed when has_p_zp)     */
     int out_bits;                  /* quantization of the context (next MatMul's operand) */
     float out_scale;
     int has_out_zp;
     int64_t out_zp;
     int8_t* out;
     int32_t* out_rowsum;           /* cleared by the library                              */
+    int8_t* p_dump;                /* optional: the emitted P bytes (code - lo_p, unsigned) as [BH, S, ld_p_dump] */
+    int64_t ld_p_dump;             /* >= round_up(S, 8), multiple of 8                    */
 } nq_attention;
 
 int nq_attention_s8(const int8_t* Q, const int8_t* Kt, const int8_t* Vt, int64_t BH, int64_t H, int64_t S, int64_t D,

@@ -35,11 +35,11 @@ class Epilogue(C.Structure):
 class Attention(C.Structure):
     """struct nq_attention"""
     _fields_ = [("scale_qk", f32), ("has_div", C.c_int), ("div", f32), ("has_zq", C.c_int), ("has_zk", C.c_int),
-                ("zq", i64), ("zk", i64), ("rowsum_q", vp), ("colsum_k", vp),
+                ("zq", i64), ("zk", i64),
                 ("p_bits", C.c_int), ("p_scale", f32), ("has_p_zp", C.c_int), ("p_zp", i64),
-                ("scale_pv", f32), ("has_zv", C.c_int), ("zv", i64), ("colsum_v", vp),
+                ("scale_pv", f32), ("has_zv", C.c_int), ("zv", i64),
                 ("out_bits", C.c_int), ("out_scale", f32), ("has_out_zp", C.c_int), ("out_zp", i64),
-                ("out", vp), ("out_rowsum", vp)]
+                ("out", vp), ("out_rowsum", vp), ("p_dump", vp), ("ld_p_dump", i64)]
 
 
 EPI_RAW, EPI_DEQUANT, EPI_REQUANT, EPI_QUANT, EPI_SOFTMAX_QUANT, EPI_GELU_QUANT = 0, 1, 2, 3, 4, 5

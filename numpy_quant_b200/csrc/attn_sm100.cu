@@ -1,22 +1,33 @@
 // Fused quantized attention: for every (image, head)
 //     S = Q . K^T  (int8 x int8 -> int32, tcgen05)      [MatMul, numpy_quantization.py:44-61]
-//     P = quantize(softmax(dequantize(S) / c))           [Div, Softmax, quantize of the next MatMul]
+//     P = quantize(softmax(dequantize(S) / c))           [Div, Softmax (tensor.py:139-146), quantize of the next MatMul]
 //     O = P . V    (int8 x int8 -> int32, tcgen05)       [MatMul]
 //     C = quantize(dequantize(O)) scattered as [B, S, H*D] (Transpose(0,2,1,3) + Reshape + quantize of the output
 //         projection's left operand)
 // in ONE kernel: the scores, the probabilities and the context accumulator never leave the SM -- S and O live in
 // TMEM, P goes from registers to a 128-byte-swizzled K-major shared-memory tile that the second MMA reads.
-// Same arithmetic as NQ_EPI_SOFTMAX_QUANT followed by NQ_EPI_QUANT (merge heads): identical codes.
 //
-// Persistent, one CTA (640 threads) per SM, tile = (image*head, 128 query rows):
-//   warp 0      TMA producer: Q tile [128 x D], K tile [208 x D], V^T tile [64 x S] per stage (3 stages)
-//   warp 1      MMA issuer:   S(i) one tile ahead of the softmax, O(i-1) as soon as P(i-1) is in shared memory
-//   warp 2      TMEM allocator (2 x 208 columns for S, 64 for O)
-//   warps 4-19  softmax of tile i (as in qgemm_sm100.cu), P(i) -> smem
-//   warps 20-23 context epilogue of tile i (dequantize O, quantize, merge heads) -- concurrent with the softmax of
-//               tile i+1, so its latencies fill the softmax warps' idle issue slots
-// Registers (launch 768 x 80 = 61440): setmaxnreg 48 / 96 / 48.
+// Round-2 design (the round-1 kernel spent ~35 CUDA-core instructions per score; this one ~7):
+//   * every zero-point term of the two MatMuls (numpy_quantization.py:49-61) comes out of the TENSOR CORE: extra
+//     accumulating MMAs against constant operand tiles (all bytes equal) add  -zq * colsum(K),  -zv * rowsum(P)  and
+//     (lo_p - zp_p) * colsum(V)  to the accumulators, so the CUDA cores never see row / column sums.  The term
+//     zk * rowsum(Q) is constant along a score row and cancels in the softmax (shift invariance), so it is not formed;
+//   * the row maximum is an INTEGER maximum of the raw accumulators (scale > 0), taken per warp over its 56 columns;
+//     exp is 2^((x - max) * c) with the integer difference converted exactly (magic-constant add) -- float glue under
+//     the 1e-5 contract; the four warps that share a row exchange (max, sum) ONCE per tile (online-softmax merge);
+//   * P is stored as the unsigned byte  code - lo_p  (0 .. 2^b - 1): the second MMA runs with an unsigned A operand,
+//     the upper / lower clamps of the quantizer are the saturation of one I2IP pack instruction;
+//   * the context is quantized with the exact reference arithmetic (one float32 multiply, correctly rounded float32
+//     division, round-half-even of zp + t): given the emitted P codes the output codes are bit-exact;
+//   * work unit = one (image, head): Q (both 128-row tiles), K^T and V^T are loaded once per head; the short second
+//     tile (S - 128 rows) alternates between the low and the high TMEM lanes from head to head so that the four
+//     sub-partitions (a warp reads only its own lane quarter) carry the same load.
+//
+// Persistent, one CTA (768 threads) per SM:
+//   warp 0      TMA producer (2 head stages)            warp 1   MMA issuer          warp 2   TMEM allocator
+//   warps 4-19  softmax of tile i, P(i) -> smem         warps 20-23  context epilogue of tile i - 1 (concurrently)
 #include <cuda.h>
+#include <string.h>
 
 #include <type_traits>
 
@@ -30,21 +41,21 @@ int make_operand_map(CUtensorMap* map, const int8_t* base, int64_t K, int64_t ro
 
 namespace attn {
 
-// Waiters that are off the critical path (TMA producer: 3 stages ahead; context warps: a tile behind) back off with
-// nanosleep: their poll loops otherwise take ~15 % of the issue slots the softmax warps need.
+// Waiters that are off the critical path (TMA producer: a head ahead; context warps: a tile behind) back off with
+// nanosleep so that their polls do not take issue slots from the softmax warps.
 __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
     for (uint32_t spin = 1; !done; ++spin) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done)
-            : "r"(bar), "r"(parity)
+            : "r"(bar), "r"(parity), "r"(100000u)
             : "memory");
         if (!done) {
-            __nanosleep(256);
-            if (spin > (1u << 24)) __trap();                              // ~4 s: protocol bug -> error instead of a hang
+            __nanosleep(128);
+            if (spin > (1u << 22)) __trap();                              // seconds: protocol bug -> error instead of a hang
         }
     }
 }
@@ -54,38 +65,92 @@ constexpr int NUM_CTX_WARPS = 4;                // context epilogue: one warp pe
 constexpr int NUM_THREADS = 128 + 32 * NUM_EPI_WARPS + 32 * NUM_CTX_WARPS;   // 768
 constexpr int BN1 = 208;                       // key columns of the score tile (S <= 208)
 constexpr int BN2 = 64;                        // head dim columns of the context tile (D <= 64)
-constexpr int STAGES = 3;
-constexpr int Q_BYTES = BM * BK;               // 16 KB (box 128 B wide; D < 128 is zero-filled by TMA)
+constexpr int STAGES = 2;                      // one stage = one (image, head)
+constexpr int Q_BYTES = BM * BK;               // 16 KB per 128-row tile (box 128 B wide; D < 128 is zero-filled by TMA)
 constexpr int K_BYTES = BN1 * BK;              // 26 KB
 constexpr int V_BYTES = 2 * BN2 * BK;          // 16 KB: two k-blocks of the key axis
-constexpr int STAGE_BYTES = Q_BYTES + K_BYTES + V_BYTES;
+constexpr int STAGE_BYTES = 2 * Q_BYTES + K_BYTES + V_BYTES;              // 74 KB
 constexpr int P_BYTES = 2 * BM * BK;           // 32 KB: P as the K-major A operand of the second MMA (two k-blocks)
-constexpr int EPI_WORDS = 4864;                // max / sum / code-sum exchange, per-warp column / row terms (cp.async targets)
+constexpr int CA_BYTES = BM * BK;              // 16 KB: constant A tile, K steps {c1q, c2q, c1p, c2p}
+constexpr int CB_BYTES = BN2 * BK;             // 8 KB:  constant B tile, K steps {c1v, c2v, 0, 0}
+constexpr int RED_WORDS = 2 * 128 * 8;         // [tile parity][row][4 x max | 4 x sum]
 constexpr int BAR_BYTES = 256;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + P_BYTES + EPI_WORDS * 4 + BAR_BYTES;
+constexpr int OFF_P = STAGES * STAGE_BYTES;
+constexpr int OFF_CA = OFF_P + P_BYTES;
+constexpr int OFF_CB = OFF_CA + CA_BYTES;
+constexpr int OFF_RED = OFF_CB + CB_BYTES;
+constexpr int OFF_BAR = OFF_RED + RED_WORDS * 4;
+constexpr int SMEM_BYTES = OFF_BAR + BAR_BYTES;
 static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB opt-in shared memory of sm_100");
+static_assert(STAGE_BYTES % 1024 == 0 && Q_BYTES % 1024 == 0 && K_BYTES % 1024 == 0, "128-byte swizzle needs 1024-byte aligned tiles");
 constexpr int O_COL = 2 * BN1;                 // TMEM column of the context accumulator (416)
+constexpr int NSUB = 7;                        // 8-column groups per softmax warp (56 columns; 4 warps span 224 >= 208)
+
+// kind::i8 instruction descriptor with the operand signedness spelled out (bit 7: A signed, bit 10: B signed)
+__host__ __device__ constexpr uint32_t idesc_i8(int bn, bool a_signed, bool b_signed) {
+    return (2u << 4) | ((a_signed ? 1u : 0u) << 7) | ((b_signed ? 1u : 0u) << 10) | ((uint32_t)(bn >> 3) << 17) |
+           ((uint32_t)(BM >> 4) << 24);
+}
 
 struct Params {
     int64_t BH, S, D, H;
-    // scores
-    float scale1;                              // s_q * s_k / c  (Div folded)
-    const int32_t* rowsum_q;                   // [BH, S]  (used when K^T is asymmetric)
-    const int32_t* colsum_k;                   // [BH, S]  (used when Q is asymmetric)
-    int zq, zk, use_row1, use_col1;
-    int64_t kterm1;                            // zq * zk * D
-    int fast22, sm_noclamp;                    // sm_noclamp: zp_p >= lo, so p / s + zp needs no lower clamp
-    float sm_top;                              // upper clamp in the magic-sum domain (1.5 * 2^23 + hi), or huge when p = 1 fits
-    QArgs qp;                                  // P quantizer
+    float c_exp;                               // s_q * s_k / c * log2(e): exponent per unit of the integer score
+    int cq[2], cp[2], cv[2];                   // int8 splits of  -zq,  lo_p - zp_p,  -zv   (0: pass skipped)
+    // P quantizer (unsigned storage code - lo_p)
+    float p_scale, p_magic;                    // p_magic = 1.5 * 2^23 + (zp_p - lo_p)
+    int p_top, p_bits8;                        // 2^b - 1; b == 8: the pack instruction's saturation is the clamp
+    int8_t* p_dump;                            // optional [BH, S, ld_dump] copy of the emitted P bytes (tests)
+    int64_t ld_dump;
     // context
     float scale2;                              // s_p * s_v
-    const int32_t* colsum_v;                   // [BH, D]
-    int zp_p, zv, use_row2, use_col2;
-    int64_t kterm2;                            // zp_p * zv * S
-    QArgs qo;                                  // output quantizer
+    int ctx_bias;                              // -(lo_p - zp_p) * zv * S: the constant term of the accumulator
+    int ctx_magic;                             // host-proved |accumulator| < 2^22: magic-constant int -> float
+    float o_rcp, o_scale, o_magic;             // output quantizer: RN(1 / s_o), s_o, 1.5 * 2^23 + zp_o
+    int o_lo, o_hi, o_bits8, o_div2;           // o_div2: second residual correction of the division needed
     int8_t* C;                                 // [B, S, H * D]
     int32_t* o_rowsum;                         // [B * S] or NULL (atomics; caller-zeroed)
 };
+
+struct TileInfo {
+    int m0;                                    // first query row held by TMEM lane 0 (may be negative)
+    int mlo;                                   // rows below mlo belong to the other tile of the head
+};
+
+// Tile `mt` of the `lh`-th head this CTA processes: the partial tile sits in the low lanes for even lh and in the
+// high lanes for odd lh (Q rows S - 128 .. S - 1, of which the first ones repeat tile 0 and are masked).
+__device__ __forceinline__ TileInfo tile_info(int S, int m_tiles, uint32_t lh, int mt) {
+    const bool high = (lh & 1u) != 0;
+    TileInfo t;
+    if (m_tiles == 1) {
+        t.m0 = high ? S - BM : 0;
+        t.mlo = 0;
+    } else if (mt == 0) {
+        t.m0 = 0;
+        t.mlo = 0;
+    } else {
+        t.m0 = high ? S - BM : BM;
+        t.mlo = BM;
+    }
+    return t;
+}
+
+__device__ __forceinline__ uint32_t pack_sat_u8(int x0, int x1, int x2, int x3) {
+    uint32_t hi, d;
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(x3), "r"(x2), "r"(0));
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(x1), "r"(x0), "r"(hi));
+    return d;
+}
+__device__ __forceinline__ uint32_t pack_sat_s8(int x0, int x1, int x2, int x3) {
+    uint32_t hi, d;
+    asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(x3), "r"(x2), "r"(0));
+    asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(x1), "r"(x0), "r"(hi));
+    return d;
+}
+__device__ __forceinline__ float ex2_fast(float a) {
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(a));
+    return e;
+}
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
@@ -93,26 +158,41 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
     uint8_t* smem = smem_raw;
-    uint8_t* smem_p = smem + STAGES * STAGE_BYTES;
-    uint32_t* epi = reinterpret_cast<uint32_t*>(smem + STAGES * STAGE_BYTES + P_BYTES);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + P_BYTES + EPI_WORDS * 4);
-    uint64_t* full_bar = bars;                 // [STAGES] TMA -> MMA
-    uint64_t* empty_bar = bars + STAGES;       // [STAGES] second MMA done with the stage
+    uint8_t* smem_p = smem + OFF_P;
+    uint8_t* smem_ca = smem + OFF_CA;
+    uint8_t* smem_cb = smem + OFF_CB;
+    uint32_t* red = reinterpret_cast<uint32_t*>(smem + OFF_RED);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+    uint64_t* full_bar = bars;                 // [STAGES] TMA -> MMA (one head landed)
+    uint64_t* empty_bar = bars + STAGES;       // [STAGES] last MMA of the head done with the stage
     uint64_t* sfull_bar = bars + 2 * STAGES;   // [2] scores ready
-    uint64_t* sempty_bar = sfull_bar + 2;      // [2] scores drained (16 warps)
+    uint64_t* sempty_bar = sfull_bar + 2;      // [2] scores drained into registers (16 warps)
     uint64_t* pfull_bar = sempty_bar + 2;      // P tile written (16 warps)
-    uint64_t* ofull_bar = pfull_bar + 1;       // context accumulator ready
+    uint64_t* ofull_bar = pfull_bar + 1;       // context accumulator ready (= second MMA done reading P)
     uint64_t* oempty_bar = ofull_bar + 1;      // context accumulator drained (4 context warps)
-    uint64_t* rs_bar = oempty_bar + 1;         // [2] row sums of P handed to the context warps (one warp per quarter);
-                                               // by tile parity: the softmax may complete tile i + 2 before a context warp
-                                               // polls for tile i + 1, which a single barrier's phase parity cannot tell apart
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rs_bar + 2);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(oempty_bar + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t m_tiles = (uint32_t)((p.S + BM - 1) / BM);
-    const uint32_t total_tiles = m_tiles * (uint32_t)p.BH;
-    const int ks1 = (int)((p.D + UMMA_K - 1) / UMMA_K);                   // K steps of Q.K^T (<= 4)
-    const int ks2 = (int)((p.S + UMMA_K - 1) / UMMA_K);                   // K steps of P.V (<= 8 over two k-blocks)
+    const int S = (int)p.S;
+    const int m_tiles = (S + BM - 1) / BM;
+    const uint32_t n_heads = (uint32_t)p.BH;
+    const int ks1 = (int)((p.D + UMMA_K - 1) / UMMA_K);                   // K steps of Q.K^T (<= 2)
+    const int ks2 = (S + UMMA_K - 1) / UMMA_K;                            // K steps of P.V (<= 7 over two k-blocks)
+
+    // ---- one-time shared-memory contents: constant operand tiles, zeroed P tile (columns >= S must read as 0)
+    for (int i = threadIdx.x; i < (CA_BYTES + CB_BYTES) / 16; i += NUM_THREADS) {
+        const bool isa = i < CA_BYTES / 16;
+        const int j = isa ? i : i - CA_BYTES / 16;
+        const int r = j >> 3, pc = j & 7;
+        const int c = pc ^ (r & 7);                                       // logical 16-byte chunk held by physical chunk pc
+        const int step = c >> 1;                                          // 32-byte K step
+        const int v = isa ? (step < 2 ? p.cq[step] : p.cp[step - 2]) : (step < 2 ? p.cv[step] : 0);
+        const uint32_t w = (uint32_t)(v & 0xff) * 0x01010101u;
+        *reinterpret_cast<uint4*>((isa ? smem_ca : smem_cb) + j * 16) = make_uint4(w, w, w, w);
+    }
+    for (int i = threadIdx.x; i < P_BYTES / 16; i += NUM_THREADS)
+        *reinterpret_cast<uint4*>(smem_p + i * 16) = make_uint4(0, 0, 0, 0);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // generic-proxy writes -> visible to the MMAs
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_q) : "memory");
@@ -131,8 +211,6 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
         mbar_init(smem_u32(pfull_bar), NUM_EPI_WARPS);
         mbar_init(smem_u32(ofull_bar), 1);
         mbar_init(smem_u32(oempty_bar), NUM_CTX_WARPS);
-        mbar_init(smem_u32(rs_bar), 4);
-        mbar_init(smem_u32(rs_bar + 1), 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -148,20 +226,20 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
     if (warp < 4) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
         if (warp == 0) {
-            // ===================== TMA producer =====================
+            // ===================== TMA producer: one stage per (image, head) =====================
             if (lane == 0) {
                 int stage = 0;
-                uint32_t phase = 0;
-                for (uint32_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-                    const int bh = (int)(t / m_tiles), m0 = (int)(t % m_tiles) * BM;
+                uint32_t phase = 0, lh = 0;
+                for (uint32_t hd = blockIdx.x; hd < n_heads; hd += gridDim.x, ++lh) {
                     mbar_wait_relaxed(smem_u32(empty_bar + stage), phase ^ 1);
                     const uint32_t fb = smem_u32(full_bar + stage);
                     uint8_t* st = smem + stage * STAGE_BYTES;
-                    mbar_expect_tx(fb, STAGE_BYTES);
-                    tma_load_3d(smem_u32(st), &tmap_q, 0, m0, bh, fb);
-                    tma_load_3d(smem_u32(st + Q_BYTES), &tmap_k, 0, 0, bh, fb);
-                    tma_load_3d(smem_u32(st + Q_BYTES + K_BYTES), &tmap_v, 0, 0, bh, fb);
-                    tma_load_3d(smem_u32(st + Q_BYTES + K_BYTES + BN2 * BK), &tmap_v, BK, 0, bh, fb);
+                    mbar_expect_tx(fb, (uint32_t)(m_tiles * Q_BYTES + K_BYTES + V_BYTES));
+                    for (int mt = 0; mt < m_tiles; ++mt)
+                        tma_load_3d(smem_u32(st + mt * Q_BYTES), &tmap_q, 0, tile_info(S, m_tiles, lh, mt).m0, (int)hd, fb);
+                    tma_load_3d(smem_u32(st + 2 * Q_BYTES), &tmap_k, 0, 0, (int)hd, fb);
+                    tma_load_3d(smem_u32(st + 2 * Q_BYTES + K_BYTES), &tmap_v, 0, 0, (int)hd, fb);
+                    tma_load_3d(smem_u32(st + 2 * Q_BYTES + K_BYTES + BN2 * BK), &tmap_v, BK, 0, (int)hd, fb);
                     if (++stage == STAGES) {
                         stage = 0;
                         phase ^= 1;
@@ -172,23 +250,32 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
         } else if (warp == 1) {
             // ===================== MMA issuer =====================
             if (lane == 0) {
-                constexpr uint32_t idesc1 = make_idesc(BN1), idesc2 = make_idesc(BN2);
-                const uint64_t pdesc = make_smem_desc(smem_u32(smem_p));
-                uint32_t li = 0;                                          // local tile counter
-                int prev_stage = -1;
-                for (uint32_t t = blockIdx.x;; t += gridDim.x, ++li) {
-                    const bool have = t < total_tiles;
-                    const int stage = (int)(li % STAGES);
-                    if (have) {
+                constexpr uint32_t id_s = idesc_i8(BN1, true, true);      // Q . K^T and the -zq pass: signed x signed
+                constexpr uint32_t id_pu = idesc_i8(BN2, false, true);    // P (unsigned bytes) . V, P . const(-zv)
+                constexpr uint32_t id_ps = idesc_i8(BN2, true, true);     // const(lo_p - zp_p) . V
+                const uint64_t ca = make_smem_desc(smem_u32(smem_ca)), cb = make_smem_desc(smem_u32(smem_cb));
+                const uint64_t pd0 = make_smem_desc(smem_u32(smem_p)), pd1 = make_smem_desc(smem_u32(smem_p + BM * BK));
+                uint32_t li = 0, lh = 0;                                  // local tile / head counters
+                int prev_stage = -1, prev_last = 0;
+                uint32_t hd = blockIdx.x;
+                bool more = hd < n_heads;
+                int mt = 0;
+                for (;; ++li) {
+                    const int stage = (int)(lh % STAGES);
+                    if (more) {
                         // ---- scores of tile li (one tile ahead of the softmax warps)
                         const int sb = (int)(li & 1);
                         mbar_wait_backoff(smem_u32(sempty_bar + sb), ((li >> 1) & 1u) ^ 1u);
-                        mbar_wait_backoff(smem_u32(full_bar + stage), (li / STAGES) & 1u);
+                        if (mt == 0) mbar_wait_backoff(smem_u32(full_bar + stage), (lh / STAGES) & 1u);
                         tc_fence_after();
                         uint8_t* st = smem + stage * STAGE_BYTES;
-                        const uint64_t qd = make_smem_desc(smem_u32(st)), kd = make_smem_desc(smem_u32(st + Q_BYTES));
-                        for (int k = 0; k < ks1; ++k)
-                            mma_i8(tmem_base + (uint32_t)(sb * BN1), qd + (uint64_t)(k * 2), kd + (uint64_t)(k * 2), idesc1, k > 0 ? 1u : 0u);
+                        const uint64_t qd = make_smem_desc(smem_u32(st + mt * Q_BYTES)), kd = make_smem_desc(smem_u32(st + 2 * Q_BYTES));
+                        const uint32_t d_s = tmem_base + (uint32_t)(sb * BN1);
+                        for (int k = 0; k < ks1; ++k) mma_i8(d_s, qd + (uint64_t)(k * 2), kd + (uint64_t)(k * 2), id_s, k > 0 ? 1u : 0u);
+#pragma unroll
+                        for (int c = 0; c < 2; ++c)
+                            if (p.cq[c] != 0)
+                                for (int k = 0; k < ks1; ++k) mma_i8(d_s, ca + (uint64_t)(c * 2), kd + (uint64_t)(k * 2), id_s, 1u);
                         tc_commit(smem_u32(sfull_bar + sb));
                     }
                     if (li > 0) {
@@ -198,299 +285,266 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
                         mbar_wait_backoff(smem_u32(oempty_bar), (lp & 1u) ^ 1u);
                         tc_fence_after();
                         uint8_t* st = smem + prev_stage * STAGE_BYTES;
-                        const uint64_t vd0 = make_smem_desc(smem_u32(st + Q_BYTES + K_BYTES));
-                        const uint64_t vd1 = make_smem_desc(smem_u32(st + Q_BYTES + K_BYTES + BN2 * BK));
-                        const uint64_t pd1 = make_smem_desc(smem_u32(smem_p + BM * BK));
+                        const uint64_t vd0 = make_smem_desc(smem_u32(st + 2 * Q_BYTES + K_BYTES));
+                        const uint64_t vd1 = make_smem_desc(smem_u32(st + 2 * Q_BYTES + K_BYTES + BN2 * BK));
+                        const uint32_t d_o = tmem_base + O_COL;
                         for (int k = 0; k < ks2; ++k) {
-                            const int kk = k & 3;
-                            if (k < 4) mma_i8(tmem_base + O_COL, pdesc + (uint64_t)(kk * 2), vd0 + (uint64_t)(kk * 2), idesc2, k > 0 ? 1u : 0u);
-                            else mma_i8(tmem_base + O_COL, pd1 + (uint64_t)(kk * 2), vd1 + (uint64_t)(kk * 2), idesc2, 1u);
+                            const uint64_t off = (uint64_t)((k & 3) * 2);
+                            mma_i8(d_o, (k < 4 ? pd0 : pd1) + off, (k < 4 ? vd0 : vd1) + off, id_pu, k > 0 ? 1u : 0u);
                         }
-                        tc_commit(smem_u32(empty_bar + prev_stage));      // Q / K / V of that tile no longer needed
+#pragma unroll
+                        for (int c = 0; c < 2; ++c) {
+                            if (p.cv[c] != 0)                               // - zv * rowsum(P)
+                                for (int k = 0; k < ks2; ++k)
+                                    mma_i8(d_o, (k < 4 ? pd0 : pd1) + (uint64_t)((k & 3) * 2), cb + (uint64_t)(c * 2), id_pu, 1u);
+                            if (p.cp[c] != 0)                               // + (lo_p - zp_p) * colsum(V)
+                                for (int k = 0; k < ks2; ++k)
+                                    mma_i8(d_o, ca + (uint64_t)((2 + c) * 2), (k < 4 ? vd0 : vd1) + (uint64_t)((k & 3) * 2), id_ps, 1u);
+                        }
+                        if (prev_last) tc_commit(smem_u32(empty_bar + prev_stage));   // Q / K / V of that head no longer needed
                         tc_commit(smem_u32(ofull_bar));
                     }
+                    if (!more) break;
                     prev_stage = stage;
-                    if (!have) break;
+                    prev_last = (mt == m_tiles - 1);
+                    if (++mt == m_tiles) {
+                        mt = 0;
+                        ++lh;
+                        hd += gridDim.x;
+                        more = hd < n_heads;
+                    }
                 }
             }
             __syncwarp();
         }
     } else if (warp >= 4 + NUM_EPI_WARPS) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
         // ===================== context epilogue (4 warps, one per TMEM lane quarter) =====================
-        // O(i) = P(i) . V is drained here while the softmax warps already work on tile i + 1.
+        // O(i) = P(i) . V (all zero-point terms already inside) is drained here while the softmax warps work on tile
+        // i + 1: exact dequantize (one multiply), exact division by the output scale, round-half-even, merge-heads store.
         const int q = warp & 3;
         const int rloc = q * 32 + lane;
-        const int* rsbuf = reinterpret_cast<const int*>(epi) + 4608;      // [2][128] row sums of P (from the softmax warps)
-        const Quantizer qzo(p.qo);
-        uint32_t li = 0;
-        for (uint32_t t = blockIdx.x; t < total_tiles; t += gridDim.x, ++li) {
-            const uint32_t bh = t / m_tiles, m0 = (t - bh * m_tiles) * BM;
-            const int64_t m = (int64_t)m0 + rloc;
-            const bool row_ok = m < p.S;
-            const bool warp_rows = (int64_t)m0 + q * 32 < p.S;
-            const uint32_t b = bh / (uint32_t)p.H, hh = bh - b * (uint32_t)p.H;
-            // column terms of this tile (colsum(V) * zp_p, 64 values, the same for every row): one 16-byte load per
-            // lane into the warp's smem strip before the waits, broadcast LDS.128 in the loop
-            int* ctv = reinterpret_cast<int*>(epi) + 4096 + q * 64;
-            __syncwarp();
-            if (lane < 16) {
-                int4 c4 = make_int4(0, 0, 0, 0);
-                if (p.use_col2 && lane * 4 < p.D) c4 = ldg_v4(p.colsum_v + (int64_t)bh * p.D + lane * 4);
-                *reinterpret_cast<int4*>(ctv + lane * 4) = make_int4(c4.x * p.zp_p, c4.y * p.zp_p, c4.z * p.zp_p, c4.w * p.zp_p);
-            }
-            __syncwarp();
-            mbar_wait_relaxed(smem_u32(rs_bar + (li & 1)), (li >> 1) & 1u);
-            int rowterm = (int)-p.kterm2;
-            if (p.use_row2) rowterm += rsbuf[(li & 1) * 128 + rloc] * p.zv;
-            mbar_wait_relaxed(smem_u32(ofull_bar), li & 1u);
-            tc_fence_after();
-            int8_t* dst = p.C + (((int64_t)b * p.S + m) * p.H + hh) * p.D;
-            int rs_out = 0;
-            if (warp_rows) {
+        const int ibias = p.ctx_bias + (p.ctx_magic ? 0x4B400000 : 0);
+        const float nb = -p.o_scale;
+        uint32_t li = 0, lh = 0;
+        for (uint32_t hd = blockIdx.x; hd < n_heads; hd += gridDim.x, ++lh) {
+            const uint32_t b = hd / (uint32_t)p.H, hh = hd - b * (uint32_t)p.H;
+            for (int mt = 0; mt < m_tiles; ++mt, ++li) {
+                const TileInfo ti = tile_info(S, m_tiles, lh, mt);
+                const int m = ti.m0 + rloc;
+                const bool row_ok = m >= ti.mlo && m < S;
+                const int mw0 = ti.m0 + q * 32;                           // rows of this warp: [mw0, mw0 + 32)
+                const bool warp_rows = mw0 + 31 >= ti.mlo && mw0 < S;
+                mbar_wait_relaxed(smem_u32(ofull_bar), li & 1u);
+                tc_fence_after();
+                int8_t* dst = p.C + (((int64_t)b * S + m) * p.H + hh) * p.D;
+                int rs_out = 0;
+                if (warp_rows) {
 #pragma unroll 1
-                for (int c16 = 0; c16 * 16 < p.D; ++c16) {
-                    uint32_t v[16];
-                    tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(O_COL + c16 * 16), v);
-                    tmem_ld_wait();
-                    int w[4];
+                    for (int c16 = 0; c16 * 16 < (int)p.D; ++c16) {
+                        uint32_t v[16];
+                        tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(O_COL + c16 * 16), v);
+                        tmem_ld_wait();
+                        uint32_t w[4];
 #pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        const int4 c4 = *reinterpret_cast<const int4*>(ctv + c16 * 16 + g * 4);
-                        const int ct[4] = {c4.x, c4.y, c4.z, c4.w};
-                        int c[4];
+                        for (int g = 0; g < 4; ++g) {
+                            int n[4];
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            // |acc - zero-point terms| <= S * 255 * 255 < 2^24: exact int -> float, one IEEE multiply
-                            const int d = (int)v[4 * g + k] - rowterm - ct[k];
-                            c[k] = qzo.code<1>(__fmul_rn(__int2float_rn(d), p.scale2));
+                            for (int k = 0; k < 4; k += 2) {
+                                const int i0 = (int)v[4 * g + k] + ibias, i1 = (int)v[4 * g + k + 1] + ibias;
+                                float2 d2;
+                                if (p.ctx_magic) d2 = __fadd2_rn(make_float2(__int_as_float(i0), __int_as_float(i1)), make_float2(-12582912.0f, -12582912.0f));
+                                else d2 = make_float2(__int2float_rn(i0), __int2float_rn(i1));
+                                // dequantize: f32(f64(acc - zp) * f64(scale)) == one float32 multiply for |.| < 2^24
+                                const float2 x = __fmul2_rn(d2, make_float2(p.scale2, p.scale2));
+                                // x / s_o correctly rounded: q0 = x * RN(1/s_o), fused residual corrections (common.cuh)
+                                const float2 r2 = make_float2(p.o_rcp, p.o_rcp), nb2 = make_float2(nb, nb);
+                                float2 qq = __fmul2_rn(x, r2);
+                                float2 e = __ffma2_rn(qq, nb2, x);
+                                qq = __ffma2_rn(e, r2, qq);
+                                if (p.o_div2) {
+                                    e = __ffma2_rn(qq, nb2, x);
+                                    qq = __ffma2_rn(e, r2, qq);
+                                }
+                                // round-half-even of zp + t: one add of 1.5 * 2^23 + zp (exact-sum rounding, common.cuh)
+                                const float2 rr = __fadd2_rn(qq, make_float2(p.o_magic, p.o_magic));
+                                n[k] = __float_as_int(rr.x) - 0x4B400000;
+                                n[k + 1] = __float_as_int(rr.y) - 0x4B400000;
+                            }
+                            if (!p.o_bits8) {
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) n[k] = min(max(n[k], p.o_lo), p.o_hi);
+                            }
+                            w[g] = pack_sat_s8(n[0], n[1], n[2], n[3]);
                         }
-                        w[g] = pack4_codes(c[0], c[1], c[2], c[3]);
-                    }
-                    if (row_ok) {
-                        *reinterpret_cast<int4*>(dst + c16 * 16) = make_int4(w[0], w[1], w[2], w[3]);
-                        rs_out = __dp4a(w[0], 0x01010101, __dp4a(w[1], 0x01010101, __dp4a(w[2], 0x01010101, __dp4a(w[3], 0x01010101, rs_out))));
+                        if (row_ok) {
+                            *reinterpret_cast<uint4*>(dst + c16 * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+                            rs_out = __dp4a((int)w[0], 0x01010101, __dp4a((int)w[1], 0x01010101, __dp4a((int)w[2], 0x01010101, __dp4a((int)w[3], 0x01010101, rs_out))));
+                        }
                     }
                 }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(oempty_bar));
+                if (p.o_rowsum && row_ok && warp_rows) atomicAdd(p.o_rowsum + (int64_t)b * S + m, rs_out);
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(oempty_bar));
-            if (p.o_rowsum && row_ok && warp_rows) atomicAdd(p.o_rowsum + (int64_t)b * p.S + m, rs_out);
         }
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 96;");
-        // ===================== softmax (16 warps) =====================
-        const int q = warp & 3, h = (warp - 4) >> 2, ew = warp - 4;
+        // ===================== softmax (16 warps: lane quarter q x column group h) =====================
+        const int q = warp & 3, h = (warp - 4) >> 2;
         const int rloc = q * 32 + lane;
-        float* red = reinterpret_cast<float*>(epi);                        // [2][4][128] max / sum exchange
-        int* redq = reinterpret_cast<int*>(epi) + 1024;                    // [4][128] code sums
-        int* ctw2 = reinterpret_cast<int*>(epi) + 2048 + ew * 128;         // this warp's 56 score column terms, 2 tile buffers
-        int* rowraw = reinterpret_cast<int*>(epi) + 1536 + ew * 32;        // this warp's rowsum(Q) values of the next tile
-        int* rsbuf = reinterpret_cast<int*>(epi) + 4608;                   // [2][128] row sums of P for the context warps
-        constexpr int NSUB = 7;
-        constexpr float kMasked = -1.0e30f;
         const int col0 = h * (NSUB * 8);
-        const int ncols_w = (int)(p.S - col0 < NSUB * 8 ? (p.S - col0 > 0 ? p.S - col0 : 0) : NSUB * 8);
-        const int nfull = ncols_w >> 3, nrem = ncols_w & 7;
-        // Per-tile operands of the zero-point correction (rowsum(Q) of this thread's row, colsum(K) of this warp's 56
-        // columns) travel global -> shared memory with cp.async ONE TILE AHEAD: no registers held across the tile, no
-        // L2 round trip at the head of a tile's critical path.
-        auto stage_next = [&](uint32_t tt, int buf) {
-            if (tt >= total_tiles) return;
-            const uint32_t bh = tt / m_tiles, m0 = (tt - bh * m_tiles) * BM;
-            const int64_t m = (int64_t)m0 + rloc;
-            if (p.use_row1 && m < p.S)
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(rowraw + lane)), "l"(p.rowsum_q + (int64_t)bh * p.S + m) : "memory");
-            if (p.use_col1) {
-                const int64_t c0i = col0 + lane, c1i = c0i + 32;
-                const int32_t* src = p.colsum_k + (int64_t)bh * p.S;
-                if (c0i < p.S)
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(ctw2 + buf * 64 + lane)), "l"(src + c0i) : "memory");
-                if (lane < 24 && c1i < p.S)
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(ctw2 + buf * 64 + 32 + lane)), "l"(src + c1i) : "memory");
-            }
-        };
-        stage_next(blockIdx.x, 0);
-        uint32_t li = 0;
-        for (uint32_t t = blockIdx.x; t < total_tiles; t += gridDim.x, ++li) {
-            const uint32_t bh = t / m_tiles, m0 = (t - bh * m_tiles) * BM;
-            const int64_t m = (int64_t)m0 + rloc;
-            const bool row_ok = m < p.S;
-            const int rows_left = (int)(p.S - (m0 + q * 32));
-            const bool warp_rows = rows_left > 0;
-            asm volatile("cp.async.wait_all;" ::: "memory");               // this tile's terms (issued one tile ago) have landed
-            __syncwarp();
-            int* ctw = ctw2 + (li & 1) * 64;
-            int rowterm = (int)-p.kterm1;
-            if (p.use_row1 && row_ok) rowterm += rowraw[lane] * p.zk;
-            if (p.use_col1) {                                              // raw column sums -> column terms, in place
-                const int v0 = ctw[lane] * p.zq, v1 = ctw[32 + lane] * p.zq;
-                __syncwarp();
-                ctw[lane] = v0;
-                ctw[32 + lane] = v1;
-            } else {
-                ctw[lane] = 0;
-                ctw[32 + lane] = 0;
-            }
-            __syncwarp();
-            stage_next(t + gridDim.x, (int)((li + 1) & 1));
-            const int sb = (int)(li & 1);
-            mbar_wait(smem_u32(sfull_bar + sb), (li >> 1) & 1u);
-            tc_fence_after();
-            const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(sb * BN1);
-            // ---------------- pass 1: scores -> registers, row max
-            float y[NSUB * 8];
-            float lmax = kMasked;
-            auto pass1 = [&](auto magic_tag) {
-                constexpr bool MAGIC = decltype(magic_tag)::value;
-                const int rm = (MAGIC ? 0x4B400000 : 0) - rowterm;
+        const int ncols_w = S - col0 < NSUB * 8 ? (S - col0 > 0 ? S - col0 : 0) : NSUB * 8;
+        int nfull = ncols_w >> 3, nrem = ncols_w & 7;
+        // byte masks of the ragged 8-column group (columns >= S must be stored as zero bytes)
+        uint32_t rmask0 = nrem >= 4 ? 0xffffffffu : (nrem == 0 ? 0u : (0xffffffffu >> (32 - 8 * nrem)));
+        uint32_t rmask1 = nrem <= 4 ? 0u : (0xffffffffu >> (32 - 8 * (nrem - 4)));
+        int qrow0 = q * 32;
+        // per-thread constants of the tile loop: opaque to the compiler, which otherwise re-derives them from %tid every tile
+        asm volatile("" : "+r"(nfull), "+r"(nrem), "+r"(rmask0), "+r"(rmask1), "+r"(qrow0));
+        // this thread's destinations inside the swizzled P tile, one per 8-column group (the same for every tile):
+        // row r, 16-byte chunk ^ (r & 7) -- the layout TMA would have produced for a K-major A operand
+        uint32_t paddr[NSUB];
 #pragma unroll
-                for (int j2 = 0; j2 < NSUB; j2 += 2) {
-                    if (j2 * 8 < ncols_w) {
-                        uint32_t a16[16];
-                        const bool two = (j2 + 1 < NSUB) && ((j2 + 1) * 8 < ncols_w);
-                        if (two) tmem_ld_32x32b_x16(t_row + (uint32_t)(col0 + j2 * 8), a16);
-                        else tmem_ld_32x32b_x8(t_row + (uint32_t)(col0 + j2 * 8), a16);
-                        int c16[16];
+        for (int j = 0; j < NSUB; ++j) {
+            const int cc0 = col0 + j * 8;
+            paddr[j] = smem_u32(smem_p) + (uint32_t)rloc * 128u + (uint32_t)((cc0 >> 7) * (BM * BK)) +
+                       (((((uint32_t)(cc0 & 127)) >> 4) ^ (uint32_t)(rloc & 7)) << 4) + (uint32_t)(cc0 & 15);
+            asm volatile("" : "+r"(paddr[j]));                             // keep it in a register (no rematerialisation per tile)
+        }
+        const float2 c2 = make_float2(p.c_exp, p.c_exp);
+        // f(j, ragged_tag) for every 8-column group of this warp that holds columns (ragged: the one cut by S)
+#define NQ_FOR_GROUPS(F)                                              \
+        _Pragma("unroll") for (int j = 0; j < NSUB; ++j) {            \
+            if (j < nfull) F(j, std::false_type{});                    \
+            else if (j == nfull && nrem > 0) F(j, std::true_type{});   \
+        }
+        uint32_t li = 0, lh = 0;
+        for (uint32_t hd = blockIdx.x; hd < n_heads; hd += gridDim.x, ++lh) {
+            for (int mt = 0; mt < m_tiles; ++mt, ++li) {
+                const TileInfo ti = tile_info(S, m_tiles, lh, mt);
+                const int mw0 = ti.m0 + qrow0;                            // rows of this warp: [mw0, mw0 + 32)
+                const bool active = mw0 + 31 >= ti.mlo && mw0 < S && (nfull | nrem) != 0;
+                const int sb = (int)(li & 1);
+                mbar_wait(smem_u32(sfull_bar + sb), (li >> 1) & 1u);
+                tc_fence_after();
+                uint32_t* redp = red + (li & 1) * 1024 + rloc * 8;        // [4 x max | 4 x sum] of this row
+                float y[NSUB * 8];                                         // scores (int bits), then exponentials
+                uint32_t* yi = reinterpret_cast<uint32_t*>(y);
+                int lmax = -(1 << 30);                                     // no columns: weight 2^(-huge) = 0, sum 0
+                float lsum = 0.f;
+                if (active) {
+                    // ---------------- pass 1: raw integer scores -> registers, integer row maximum
+                    const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(sb * BN1 + col0);
+                    tmem_ld_32x32b_x16(t_row, yi);
+                    if (nfull >= 2) tmem_ld_32x32b_x16(t_row + 16, yi + 16);
+                    if (nfull >= 4) tmem_ld_32x32b_x16(t_row + 32, yi + 32);
+                    if (nfull >= 6) tmem_ld_32x32b_x8(t_row + 48, yi + 48);
+                    tmem_ld_wait();
+                    auto pass1 = [&](int j, auto ragged_tag) {
+                        constexpr bool RAGGED = decltype(ragged_tag)::value;
 #pragma unroll
-                        for (int g = 0; g < 4; ++g) {
-                            const int4 c4 = *reinterpret_cast<const int4*>(ctw + j2 * 8 + g * 4);
-                            c16[4 * g] = c4.x; c16[4 * g + 1] = c4.y; c16[4 * g + 2] = c4.z; c16[4 * g + 3] = c4.w;
-                        }
-                        tmem_ld_wait();
-                        const bool clean = j2 * 8 + 16 <= ncols_w || (j2 + 1 >= NSUB && j2 * 8 + 8 <= ncols_w);
-                        if (clean) {
-                            // two columns per instruction (packed add, packed multiply: each lane IEEE-rounded exactly
-                            // like the scalar pair, so the codes stay those of the SOFTMAX_QUANT epilogue)
-#pragma unroll
-                            for (int k = 0; k < 16; k += 2) {
-                                if (j2 * 8 + k >= NSUB * 8) break;
-                                const int x0 = (int)a16[k] + rm - c16[k], x1 = (int)a16[k + 1] + rm - c16[k + 1];
-                                const float2 s2 = make_float2(p.scale1, p.scale1);
-                                const float2 f = MAGIC ? __fmul2_rn(__fadd2_rn(make_float2(__int_as_float(x0), __int_as_float(x1)),
-                                                                               make_float2(-12582912.0f, -12582912.0f)), s2)
-                                                       : __fmul2_rn(make_float2(__int2float_rn(x0), __int2float_rn(x1)), s2);
-                                y[j2 * 8 + k] = f.x;
-                                y[j2 * 8 + k + 1] = f.y;
-                                lmax = fmaxf(lmax, fmaxf(f.x, f.y));
-                            }
-                        } else {
-#pragma unroll
-                            for (int k = 0; k < 16; ++k) {
-                                if (j2 * 8 + k >= NSUB * 8) break;
-                                const int x = (int)a16[k] + rm - c16[k];
-                                float f = MAGIC ? __fmul_rn(__fadd_rn(__int_as_float(x), -12582912.0f), p.scale1)
-                                                : __fmul_rn(__int2float_rn(x), p.scale1);
-                                if (j2 * 8 + k >= ncols_w) f = kMasked;
-                                y[j2 * 8 + k] = f;
-                                lmax = fmaxf(lmax, f);
-                            }
-                        }
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < 16; ++k)
-                            if (j2 * 8 + k < NSUB * 8) y[j2 * 8 + k] = kMasked;
-                    }
+                        for (int k = 0; k < 8; ++k)
+                            if (!RAGGED || k < nrem) lmax = max(lmax, (int)yi[j * 8 + k]);
+                    };
+                    NQ_FOR_GROUPS(pass1)
                 }
-            };
-            if (warp_rows) {
-                pass1(std::true_type{});               // host-checked: |score - zero-point terms| < 2^22
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(sempty_bar + sb));        // scores are in registers
-            red[h * 128 + rloc] = lmax;
-            named_bar_sync(1 + q, 128);
-            const float gmax = fmaxf(fmaxf(red[rloc], red[128 + rloc]), fmaxf(red[256 + rloc], red[384 + rloc]));
-            // ---------------- pass 2: exp, row sum
-            float lsum = 0.f;
-            if (warp_rows) {
-                const float l2e = 1.44269502162933349609375f;
-                const float m2 = __fmul_rn(gmax, l2e);
-                // four partial sums (columns k & 3) as two packed accumulators: same additions, same order
-                float2 s01 = make_float2(0.f, 0.f), s23 = make_float2(0.f, 0.f);
-                const float2 l2e2 = make_float2(l2e, l2e), nm2 = make_float2(-m2, -m2);
-#pragma unroll
-                for (int j = 0; j < NSUB; ++j) {
-                    if (j * 8 < ncols_w) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(sempty_bar + sb));    // scores are in registers
+                if (active) {
+                    // ---------------- pass 2: e = 2^((x - max) * c): x - max in (-2^23, 0] enters the float domain
+                    // exactly as (2^24 - 1 + (x - max)) - (2^24 - 1)
+                    const int bias = 0x4B7FFFFF - lmax;
+                    float2 s01 = make_float2(0.f, 0.f), s23 = make_float2(0.f, 0.f);
+                    auto pass2 = [&](int j, auto ragged_tag) {
+                        constexpr bool RAGGED = decltype(ragged_tag)::value;
 #pragma unroll
                         for (int k = 0; k < 8; k += 2) {
-                            const float2 a = __ffma2_rn(make_float2(y[j * 8 + k], y[j * 8 + k + 1]), l2e2, nm2);
-                            float2 e;
-                            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(a.x));
-                            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(a.y));
+                            float2 a = make_float2(__int_as_float((int)yi[j * 8 + k] + bias), __int_as_float((int)yi[j * 8 + k + 1] + bias));
+                            a = __fmul2_rn(__fadd2_rn(a, make_float2(-16777215.0f, -16777215.0f)), c2);
+                            float2 e = make_float2(ex2_fast(a.x), ex2_fast(a.y));
+                            if (RAGGED) {
+                                e.x = k < nrem ? e.x : 0.f;
+                                e.y = k + 1 < nrem ? e.y : 0.f;
+                            }
                             y[j * 8 + k] = e.x;
                             y[j * 8 + k + 1] = e.y;
                             if ((k & 3) == 0) s01 = __fadd2_rn(s01, e);
                             else s23 = __fadd2_rn(s23, e);
                         }
-                    }
+                    };
+                    NQ_FOR_GROUPS(pass2)
+                    lsum = __fadd_rn(__fadd_rn(s01.x, s01.y), __fadd_rn(s23.x, s23.y));
                 }
-                lsum = __fadd_rn(__fadd_rn(s01.x, s01.y), __fadd_rn(s23.x, s23.y));
-            }
-            red[512 + h * 128 + rloc] = lsum;
-            named_bar_sync(1 + q, 128);
-            const float gsum = __fadd_rn(__fadd_rn(red[512 + rloc], red[640 + rloc]), __fadd_rn(red[768 + rloc], red[896 + rloc]));
-            // ---------------- the second MMA of the previous tile has finished reading the P tile (long ago: it was
-            // issued before this tile's pass 1); from here on P(i) may overwrite it
-            if (li > 0) {
-                mbar_wait(smem_u32(ofull_bar), (li - 1) & 1u);
-                tc_fence_after();
-            }
-            // ---------------- pass 3: codes of P straight into shared memory: K-major, 128-byte swizzle
-            // (row r, 16-byte chunk ^ (r & 7)), i.e. the layout TMA would have produced for an A operand
-            int qsum = 0;
-            if (warp_rows) {
-                const float kr = __frcp_rn(__fmul_rn(gsum, p.qp.scale));
-                const Quantizer qzp(p.qp);
-                auto emit_group = [&](int j, auto ragged_tag) {
-                    constexpr bool RAGGED = decltype(ragged_tag)::value;
-                    int c[8];
-                    const float2 kr2 = make_float2(kr, kr), mg2 = make_float2(qzp.magic, qzp.magic);
+                // ---------------- the four warps of this row meet once: (max, sum) of each column group
+                redp[h] = (uint32_t)lmax;
+                redp[4 + h] = __float_as_uint(lsum);
+                named_bar_sync(1 + q, 128);
+                // ---------------- the second MMA of the previous tile has finished reading the P tile
+                if (li > 0) {
+                    mbar_wait(smem_u32(ofull_bar), (li - 1) & 1u);
+                    tc_fence_after();
+                }
+                if (active) {
+                    const int4 mx4 = *reinterpret_cast<const int4*>(redp);
+                    const float4 sm4 = *reinterpret_cast<const float4*>(redp + 4);
+                    const int gmax = max(max(mx4.x, mx4.y), max(mx4.z, mx4.w));
+                    // weight of a group's partial sum: 2^((max_h - gmax) * c); a group without columns has sum 0 and a huge
+                    // negative difference (clamped so that the int -> float conversion stays finite)
+                    const float w0 = ex2_fast(__fmul_rn(__int2float_rn(max(mx4.x - gmax, -(1 << 24))), p.c_exp));
+                    const float w1 = ex2_fast(__fmul_rn(__int2float_rn(max(mx4.y - gmax, -(1 << 24))), p.c_exp));
+                    const float w2 = ex2_fast(__fmul_rn(__int2float_rn(max(mx4.z - gmax, -(1 << 24))), p.c_exp));
+                    const float w3 = ex2_fast(__fmul_rn(__int2float_rn(max(mx4.w - gmax, -(1 << 24))), p.c_exp));
+                    const float gsum = __fadd_rn(__fadd_rn(__fmul_rn(sm4.x, w0), __fmul_rn(sm4.y, w1)),
+                                                 __fadd_rn(__fmul_rn(sm4.z, w2), __fmul_rn(sm4.w, w3)));
+                    const float wown = h == 0 ? w0 : (h == 1 ? w1 : (h == 2 ? w2 : w3));
+                    // p / s_p = e * w / (sum * s_p)
+                    const float kr = __fmul_rn(wown, __frcp_rn(__fmul_rn(gsum, p.p_scale)));
+                    const float2 kr2 = make_float2(kr, kr), mg2 = make_float2(p.p_magic, p.p_magic);
+                    // ---------------- pass 3: bytes of P (code - lo) straight into the swizzled shared-memory tile
+                    auto pass3 = [&](int j, auto ragged_tag) {
+                        constexpr bool RAGGED = decltype(ragged_tag)::value;
+                        int n[8];
 #pragma unroll
-                    for (int k = 0; k < 8; k += 2) {
-                        const float2 e = make_float2(y[j * 8 + k], y[j * 8 + k + 1]);
-                        if (p.sm_noclamp) {
-                            const float2 r = __ffma2_rn(e, kr2, mg2);
-                            c[k] = __float_as_int(fminf(r.x, p.sm_top));
-                            c[k + 1] = __float_as_int(fminf(r.y, p.sm_top));
-                        } else {
-                            const float2 t = __fmul2_rn(e, kr2);
-                            const float2 r = __fadd2_rn(make_float2(fminf(fmaxf(t.x, qzp.tlo), qzp.thi), fminf(fmaxf(t.y, qzp.tlo), qzp.thi)), mg2);
-                            c[k] = __float_as_int(r.x);
-                            c[k + 1] = __float_as_int(r.y);
+                        for (int k = 0; k < 8; k += 2) {
+                            const float2 r = __ffma2_rn(make_float2(y[j * 8 + k], y[j * 8 + k + 1]), kr2, mg2);
+                            n[k] = __float_as_int(r.x) - 0x4B400000;
+                            n[k + 1] = __float_as_int(r.y) - 0x4B400000;
                         }
+                        if (!p.p_bits8) {
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) n[k] = min(n[k], p.p_top);
+                        }
+                        uint32_t w0b = pack_sat_u8(n[0], n[1], n[2], n[3]), w1b = pack_sat_u8(n[4], n[5], n[6], n[7]);
                         if (RAGGED) {
-                            c[k] = (k < nrem) ? c[k] : 0;
-                            c[k + 1] = (k + 1 < nrem) ? c[k + 1] : 0;
+                            w0b &= rmask0;
+                            w1b &= rmask1;
+                        }
+                        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(paddr[j]), "r"(w0b), "r"(w1b) : "memory");
+                    };
+                    NQ_FOR_GROUPS(pass3)
+                    if (p.p_dump) {
+                        // test hook (off the hot path): copy this row's bytes from the tile to global memory
+                        const int m = ti.m0 + rloc;
+                        if (m >= ti.mlo && m < S) {
+                            __syncwarp();
+                            auto dump = [&](int j, auto) {
+                                uint32_t a0, a1;
+                                asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(a0), "=r"(a1) : "r"(paddr[j]) : "memory");
+                                *reinterpret_cast<uint2*>(p.p_dump + ((int64_t)hd * S + m) * p.ld_dump + col0 + j * 8) = make_uint2(a0, a1);
+                            };
+                            NQ_FOR_GROUPS(dump)
                         }
                     }
-                    int w0 = pack4_codes(c[0], c[1], c[2], c[3]), w1 = pack4_codes(c[4], c[5], c[6], c[7]);
-                    if (!row_ok) w0 = w1 = 0;                             // rows past S: zeros (their outputs are never stored)
-                    qsum = __dp4a(w0, 0x01010101, __dp4a(w1, 0x01010101, qsum));
-                    const int cc0 = col0 + j * 8, kb = cc0 >> 7, cc = cc0 & 127;
-                    uint8_t* dst = smem_p + kb * (BM * BK) + rloc * 128 + ((((cc >> 4) ^ (rloc & 7)) << 4) | (cc & 15));
-                    *reinterpret_cast<int2*>(dst) = make_int2(w0, w1);
-                };
-#pragma unroll
-                for (int j = 0; j < NSUB; ++j) {
-                    if (j < nfull) emit_group(j, std::false_type{});
-                    else if (j == nfull && nrem > 0) emit_group(j, std::true_type{});
                 }
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA
-            __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(pfull_bar));
-            redq[h * 128 + rloc] = qsum;
-            named_bar_sync(1 + q, 128);
-            if (h == 0) {
-                // row sums of P(i) -> the context warps (double-buffered by tile parity)
-                rsbuf[(li & 1) * 128 + rloc] = (redq[rloc] + redq[128 + rloc]) + (redq[256 + rloc] + redq[384 + rloc]);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA
                 __syncwarp();
-                if (lane == 0) mbar_arrive(smem_u32(rs_bar + (li & 1)));
+                if (lane == 0) mbar_arrive(smem_u32(pfull_bar));
             }
         }
+#undef NQ_FOR_GROUPS
     }
 
     tc_fence_before();
@@ -499,6 +553,19 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
     }
+}
+
+// int8 split of a zero-point term c = c1 + c2, |c1|, |c2| <= 127 (c2 == 0 whenever c itself fits)
+static bool split_i8(int64_t c, int out[2]) {
+    if (c < -254 || c > 254) return false;
+    if (c >= -127 && c <= 127) {
+        out[0] = (int)c;
+        out[1] = 0;
+    } else {
+        out[0] = c > 0 ? 127 : -127;
+        out[1] = (int)c - out[0];
+    }
+    return true;
 }
 
 }  // namespace attn
@@ -517,52 +584,72 @@ extern "C" int nq_attention_s8(const int8_t* Q, const int8_t* Kt, const int8_t* 
     NQ_REQUIRE(((uintptr_t)Q % 16 == 0) && ((uintptr_t)Kt % 16 == 0) && ((uintptr_t)Vt % 16 == 0) && ((uintptr_t)a->out % 16 == 0),
                "nq_attention_s8: operands must be 16-byte aligned");
     NQ_REQUIRE(a->p_bits >= 2 && a->p_bits <= 8 && a->out_bits >= 2 && a->out_bits <= 8, "nq_attention_s8: bit widths outside 2..8");
-    NQ_REQUIRE(!a->has_zk || a->rowsum_q, "nq_attention_s8: rowsum_q required when K is asymmetric");
-    NQ_REQUIRE(!a->has_zq || a->colsum_k, "nq_attention_s8: colsum_k required when Q is asymmetric");
-    NQ_REQUIRE(!a->has_p_zp || a->colsum_v, "nq_attention_s8: colsum_v required when P is asymmetric");
-    NQ_REQUIRE(BH * ((S + 127) / 128) < (1ll << 31), "nq_attention_s8: too many tiles");
+    NQ_REQUIRE(BH < (1ll << 30), "nq_attention_s8: too many heads");
+    NQ_REQUIRE((H * D) % 16 == 0, "nq_attention_s8: H * D must be a multiple of 16 (16-byte stores of the merged heads)");
     attn::Params p{};
     p.BH = BH; p.S = S; p.D = D; p.H = H;
-    p.scale1 = a->scale_qk;
+    float scale1 = a->scale_qk;
     if (a->has_div) {
         NQ_REQUIRE(a->div > 0.f && isfinite(a->div), "nq_attention_s8: divisor must be positive and finite");
-        p.scale1 = a->scale_qk / a->div;
+        scale1 = a->scale_qk / a->div;
     }
-    NQ_REQUIRE(p.scale1 > 1e-30f && p.scale1 < 1e30f, "nq_attention_s8: scale / divisor out of range");
-    p.rowsum_q = a->rowsum_q; p.colsum_k = a->colsum_k;
-    p.zq = a->has_zq ? (int)a->zq : 0; p.zk = a->has_zk ? (int)a->zk : 0;
-    p.use_row1 = a->has_zk; p.use_col1 = a->has_zq;
-    p.kterm1 = (a->has_zq && a->has_zk) ? (int64_t)a->zq * a->zk * D : 0;
+    NQ_REQUIRE(scale1 > 1e-30f && scale1 < 1e30f, "nq_attention_s8: scale / divisor out of range");
+    p.c_exp = (float)((double)scale1 * 1.4426950408889634);
+    const int64_t zq = a->has_zq ? a->zq : 0, zv = a->has_zv ? a->zv : 0;
+    const int64_t p_lo = -(1ll << (a->p_bits - 1)), p_hi = (1ll << (a->p_bits - 1)) - 1;
+    const int64_t zp_p = a->has_p_zp ? a->p_zp : 0;
+    NQ_REQUIRE(attn::split_i8(-zq, p.cq), "nq_attention_s8: |zq| must be <= 254 (zero-point term as int8 constant passes)");
+    NQ_REQUIRE(attn::split_i8(p_lo - zp_p, p.cp), "nq_attention_s8: lo_p - zp_p must lie in [-254, 254] (zp_p=%lld)", (long long)zp_p);
+    NQ_REQUIRE(attn::split_i8(-zv, p.cv), "nq_attention_s8: |zv| must be <= 254");
     {
-        const long double zq = p.zq, zk = p.zk;
-        const long double ra = fmaxl(fabsl(-128.0L - zq), fabsl(127.0L - zq)), rb = fmaxl(fabsl(-128.0L - zk), fabsl(127.0L - zk));
-        NQ_REQUIRE(ra * rb * (long double)D < 2147483000.0L, "nq_attention_s8: score zero-point terms exceed int32");
-        p.fast22 = (ra * rb * (long double)D) < 4194304.0L;
-        NQ_REQUIRE(p.fast22, "nq_attention_s8: max|q - zq| * max|k - zk| * D must stay below 2^22 (zero-points outside the int8 range?)");
+        // integer scores x = sum_d (q - zq) k: the row-constant zk * rowsum(Q) term is dropped (softmax shift invariance),
+        // so |x| <= max|q - zq| * 128 * D; x - max(x) must stay inside (-2^23, 0] for the exact float conversion
+        const long double ra = fmaxl(fabsl(-128.0L - (long double)zq), fabsl(127.0L - (long double)zq));
+        NQ_REQUIRE(ra * 128.0L * (long double)D < 4194304.0L, "nq_attention_s8: max|q - zq| * 128 * D must stay below 2^22");
     }
-    int qmode;
-    p.qp = make_qargs(a->p_bits, a->p_scale, a->has_p_zp, a->p_zp, &qmode);
-    NQ_REQUIRE(qmode != 2, "nq_attention_s8: |p_zp| must be < 2^20");
-    {
-        // probabilities lie in [0, 1]: with zp >= lo the quotient p / s + zp never needs the lower clamp and rounds
-        // straight out of one FMA with the magic constant; the upper clamp is a min in that domain, and vanishes
-        // (huge bound) when even p = 1 maps inside the code range
-        const double top = (double)p.qp.zpf + 1.0 / (double)p.qp.scale * (1.0 + 1e-6);
-        p.sm_noclamp = (double)p.qp.zpf >= (double)p.qp.lo;
-        p.sm_top = (top < (double)p.qp.hi + 0.49) ? 3.0e38f : 12582912.0f + p.qp.hi;
-    }
+    NQ_REQUIRE(a->p_scale >= 1e-6f && a->p_scale < 1e30f, "nq_attention_s8: p_scale out of range (1 / p_scale must stay below 2^20)");
+    p.p_scale = a->p_scale;
+    p.p_magic = (float)(12582912.0 + (double)(zp_p - p_lo));
+    p.p_top = (int)(p_hi - p_lo);
+    p.p_bits8 = a->p_bits == 8;
+    p.p_dump = a->p_dump;
+    p.ld_dump = a->ld_p_dump;
+    NQ_REQUIRE(!a->p_dump || (a->ld_p_dump >= ((S + 7) / 8) * 8 && a->ld_p_dump % 8 == 0 && (uintptr_t)a->p_dump % 8 == 0),
+               "nq_attention_s8: p_dump rows must be 8-byte aligned and hold round_up(S, 8) bytes");
     p.scale2 = a->scale_pv;
-    p.colsum_v = a->colsum_v;
-    p.zp_p = a->has_p_zp ? (int)a->p_zp : 0; p.zv = a->has_zv ? (int)a->zv : 0;
-    p.use_row2 = a->has_zv; p.use_col2 = a->has_p_zp;
-    p.kterm2 = (a->has_p_zp && a->has_zv) ? (int64_t)a->p_zp * a->zv * S : 0;
     {
-        const long double zp = p.zp_p, zv = p.zv;
-        const long double ra = fmaxl(fabsl(-128.0L - zp), fabsl(127.0L - zp)), rb = fmaxl(fabsl(-128.0L - zv), fabsl(127.0L - zv));
-        NQ_REQUIRE(ra * rb * (long double)S <= 16777216.0L, "nq_attention_s8: context accumulator exceeds 2^24 (exact float window)");
+        // context accumulator  sum_k (code_k - zp_p)(v_k - zv):  sum_k (code_k - zp_p) <= 1 / s_p + S * (1.5 + max(lo_p - zp_p, 0))
+        // (probabilities sum to 1; each code rounds up by at most 0.5 or is clamped up to lo_p; generous slack)
+        const long double cpv = (long double)(p_lo - zp_p);
+        const long double sum_p = (1.0L / (long double)a->p_scale) * 1.001L + (long double)S * (1.5L + fabsl(cpv));
+        const long double rv = fmaxl(fabsl(-128.0L - (long double)zv), fabsl(127.0L - (long double)zv));
+        const long double bound = sum_p * rv;
+        NQ_REQUIRE(bound < 16777216.0L, "nq_attention_s8: context accumulator may exceed 2^24 (exact float window)");
+        p.ctx_magic = bound < 4194304.0L;
+        p.ctx_bias = (int)(-(p_lo - zp_p) * zv * S);
+        // quotient fed to the rounding add must stay far inside 2^22
+        // residual-corrected division: exact while nothing under / overflows near the rounding boundaries (|t| >= 0.5)
+        NQ_REQUIRE(a->out_scale > 1e-12f && a->out_scale < 1e12f && a->scale_pv > 1e-20f && a->scale_pv < 1e12f,
+                   "nq_attention_s8: scales out of the safe window of the residual-corrected division");
+        NQ_REQUIRE((double)bound * (double)a->scale_pv / (double)a->out_scale < 2097152.0,
+                   "nq_attention_s8: context / out_scale out of range");
     }
-    p.qo = make_qargs(a->out_bits, a->out_scale, a->has_out_zp, a->out_zp, &qmode);
-    NQ_REQUIRE(qmode != 2, "nq_attention_s8: |out_zp| must be < 2^20");
+    const int64_t o_lo = -(1ll << (a->out_bits - 1)), o_hi = (1ll << (a->out_bits - 1)) - 1;
+    const int64_t zo = a->has_out_zp ? a->out_zp : 0;
+    NQ_REQUIRE(zo > -(1 << 20) && zo < (1 << 20), "nq_attention_s8: |out_zp| must be < 2^20");
+    p.o_scale = a->out_scale;
+    p.o_rcp = 1.0f / a->out_scale;                                        // IEEE-rounded reciprocal (host division)
+    p.o_magic = (float)(12582912.0 + (double)zo);
+    p.o_lo = (int)o_lo; p.o_hi = (int)o_hi;
+    p.o_bits8 = a->out_bits == 8;
+    {
+        // One residual correction rounds the quotient correctly unless the divisor's significand is all ones
+        // (Markstein); the second correction is kept for that class and on request (NQ_ATTN_DIV1 unset: always two).
+        uint32_t bits;
+        memcpy(&bits, &a->out_scale, 4);
+        static const bool single = getenv("NQ_ATTN_DIV1") != nullptr;
+        p.o_div2 = !single || (bits & 0x007fffffu) == 0x007fffffu;
+    }
     p.C = a->out;
     p.o_rowsum = a->out_rowsum;
     cudaStream_t s = (cudaStream_t)stream;
@@ -574,14 +661,9 @@ extern "C" int nq_attention_s8(const int8_t* Q, const int8_t* Kt, const int8_t* 
     if (int rc = make_operand_map(&tq, Q, D, S, BH, ld_q, S * ld_q, BM)) return rc;
     if (int rc = make_operand_map(&tk, Kt, D, S, BH, ld_k, S * ld_k, attn::BN1)) return rc;
     if (int rc = make_operand_map(&tv, Vt, S, D, BH, ld_v, D * ld_v, attn::BN2)) return rc;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(attn::attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::SMEM_BYTES);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(attn)");
-        configured = true;
-    }
-    const int64_t tiles = BH * ((S + BM - 1) / BM);
-    const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
+    static bool configured[64] = {false};                                 // per device
+    if (int rc = configure_smem_once(configured, attn::attn_kernel, attn::SMEM_BYTES, "cudaFuncSetAttribute(attn)")) return rc;
+    const int grid = (int)(BH < sm_count() ? BH : sm_count());
     attn::attn_kernel<<<grid, attn::NUM_THREADS, attn::SMEM_BYTES, s>>>(tq, tk, tv, p);
     NQ_CHECK_LAUNCH("nq_attention_s8");
     return NQ_OK;

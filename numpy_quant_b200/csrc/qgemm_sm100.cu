@@ -1143,12 +1143,8 @@ static int make_conv_maps(CUtensorMap* ta, CUtensorMap* tb, const int8_t* X, con
 template <int BN, int EMODE, bool TWO>
 static int launch_qgemm_impl(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t s) {
     using C = Cfg<BN, (EMODE == EM_DEQ_WIDE || EMODE == EM_DEQ_WIDE_RES), TWO>;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(qgemm_kernel<BN, EMODE, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(qgemm)");
-        configured = true;
-    }
+    static bool configured[64] = {false};                                 // per device (cudaFuncSetAttribute is per device)
+    if (int rc = configure_smem_once(configured, qgemm_kernel<BN, EMODE, TWO>, C::SMEM_BYTES, "cudaFuncSetAttribute(qgemm)")) return rc;
     constexpr int BMT = TWO ? 2 * BM : BM;
     const int64_t tiles = ((p.M + BMT - 1) / BMT) * ((p.N + BN - 1) / BN) * p.batch;
     if constexpr (TWO) {

@@ -47,12 +47,13 @@ __global__ void __launch_bounds__(256) quantize_scalar_kernel(const float* __res
 
 // wide symmetric/asymmetric quantize to int64 codes (4*bit_width-bit biases, model.py:383-389, 405-410)
 __global__ void quantize_i64_kernel(const float* __restrict__ x, int64_t n, float scale, int has_zp, double zp,
-                                    float lo, float hi, int64_t* __restrict__ out) {
+                                    float lo, float hi, double dlo, double dhi, int64_t* __restrict__ out) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         float t = __fdiv_rn(x[i], scale);
         if (has_zp) {
-            double u = fmin(fmax(zp + (double)t, (double)lo), (double)hi);
+            // int64 zero-point + float32 quotient -> float64 (NEP 50); np.clip keeps the float64 bounds exact
+            double u = fmin(fmax(zp + (double)t, dlo), dhi);
             out[i] = __double2ll_rn(u);
         } else {
             t = fminf(fmaxf(t, lo), hi);          // lo/hi already rounded to float32 like np.clip does
@@ -511,11 +512,11 @@ extern "C" int nq_quantize_f32_i64(const float* x, int64_t n, int bit_width, flo
     if (n <= 0) return NQ_OK;
     // np.clip converts the Python-float bounds to the array dtype: float32 when symmetric
     // (2^31-1 rounds to 2^31), float64 when the zero-point add promoted the data.
-    NQ_REQUIRE(!has_zp, "nq_quantize_f32_i64: asymmetric wide quantization is not used by the reference path");
-    (void)zp;
+    // (float64 when the int64 zero-point add promoted the data: the asymmetric branch of the kernel)
+    NQ_REQUIRE(!has_zp || (zp > -(1ll << 52) && zp < (1ll << 52)), "nq_quantize_f32_i64: |zero_point| must be < 2^52");
     const double dlo = -ldexp(1.0, bit_width - 1), dhi = ldexp(1.0, bit_width - 1) - 1.0;
-    quantize_i64_kernel<<<stream_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(x, n, scale, 0, 0.0, (float)dlo,
-                                                                              (float)dhi, out);
+    quantize_i64_kernel<<<stream_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(x, n, scale, has_zp ? 1 : 0, has_zp ? (double)zp : 0.0,
+                                                                              (float)dlo, (float)dhi, dlo, dhi, out);
     NQ_CHECK_LAUNCH("nq_quantize_f32_i64");
     return NQ_OK;
 }

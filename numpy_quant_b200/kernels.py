@@ -56,12 +56,13 @@ def quantize(x: torch.Tensor, bits: int, scale, zp) -> torch.Tensor:
     return out
 
 
-def quantize_i64(x: torch.Tensor, bits: int, scale) -> torch.Tensor:
-    """Symmetric wide quantize (4*bit_width-bit biases) -> int64 codes."""
+def quantize_i64(x: torch.Tensor, bits: int, scale, zp=None) -> torch.Tensor:
+    """Wide quantize (4*bit_width-bit biases; 9..32 bit codes) -> int64 codes; `zp` as in numpy_quantization.py:24-34."""
     _need_cuda(x, torch.float32)
     x = materialize(x)
     out = torch.empty(x.shape, dtype=torch.int64, device=x.device)
-    call("nq_quantize_f32_i64", x.data_ptr(), x.numel(), bits, float(scale), 0, 0, out.data_ptr(), _stream())
+    call("nq_quantize_f32_i64", x.data_ptr(), x.numel(), bits, float(scale), int(zp is not None), 0 if zp is None else int(zp),
+         out.data_ptr(), _stream())
     _count()
     return out
 
@@ -445,21 +446,24 @@ def can_fuse_attention(q: Operand, k: Operand, v: Operand) -> bool:
 
 
 def can_fuse_attention_qk(q: Operand, k: Operand, zq=None, zk=None) -> bool:
-    """The part of `can_fuse_attention` that is known at the score MatMul (V has the same S and D).  zq / zk: the
-    operands' zero-points -- the kernel converts the corrected scores with the 2^22 magic-constant route, which needs
-    max|q - zq| * max|k - zk| * D < 2^22 (true for any zero-point inside the int8 range at D <= 64)."""
+    """The part of `can_fuse_attention` that is known at the score MatMul (V has the same S and D).  zq: the kernel
+    folds -zq * colsum(K) into the score MMA as int8 constant passes (|zq| <= 254) and converts x - max(x) exactly,
+    which needs max|q - zq| * 128 * D < 2^22 (true for any zero-point inside the int8 range at D <= 64); the zk term is
+    constant along a row and cancels in the softmax."""
     if not (q.batch == k.batch and q.rows == k.rows and q.k == k.k and q.rows <= 208 and q.k <= 64 and q.k % 16 == 0
             and len(q.batch_shape) == 2):
         return False
-    ra = max(abs(-128 - int(zq or 0)), abs(127 - int(zq or 0)))
-    rb = max(abs(-128 - int(zk or 0)), abs(127 - int(zk or 0)))
-    return ra * rb * q.k < (1 << 22)
+    z = int(zq or 0)
+    ra = max(abs(-128 - z), abs(127 - z))
+    return abs(z) <= 254 and ra * 128 * q.k < (1 << 22)
 
 
 def attention(q: Operand, k: Operand, v: Operand, scale_qk: float, zq, zk, div_c, p_bits: int, p_scale, p_zp,
-              scale_pv: float, zv, out_bits: int, out_scale, out_zp, want_rowsum: bool) -> Operand:
+              scale_pv: float, zv, out_bits: int, out_scale, out_zp, want_rowsum: bool, dump_p: bool = False):
     """softmax(Q.K^T / c) . V for every (image, head) in one kernel (nq_attention_s8); returns the int8 left
-    operand [1, B*S, H*D] of the output projection (merge heads), plus its row sums on request."""
+    operand [1, B*S, H*D] of the output projection (merge heads), plus its row sums on request.  The zero-point
+    terms of both MatMuls are accumulated by the tensor core (no row / column sums needed).  dump_p=True additionally
+    returns the emitted P codes as an int8 tensor [B*H, S, S] (test hook: unsigned bytes code - lo, converted back)."""
     assert can_fuse_attention(q, k, v)
     B, H = (int(x) for x in q.batch_shape)
     S, D = q.rows, q.k
@@ -471,28 +475,21 @@ def attention(q: Operand, k: Operand, v: Operand, scale_qk: float, zq, zk, div_c
     a.has_div, a.div = int(div_c is not None), 1.0 if div_c is None else float(div_c)
     a.has_zq, a.zq = int(zq is not None), 0 if zq is None else int(zq)
     a.has_zk, a.zk = int(zk is not None), 0 if zk is None else int(zk)
-    if zk is not None:
-        if q.rowsum is None:
-            q.rowsum = rowsum(q)
-        a.rowsum_q = q.rowsum.data_ptr()
-    if zq is not None:
-        if k.rowsum is None:
-            k.rowsum = rowsum(k)
-        a.colsum_k = k.rowsum.data_ptr()
     a.p_bits, a.p_scale = int(p_bits), float(p_scale)
     a.has_p_zp, a.p_zp = int(p_zp is not None), 0 if p_zp is None else int(p_zp)
     a.scale_pv = float(scale_pv)
     a.has_zv, a.zv = int(zv is not None), 0 if zv is None else int(zv)
-    if p_zp is not None:
-        if v.rowsum is None:
-            v.rowsum = rowsum(v)
-        a.colsum_v = v.rowsum.data_ptr()
     a.out_bits, a.out_scale = int(out_bits), float(out_scale)
     a.has_out_zp, a.out_zp = int(out_zp is not None), 0 if out_zp is None else int(out_zp)
     a.out = out.data_ptr()
     if want_rowsum:
         res.rowsum = torch.empty((1, B * S), dtype=torch.int32, device=dev)
         a.out_rowsum = res.rowsum.data_ptr()
+    pd = None
+    if dump_p:
+        ldp = round_up(S, 8)
+        pd = torch.zeros((B * H, S, ldp), dtype=torch.uint8, device=dev)
+        a.p_dump, a.ld_p_dump = pd.data_ptr(), ldp
     timer = GEMM_TIMER
     if timer is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -503,6 +500,9 @@ def attention(q: Operand, k: Operand, v: Operand, scale_qk: float, zq, zk, div_c
         e1.record()
         timer.append((4 * B * H * S * S * D, e0, e1, "attention"))
     _count()
+    if dump_p:
+        lo = -(1 << (int(p_bits) - 1))
+        return res, (pd[:, :, :S].to(torch.int16) + lo).to(torch.int8)
     return res
 
 

@@ -17,7 +17,7 @@ from typing import Any, List, Optional, Union
 import numpy as np
 import torch
 
-from . import kernels as K
+from . import _lib, kernels as K
 from . import onnx_lite
 from .numpy_quantization import quant_parameters
 from .tensor import (FTensor, ITensor, QTensor, Tensor, concat, fconv2d, qconv2d, qtensor_from_operand, quantize_tensor_nhwc,
@@ -1092,11 +1092,19 @@ class QModel(Model):
                 outv = plan["node"][spec["reshape"]].outputs[0]
                 qp_p, qp_o = self.quant_params[smv.name], self.quant_params[outv.name]
                 t0 = tick()
-                qctx = rec["scores"].attention_into_operand(rec["c"], rec["v"], bits, qp_p.scale, qp_p.zero_point, qp_o.scale,
-                                                            qp_o.zero_point, self._rowsum_needed(outv))
+                try:
+                    qctx = rec["scores"].attention_into_operand(rec["c"], rec["v"], bits, qp_p.scale, qp_p.zero_point, qp_o.scale,
+                                                                qp_o.zero_point, self._rowsum_needed(outv))
+                except (_lib.NqError, ValueError):
+                    # parameters outside the fused kernel's host-checked windows (e.g. a softmax range calibrated far
+                    # from zero, huge zero-points): the pending score GEMM is still alive -- two-GEMM route
+                    qctx = self._attention_unfused(rec, smv, outv, qp_p, qp_o, bits)
                 tock("MatMul", t0)
-                qcache[(outv.name, "A")] = qctx
-                dyn_skip.add(spec["reshape"])
+                if isinstance(qctx, QTensor):
+                    qcache[(outv.name, "A")] = qctx
+                    stash[spec["reshape"]] = None
+                else:
+                    stash[spec["reshape"]] = qctx                # float32 context [B, S, H*D]: quantized by its consumer
                 outputs_data = [None]
             elif node.op == "Constant" and out0.data is not None:
                 outputs_data = [out0.data]                      # immutable: uploaded once, reused
@@ -1251,6 +1259,31 @@ class QModel(Model):
                     i.data = None
                     qcache.pop((i.name, "A"), None)
                     qcache.pop((i.name, "B"), None)
+
+    def _attention_unfused(self, rec: dict, smv: Value, outv: Value, qp_p, qp_o, bits: int):
+        """The attention block without nq_attention_s8, from the pending score GEMM: softmax in the score GEMM's epilogue
+        (or the separate softmax -> quantize kernel), P.V as its own GEMM, merge heads + quantize in its epilogue (or as
+        float32 when even that does not apply).  Returns the [B, S, H*D] QTensor operand or an FTensor."""
+        scores, c, v = rec["scores"], rec["c"], rec["v"]
+        qP = scores.softmax_into_operand(c, bits, qp_p.scale, qp_p.zero_point, True) if self.fuse_softmax_epilogue else None
+        if qP is None:
+            xt = scores.dequantize().device_tensor
+            if K.can_fuse_softmax_quantize(xt):
+                op = K.softmax_quantize(xt, c, bits, float(qp_p.scale), _zp_int(qp_p.zero_point), True)
+                qP = qtensor_from_operand(op, "A", tuple(xt.shape), bits, qp_p.scale, qp_p.zero_point)
+            else:
+                qP = quantize_tensor(FTensor(K.softmax_div_lastdim(xt, c)), bits, qp_p.scale, qp_p.zero_point, role="A",
+                                     want_rowsum=True)
+        acc = qP.matmul(v)
+        B, H, S, D = (int(x) for x in acc.shape)
+        q = acc.quantize_into_operand(None, bits, qp_o.scale, qp_o.zero_point, "merge_heads", H, S, self._rowsum_needed(outv),
+                                      "A", (B, S, H * D))
+        if q is not None:
+            return q
+        ctx = acc.dequantize_heads_last()
+        if ctx is None:
+            ctx = FTensor(K.materialize(acc.dequantize().device_tensor.permute(0, 2, 1, 3)))
+        return FTensor(ctx.device_tensor.reshape(B, S, H * D))
 
     def _emit_split_heads(self, acc: QTensor, bias: FTensor, spec: dict, qcache: dict) -> bool:
         """bias Add -> Reshape -> Transpose -> MatMul operand, inside the GEMM epilogue."""

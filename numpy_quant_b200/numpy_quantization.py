@@ -51,8 +51,10 @@ def quantize(data, bit_width: int, scale, zero_point):
     """float32 -> integer codes (reference numpy_quantization.py:24-34)."""
     from . import kernels as K
     t, was_host = _dev(np.asarray(data, dtype=np.float32) if not hasattr(data, "is_cuda") else data)
+    if not 2 <= int(bit_width) <= 32:
+        raise ValueError("quantize: bit_width must be in 2..32 on the B200 path")
     if bit_width > 8:
-        q = K.quantize_i64(t, bit_width, float(scale))
+        q = K.quantize_i64(t, bit_width, float(scale), _zp_int(zero_point))
     else:
         q = K.quantize(t, bit_width, float(scale), _zp_int(zero_point))
     return q.cpu().numpy().astype(np.int64) if was_host else q
@@ -75,6 +77,11 @@ def q_matmul(arr_a, scale_a, zero_point_a, arr_b, scale_b, zero_point_b):
     """Exact integer matmul + zero-point bookkeeping (reference numpy_quantization.py:44-61).
     Returns (acc int64, scale float32, zero_point int64 array | None) for host inputs."""
     from .tensor import QTensor
+    for name, arr in (("arr_a", arr_a), ("arr_b", arr_b)):
+        h = np.asarray(arr)
+        if h.size and (h.min() < -128 or h.max() > 127):
+            raise ValueError(f"q_matmul: {name} holds codes outside the int8 range (the tensor-core path contracts "
+                             "2..8-bit operands; the reference's NumPy int64 matmul has no such limit)")
     a = QTensor(np.asarray(arr_a, dtype=np.int64), 8, scale_a, zero_point_a)
     b = QTensor(np.asarray(arr_b, dtype=np.int64), 8, scale_b, zero_point_b)
     y = a.matmul(b)
@@ -84,6 +91,8 @@ def q_matmul(arr_a, scale_a, zero_point_a, arr_b, scale_b, zero_point_b):
 def requantize(arr, arr_scale, arr_zero_points, res_scale, res_zero_point, bit_width: int):
     """Wide accumulator -> `bit_width`-bit codes (reference numpy_quantization.py:64-72)."""
     from . import kernels as K
+    if not 2 <= int(bit_width) <= 8:
+        raise ValueError("requantize: bit_width must be in 2..8 on the B200 path (int8 code storage)")
     d = dequantize(arr, arr_scale, arr_zero_points)
     t, was_host = _dev(d)
     q = K.requantize_f32(t, bit_width, float(res_scale), _zp_int(res_zero_point))

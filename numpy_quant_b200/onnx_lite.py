@@ -354,7 +354,15 @@ def load_external_data(m: ModelProto, base_dir) -> ModelProto:
         loc = t.external_data.get("location")
         if not loc:
             raise ValueError(f"tensor {t.name!r} is EXTERNAL but names no location")
-        full = os.path.normpath(os.path.join(str(base_dir), loc))
+        # containment: `location` comes from the (untrusted) model file -- it must name a regular file inside the
+        # model's own directory (no absolute paths, no `..`, no symlinks leading elsewhere)
+        base = os.path.realpath(str(base_dir))
+        if os.path.isabs(loc) or loc.startswith(("/", "\\")):
+            raise ValueError(f"tensor {t.name!r}: absolute external-data location {loc!r} refused")
+        joined = os.path.join(base, loc)
+        full = os.path.realpath(joined)
+        if os.path.commonpath([base, full]) != base or os.path.islink(joined):
+            raise ValueError(f"tensor {t.name!r}: external-data location {loc!r} escapes the model directory")
         if full not in cache:
             with open(full, "rb") as fh:
                 cache[full] = memoryview(fh.read())

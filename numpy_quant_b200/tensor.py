@@ -481,7 +481,7 @@ class QTensor:
         projection.  Same codes as softmax_into_operand + quantize_into_operand(merge_heads)."""
         L = self._lazy
         qa, kb = L["a"], L["b"]
-        vb = v._operand("B", True)
+        vb = v._operand("B", False)
         if not K.can_fuse_attention(qa, kb, vb):
             raise ValueError("attention_into_operand: geometry not supported by the fused kernel")
         za, zk = _as_opt_int(self._zp.zp_a), _as_opt_int(self._zp.zp_b)
@@ -667,10 +667,10 @@ def quantize_tensor(tensor: FTensor, bit_width: int, scale: np.float32, zero_poi
     """tensor.py:227-229. With `role` ('A' / 'B') the codes are written directly in the
     K-major operand layout of the tensor-core GEMM (`.data` un-pads them on demand)."""
     if bit_width > 8:
-        if zero_point is not None:
-            raise ValueError("wide (> 8 bit) quantization is symmetric only")
-        return QTensor(K.quantize_i64(tensor.device_tensor, bit_width, float(scale)), bit_width, scale=scale,
-                       zero_point=None)
+        if bit_width > 32:
+            raise ValueError("bit_width must be <= 32 on the B200 path")
+        return QTensor(K.quantize_i64(tensor.device_tensor, bit_width, float(scale), _as_opt_int(zero_point)), bit_width,
+                       scale=scale, zero_point=zero_point)
     if bit_width < 2:
         raise ValueError("bit_width must be in 2..8 on the B200 path")
     zi = _as_opt_int(zero_point)

@@ -20,6 +20,8 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 REF = "/root/reference"
+# output directory: tests/golden/ by default; `python make_golden.py <dir>` writes elsewhere (the regeneration test)
+OUT = os.path.abspath(sys.argv[1]) if len(sys.argv) > 1 else HERE
 sys.path.insert(0, ROOT)
 
 from numpy_quant_b200 import onnx_lite as ol, zoo  # noqa: E402
@@ -114,7 +116,7 @@ def kernel_vectors():
     cb = rng.normal(size=2).astype(np.float32)
     out["conv_x"], out["conv_w"], out["conv_b"] = cx, cw, cb
     out["conv_y"] = fconv2d(FTensor(cx), FTensor(cw), FTensor(cb), (0, 2, 2, 1), (2, 1)).data
-    np.savez_compressed(os.path.join(HERE, "kernels.npz"), **out)
+    np.savez_compressed(os.path.join(OUT, "kernels.npz"), **out)
     print("kernels.npz", len(out), "arrays")
 
 
@@ -141,7 +143,7 @@ def ka1():
             out[f"accz_{tag}"] = np.array(0, I64) if r.zero_point is None else np.asarray(r.zero_point)
             out[f"rq_{tag}"] = r.requantize(8, ys, yz).data
             out[f"dq_{tag}"] = r.dequantize().data
-    np.savez_compressed(os.path.join(HERE, "ka1.npz"), **out)
+    np.savez_compressed(os.path.join(OUT, "ka1.npz"), **out)
     print("ka1.npz")
 
 
@@ -178,8 +180,8 @@ def dump_qmodel(prefix, out, model, qmodel, inputs, keep_values=()):
 def graphs():
     out = {}
     # ---- config 1: the reference's own models/mlp.onnx (KA-2) -------------------
-    shutil.copyfile(os.path.join(REF, "models", "mlp.onnx"), os.path.join(HERE, "mlp.onnx"))
-    proto = ol.load(os.path.join(HERE, "mlp.onnx"))
+    shutil.copyfile(os.path.join(REF, "models", "mlp.onnx"), os.path.join(OUT, "mlp.onnx"))
+    proto = ol.load(os.path.join(OUT, "mlp.onnx"))
     X = np.array([[0.5, -0.25], [-1.0, 0.75], [0.1, 0.9]], np.float32)
     out["mlp/x"] = X
     for bits in (2, 3, 4, 5, 6, 7, 8):
@@ -218,13 +220,13 @@ def graphs():
     for bits in (8, 4, 2):
         model = Model.from_onnx(vp)
         dump_qmodel(f"vit/b{bits}", out, model, model.quantize([vi], bits), [vi], keep_values=keep)
-    np.savez_compressed(os.path.join(HERE, "graphs.npz"), **out)
+    np.savez_compressed(os.path.join(OUT, "graphs.npz"), **out)
     print("graphs.npz", len(out), "arrays")
 
 
 def topology_check():
     """The zoo builder must reproduce the committed ViT-B export node for node."""
-    ref = ol.load(os.path.join(REF, "models/vit/vit_image_classifier_no_weights.onnx"))
+    ref = ol.load(os.path.join(REF, "models/vit/vit_image_classifier_no_weights.onnx"), load_external=False)   # the .data sidecar is not shipped
     mine = zoo.vit_graph()
 
     def val(a):

@@ -161,7 +161,7 @@ def test_streaming_calibration_gives_the_same_parameters():
     np.testing.assert_array_equal(ya, yb)
 
 
-@pytest.mark.parametrize("bits", [8, 4])
+@pytest.mark.parametrize("bits", [8, 4, 2])
 def test_small_vit(gv, bits):
     proto = zoo.vit_graph(seed=0, **VIT_CFG)
     x = gv["vit/x"]
@@ -189,6 +189,31 @@ def test_small_vit(gv, bits):
     assert qm.bit_width == 4 * bits
     mism = np.mean(qm.data != ref)
     assert mism < 0.02, f"query accumulator mismatch fraction {mism}"
+    # TEACHER-FORCED against the reference's own layer-0 intermediates (golden vectors of the unmodified reference):
+    # integer stages fed the reference's values must reproduce the reference's accumulators bit for bit
+    rg.run_quant(plan, [x])
+    env = plan.env
+    consts = {v.name: v.data for v in q.values if isinstance(v, Constant)}
+    ln_codes = rq.quantize(gv[f"{pre}/val_f/{ln}"], bits, *plan.qparams[ln])
+    acc_q = QTensor(ln_codes, bits, *plan.qparams[ln]).matmul(consts["onnx::MatMul_q0"])
+    np.testing.assert_array_equal(acc_q.data, ref)                                       # query accumulator: exact
+    np.testing.assert_array_equal(np.broadcast_to(acc_q.zero_point, ref.shape), gv[f"{pre}/val_qzp/{a0}/query/MatMul_output_0"])
+    qn, kn, vn, pn = (a0 + "/Transpose_1_output_0", a0 + "/Transpose_2_output_0", a0 + "/Transpose_output_0", a0 + "/Softmax_output_0")
+    qt = QTensor(rq.quantize(env[qn].a, bits, *plan.qparams[qn]), bits, *plan.qparams[qn])
+    kt = QTensor(rq.quantize(env[kn].a, bits, *plan.qparams[kn]), bits, *plan.qparams[kn])
+    sc = qt.matmul(kt)
+    np.testing.assert_array_equal(sc.data, gv[f"{pre}/val_q/{a0}/MatMul_output_0"])     # score accumulator: exact
+    np.testing.assert_array_equal(np.broadcast_to(sc.zero_point, sc.data.shape), np.broadcast_to(gv[f"{pre}/val_qzp/{a0}/MatMul_output_0"], sc.data.shape))
+    pt = QTensor(rq.quantize(gv[f"{pre}/val_f/{pn}"], bits, *plan.qparams[pn]), bits, *plan.qparams[pn])
+    vt = QTensor(rq.quantize(env[vn].a, bits, *plan.qparams[vn]), bits, *plan.qparams[vn])
+    pv = pt.matmul(vt)
+    np.testing.assert_array_equal(pv.data, gv[f"{pre}/val_q/{a0}/MatMul_1_output_0"])   # P.V accumulator: exact
+    # float glue fed the reference's values: softmax and GELU within 1e-5 of the reference's float32 results
+    np.testing.assert_allclose(sc.dequantize().div(FTensor(np.array(np.sqrt(8.0), np.float32))).softmax(axis=-1).data,
+                               gv[f"{pre}/val_f/{pn}"], rtol=1e-5, atol=1e-8)
+    gel = "/vit/encoder/layer.0/intermediate/intermediate_act_fn/Mul_1_output_0"
+    hin = FTensor(env["/vit/encoder/layer.0/intermediate/dense/Add_output_0"].a)
+    np.testing.assert_allclose(hin.gelu_erf(1.4142135381698608, 1.0, 0.5).data, gv[f"{pre}/val_f/{gel}"], rtol=1e-5, atol=1e-6)
     out_scale = float(plan.qparams["logits"][0])
     want = gv[f"{pre}/out0"]
     assert np.abs(out - want).max() <= 4 * out_scale and np.abs(out - want).mean() <= 0.5 * out_scale
@@ -238,6 +263,26 @@ def test_fused_executor_is_bit_identical_with_epilogue_quantization(bits):
     fused2 = q([x], retain=False)[0]
     assert np.abs(fused2 - want).max() <= 4 * step and np.abs(fused2 - ref).max() <= 2 * step
     np.testing.assert_array_equal(q([x], graph=True)[0], fused2)
+
+
+def test_fused_attention_falls_back_when_parameters_leave_its_window():
+    """A softmax range calibrated far from zero (near-uniform attention: min and max both ~1/S) gives a P zero-point
+    far below the code range; nq_attention_s8 refuses it (host-checked window) and the executor must take the two-GEMM
+    route instead of failing -- same bits as running with fuse_attention=False."""
+    cfg = dict(batch=3, image_size=32, patch_size=16, hidden=64, heads=4, intermediate=128, layers=2, classes=10)
+    proto = zoo.vit_graph(seed=3, **cfg)
+    x = np.random.default_rng(5).normal(size=(3, 3, 32, 32)).astype(np.float32)
+    q = Model.from_onnx(proto).quantize([x], bit_width=8)
+    names = [n.outputs[0].name for n in q.nodes if n.op == "Softmax"]
+    assert len(names) == 2
+    for n in names:
+        q.quant_params[n] = QuantizationParams(np.float32(7.8e-6), np.int64(-638))      # range ~[0.004, 0.006]
+    fused = q([x], retain=False)[0]
+    assert q._plan["attention"]
+    q.fuse_attention = False
+    two_gemm = q([x], retain=False)[0]
+    np.testing.assert_array_equal(fused, two_gemm)
+    assert np.isfinite(fused).all()
 
 
 @pytest.mark.parametrize("bits", [4, 2])

@@ -73,6 +73,30 @@ def test_onnx_lite_external_data_roundtrip(tmp_path):
         ol.load(path)
 
 
+def test_onnx_lite_external_data_stays_inside_the_model_directory(tmp_path):
+    """`location` comes from the model file: absolute paths, `..` escapes and symlinks out of the model's directory
+    are refused instead of being read into tensors."""
+    secret = tmp_path / "secret.bin"
+    secret.write_bytes(np.arange(4, dtype=np.float32).tobytes())
+    mdir = tmp_path / "model"
+    mdir.mkdir()
+    m = zoo.vit_graph(batch=1, layers=1, hidden=32, heads=4, intermediate=64, image_size=32, classes=3)
+    path = mdir / "vit.onnx"
+    ol.save(m, path, save_as_external_data=True, size_threshold=256)
+    for loc in ("../secret.bin", str(secret), "sub/../../secret.bin"):
+        bare = ol.load(path, load_external=False)
+        t = next(t for t in bare.graph.initializer if t.data_location == 1)
+        t.external_data = {"location": loc, "offset": "0", "length": "16"}
+        with pytest.raises(ValueError, match="refused|escapes"):
+            ol.load_external_data(bare, mdir)
+    (mdir / "link.data").symlink_to(secret)
+    bare = ol.load(path, load_external=False)
+    t = next(t for t in bare.graph.initializer if t.data_location == 1)
+    t.external_data = {"location": "link.data", "offset": "0", "length": "16"}
+    with pytest.raises(ValueError, match="escapes"):
+        ol.load_external_data(bare, mdir)
+
+
 def test_vit_zoo_census_matches_committed_topology():
     """SURVEY.md §3.5 census of models/vit/vit_image_classifier_no_weights.onnx."""
     from collections import Counter

@@ -183,3 +183,22 @@ def test_small_vit(gv, bits):
             a0 + "/MatMul_1_output_0", "/vit/encoder/layer.0/intermediate/intermediate_act_fn/Mul_1_output_0",
             "/vit/encoder/layer.1/output/Add_output_0", "logits"]
     _check_graph(gv, f"vit/b{bits}", plan, outs, keep=keep)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/numpy_quant"), reason="the reference checkout is only present in the build container")
+def test_golden_recipe_regenerates_the_committed_vectors(tmp_path):
+    """The committed recipe must run: tests/golden/make_golden.py imports the UNMODIFIED reference and rewrites every
+    fixture into a scratch directory; the result must equal the committed files array for array (and mlp.onnx byte
+    for byte)."""
+    import filecmp
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(G, "make_golden.py"), str(tmp_path)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    for f in ("kernels.npz", "ka1.npz", "graphs.npz"):
+        new, old = np.load(tmp_path / f), np.load(os.path.join(G, f))
+        assert sorted(new.files) == sorted(old.files), f
+        for k in new.files:
+            assert new[k].dtype == old[k].dtype and new[k].shape == old[k].shape, (f, k)
+            assert np.array_equal(new[k], old[k], equal_nan=new[k].dtype.kind == "f"), (f, k)
+    assert filecmp.cmp(tmp_path / "mlp.onnx", os.path.join(G, "mlp.onnx"), shallow=False)
