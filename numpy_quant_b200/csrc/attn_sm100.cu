@@ -83,7 +83,7 @@ constexpr int OFF_BAR = OFF_RED + RED_WORDS * 4;
 constexpr int SMEM_BYTES = OFF_BAR + BAR_BYTES;
 static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB opt-in shared memory of sm_100");
 static_assert(STAGE_BYTES % 1024 == 0 && Q_BYTES % 1024 == 0 && K_BYTES % 1024 == 0, "128-byte swizzle needs 1024-byte aligned tiles");
-constexpr int O_COL = 2 * BN1;                 // TMEM column of the context accumulator (416)
+constexpr int O_COL = 256;                     // TMEM columns of the two context accumulators (256 .. 383); scores: 0 .. 207
 constexpr int NSUB = 7;                        // 8-column groups per softmax warp (56 columns; 4 warps span 224 >= 208)
 
 // kind::i8 instruction descriptor with the operand signedness spelled out (bit 7: A signed, bit 10: B signed)
@@ -152,6 +152,9 @@ __device__ __forceinline__ float ex2_fast(float a) {
     return e;
 }
 
+// FAST8: 8-bit P and output codes and a host-proved |context accumulator| < 2^22 -- the benchmarked configuration; the
+// saturating pack instructions are then the quantizers' clamps and every int -> float step is a magic-constant add.
+template <bool FAST8>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
             const __grid_constant__ CUtensorMap tmap_v, const Params p) {
@@ -165,12 +168,17 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
     uint64_t* full_bar = bars;                 // [STAGES] TMA -> MMA (one head landed)
     uint64_t* empty_bar = bars + STAGES;       // [STAGES] last MMA of the head done with the stage
-    uint64_t* sfull_bar = bars + 2 * STAGES;   // [2] scores ready
-    uint64_t* sempty_bar = sfull_bar + 2;      // [2] scores drained into registers (16 warps)
-    uint64_t* pfull_bar = sempty_bar + 2;      // P tile written (16 warps)
-    uint64_t* ofull_bar = pfull_bar + 1;       // context accumulator ready (= second MMA done reading P)
-    uint64_t* oempty_bar = ofull_bar + 1;      // context accumulator drained (4 context warps)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(oempty_bar + 1);
+    // One score buffer is enough: the softmax warps copy it into registers at the very start of a tile (sempty), so the
+    // next tile's scores are computed while this tile's softmax runs.  The CONTEXT accumulator is double-buffered: the
+    // second MMA of tile i must not wait for the context warps to drain tile i - 1 -- with a single buffer the chain
+    // drain(i-1) -> MMA(i) -> P tile free -> softmax pass 3 (i+1) set the tile period (measured: the softmax warps
+    // spent a quarter of their instructions polling for it).
+    uint64_t* sfull_bar = bars + 2 * STAGES;   // scores ready
+    uint64_t* sempty_bar = sfull_bar + 1;      // scores drained into registers (16 warps)
+    uint64_t* pfull_bar = sempty_bar + 1;      // P tile written (16 warps)
+    uint64_t* ofull_bar = pfull_bar + 1;       // [2] context accumulator ready (= second MMA done reading P)
+    uint64_t* oempty_bar = ofull_bar + 2;      // [2] context accumulator drained (4 context warps)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(oempty_bar + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int S = (int)p.S;
@@ -204,13 +212,13 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
             mbar_init(smem_u32(full_bar + i), 1);
             mbar_init(smem_u32(empty_bar + i), 1);
         }
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(smem_u32(sfull_bar + i), 1);
-            mbar_init(smem_u32(sempty_bar + i), NUM_EPI_WARPS);
-        }
+        mbar_init(smem_u32(sfull_bar), 1);
+        mbar_init(smem_u32(sempty_bar), NUM_EPI_WARPS);
         mbar_init(smem_u32(pfull_bar), NUM_EPI_WARPS);
-        mbar_init(smem_u32(ofull_bar), 1);
-        mbar_init(smem_u32(oempty_bar), NUM_CTX_WARPS);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(smem_u32(ofull_bar + i), 1);
+            mbar_init(smem_u32(oempty_bar + i), NUM_CTX_WARPS);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -223,6 +231,8 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // Register budget: the CTA owns 768 x 80 = 61440 registers; setmaxnreg only moves them between warpgroups, so the
+    // budgets must add up to at most that: 128 x 48 (roles) + 128 x 48 (context) + 512 x 96 (softmax) = 61440.
     if (warp < 4) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
         if (warp == 0) {
@@ -263,31 +273,31 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
                 for (;; ++li) {
                     const int stage = (int)(lh % STAGES);
                     if (more) {
-                        // ---- scores of tile li (one tile ahead of the softmax warps)
-                        const int sb = (int)(li & 1);
-                        mbar_wait_backoff(smem_u32(sempty_bar + sb), ((li >> 1) & 1u) ^ 1u);
+                        // ---- scores of tile li, as soon as the softmax warps hold tile li - 1 in registers
+                        mbar_wait_backoff(smem_u32(sempty_bar), (li & 1u) ^ 1u);
                         if (mt == 0) mbar_wait_backoff(smem_u32(full_bar + stage), (lh / STAGES) & 1u);
                         tc_fence_after();
                         uint8_t* st = smem + stage * STAGE_BYTES;
                         const uint64_t qd = make_smem_desc(smem_u32(st + mt * Q_BYTES)), kd = make_smem_desc(smem_u32(st + 2 * Q_BYTES));
-                        const uint32_t d_s = tmem_base + (uint32_t)(sb * BN1);
+                        const uint32_t d_s = tmem_base;
                         for (int k = 0; k < ks1; ++k) mma_i8(d_s, qd + (uint64_t)(k * 2), kd + (uint64_t)(k * 2), id_s, k > 0 ? 1u : 0u);
 #pragma unroll
                         for (int c = 0; c < 2; ++c)
                             if (p.cq[c] != 0)
                                 for (int k = 0; k < ks1; ++k) mma_i8(d_s, ca + (uint64_t)(c * 2), kd + (uint64_t)(k * 2), id_s, 1u);
-                        tc_commit(smem_u32(sfull_bar + sb));
+                        tc_commit(smem_u32(sfull_bar));
                     }
                     if (li > 0) {
                         // ---- context of tile li - 1: P is in shared memory, the accumulator buffer is free
                         const uint32_t lp = li - 1;
+                        const uint32_t ob = lp & 1u;                      // context accumulator buffer of that tile
                         mbar_wait_backoff(smem_u32(pfull_bar), lp & 1u);
-                        mbar_wait_backoff(smem_u32(oempty_bar), (lp & 1u) ^ 1u);
+                        mbar_wait_backoff(smem_u32(oempty_bar + ob), ((lp >> 1) & 1u) ^ 1u);
                         tc_fence_after();
                         uint8_t* st = smem + prev_stage * STAGE_BYTES;
                         const uint64_t vd0 = make_smem_desc(smem_u32(st + 2 * Q_BYTES + K_BYTES));
                         const uint64_t vd1 = make_smem_desc(smem_u32(st + 2 * Q_BYTES + K_BYTES + BN2 * BK));
-                        const uint32_t d_o = tmem_base + O_COL;
+                        const uint32_t d_o = tmem_base + (uint32_t)(O_COL + BN2 * ob);
                         for (int k = 0; k < ks2; ++k) {
                             const uint64_t off = (uint64_t)((k & 3) * 2);
                             mma_i8(d_o, (k < 4 ? pd0 : pd1) + off, (k < 4 ? vd0 : vd1) + off, id_pu, k > 0 ? 1u : 0u);
@@ -302,7 +312,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
                                     mma_i8(d_o, ca + (uint64_t)((2 + c) * 2), (k < 4 ? vd0 : vd1) + (uint64_t)((k & 3) * 2), id_ps, 1u);
                         }
                         if (prev_last) tc_commit(smem_u32(empty_bar + prev_stage));   // Q / K / V of that head no longer needed
-                        tc_commit(smem_u32(ofull_bar));
+                        tc_commit(smem_u32(ofull_bar + ob));
                     }
                     if (!more) break;
                     prev_stage = stage;
@@ -318,13 +328,14 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
             __syncwarp();
         }
     } else if (warp >= 4 + NUM_EPI_WARPS) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
         // ===================== context epilogue (4 warps, one per TMEM lane quarter) =====================
         // O(i) = P(i) . V (all zero-point terms already inside) is drained here while the softmax warps work on tile
         // i + 1: exact dequantize (one multiply), exact division by the output scale, round-half-even, merge-heads store.
         const int q = warp & 3;
         const int rloc = q * 32 + lane;
-        const int ibias = p.ctx_bias + (p.ctx_magic ? 0x4B400000 : 0);
+        const bool ctx_magic = FAST8 || p.ctx_magic;
+        const int ibias = p.ctx_bias + (ctx_magic ? 0x4B400000 : 0);
         const float nb = -p.o_scale;
         uint32_t li = 0, lh = 0;
         for (uint32_t hd = blockIdx.x; hd < n_heads; hd += gridDim.x, ++lh) {
@@ -335,7 +346,8 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
                 const bool row_ok = m >= ti.mlo && m < S;
                 const int mw0 = ti.m0 + q * 32;                           // rows of this warp: [mw0, mw0 + 32)
                 const bool warp_rows = mw0 + 31 >= ti.mlo && mw0 < S;
-                mbar_wait_relaxed(smem_u32(ofull_bar), li & 1u);
+                const uint32_t ob = li & 1u;
+                mbar_wait_relaxed(smem_u32(ofull_bar + ob), (li >> 1) & 1u);
                 tc_fence_after();
                 int8_t* dst = p.C + (((int64_t)b * S + m) * p.H + hh) * p.D;
                 int rs_out = 0;
@@ -343,7 +355,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
 #pragma unroll 1
                     for (int c16 = 0; c16 * 16 < (int)p.D; ++c16) {
                         uint32_t v[16];
-                        tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(O_COL + c16 * 16), v);
+                        tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(O_COL + BN2 * ob + c16 * 16), v);
                         tmem_ld_wait();
                         uint32_t w[4];
 #pragma unroll
@@ -353,7 +365,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
                             for (int k = 0; k < 4; k += 2) {
                                 const int i0 = (int)v[4 * g + k] + ibias, i1 = (int)v[4 * g + k + 1] + ibias;
                                 float2 d2;
-                                if (p.ctx_magic) d2 = __fadd2_rn(make_float2(__int_as_float(i0), __int_as_float(i1)), make_float2(-12582912.0f, -12582912.0f));
+                                if (ctx_magic) d2 = __fadd2_rn(make_float2(__int_as_float(i0), __int_as_float(i1)), make_float2(-12582912.0f, -12582912.0f));
                                 else d2 = make_float2(__int2float_rn(i0), __int2float_rn(i1));
                                 // dequantize: f32(f64(acc - zp) * f64(scale)) == one float32 multiply for |.| < 2^24
                                 const float2 x = __fmul2_rn(d2, make_float2(p.scale2, p.scale2));
@@ -371,7 +383,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
                                 n[k] = __float_as_int(rr.x) - 0x4B400000;
                                 n[k + 1] = __float_as_int(rr.y) - 0x4B400000;
                             }
-                            if (!p.o_bits8) {
+                            if (!(FAST8 || p.o_bits8)) {
 #pragma unroll
                                 for (int k = 0; k < 4; ++k) n[k] = min(max(n[k], p.o_lo), p.o_hi);
                             }
@@ -385,7 +397,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(smem_u32(oempty_bar));
+                if (lane == 0) mbar_arrive(smem_u32(oempty_bar + ob));
                 if (p.o_rowsum && row_ok && warp_rows) atomicAdd(p.o_rowsum + (int64_t)b * S + m, rs_out);
             }
         }
@@ -414,20 +426,20 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
             asm volatile("" : "+r"(paddr[j]));                             // keep it in a register (no rematerialisation per tile)
         }
         const float2 c2 = make_float2(p.c_exp, p.c_exp);
-        // f(j, ragged_tag) for every 8-column group of this warp that holds columns (ragged: the one cut by S)
-#define NQ_FOR_GROUPS(F)                                              \
-        _Pragma("unroll") for (int j = 0; j < NSUB; ++j) {            \
-            if (j < nfull) F(j, std::false_type{});                    \
-            else if (j == nfull && nrem > 0) F(j, std::true_type{});   \
-        }
+        // 8-column groups of this warp that hold columns; the one cut by S (if any) is processed like a full group:
+        // its columns >= S get a score far below every real one right after the TMEM load (they never win the maximum,
+        // their exponentials are subtracted from the sum again, their bytes are masked to zero), so the three passes
+        // exist once per group instead of twice -- the unrolled tile loop has to stay inside the instruction cache.
+        int ngroups = nfull + (nrem > 0 ? 1 : 0);
+        asm volatile("" : "+r"(ngroups));
+        constexpr int kJunk = -(1 << 22);                                 // |real score| < 2^21 (host-checked)
         uint32_t li = 0, lh = 0;
         for (uint32_t hd = blockIdx.x; hd < n_heads; hd += gridDim.x, ++lh) {
             for (int mt = 0; mt < m_tiles; ++mt, ++li) {
                 const TileInfo ti = tile_info(S, m_tiles, lh, mt);
                 const int mw0 = ti.m0 + qrow0;                            // rows of this warp: [mw0, mw0 + 32)
-                const bool active = mw0 + 31 >= ti.mlo && mw0 < S && (nfull | nrem) != 0;
-                const int sb = (int)(li & 1);
-                mbar_wait(smem_u32(sfull_bar + sb), (li >> 1) & 1u);
+                const bool active = mw0 + 31 >= ti.mlo && mw0 < S && ngroups != 0;
+                mbar_wait(smem_u32(sfull_bar), li & 1u);
                 tc_fence_after();
                 uint32_t* redp = red + (li & 1) * 1024 + rloc * 8;        // [4 x max | 4 x sum] of this row
                 float y[NSUB * 8];                                         // scores (int bits), then exponentials
@@ -436,47 +448,55 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
                 float lsum = 0.f;
                 if (active) {
                     // ---------------- pass 1: raw integer scores -> registers, integer row maximum
-                    const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(sb * BN1 + col0);
+                    const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)col0;
                     tmem_ld_32x32b_x16(t_row, yi);
-                    if (nfull >= 2) tmem_ld_32x32b_x16(t_row + 16, yi + 16);
-                    if (nfull >= 4) tmem_ld_32x32b_x16(t_row + 32, yi + 32);
-                    if (nfull >= 6) tmem_ld_32x32b_x8(t_row + 48, yi + 48);
+                    if (ngroups > 2) tmem_ld_32x32b_x16(t_row + 16, yi + 16);
+                    if (ngroups > 4) tmem_ld_32x32b_x16(t_row + 32, yi + 32);
+                    if (ngroups > 6) tmem_ld_32x32b_x8(t_row + 48, yi + 48);
                     tmem_ld_wait();
-                    auto pass1 = [&](int j, auto ragged_tag) {
-                        constexpr bool RAGGED = decltype(ragged_tag)::value;
+                    if (nrem > 0) {
 #pragma unroll
-                        for (int k = 0; k < 8; ++k)
-                            if (!RAGGED || k < nrem) lmax = max(lmax, (int)yi[j * 8 + k]);
-                    };
-                    NQ_FOR_GROUPS(pass1)
+                        for (int j = 0; j < NSUB; ++j)
+                            if (j == nfull) {
+#pragma unroll
+                                for (int k = 0; k < 8; ++k) yi[j * 8 + k] = k < nrem ? yi[j * 8 + k] : (uint32_t)kJunk;
+                            }
+                    }
+#pragma unroll
+                    for (int j = 0; j < NSUB; ++j)
+                        if (j < ngroups) {
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) lmax = max(lmax, (int)yi[j * 8 + k]);
+                        }
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(smem_u32(sempty_bar + sb));    // scores are in registers
+                if (lane == 0) mbar_arrive(smem_u32(sempty_bar));         // scores are in registers
                 if (active) {
                     // ---------------- pass 2: e = 2^((x - max) * c): x - max in (-2^23, 0] enters the float domain
                     // exactly as (2^24 - 1 + (x - max)) - (2^24 - 1)
                     const int bias = 0x4B7FFFFF - lmax;
                     float2 s01 = make_float2(0.f, 0.f), s23 = make_float2(0.f, 0.f);
-                    auto pass2 = [&](int j, auto ragged_tag) {
-                        constexpr bool RAGGED = decltype(ragged_tag)::value;
 #pragma unroll
-                        for (int k = 0; k < 8; k += 2) {
-                            float2 a = make_float2(__int_as_float((int)yi[j * 8 + k] + bias), __int_as_float((int)yi[j * 8 + k + 1] + bias));
-                            a = __fmul2_rn(__fadd2_rn(a, make_float2(-16777215.0f, -16777215.0f)), c2);
-                            float2 e = make_float2(ex2_fast(a.x), ex2_fast(a.y));
-                            if (RAGGED) {
-                                e.x = k < nrem ? e.x : 0.f;
-                                e.y = k + 1 < nrem ? e.y : 0.f;
+                    for (int j = 0; j < NSUB; ++j)
+                        if (j < ngroups) {
+#pragma unroll
+                            for (int k = 0; k < 8; k += 2) {
+                                float2 a = make_float2(__int_as_float((int)yi[j * 8 + k] + bias), __int_as_float((int)yi[j * 8 + k + 1] + bias));
+                                a = __fmul2_rn(__fadd2_rn(a, make_float2(-16777215.0f, -16777215.0f)), c2);
+                                const float2 e = make_float2(ex2_fast(a.x), ex2_fast(a.y));
+                                y[j * 8 + k] = e.x;
+                                y[j * 8 + k + 1] = e.y;
+                                if ((k & 3) == 0) s01 = __fadd2_rn(s01, e);
+                                else s23 = __fadd2_rn(s23, e);
                             }
-                            y[j * 8 + k] = e.x;
-                            y[j * 8 + k + 1] = e.y;
-                            if ((k & 3) == 0) s01 = __fadd2_rn(s01, e);
-                            else s23 = __fadd2_rn(s23, e);
                         }
-                    };
-                    NQ_FOR_GROUPS(pass2)
                     lsum = __fadd_rn(__fadd_rn(s01.x, s01.y), __fadd_rn(s23.x, s23.y));
+                    if (nrem > 0) {
+                        // the 8 - nrem columns past S all carry the same (tiny) exponential: take them out of the sum
+                        const float ej = ex2_fast(__fmul_rn(__fadd_rn(__int_as_float(kJunk + bias), -16777215.0f), p.c_exp));
+                        lsum = __fmaf_rn(-(float)(8 - nrem), ej, lsum);
+                    }
                 }
                 // ---------------- the four warps of this row meet once: (max, sum) of each column group
                 redp[h] = (uint32_t)lmax;
@@ -484,7 +504,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
                 named_bar_sync(1 + q, 128);
                 // ---------------- the second MMA of the previous tile has finished reading the P tile
                 if (li > 0) {
-                    mbar_wait(smem_u32(ofull_bar), (li - 1) & 1u);
+                    mbar_wait(smem_u32(ofull_bar + ((li - 1) & 1u)), ((li - 1) >> 1) & 1u);
                     tc_fence_after();
                 }
                 if (active) {
@@ -504,39 +524,39 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
                     const float kr = __fmul_rn(wown, __frcp_rn(__fmul_rn(gsum, p.p_scale)));
                     const float2 kr2 = make_float2(kr, kr), mg2 = make_float2(p.p_magic, p.p_magic);
                     // ---------------- pass 3: bytes of P (code - lo) straight into the swizzled shared-memory tile
-                    auto pass3 = [&](int j, auto ragged_tag) {
-                        constexpr bool RAGGED = decltype(ragged_tag)::value;
-                        int n[8];
 #pragma unroll
-                        for (int k = 0; k < 8; k += 2) {
-                            const float2 r = __ffma2_rn(make_float2(y[j * 8 + k], y[j * 8 + k + 1]), kr2, mg2);
-                            n[k] = __float_as_int(r.x) - 0x4B400000;
-                            n[k + 1] = __float_as_int(r.y) - 0x4B400000;
-                        }
-                        if (!p.p_bits8) {
+                    for (int j = 0; j < NSUB; ++j)
+                        if (j < ngroups) {
+                            int n[8];
 #pragma unroll
-                            for (int k = 0; k < 8; ++k) n[k] = min(n[k], p.p_top);
+                            for (int k = 0; k < 8; k += 2) {
+                                const float2 r = __ffma2_rn(make_float2(y[j * 8 + k], y[j * 8 + k + 1]), kr2, mg2);
+                                n[k] = __float_as_int(r.x) - 0x4B400000;
+                                n[k + 1] = __float_as_int(r.y) - 0x4B400000;
+                            }
+                            if (!(FAST8 || p.p_bits8)) {
+#pragma unroll
+                                for (int k = 0; k < 8; ++k) n[k] = min(n[k], p.p_top);
+                            }
+                            uint32_t w0b = pack_sat_u8(n[0], n[1], n[2], n[3]), w1b = pack_sat_u8(n[4], n[5], n[6], n[7]);
+                            if (j == nfull) {                                // the group cut by S: zero bytes past it
+                                w0b &= rmask0;
+                                w1b &= rmask1;
+                            }
+                            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(paddr[j]), "r"(w0b), "r"(w1b) : "memory");
                         }
-                        uint32_t w0b = pack_sat_u8(n[0], n[1], n[2], n[3]), w1b = pack_sat_u8(n[4], n[5], n[6], n[7]);
-                        if (RAGGED) {
-                            w0b &= rmask0;
-                            w1b &= rmask1;
-                        }
-                        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(paddr[j]), "r"(w0b), "r"(w1b) : "memory");
-                    };
-                    NQ_FOR_GROUPS(pass3)
                     if (p.p_dump) {
                         // test hook (off the hot path): copy this row's bytes from the tile to global memory
                         const int m = ti.m0 + rloc;
-                        if (m >= ti.mlo && m < S) {
-                            __syncwarp();
-                            auto dump = [&](int j, auto) {
+                        const bool row_ok = m >= ti.mlo && m < S;
+#pragma unroll
+                        for (int j = 0; j < NSUB; ++j)
+                            if (j < ngroups) {
                                 uint32_t a0, a1;
                                 asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(a0), "=r"(a1) : "r"(paddr[j]) : "memory");
-                                *reinterpret_cast<uint2*>(p.p_dump + ((int64_t)hd * S + m) * p.ld_dump + col0 + j * 8) = make_uint2(a0, a1);
-                            };
-                            NQ_FOR_GROUPS(dump)
-                        }
+                                if (row_ok)
+                                    *reinterpret_cast<uint2*>(p.p_dump + ((int64_t)hd * S + m) * p.ld_dump + col0 + j * 8) = make_uint2(a0, a1);
+                            }
                     }
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA
@@ -544,7 +564,6 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
                 if (lane == 0) mbar_arrive(smem_u32(pfull_bar));
             }
         }
-#undef NQ_FOR_GROUPS
     }
 
     tc_fence_before();
@@ -603,9 +622,10 @@ extern "C" int nq_attention_s8(const int8_t* Q, const int8_t* Kt, const int8_t* 
     NQ_REQUIRE(attn::split_i8(-zv, p.cv), "nq_attention_s8: |zv| must be <= 254");
     {
         // integer scores x = sum_d (q - zq) k: the row-constant zk * rowsum(Q) term is dropped (softmax shift invariance),
-        // so |x| <= max|q - zq| * 128 * D; x - max(x) must stay inside (-2^23, 0] for the exact float conversion
+        // so |x| <= max|q - zq| * 128 * D < 2^21; x - max(x), also for the -2^22 placeholder of the columns past S, stays inside
+        // (-2^23, 0] for the exact float conversion
         const long double ra = fmaxl(fabsl(-128.0L - (long double)zq), fabsl(127.0L - (long double)zq));
-        NQ_REQUIRE(ra * 128.0L * (long double)D < 4194304.0L, "nq_attention_s8: max|q - zq| * 128 * D must stay below 2^22");
+        NQ_REQUIRE(ra * 128.0L * (long double)D < 2097152.0L, "nq_attention_s8: max|q - zq| * 128 * D must stay below 2^21");
     }
     NQ_REQUIRE(a->p_scale >= 1e-6f && a->p_scale < 1e30f, "nq_attention_s8: p_scale out of range (1 / p_scale must stay below 2^20)");
     p.p_scale = a->p_scale;
@@ -661,10 +681,16 @@ extern "C" int nq_attention_s8(const int8_t* Q, const int8_t* Kt, const int8_t* 
     if (int rc = make_operand_map(&tq, Q, D, S, BH, ld_q, S * ld_q, BM)) return rc;
     if (int rc = make_operand_map(&tk, Kt, D, S, BH, ld_k, S * ld_k, attn::BN1)) return rc;
     if (int rc = make_operand_map(&tv, Vt, S, D, BH, ld_v, D * ld_v, attn::BN2)) return rc;
-    static bool configured[64] = {false};                                 // per device
-    if (int rc = configure_smem_once(configured, attn::attn_kernel, attn::SMEM_BYTES, "cudaFuncSetAttribute(attn)")) return rc;
     const int grid = (int)(BH < sm_count() ? BH : sm_count());
-    attn::attn_kernel<<<grid, attn::NUM_THREADS, attn::SMEM_BYTES, s>>>(tq, tk, tv, p);
+    if (p.p_bits8 && p.o_bits8 && p.ctx_magic) {
+        static bool configured[64] = {false};                             // per device
+        if (int rc = configure_smem_once(configured, attn::attn_kernel<true>, attn::SMEM_BYTES, "cudaFuncSetAttribute(attn)")) return rc;
+        attn::attn_kernel<true><<<grid, attn::NUM_THREADS, attn::SMEM_BYTES, s>>>(tq, tk, tv, p);
+    } else {
+        static bool configured[64] = {false};
+        if (int rc = configure_smem_once(configured, attn::attn_kernel<false>, attn::SMEM_BYTES, "cudaFuncSetAttribute(attn)")) return rc;
+        attn::attn_kernel<false><<<grid, attn::NUM_THREADS, attn::SMEM_BYTES, s>>>(tq, tk, tv, p);
+    }
     NQ_CHECK_LAUNCH("nq_attention_s8");
     return NQ_OK;
 }

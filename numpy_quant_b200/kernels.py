@@ -448,14 +448,14 @@ def can_fuse_attention(q: Operand, k: Operand, v: Operand) -> bool:
 def can_fuse_attention_qk(q: Operand, k: Operand, zq=None, zk=None) -> bool:
     """The part of `can_fuse_attention` that is known at the score MatMul (V has the same S and D).  zq: the kernel
     folds -zq * colsum(K) into the score MMA as int8 constant passes (|zq| <= 254) and converts x - max(x) exactly,
-    which needs max|q - zq| * 128 * D < 2^22 (true for any zero-point inside the int8 range at D <= 64); the zk term is
+    which needs max|q - zq| * 128 * D < 2^21 (true for any zero-point inside the int8 range at D <= 64); the zk term is
     constant along a row and cancels in the softmax."""
     if not (q.batch == k.batch and q.rows == k.rows and q.k == k.k and q.rows <= 208 and q.k <= 64 and q.k % 16 == 0
             and len(q.batch_shape) == 2):
         return False
     z = int(zq or 0)
     ra = max(abs(-128 - z), abs(127 - z))
-    return abs(z) <= 254 and ra * 128 * q.k < (1 << 22)
+    return abs(z) <= 254 and ra * 128 * q.k < (1 << 21)
 
 
 def attention(q: Operand, k: Operand, v: Operand, scale_qk: float, zq, zk, div_c, p_bits: int, p_scale, p_zp,
