@@ -380,6 +380,7 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
         constexpr bool FASTF = (EMODE == EM_DEQ_FAST);                   // float result via the 32-bit fast path
         constexpr bool Q8 = (EMODE == EM_Q8_ROWS || EMODE == EM_Q8_COLS || EMODE == EM_Q8_GELU);
         const Quantizer qz(p.qargs);
+        const int qlo = (int)p.qargs.lo, qhi = (int)p.qargs.hi;          // integer code range of the QUANT epilogues
         constexpr bool SOFTMAX = (EMODE == EM_SOFTMAX_SYM || EMODE == EM_SOFTMAX_ASYM);
         // Per-tile operands of the zero-point correction (this row's rowsum(A), this warp's colsum(B) and bias
         // columns) are fetched ONE TILE AHEAD: with 227 KB of smem there is no L1 to hit, so each of these
@@ -508,27 +509,54 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                         }
                     }
                     const bool gelu_scaled = (bad & 0xFF800000u) != 0;    // warp-divergent only on the rare slow route
-                    int w[4];
+                    // Quantizer tail, two columns per instruction: the quotient t = y / s_out (ROWS / COLS: correctly
+                    // rounded -- q0 = y * RN(1 / s), two fused residual corrections, common.cuh; GELU: already folded into
+                    // the chain's last constant) is rounded half-to-even by ONE add of 1.5 * 2^23 + zp; the integer
+                    // n = zp + rint(t) sits in the low bits of the sum and the saturating pack instruction clamps it to
+                    // the int8 range (narrower codes: an integer min / max first).  A quotient below -2^22 would leave
+                    // the magic window on the wrong side (n would wrap), hence the one-sided max; above it the bit
+                    // pattern only grows, which saturates correctly.
+                    const float2 r2 = make_float2(qz.sd.r, qz.sd.r), nb2 = make_float2(-qz.sd.b, -qz.sd.b), mg2 = make_float2(qz.magic, qz.magic);
+                    uint32_t w[4];
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
                         const float4 b4 = *reinterpret_cast<const float4*>(bsw + i * 16 + g * 4);
+                        float2 ta, tb;
                         if constexpr (EMODE == EM_Q8_GELU) {
                             // float glue (1e-5 contract): dequant * scale + bias as one FMA, GELU, and the
                             // quantizer's division folded into the chain's last constant; two elements per FFMA2
                             const float sc = gelu_scaled ? 1.0f : p.scale;
                             const float2 sc2 = make_float2(sc, sc);
-                            const float2 ya = gelu_fast2(__ffma2_rn(make_float2(f[4 * g], f[4 * g + 1]), sc2, make_float2(b4.x, b4.y)),
-                                                         p.g_prdiv, p.g_nl2e, p.g_add, p.g_out);
-                            const float2 yb = gelu_fast2(__ffma2_rn(make_float2(f[4 * g + 2], f[4 * g + 3]), sc2, make_float2(b4.z, b4.w)),
-                                                         p.g_prdiv, p.g_nl2e, p.g_add, p.g_out);
-                            w[g] = pack4_codes(qz.template code_of_quotient<1>(ya.x), qz.template code_of_quotient<1>(ya.y),
-                                               qz.template code_of_quotient<1>(yb.x), qz.template code_of_quotient<1>(yb.y));
+                            ta = gelu_fast2(__ffma2_rn(make_float2(f[4 * g], f[4 * g + 1]), sc2, make_float2(b4.x, b4.y)),
+                                            p.g_prdiv, p.g_nl2e, p.g_add, p.g_out);
+                            tb = gelu_fast2(__ffma2_rn(make_float2(f[4 * g + 2], f[4 * g + 3]), sc2, make_float2(b4.z, b4.w)),
+                                            p.g_prdiv, p.g_nl2e, p.g_add, p.g_out);
                         } else {
-                            const float y0 = __fadd_rn(b4.x, f[4 * g]), y1 = __fadd_rn(b4.y, f[4 * g + 1]);
-                            const float y2 = __fadd_rn(b4.z, f[4 * g + 2]), y3 = __fadd_rn(b4.w, f[4 * g + 3]);
-                            w[g] = pack4_codes(qz.template code<1>(y0), qz.template code<1>(y1), qz.template code<1>(y2),
-                                               qz.template code<1>(y3));
+                            // bias adds stay scalar: ptxas contracts a packed multiply followed by a packed add into one
+                            // FFMA2 (a single rounding) even when both carry .rn
+                            const float2 ya = make_float2(__fadd_rn(b4.x, f[4 * g]), __fadd_rn(b4.y, f[4 * g + 1]));
+                            const float2 yb = make_float2(__fadd_rn(b4.z, f[4 * g + 2]), __fadd_rn(b4.w, f[4 * g + 3]));
+                            ta = __fmul2_rn(ya, r2);
+                            tb = __fmul2_rn(yb, r2);
+                            float2 ea = __ffma2_rn(ta, nb2, ya), eb = __ffma2_rn(tb, nb2, yb);
+                            ta = __ffma2_rn(ea, r2, ta);
+                            tb = __ffma2_rn(eb, r2, tb);
+                            ea = __ffma2_rn(ta, nb2, ya);
+                            eb = __ffma2_rn(tb, nb2, yb);
+                            ta = __ffma2_rn(ea, r2, ta);
+                            tb = __ffma2_rn(eb, r2, tb);
                         }
+                        ta = __fadd2_rn(make_float2(fmaxf(ta.x, -4194304.0f), fmaxf(ta.y, -4194304.0f)), mg2);
+                        tb = __fadd2_rn(make_float2(fmaxf(tb.x, -4194304.0f), fmaxf(tb.y, -4194304.0f)), mg2);
+                        int n0q = __float_as_int(ta.x) - 0x4B400000, n1q = __float_as_int(ta.y) - 0x4B400000;
+                        int n2q = __float_as_int(tb.x) - 0x4B400000, n3q = __float_as_int(tb.y) - 0x4B400000;
+                        if (qlo != -128) {                                 // codes narrower than 8 bits (warp-uniform)
+                            n0q = min(max(n0q, qlo), qhi); n1q = min(max(n1q, qlo), qhi);
+                            n2q = min(max(n2q, qlo), qhi); n3q = min(max(n3q, qlo), qhi);
+                        }
+                        uint32_t hi16;
+                        asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(hi16) : "r"(n3q), "r"(n2q), "r"(0));
+                        asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(w[g]) : "r"(n1q), "r"(n0q), "r"(hi16));
                     }
                     if (i > 0) {                                          // next 16 columns: step (head, column in head)
                         nd += 16;
@@ -563,14 +591,14 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                     } else {
                         if (row_ok)
                             *reinterpret_cast<int4*>(reinterpret_cast<int8_t*>(p.C) + row_off + (int64_t)nh * p.q_off[4] + nd) =
-                                make_int4(w[0], w[1], w[2], w[3]);
+                                make_int4((int)w[0], (int)w[1], (int)w[2], (int)w[3]);
                         if (p.q_rowsum) {
                             if (nh != rs_nh) {
                                 flush_rowsum();
                                 rs_acc = 0;
                                 rs_nh = nh;
                             }
-                            rs_acc = __dp4a(w[0], 0x01010101, __dp4a(w[1], 0x01010101, __dp4a(w[2], 0x01010101, __dp4a(w[3], 0x01010101, rs_acc))));
+                            rs_acc = __dp4a((int)w[0], 0x01010101, __dp4a((int)w[1], 0x01010101, __dp4a((int)w[2], 0x01010101, __dp4a((int)w[3], 0x01010101, rs_acc))));
                         }
                     }
                 }
