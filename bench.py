@@ -301,6 +301,27 @@ def extra_config5(torch, dev, local, peaks, lib_tops) -> dict:
         put(f"pack_s8_to_{bits}bit", _timed_flush(torch, lambda: K.pack(qb, bits), flush), (1 + bits / 8) * ne)
         pk = K.pack(qb, bits)
         put(f"unpack_{bits}bit_to_s8", _timed_flush(torch, lambda: K.unpack(pk, ne, bits), flush), (1 + bits / 8) * ne)
+    # the same kernels at the ViT-B batch-256 activation size [50432, 3072] (618 MB in): where a launch is long enough for
+    # the fixed ~8 us of launch + ramp-up + tail of a [4096, 4096] call (13 us of traffic at peak) not to dominate
+    big = {}
+    xb = torch.randn(50432, 3072, device=dev)
+    nb_ = xb.numel()
+    for name, fn, byts in (("quantize_f32_to_s8_asym", lambda: K.quantize(xb, 8, 0.03, -5), 5 * nb_),
+                           ("quantize_to_gemm_operand_with_rowsum", lambda: K.quantize_operand(xb, "A", 8, 0.03, -5, True), 5 * nb_)):
+        msb = _timed_flush(torch, fn, flush, iters=5)
+        big[name] = {"ms": msb, "gb_s": byts / (msb * 1e-3) / 1e9, "frac_of_measured_hbm": byts / (msb * 1e-3) / 1e9 / hbm}
+    accb = torch.randint(-(1 << 20), 1 << 20, (1, 50432, 3072), device=dev, dtype=torch.int32)
+    csb = torch.randint(-5000, 5000, (1, 3072), device=dev, dtype=torch.int32)
+    azb = K.AccZeroPoint(3, None, 768, None, csb, True)
+    for name, fn, byts in (("dequantize_s32_acc_to_f32", lambda: K.dequantize_acc(accb, 1e-4, azb), 8 * nb_),
+                           ("requantize_s32_acc_to_s8", lambda: K.requantize_acc(accb, 1e-4, azb, None, 8, 0.05, -3), 5 * nb_)):
+        msb = _timed_flush(torch, fn, flush, iters=5)
+        big[name] = {"ms": msb, "gb_s": byts / (msb * 1e-3) / 1e9, "frac_of_measured_hbm": byts / (msb * 1e-3) / 1e9 / hbm}
+    q4 = K.quantize(xb, 4, 0.5, -1).reshape(-1)
+    msb = _timed_flush(torch, lambda: K.pack(q4, 4), flush, iters=5)
+    big["pack_s8_to_4bit"] = {"ms": msb, "gb_s": 1.5 * nb_ / (msb * 1e-3) / 1e9, "frac_of_measured_hbm": 1.5 * nb_ / (msb * 1e-3) / 1e9 / hbm}
+    del xb, accb, q4
+    torch.cuda.empty_cache()
     clocks = sampler.stop()
     # ---- the reference's NumPy routines on the host, identical arrays (single thread: NumPy ufuncs / int64 matmul)
     cpu = {}
@@ -328,7 +349,7 @@ def extra_config5(torch, dev, local, peaks, lib_tops) -> dict:
              "requantize_vs_numpy": cpu["requantize_4096x4096_s"] / (quant["requantize_s32_acc_to_s8"]["ms"] * 1e-3)}
     return {"workload": "configs[4]: qGEMM 4096^3 at bit_width 2..8 + quantize / dequantize / requantize / pack on f32 [4096, 4096]",
             "timing": "each kernel alone, CUDA events, L2 flushed (256 MB write) before every call, median",
-            "qgemm_4096_cubed": gemm, "quant_kernels_4096x4096": quant, "numpy_host_baseline": cpu, "gpu_over_numpy": speed,
+            "qgemm_4096_cubed": gemm, "quant_kernels_4096x4096": quant, "quant_kernels_50432x3072": big, "numpy_host_baseline": cpu, "gpu_over_numpy": speed,
             "clocks": clocks}
 
 

@@ -79,6 +79,7 @@ struct GemmParams {
     float g_prdiv, g_nl2e, g_add, g_out;   // GELU_QUANT: 0.3275911 / c1, -log2(e) / c1^2, c2, c3 / s_out
     int two_cta;                     // CTA-pair kernel (256-row tiles, cta_group::2)
     int deq_wide;                    // DEQUANT: alignment / extent conditions of the 32-column epilogue hold (host-checked)
+    int req_rows;                    // REQUANT: 32-bit windows and alignment of the thread-per-row epilogue hold (host-checked)
     int sm_noclamp;                  // SOFTMAX: out_zp >= lo: p / s_out + zp (p in [0, 1]) needs no lower clamp
     float sm_top;                    // SOFTMAX: upper clamp in the magic-sum domain (1.5 * 2^23 + hi), huge when p = 1 fits
     int fast22;                      // SOFTMAX: |acc - zero-point terms| < 2^22 proved on the host (magic int->float route)
@@ -172,7 +173,18 @@ __device__ __noinline__ void deq_wide_fix(const uint32_t* slab, const uint32_t* 
 }
 
 constexpr int EM_RAW = 0, EM_DEQ_FAST = 1, EM_DEQ_GENERAL = 2, EM_REQUANT = 3, EM_Q8_ROWS = 4, EM_Q8_COLS = 5,
-              EM_SOFTMAX_SYM = 6, EM_SOFTMAX_ASYM = 7, EM_Q8_GELU = 8, EM_DEQ_WIDE = 9, EM_DEQ_WIDE_RES = 10;
+              EM_SOFTMAX_SYM = 6, EM_SOFTMAX_ASYM = 7, EM_Q8_GELU = 8, EM_DEQ_WIDE = 9, EM_DEQ_WIDE_RES = 10, EM_REQ_ROWS = 11;
+
+// requantize (numpy_quantization.py:64-72) of one element on the general 64-bit route: int64 bias add, int64 zero-point
+// terms, dequantize, reciprocal multiply, clip(rint(zp + t)).  Out of line: the fast REQUANT epilogue calls it only for
+// tiles whose bias / accumulators leave the 32-bit windows.
+__device__ __noinline__ int requant_slow(int acc, int64_t rowterm, const AccZp z, int64_t b, int64_t n, const int64_t* bias_q,
+                                         float scale, float inv_out_scale, int asym_out, double out_zp, float lo, float hi) {
+    int64_t a = (int64_t)acc;
+    if (bias_q) a += __ldg(bias_q + n);
+    const float d = dequantize_one(a - tile_zp(z, rowterm, b, n), scale);
+    return asym_out ? requantize_one<true>(d, inv_out_scale, out_zp, lo, hi) : requantize_one<false>(d, inv_out_scale, 0.0, lo, hi);
+}
 
 template <int BN, int EMODE, bool TWO = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -378,16 +390,17 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                              ((p.stride_r & 3) == 0);
         const int zpa = (int)z.zp_a;
         constexpr bool FASTF = (EMODE == EM_DEQ_FAST);                   // float result via the 32-bit fast path
-        constexpr bool Q8 = (EMODE == EM_Q8_ROWS || EMODE == EM_Q8_COLS || EMODE == EM_Q8_GELU);
+        constexpr bool REQ = (EMODE == EM_REQ_ROWS);                     // Gemm: int bias + requantize, plain [M, N] int8 rows
+        constexpr bool Q8 = (EMODE == EM_Q8_ROWS || EMODE == EM_Q8_COLS || EMODE == EM_Q8_GELU || REQ);
         const Quantizer qz(p.qargs);
         const int qlo = (int)p.qargs.lo, qhi = (int)p.qargs.hi;          // integer code range of the QUANT epilogues
         constexpr bool SOFTMAX = (EMODE == EM_SOFTMAX_SYM || EMODE == EM_SOFTMAX_ASYM);
         // Per-tile operands of the zero-point correction (this row's rowsum(A), this warp's colsum(B) and bias
         // columns) are fetched ONE TILE AHEAD: with 227 KB of smem there is no L1 to hit, so each of these
         // loads is an L2 round trip that would otherwise sit at the head of every tile's critical path.
-        struct TilePre { int rowsum, c0, c1, b0, b1; };
+        struct TilePre { int rowsum, c0, c1, b0, b1, wide; };
         auto prefetch_tile = [&](uint32_t tt, TilePre& o) {
-            o.rowsum = o.c0 = o.c1 = o.b0 = o.b1 = 0;
+            o.rowsum = o.c0 = o.c1 = o.b0 = o.b1 = o.wide = 0;
             if (tt >= total_tiles) return;
             const uint32_t pb = tt / tiles_per_batch, pr = tt - pb * tiles_per_batch;
             const uint32_t pm0 = (pr / n_tiles) * BMT + cta_rank * BM, pn0 = (pr % n_tiles) * BN;
@@ -399,11 +412,21 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                 const int32_t* pcs = z.use_col ? z.colsum_b + (int64_t)pb * z.cs_stride : nullptr;
                 if (lane < W && c0i < p.N) {
                     if (pcs) o.c0 = ldg_s32(pcs + c0i);
-                    if (Q8 && p.bias_f32) o.b0 = ldg_s32(p.bias_f32 + c0i);
+                    if (Q8 && !REQ && p.bias_f32) o.b0 = ldg_s32(p.bias_f32 + c0i);
+                    if (REQ && p.bias_q) {
+                        const int64_t bq = __ldg(p.bias_q + c0i);
+                        o.b0 = (int)bq;
+                        o.wide |= (bq < -(1ll << 29) || bq > (1ll << 29)) ? 1 : 0;
+                    }
                 }
                 if (lane + 32 < W && c1i < p.N) {
                     if (pcs) o.c1 = ldg_s32(pcs + c1i);
-                    if (Q8 && p.bias_f32) o.b1 = ldg_s32(p.bias_f32 + c1i);
+                    if (Q8 && !REQ && p.bias_f32) o.b1 = ldg_s32(p.bias_f32 + c1i);
+                    if (REQ && p.bias_q) {
+                        const int64_t bq = __ldg(p.bias_q + c1i);
+                        o.b1 = (int)bq;
+                        o.wide |= (bq < -(1ll << 29) || bq > (1ll << 29)) ? 1 : 0;
+                    }
                 }
             }
         };
@@ -439,14 +462,16 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                 int* ctw = reinterpret_cast<int*>(epi) + ew * 128;        // [64] colsum * zp_a
                 float* bsw = reinterpret_cast<float*>(ctw + 64);          // [64] bias
                 __syncwarp();
+                // REQUANT: the integer bias joins the column term (acc + bias - zero-point, all int32 by the host bound)
                 if (lane < WCOLS) {
-                    ctw[lane] = cur.c0 * zpa;
+                    ctw[lane] = cur.c0 * zpa - (REQ ? cur.b0 : 0);
                     bsw[lane] = __int_as_float(cur.b0);
                 }
                 if (lane + 32 < WCOLS) {
-                    ctw[lane + 32] = cur.c1 * zpa;
+                    ctw[lane + 32] = cur.c1 * zpa - (REQ ? cur.b1 : 0);
                     bsw[lane + 32] = __int_as_float(cur.b1);
                 }
+                const bool wide_bias = REQ && __any_sync(0xffffffffu, cur.wide != 0);   // some |bias| >= 2^29: general route
                 // row part of the scatter offsets (m = mb * S + ms, batch = bo * inner + bi)
                 const uint32_t mu = (uint32_t)(row_ok ? m : p.M - 1);
                 const uint32_t mb = mu / p.q_S, ms = mu - mb * p.q_S;
@@ -492,6 +517,26 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                         bad |= (uint32_t)(x[j] ^ 0x4B000000);
                     }
                     float f[16];
+                    if constexpr (REQ) {
+                        if (__builtin_expect(wide_bias || __any_sync(0xffffffffu, (bad & 0xFF800000u) != 0), 0)) {
+                            // general 64-bit route for this 16-column step (whole warp: the store below is per thread)
+                            uint32_t wq[4] = {0, 0, 0, 0};
+#pragma unroll 1
+                            for (int j = 0; j < 16; ++j) {
+                                const int c = requant_slow((int)v[j], rowterm, z, b, nc + j, p.bias_q, p.scale, p.inv_out_scale,
+                                                           p.asym_out, p.out_zp, p.lo, p.hi);
+                                wq[j >> 2] |= (uint32_t)(c & 0xff) << ((j & 3) * 8);
+                            }
+                            if (i > 0) {
+                                nd += 16;
+                                if (nd >= p.q_D) { nd = 0; ++nh; }
+                            }
+                            if (row_ok)
+                                *reinterpret_cast<int4*>(reinterpret_cast<int8_t*>(p.C) + row_off + (int64_t)nh * p.q_off[4] + nd) =
+                                    make_int4((int)wq[0], (int)wq[1], (int)wq[2], (int)wq[3]);
+                            continue;
+                        }
+                    }
                     if (__builtin_expect((bad & 0xFF800000u) != 0, 0)) {  // some |d| >= 2^22: exact slow route
 #pragma unroll
                         for (int j = 0; j < 16; ++j) f[j] = deq_slow(x[j] - 0x4B400000, p.scale);
@@ -531,6 +576,12 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                                             p.g_prdiv, p.g_nl2e, p.g_add, p.g_out);
                             tb = gelu_fast2(__ffma2_rn(make_float2(f[4 * g + 2], f[4 * g + 3]), sc2, make_float2(b4.z, b4.w)),
                                             p.g_prdiv, p.g_nl2e, p.g_add, p.g_out);
+                        } else if constexpr (REQ) {
+                            // requantize: t = (1 / s_out) * dequant, a float32 multiply by the IEEE-rounded reciprocal
+                            const float2 inv2 = make_float2(p.inv_out_scale, p.inv_out_scale);
+                            ta = __fmul2_rn(inv2, make_float2(f[4 * g], f[4 * g + 1]));
+                            tb = __fmul2_rn(inv2, make_float2(f[4 * g + 2], f[4 * g + 3]));
+                            (void)b4;
                         } else {
                             // bias adds stay scalar: ptxas contracts a packed multiply followed by a packed add into one
                             // FFMA2 (a single rounding) even when both carry .rn
@@ -1212,7 +1263,7 @@ static int launch_qgemm(const CUtensorMap& ta, const CUtensorMap& tb, const Gemm
 template <int BN>
 static int launch_qgemm_mode(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t s) {
     if (p.mode == NQ_EPI_RAW) return launch_qgemm<BN, EM_RAW>(ta, tb, p, s);
-    if (p.mode == NQ_EPI_REQUANT) return launch_qgemm<BN, EM_REQUANT>(ta, tb, p, s);
+    if (p.mode == NQ_EPI_REQUANT) return p.req_rows ? launch_qgemm<BN, EM_REQ_ROWS>(ta, tb, p, s) : launch_qgemm<BN, EM_REQUANT>(ta, tb, p, s);
     if (p.mode == NQ_EPI_SOFTMAX_QUANT) {
         if constexpr (BN == 256)
             return p.asym_out ? launch_qgemm<BN, EM_SOFTMAX_ASYM>(ta, tb, p, s) : launch_qgemm<BN, EM_SOFTMAX_SYM>(ta, tb, p, s);
@@ -1380,6 +1431,27 @@ static int qgemm_run(const int8_t* A, const int8_t* B, void* Cout, int64_t M, in
         p.out_zp = ep->has_out_zp ? (double)ep->out_zp : 0.0;
         p.lo = -ldexpf(1.f, ep->out_bits - 1);
         p.hi = ldexpf(1.f, ep->out_bits - 1) - 1.f;
+        // Thread-per-row epilogue (the QUANT epilogues' structure): acc + int bias - zero-point terms in int32 (each of
+        // the three below 2^29: host bound here, bias checked on the device per tile), magic-constant conversion, the
+        // reciprocal multiply and the single-add rounding of zp + t.  Needs 16-byte rows; everything else -- and any tile
+        // whose values leave the windows -- takes the general 64-bit route.
+        int qmode;
+        p.qargs = make_qargs(ep->out_bits, ep->out_scale, ep->has_out_zp, ep->out_zp, &qmode);
+        const long double za = (long double)llabs(p.zp.zp_a), zb = (long double)llabs(p.zp.zp_b);
+        const long double bound = 16384.0L * K + 128.0L * K * (za + zb) + za * zb * K;
+        static const bool no_fast = getenv("NQ_NO_FAST_REQUANT") != nullptr;      // A/B switch
+        p.req_rows = !no_fast && qmode != 2 && bound < 536870000.0L && N % 16 == 0 && ldc % 16 == 0 && stride_c % 16 == 0 &&
+                     ((uintptr_t)Cout % 16 == 0) && p.c_inner == 1 && M < (1ll << 31);
+        if (p.req_rows) {
+            p.q_S = (uint32_t)M;                                          // one "image" of M rows, one "head" of N columns
+            p.q_D = (uint32_t)N;
+            const int64_t off[6] = {stride_c, 0, 0, ldc, 0, 1};
+            for (int i = 0; i < 6; ++i) {
+                p.q_off[i] = off[i];
+                p.q_rs[i] = 0;
+            }
+            p.q_rowsum = nullptr;
+        }
     }
 
     {

@@ -86,7 +86,20 @@ __global__ void __launch_bounds__(256) quantize_rows_kernel(const float* __restr
             int8_t* dst = out + (int64_t)row * ldo;
             if (sc == 1 && ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && (ldo & 3) == 0) {
                 const int c4 = (int)(C >> 2);
-                for (int c = sub; c < c4; c += lpr) {
+                // four 16-byte loads per lane in flight before the first use (long rows were one load deep: latency-bound)
+                int c = sub;
+                for (; c + 3 * lpr < c4; c += 4 * lpr) {
+                    float4 v[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) v[u] = __ldcs(reinterpret_cast<const float4*>(src) + c + u * lpr);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int w = pack4_codes(qz.code<QMODE>(v[u].x), qz.code<QMODE>(v[u].y), qz.code<QMODE>(v[u].z), qz.code<QMODE>(v[u].w));
+                        sum = __dp4a(w, 0x01010101, sum);
+                        __stcs(reinterpret_cast<int*>(dst) + c + u * lpr, w);
+                    }
+                }
+                for (; c < c4; c += lpr) {
                     const float4 v = __ldcs(reinterpret_cast<const float4*>(src) + c);
                     const int w = pack4_codes(qz.code<QMODE>(v.x), qz.code<QMODE>(v.y), qz.code<QMODE>(v.z), qz.code<QMODE>(v.w));
                     sum = __dp4a(w, 0x01010101, sum);
@@ -219,6 +232,58 @@ __global__ void __launch_bounds__(256) acc_post_kernel(const int32_t* __restrict
 // row term once, the 4 column terms as one int4 load, float4 / packed-int8 store.  Same arithmetic as above;
 // the asymmetric requantize tail rint(zp + t) runs through the quantizer's single-add rounding (|zp| < 2^20:
 // exactly round-half-even of zp + t, see common.cuh) instead of float64.
+// Lean variant for the common case (no int64 bias, |out_zp| < 2^20): all eight 16-byte loads of a lane (accumulators and
+// column sums) are in flight before the first use, the zero-point terms are formed in 64-bit once per row / 4 columns,
+// |d| <= 2^24 takes the one-multiply route (exact, see dequantize_one), the requantize tail is the reciprocal multiply
+// and the single-add rounding.  Same bits as the general kernel for every int32 input.
+template <int MODE>
+__global__ void __launch_bounds__(256) acc_post_fast_kernel(const int32_t* __restrict__ acc, int64_t rows, int64_t M, int N4,
+                                                           int64_t ldacc, float scale, AccZp z, float inv_out_scale,
+                                                           float zpf, float lo, float hi, void* __restrict__ out) {
+    const float tlo = lo - zpf, thi = hi - zpf, magic = kMagic + zpf;
+    const int lane = threadIdx.x & 31;
+    const int segs = (N4 + 127) >> 7;                                     // 128 int4 (512 columns) per warp unit
+    const int64_t units = rows * segs, warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t u = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; u < units; u += warps) {
+        const int64_t row = u / segs;
+        const int c40 = (int)(u - row * segs) << 7;
+        const int4* arow = reinterpret_cast<const int4*>(acc + row * ldacc);
+        const int4* csrow = z.use_col ? reinterpret_cast<const int4*>(z.colsum_b + (row / M) * z.cs_stride) : nullptr;
+        int4 a4[4], cs4[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int c4 = c40 + k * 32 + lane;
+            a4[k] = c4 < N4 ? __ldcs(arow + c4) : make_int4(0, 0, 0, 0);
+            cs4[k] = (csrow && c4 < N4) ? __ldg(csrow + c4) : make_int4(0, 0, 0, 0);
+        }
+        int64_t rowterm = -z.kterm;
+        if (z.use_row) rowterm += (int64_t)__ldg(z.rowsum_a + row) * z.zp_b;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int c4 = c40 + k * 32 + lane;
+            if (c4 >= N4) continue;
+            const int av[4] = {a4[k].x, a4[k].y, a4[k].z, a4[k].w}, cv[4] = {cs4[k].x, cs4[k].y, cs4[k].z, cs4[k].w};
+            float d[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int64_t dv = (int64_t)av[e] - rowterm - (int64_t)cv[e] * z.zp_a;
+                d[e] = (dv >= -16777216 && dv <= 16777216) ? __fmul_rn(__int2float_rn((int)dv), scale)
+                                                           : (float)((double)dv * (double)scale);
+            }
+            const int64_t i = row * N4 + c4;
+            if (MODE == 1) {
+                __stcs(reinterpret_cast<float4*>(out) + i, make_float4(d[0], d[1], d[2], d[3]));
+            } else {
+                int c[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    c[e] = __float_as_int(__fadd_rn(fminf(fmaxf(__fmul_rn(inv_out_scale, d[e]), tlo), thi), magic));
+                __stcs(reinterpret_cast<int*>(out) + i, pack4_codes(c[0], c[1], c[2], c[3]));
+            }
+        }
+    }
+}
+
 template <int MODE, bool F64>   // MODE 1 dequant -> f32, 2 requant -> s8; F64: float64 requantize tail (huge zp)
 __global__ void __launch_bounds__(256) acc_post_vec_kernel(const int32_t* __restrict__ acc, int64_t rows, int64_t M,
                                                           int N4, int64_t ldacc, float scale, AccZp z,
@@ -582,8 +647,9 @@ extern "C" int nq_dequantize_acc(const int32_t* acc, int64_t batch, int64_t M, i
     const bool vec = N % 4 == 0 && ldacc % 4 == 0 && ((uintptr_t)acc % 16 == 0) && ((uintptr_t)out % 16 == 0) && N / 4 < (1ll << 31) &&
                      (!z.use_col || (((uintptr_t)z.colsum_b % 16 == 0) && z.cs_stride % 4 == 0));
     if (vec)
-        acc_post_vec_kernel<1, false><<<stream_grid(batch * M * (N / 4), 256), 256, 0, (cudaStream_t)stream>>>(
-            acc, batch * M, M, (int)(N / 4), ldacc, scale, z, nullptr, 0.f, 0, 0.0, 0.f, 0.f, out);
+        acc_post_fast_kernel<1><<<stream_grid(batch * M * (N / 4), 256), 256, 0, (cudaStream_t)stream>>>(
+            acc, batch * M, M, (int)(N / 4), ldacc, scale, z, 0.f, 0.f, 0.f, 0.f, out);
+
     else
         acc_post_kernel<1, false><<<stream_grid(batch * M * N, 256), 256, 0, (cudaStream_t)stream>>>(
             acc, batch, M, N, ldacc, scale, z, nullptr, 0.f, 0.0, 0.f, 0.f, out);
@@ -609,6 +675,12 @@ extern "C" int nq_requantize_acc(const int32_t* acc, int64_t batch, int64_t M, i
         if (vec) {
             const int g4 = stream_grid(batch * M * (N / 4), 256);
             const bool f64 = has_out_zp && !(out_zp > -(1 << 20) && out_zp < (1 << 20));
+            if (!f64 && !bias_q) {
+                acc_post_fast_kernel<2><<<g4, 256, 0, s>>>(acc, batch * M, M, (int)(N / 4), ldacc, scale, z, inv,
+                                                           has_out_zp ? (float)out_zp : 0.f, lo, hi, out);
+                NQ_CHECK_LAUNCH("nq_requantize_acc");
+                return NQ_OK;
+            }
             if (f64)
                 acc_post_vec_kernel<2, true><<<g4, 256, 0, s>>>(acc, batch * M, M, (int)(N / 4), ldacc, scale, z, bias_q, inv,
                                                                 has_out_zp, (double)out_zp, lo, hi, out);

@@ -254,10 +254,11 @@ def test_qgemm_4096_cubed_vs_cuda_core_gemm():
 
 @pytest.mark.parametrize("za,zb", [(None, None), (None, -3), (5, None), (5, -3)])
 @pytest.mark.parametrize("bits", [8, 4])
-def test_qgemm_fused_epilogues(za, zb, bits):
+@pytest.mark.parametrize("shape", [(3, 150, 200, 320), (2, 300, 256, 768)])     # ragged N: general epilogues; N % 16 == 0: row epilogues
+def test_qgemm_fused_epilogues(za, zb, bits, shape):
     rng = np.random.default_rng(11)
     lo, hi = -2 ** (bits - 1), 2 ** (bits - 1) - 1
-    batch, M, N, Kd = 3, 150, 200, 320
+    batch, M, N, Kd = shape
     a = rng.integers(lo, hi + 1, size=(batch, M, Kd)).astype(np.int64)
     b = rng.integers(lo, hi + 1, size=(batch, Kd, N)).astype(np.int64)
     sa, sb = np.float32(0.021), np.float32(0.0043)
@@ -286,6 +287,17 @@ def test_qgemm_fused_epilogues(za, zb, bits):
         np.testing.assert_array_equal(host(got_q).astype(np.int64), want_q)
         np.testing.assert_array_equal(
             host(K.requantize_acc(raw, s, azp, dev(bq), bits, so, None if zo is None else int(zo))).astype(np.int64), want_q)
+        # without a bias (the standalone kernel's lean route) and with bias values beyond 2^29 (general 64-bit route)
+        want_nb = rq.requantize(acc, s, z, so, zo, bits)
+        np.testing.assert_array_equal(host(K.requantize_acc(raw, s, azp, None, bits, so, None if zo is None else int(zo))).astype(np.int64), want_nb)
+        np.testing.assert_array_equal(host(K.qgemm(oa, ob, _lib.EPI_REQUANT, s, azp, out_bits=bits, out_scale=so,
+                                                   out_zp=None if zo is None else int(zo))).astype(np.int64), want_nb)
+        bw = bq.copy()
+        bw[::7] = (1 << 33) + 12345
+        bw[3::11] = -(1 << 31) - 77
+        want_w = rq.requantize(acc + bw, s, z, so, zo, bits)
+        np.testing.assert_array_equal(host(K.qgemm(oa, ob, _lib.EPI_REQUANT, s, azp, bias_q=dev(bw), out_bits=bits, out_scale=so,
+                                                   out_zp=None if zo is None else int(zo))).astype(np.int64), want_w)
 
 
 def test_qgemm_residual_epilogue_and_ragged_output_rows():
