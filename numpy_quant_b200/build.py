@@ -15,7 +15,7 @@ LIB = os.path.join(HERE, "libnq_b200.so")
 SOURCES = ["runtime.cu", "quant_kernels.cu", "float_kernels.cu", "qgemm_sm100.cu", "attn_sm100.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "--fmad=false",                     # explicit IEEE ops; never contract the float glue
-              "-Xcompiler", "-fPIC", "-cudart", "static"]
+              "-Xcompiler", "-fPIC", "-cudart", "static"] + os.environ.get("NQ_EXTRA_NVCC_FLAGS", "").split()
 
 
 def _nvcc() -> str:

@@ -79,6 +79,8 @@ struct GemmParams {
     float g_prdiv, g_nl2e, g_add, g_out;   // GELU_QUANT: 0.3275911 / c1, -log2(e) / c1^2, c2, c3 / s_out
     int two_cta;                     // CTA-pair kernel (256-row tiles, cta_group::2)
     int deq_wide;                    // DEQUANT: alignment / extent conditions of the 32-column epilogue hold (host-checked)
+    int dbg;                         // NQ_GEMM_DBG bit mask (measurement only, benchmarks/probe_epilogue_parts.py): 1 no epilogue
+                                     // math, 2 no TMEM loads, 4 no stores, 8 no MMAs, 16 no epilogue chunks -- garbage results
     int req_rows;                    // REQUANT: 32-bit windows and alignment of the thread-per-row epilogue hold (host-checked)
     int sm_noclamp;                  // SOFTMAX: out_zp >= lo: p / s_out + zp (p in [0, 1]) needs no lower clamp
     float sm_top;                    // SOFTMAX: upper clamp in the magic-sum domain (1.5 * 2^23 + hi), huge when p = 1 fits
@@ -336,7 +338,7 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         // advance 32 bytes along K inside the swizzle atom: +2 in 16-byte units
-                        if (k < ksteps) {
+                        if (k < ksteps && !(p.dbg & 8)) {
                             if constexpr (TWO)
                                 mma_i8_pair(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
                                             (kb > 0 || k > 0) ? 1u : 0u);
@@ -501,7 +503,12 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                     const int64_t nc = n0 + cw;
                     if (nc >= p.N) break;                                 // warp-uniform (N % 16 == 0)
                     uint32_t v[16];
-                    tmem_ld_32x32b_x16(t_row + (uint32_t)cw, v);
+                    if (p.dbg & 16) continue;
+                    if (!(p.dbg & 2)) tmem_ld_32x32b_x16(t_row + (uint32_t)cw, v);
+                    else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] = (uint32_t)(i + j);
+                    }
                     int ct[16];
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
@@ -563,6 +570,9 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                     // pattern only grows, which saturates correctly.
                     const float2 r2 = make_float2(qz.sd.r, qz.sd.r), nb2 = make_float2(-qz.sd.b, -qz.sd.b), mg2 = make_float2(qz.magic, qz.magic);
                     uint32_t w[4];
+                    if (p.dbg & 1) {
+                        w[0] = __float_as_uint(f[0]); w[1] = __float_as_uint(f[5]); w[2] = __float_as_uint(f[10]); w[3] = __float_as_uint(f[15]);
+                    } else
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
                         const float4 b4 = *reinterpret_cast<const float4*>(bsw + i * 16 + g * 4);
@@ -640,7 +650,7 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                             }
                         }
                     } else {
-                        if (row_ok)
+                        if (row_ok && !(p.dbg & 4))
                             *reinterpret_cast<int4*>(reinterpret_cast<int8_t*>(p.C) + row_off + (int64_t)nh * p.q_off[4] + nd) =
                                 make_int4((int)w[0], (int)w[1], (int)w[2], (int)w[3]);
                         if (p.q_rowsum) {
@@ -1408,6 +1418,7 @@ static int qgemm_run(const int8_t* A, const int8_t* B, void* Cout, int64_t M, in
     }
     p.bias_f32 = ep->bias_f32;
     p.bias_q = ep->bias_q;
+    p.dbg = getenv("NQ_GEMM_DBG") ? atoi(getenv("NQ_GEMM_DBG")) : 0;
     p.c_inner = ep->c_batch_inner > 1 ? ep->c_batch_inner : 1;
     p.stride_c_inner = ep->c_batch_inner > 1 ? ep->stride_c_inner : 0;
     NQ_REQUIRE(p.c_inner == 1 || (batch % p.c_inner == 0 && ep->mode != NQ_EPI_REQUANT),

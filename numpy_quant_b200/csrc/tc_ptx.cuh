@@ -59,7 +59,9 @@ __device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity)
             : "r"(bar), "r"(parity), "r"(20000u)
             : "memory");
         if (!done && spin > 4) {
+#ifndef NQ_NO_BACKOFF_SLEEP
             asm volatile("nanosleep.u32 %0;" ::"r"(spin > 32 ? 200u : 60u));
+#endif
             if ((spin & 255u) == 0) {
                 uint64_t now;
                 asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
