@@ -364,7 +364,7 @@ def extra_config3(torch, dev, local, peaks, lib_tops, steps: int) -> dict:
     proto = zoo.conv_graph(nb, 64, (57, 58), 128, (3, 2), (0, 2, 2, 1), (2, 1), seed=0)
     x = torch.from_numpy(np.random.default_rng(0).normal(size=(nb, 64, 57, 58)).astype(np.float32)).to(dev)
     model = Model.from_onnx(proto)
-    q = model.quantize([x[:8]], bit_width=8)
+    q = model.quantize([x[:8]], bit_width=8, group=False)    # rank 0 only: no statistics exchange
     model.release()
     q.release()
     for _ in range(3):
@@ -605,9 +605,6 @@ def run_own_arm(args) -> None:
         extra["config4_vit_int4_int2_packed"] = {
             "workload": f"configs[3]: ViT-B/16 int4 / int2, packed weights, 512 images per GPU x {ws} GPU(s) = global batch {512 * ws} "
                         "(4096 at 8 GPUs), calibration sharded with the min/max all-reduce", "runs": c4}
-        if rank == 0:
-            extra["config3_conv_block_b1024"] = extra_config3(torch, dev, local, peaks, lib_tops, max(3, min(args.steps, 10)))
-            extra["config5_microbench_4096"] = extra_config5(torch, dev, local, peaks, lib_tops)
 
     per_rank = [ms_rank]
     if ws > 1:
@@ -621,6 +618,11 @@ def run_own_arm(args) -> None:
     else:
         e2e_ms = e2e_s * 1e3
         sus_ms_max, strong_ms = (sustained["ms_rank"] if sustained else 0.0), 0.0
+
+    # single-GPU configurations: rank 0 alone, after the job's last collective (nothing below may touch the process group)
+    if rank == 0 and not args.no_extra:
+        extra["config3_conv_block_b1024"] = extra_config3(torch, dev, local, peaks, lib_tops, max(3, min(args.steps, 10)))
+        extra["config5_microbench_4096"] = extra_config5(torch, dev, local, peaks, lib_tops)
 
     # timer entries: (ops, start, end[, tag]); the fused attention kernel is reported next to the GEMM family
     gemm = [e for e in timer if len(e) == 3]
@@ -663,9 +665,10 @@ def run_own_arm(args) -> None:
                      "frac_all_denominators": tops_fractions(achieved, peaks, lib_tops) if achieved else None,
                      "library_int8_tops_8192": lib_tops,
                      "bound_note": ("the int8 GEMMs of this graph carry fused epilogues (dequantize / GELU / quantize for the next "
-                                    "MatMul); the K = 768 ones are bound by per-tile epilogue work on the CUDA cores (K-sweep: "
-                                    "K 768 -> 128 changes them by 7 %), the K = 3072 one by the tensor pipe / operand feed -- "
-                                    "profiles/r02_*.md"),
+                                    "MatMul). Ablation (NQ_GEMM_DBG, profiles/r02_gemm_ablation.md): the N = K = 768 launches have a ~40 us "
+                                    "operand-feed floor (L2 -> SM) under a ~45 us epilogue that only partly overlap; MLP-1 "
+                                    "(N = 3072, GELU + quantize) is epilogue-bound with the MUFU pipe as its floor; MLP-2 "
+                                    "(K = 3072) runs closest to the tensor pipe"),
                      "kernel": "nq::qgemm_kernel<BN, epilogue> (all instantiations launched in the step: the int8 GEMMs)",
                      "launches_per_step": len(gemm) // max(args.steps, 1),
                      "share_of_step": gemm_ms / eager_ms if eager_ms else None,

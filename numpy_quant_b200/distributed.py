@@ -30,11 +30,14 @@ def init_from_env(backend: Optional[str] = None) -> tuple[int, int, int]:
     if ws > 1 and not dist.is_initialized():
         if backend is None:
             backend = "nccl" if torch.cuda.is_available() else "gloo"
+        import datetime
+        # a rank that dies or diverges must fail the job in minutes, not after the 10-minute default watchdog
+        tmo = datetime.timedelta(seconds=int(os.environ.get("NQ_DIST_TIMEOUT_S", "240")))
         if backend == "nccl":
             torch.cuda.set_device(local)
-            dist.init_process_group(backend=backend, rank=rank, world_size=ws, device_id=torch.device("cuda", local))
+            dist.init_process_group(backend=backend, rank=rank, world_size=ws, device_id=torch.device("cuda", local), timeout=tmo)
         else:
-            dist.init_process_group(backend=backend, rank=rank, world_size=ws)
+            dist.init_process_group(backend=backend, rank=rank, world_size=ws, timeout=tmo)
     elif torch.cuda.is_available():
         torch.cuda.set_device(local)
     return rank, local, ws
@@ -57,12 +60,15 @@ def shard_batch(arrays: list, rank: int, world_size: int) -> list:
 
 
 def allreduce_minmax(mm: torch.Tensor, group=None) -> torch.Tensor:
-    """mm[n, 2] = (min, max) per value on this rank -> global (min, max) on every rank.
+    """mm[n, 2] = (min, max) per value on this rank -> global (min, max) on every rank (`group=False`: no exchange,
+    this rank calibrates on its own -- for work that only one rank of a job performs).
 
     One all-reduce(MAX) over the packed vector [max_0.., -min_0..]; min/max are exact under
     any reduction order, so all ranks end up with bit-identical statistics (and therefore
     bit-identical quantization parameters) regardless of how the calibration batch was split.
     """
+    if group is False:                                   # explicitly local calibration inside a multi-rank job
+        return mm
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return mm
     packed = torch.cat([mm[:, 1], -mm[:, 0]]).contiguous()
