@@ -158,6 +158,8 @@ typedef struct nq_epilogue {
                                       library zeroes them itself when partial sums have to meet through atomics */
     float gelu_div, gelu_add, gelu_mul;   /* NQ_EPI_GELU_QUANT: constants c1, c2, c3 of the graph's
                                              Div(x, c1) -> Erf -> Add(., c2) -> Mul(x, .) -> Mul(., c3) chain */
+    int reverse_tiles;             /* != 0: walk the output tiles from the last to the first (same results): the tail of
+                                      an A operand written front to back by the previous kernel is still in L2 */
 } nq_epilogue;
 
 /* ---- fused quantized attention (one kernel per layer; replaces, for every image and head, the chain
@@ -294,9 +296,12 @@ int nq_softmax_div_f32(const float* x, int64_t rows, int64_t cols, int64_t ldx, 
 int nq_layernorm_quantize_f32(const float* x, int64_t rows, int64_t cols, int64_t ldx, const float* gamma,
                               const float* beta, float eps, int bit_width, float scale, int has_zp, int64_t zp,
                               int8_t* out, int64_t ldo, int32_t* rowsum, int float_glue, void* stream);
-/* float_glue != 0: the normalised value is float glue under the 1e-5 contract (one FMA for gamma/beta, division
- * by the scale through its reciprocal); rounding, clamp and row sums stay exact.  0: the same float32 roundings as
- * nq_layernorm_f32 followed by nq_quantize_f32. */
+/* float_glue bit 0: the normalised value is float glue under the 1e-5 contract (one FMA for gamma/beta, division
+ * by the scale through its reciprocal); rounding, clamp and row sums stay exact.  Clear: the same float32 roundings as
+ * nq_layernorm_f32 followed by nq_quantize_f32.
+ * float_glue bit 1 (with bit 0): walk the rows from the last to the first.  Same results; a producer that wrote x
+ * front to back immediately before this call left its last rows in L2 (x is larger than L2 at the batch sizes of
+ * BASELINE.json), so the reverse walk reads them from there instead of from HBM. */
 int nq_softmax_quantize_f32(const float* x, int64_t rows, int64_t cols, int64_t ldx, int has_div, float div_const,
                             int bit_width, float scale, int has_zp, int64_t zp,
                             int8_t* out, int64_t ldo, int32_t* rowsum, void* stream);

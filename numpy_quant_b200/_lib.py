@@ -29,7 +29,7 @@ class Epilogue(C.Structure):
                 ("c_batch_inner", i64), ("stride_c_inner", i64),
                 ("q_rows_per_image", i64), ("q_cols_per_head", i64), ("q_off", i64 * 6), ("q_rs", i64 * 6),
                 ("q_rowsum", vp), ("sm_has_div", C.c_int), ("sm_div", f32),
-                ("q_rowsum_count", i64), ("gelu_div", f32), ("gelu_add", f32), ("gelu_mul", f32)]
+                ("q_rowsum_count", i64), ("gelu_div", f32), ("gelu_add", f32), ("gelu_mul", f32), ("reverse_tiles", C.c_int)]
 
 
 class Attention(C.Structure):

@@ -285,7 +285,7 @@ template <int NV>
 __global__ void __launch_bounds__(256, 3) layernorm_glue_kernel(const float* __restrict__ x, int64_t rows, int cols, int64_t ldx,
                                                                const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                float eps, QArgs qa, int8_t* __restrict__ qout, int64_t ldo,
-                                                               int32_t* __restrict__ rowsum) {
+                                                               int32_t* __restrict__ rowsum, int reverse) {
     extern __shared__ __align__(16) unsigned char ln_smem[];
     float4* gs = reinterpret_cast<float4*>(ln_smem);                       // [c4] gamma / s_out
     float4* bs = gs + (cols >> 2);                                         // [c4] beta / s_out
@@ -301,8 +301,11 @@ __global__ void __launch_bounds__(256, 3) layernorm_glue_kernel(const float* __r
         bs[c] = make_float4(b.x * rscale, b.y * rscale, b.z * rscale, b.w * rscale);
     }
     __syncthreads();
+    // reverse: walk the rows from the last to the first -- a producer that wrote x front to back right before this
+    // launch left its most recent (= last) rows in L2
     auto load_row = [&](int64_t r, float4* dstv) {
         r = r < rows ? r : rows - 1;                                       // past the end: a harmless re-read, never used
+        if (reverse) r = rows - 1 - r;
         const float4* src = reinterpret_cast<const float4*>(x + r * ldx) + lane;
 #pragma unroll
         for (int j = 0; j < NV; ++j)
@@ -312,14 +315,15 @@ __global__ void __launch_bounds__(256, 3) layernorm_glue_kernel(const float* __r
     float4 nx[NV];
     load_row(row0, nx);
     const float2 mg2 = make_float2(qz.magic, qz.magic);
-    for (int64_t row = row0; row < rows; row += warps) {
+    for (int64_t rowi = row0; rowi < rows; rowi += warps) {
+        const int64_t row = reverse ? rows - 1 - rowi : rowi;
         float2 a[NV], b[NV];                                               // (x, y) and (z, w) halves of the row's float4s
 #pragma unroll
         for (int j = 0; j < NV; ++j) {
             a[j] = make_float2(nx[j].x, nx[j].y);
             b[j] = make_float2(nx[j].z, nx[j].w);
         }
-        load_row(row + warps, nx);
+        load_row(rowi + warps, nx);
         float2 s2 = make_float2(0.f, 0.f);
 #pragma unroll
         for (int j = 0; j < NV; ++j) s2 = __fadd2_rn(s2, __fadd2_rn(a[j], b[j]));       // padding lanes hold zeros
@@ -923,7 +927,7 @@ extern "C" int nq_binary_f32(int op, const float* a, const int64_t* sa_host, con
 
 static int launch_layernorm(const float* x, int64_t rows, int64_t cols, int64_t ldx, const float* gamma,
                             const float* beta, float eps, float* out, int qmode, const QArgs& qa, int8_t* qout,
-                            int64_t ldo, int32_t* rowsum, cudaStream_t s) {
+                            int64_t ldo, int32_t* rowsum, cudaStream_t s, int reverse = 0) {
     const int grid = stream_grid(rows * 32, 256);
     const bool vec = (cols % 4 == 0) && (ldx % 4 == 0) && aligned16(x) && aligned16(gamma) && aligned16(beta) &&
                      (qmode >= 0 ? ((ldo & 3) == 0) : aligned16(out));
@@ -944,7 +948,7 @@ static int launch_layernorm(const float* x, int64_t rows, int64_t cols, int64_t 
     do {                                                                                                                \
         const size_t sm_ = (size_t)cols * 8;                                                                            \
         const int g_ = resident_grid(layernorm_glue_kernel<NV>, rows * 32, 256, sm_);                                   \
-        layernorm_glue_kernel<NV><<<g_, 256, sm_, s>>>(x, rows, (int)cols, ldx, gamma, beta, eps, qa, qout, ldo, rowsum); \
+        layernorm_glue_kernel<NV><<<g_, 256, sm_, s>>>(x, rows, (int)cols, ldx, gamma, beta, eps, qa, qout, ldo, rowsum, reverse); \
     } while (0)
     if (qmode == 3 && vec && cols <= 512) NQ_LN_GLUE(4);
     else if (qmode == 3 && vec && cols <= 768) NQ_LN_GLUE(6);
@@ -981,8 +985,10 @@ extern "C" int nq_layernorm_quantize_f32(const float* x, int64_t rows, int64_t c
     if (rows <= 0 || cols <= 0) return NQ_OK;
     int qmode;
     const QArgs qa = make_qargs(bit_width, scale, has_zp, zp, &qmode);
-    if (float_glue && qmode != 2) qmode = 3;
-    if (int rc = launch_layernorm(x, rows, cols, ldx, gamma, beta, eps, nullptr, qmode, qa, out, ldo, rowsum, (cudaStream_t)stream)) return rc;
+    if ((float_glue & 1) && qmode != 2) qmode = 3;
+    if (int rc = launch_layernorm(x, rows, cols, ldx, gamma, beta, eps, nullptr, qmode, qa, out, ldo, rowsum, (cudaStream_t)stream,
+                                  (float_glue & 2) ? 1 : 0))
+        return rc;
     NQ_CHECK_LAUNCH("nq_layernorm_quantize_f32");
     return NQ_OK;
 }

@@ -81,6 +81,7 @@ struct GemmParams {
     int deq_wide;                    // DEQUANT: alignment / extent conditions of the 32-column epilogue hold (host-checked)
     int dbg;                         // NQ_GEMM_DBG bit mask (measurement only, benchmarks/probe_epilogue_parts.py): 1 no epilogue
                                      // math, 2 no TMEM loads, 4 no stores, 8 no MMAs, 16 no epilogue chunks -- garbage results
+    int reverse;                     // tile i of the schedule is output tile total - 1 - i (L2 reuse of the producer's tail)
     int req_rows;                    // REQUANT: 32-bit windows and alignment of the thread-per-row epilogue hold (host-checked)
     int sm_noclamp;                  // SOFTMAX: out_zp >= lo: p / s_out + zp (p in [0, 1]) needs no lower clamp
     float sm_top;                    // SOFTMAX: upper clamp in the magic-sum domain (1.5 * 2^23 + hi), huge when p = 1 fits
@@ -262,7 +263,8 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (uint32_t t = tile_first; t < total_tiles; t += tile_step) {
+            for (uint32_t ts = tile_first; ts < total_tiles; ts += tile_step) {
+                const uint32_t t = p.reverse ? total_tiles - 1u - ts : ts;
                 const uint32_t b = t / tiles_per_batch, r = t % tiles_per_batch;
                 // pair: this CTA stages its own 128 rows of A and its half of the B rows
                 const int m0 = (int)(r / n_tiles) * BMT + (int)cta_rank * BM;
@@ -404,6 +406,7 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
         auto prefetch_tile = [&](uint32_t tt, TilePre& o) {
             o.rowsum = o.c0 = o.c1 = o.b0 = o.b1 = o.wide = 0;
             if (tt >= total_tiles) return;
+            if (p.reverse) tt = total_tiles - 1u - tt;
             const uint32_t pb = tt / tiles_per_batch, pr = tt - pb * tiles_per_batch;
             const uint32_t pm0 = (pr / n_tiles) * BMT + cta_rank * BM, pn0 = (pr % n_tiles) * BN;
             const int64_t pm = (int64_t)pm0 + q * 32 + lane;
@@ -436,7 +439,8 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
         prefetch_tile(tile_first + grp * tile_step, nxt);
         // this CTA's (pair's) i-th tile is t = tile_first + i * tile_step, lives in accumulator buffer i % NACC and is
         // drained by group i % GROUPS
-        for (uint32_t li = grp, t = tile_first + grp * tile_step; t < total_tiles; li += C::GROUPS, t += C::GROUPS * tile_step) {
+        for (uint32_t li = grp, ts = tile_first + grp * tile_step; ts < total_tiles; li += C::GROUPS, ts += C::GROUPS * tile_step) {
+            const uint32_t t = p.reverse ? total_tiles - 1u - ts : ts;
             const int acc = (int)(li % C::NACC);
             const uint32_t acc_phase = (li / C::NACC) & 1u;
             const int64_t b = t / tiles_per_batch;
@@ -447,7 +451,7 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
             const bool row_ok = m < p.M;
             const int32_t* cs_b = z.use_col ? z.colsum_b + b * z.cs_stride : nullptr;
             const TilePre cur = nxt;
-            prefetch_tile(t + C::GROUPS * tile_step, nxt);
+            prefetch_tile(ts + C::GROUPS * tile_step, nxt);
             int64_t rowterm = -z.kterm;
             if (z.use_row && row_ok) rowterm += (int64_t)cur.rowsum * z.zp_b;
             if constexpr (Q8) {
@@ -1419,6 +1423,7 @@ static int qgemm_run(const int8_t* A, const int8_t* B, void* Cout, int64_t M, in
     p.bias_f32 = ep->bias_f32;
     p.bias_q = ep->bias_q;
     p.dbg = getenv("NQ_GEMM_DBG") ? atoi(getenv("NQ_GEMM_DBG")) : 0;
+    p.reverse = ep->reverse_tiles != 0;
     p.c_inner = ep->c_batch_inner > 1 ? ep->c_batch_inner : 1;
     p.stride_c_inner = ep->c_batch_inner > 1 ? ep->stride_c_inner : 0;
     NQ_REQUIRE(p.c_inner == 1 || (batch % p.c_inner == 0 && ep->mode != NQ_EPI_REQUANT),

@@ -7,6 +7,7 @@ asynchronous on `torch.cuda.current_stream()`.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 from typing import Optional
 
@@ -217,6 +218,29 @@ def requantize_f32(d: torch.Tensor, bits: int, out_scale, out_zp) -> torch.Tenso
 
 
 # --------------------------------------------------------------------------- K4 / K5
+# Walk direction of the large row-ordered producers (L2 reuse between consecutive kernels).  An activation of the
+# BASELINE.json batch sizes (155 MB float32 / int8) does not fit the 126 MB L2, but its most recently written part
+# does: a consumer launched right after a producer that walked the rows front to back finds the LAST rows in L2 and
+# therefore walks back to front (and the other way round).  Results do not depend on the direction.
+# _WALK: data_ptr of a recently produced tensor -> True if its producer walked back to front.
+_WALK: dict = {}
+WALK_REUSE = os.environ.get("NQ_NO_L2_WALK") is None      # A/B switch
+_WALK_MIN_BYTES = 48 << 20
+
+
+def _walk_note(ptr: int, reverse: bool) -> None:
+    if len(_WALK) > 256:
+        _WALK.clear()
+    _WALK[ptr] = bool(reverse)
+
+
+def _walk_opposite(ptr: int, nbytes: int) -> bool:
+    """Direction for a consumer of the tensor at `ptr`: the opposite of its producer's (unknown producer: front to back)."""
+    if not WALK_REUSE or nbytes < _WALK_MIN_BYTES:
+        return False
+    return not _WALK.get(ptr, False)
+
+
 def qgemm(a: Operand, b: Operand, mode: int = _lib.EPI_RAW, scale: float = 1.0,
           azp: Optional[AccZeroPoint] = None, bias_f32: Optional[torch.Tensor] = None,
           bias_q: Optional[torch.Tensor] = None, out_bits: int = 8, out_scale: float = 1.0, out_zp=None,
@@ -263,6 +287,10 @@ def qgemm(a: Operand, b: Operand, mode: int = _lib.EPI_RAW, scale: float = 1.0,
     ep.out_scale = float(out_scale)
     ep.has_out_zp = int(out_zp is not None)
     ep.out_zp = 0 if out_zp is None else int(out_zp)
+    if a.batch == 1 and mode == _lib.EPI_DEQUANT:
+        # a large A written by the previous kernel: start where that kernel stopped
+        ep.reverse_tiles = int(a.data.data_ptr() in _WALK and _walk_opposite(a.data.data_ptr(), M * a.ld))
+        _walk_note(out.data_ptr(), bool(ep.reverse_tiles))
     timer = GEMM_TIMER
     if timer is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -393,6 +421,8 @@ def qgemm_to_operand(a: Operand, b: Operand, scale: float, azp: AccZeroPoint, bi
     if timer is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+    if kind == "rows" and batch == 1:
+        _walk_note(out.data_ptr(), False)                                 # row-ordered producer of a plain [M, N] operand
     call("nq_qgemm_s8", a.data.data_ptr(), b.data.data_ptr(), out.data_ptr(), M, N, Kd, batch, a.ld, b.ld, N,
          sa, sb, M * N, C.byref(ep), _stream())
     if timer is not None:
@@ -659,9 +689,10 @@ def layernorm_quantize(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor,
     layernorm() followed by quantize_operand(); True: the normalised value is float glue (1e-5 contract)."""
     _need_cuda(x, torch.float32)
     op, rows, cols, ld = _rows_operand(x, want_rowsum)
+    flags = int(float_glue) | (2 if float_glue and _walk_opposite(x.data_ptr(), x.numel() * 4) else 0)
     call("nq_layernorm_quantize_f32", x.data_ptr(), rows, cols, cols, gamma.contiguous().data_ptr(),
          beta.contiguous().data_ptr(), float(eps), bits, float(scale), int(zp is not None), 0 if zp is None else int(zp),
-         op.data.data_ptr(), ld, _ptr(op.rowsum), int(float_glue), _stream())
+         op.data.data_ptr(), ld, _ptr(op.rowsum), flags, _stream())
     _count()
     return op
 
