@@ -27,6 +27,14 @@ __global__ void __launch_bounds__(512) k(float* out, long long* cyc, float a, fl
             if (MODE == 7) { asm volatile("rcp.approx.ftz.f32 %0, %0;" : "+f"(r[i].x)); }
             if (MODE == 8) { r[i].x = fmaxf(r[i].x, a); r[i].y = fminf(r[i].y, b); }                           // 2 FMNMX
             if (MODE == 9) { n[i] = n[i] + it; n[i] ^= 0x4b000000; }                                           // IADD + LOP3
+            if (MODE == 10) { r[i] = __ffma2_rn(r[i], a2, b2); n[i] = n[i] + it; r[i] = __ffma2_rn(r[i], b2, a2); n[i] ^= 0x4b000000; }   // 2 FFMA2 + 2 ALU
+            if (MODE == 11) {                                                                                  // epilogue mix 4 FFMA2 : 3 ALU : 1 MUFU
+                r[i] = __ffma2_rn(r[i], a2, b2); n[i] = n[i] + it; r[i] = __ffma2_rn(r[i], b2, a2); n[i] ^= 0x4b000000;
+                asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(r[i].x));
+                r[i] = __ffma2_rn(r[i], a2, b2); n[(i + 3) & 7] = max(n[(i + 3) & 7], n[i]); r[i] = __ffma2_rn(r[i], b2, a2);
+            }
+            if (MODE == 12) { r[i].x = __fmaf_rn(r[i].x, a, b); n[i] = n[i] + it; r[i].y = __fmaf_rn(r[i].y, a, b); n[i] ^= 0x4b000000; }   // 2 FFMA + 2 ALU
+            if (MODE == 13) { asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(r[i].x)); n[i] = n[i] + it; n[i] ^= 0x4b000000; n[(i + 3) & 7] = max(n[(i + 3) & 7], n[i]); n[i] += 3; }   // MUFU + 4 ALU
         }
     }
     const long long t1 = clock64();
@@ -49,7 +57,7 @@ void run(const char* name, int per_iter_instr, int threads) {
     cudaFree(out); cudaFree(cyc);
 }
 int main() {
-    for (int th : {128, 512}) {
+    for (int th : {128, 256, 512}) {
         run<0>("FFMA (3 reg) x2", 2, th);
         run<1>("FFMA2 x1", 1, th);
         run<2>("FFMA2 x2 dependent pair", 2, th);
@@ -60,6 +68,10 @@ int main() {
         run<7>("MUFU.RCP", 1, th);
         run<8>("FMNMX x2", 2, th);
         run<9>("IADD + LOP3", 2, th);
+        run<10>("2 FFMA2 + 2 ALU interleaved", 4, th);
+        run<11>("mix 4 FFMA2 + 3 ALU + 1 MUFU", 8, th);
+        run<12>("2 FFMA + 2 ALU interleaved", 4, th);
+        run<13>("1 MUFU + 4 ALU", 5, th);
     }
     return 0;
 }

@@ -237,49 +237,55 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
         asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
         if (warp == 0) {
             // ===================== TMA producer: one stage per (image, head) =====================
-            if (lane == 0) {
-                int stage = 0;
-                uint32_t phase = 0, lh = 0;
-                for (uint32_t hd = blockIdx.x; hd < n_heads; hd += gridDim.x, ++lh) {
-                    mbar_wait_relaxed(smem_u32(empty_bar + stage), phase ^ 1);
-                    const uint32_t fb = smem_u32(full_bar + stage);
-                    uint8_t* st = smem + stage * STAGE_BYTES;
+            // Both single-issuer roles run the schedule with the whole warp in uniform control flow; one elected lane
+            // executes the TMA / tcgen05 instructions, so their operands stay in uniform registers (inside an
+            // `if (lane == 0)` region every such instruction is wrapped in a register -> uniform-register loop).
+            const bool leader = elect_one_sync();
+            int stage = 0;
+            uint32_t phase = 0, lh = 0;
+            for (uint32_t hd = blockIdx.x; hd < n_heads; hd += gridDim.x, ++lh) {
+                mbar_wait_relaxed(smem_u32(empty_bar + stage), phase ^ 1);
+                const uint32_t fb = smem_u32(full_bar + stage);
+                uint8_t* st = smem + stage * STAGE_BYTES;
+                const int m0a = tile_info(S, m_tiles, lh, 0).m0, m0b = m_tiles > 1 ? tile_info(S, m_tiles, lh, 1).m0 : 0;
+                if (leader) {
                     mbar_expect_tx(fb, (uint32_t)(m_tiles * Q_BYTES + K_BYTES + V_BYTES));
-                    for (int mt = 0; mt < m_tiles; ++mt)
-                        tma_load_3d(smem_u32(st + mt * Q_BYTES), &tmap_q, 0, tile_info(S, m_tiles, lh, mt).m0, (int)hd, fb);
+                    tma_load_3d(smem_u32(st), &tmap_q, 0, m0a, (int)hd, fb);
+                    if (m_tiles > 1) tma_load_3d(smem_u32(st + Q_BYTES), &tmap_q, 0, m0b, (int)hd, fb);
                     tma_load_3d(smem_u32(st + 2 * Q_BYTES), &tmap_k, 0, 0, (int)hd, fb);
                     tma_load_3d(smem_u32(st + 2 * Q_BYTES + K_BYTES), &tmap_v, 0, 0, (int)hd, fb);
                     tma_load_3d(smem_u32(st + 2 * Q_BYTES + K_BYTES + BN2 * BK), &tmap_v, BK, 0, (int)hd, fb);
-                    if (++stage == STAGES) {
-                        stage = 0;
-                        phase ^= 1;
-                    }
+                }
+                if (++stage == STAGES) {
+                    stage = 0;
+                    phase ^= 1;
                 }
             }
             __syncwarp();
         } else if (warp == 1) {
             // ===================== MMA issuer =====================
-            if (lane == 0) {
-                constexpr uint32_t id_s = idesc_i8(BN1, true, true);      // Q . K^T and the -zq pass: signed x signed
-                constexpr uint32_t id_pu = idesc_i8(BN2, false, true);    // P (unsigned bytes) . V, P . const(-zv)
-                constexpr uint32_t id_ps = idesc_i8(BN2, true, true);     // const(lo_p - zp_p) . V
-                const uint64_t ca = make_smem_desc(smem_u32(smem_ca)), cb = make_smem_desc(smem_u32(smem_cb));
-                const uint64_t pd0 = make_smem_desc(smem_u32(smem_p)), pd1 = make_smem_desc(smem_u32(smem_p + BM * BK));
-                uint32_t li = 0, lh = 0;                                  // local tile / head counters
-                int prev_stage = -1, prev_last = 0;
-                uint32_t hd = blockIdx.x;
-                bool more = hd < n_heads;
-                int mt = 0;
-                for (;; ++li) {
-                    const int stage = (int)(lh % STAGES);
-                    if (more) {
-                        // ---- scores of tile li, as soon as the softmax warps hold tile li - 1 in registers
-                        mbar_wait_backoff(smem_u32(sempty_bar), (li & 1u) ^ 1u);
-                        if (mt == 0) mbar_wait_backoff(smem_u32(full_bar + stage), (lh / STAGES) & 1u);
-                        tc_fence_after();
-                        uint8_t* st = smem + stage * STAGE_BYTES;
-                        const uint64_t qd = make_smem_desc(smem_u32(st + mt * Q_BYTES)), kd = make_smem_desc(smem_u32(st + 2 * Q_BYTES));
-                        const uint32_t d_s = tmem_base;
+            const bool leader = elect_one_sync();
+            constexpr uint32_t id_s = idesc_i8(BN1, true, true);          // Q . K^T and the -zq pass: signed x signed
+            constexpr uint32_t id_pu = idesc_i8(BN2, false, true);        // P (unsigned bytes) . V, P . const(-zv)
+            constexpr uint32_t id_ps = idesc_i8(BN2, true, true);         // const(lo_p - zp_p) . V
+            const uint64_t ca = make_smem_desc(smem_u32(smem_ca)), cb = make_smem_desc(smem_u32(smem_cb));
+            const uint64_t pd0 = make_smem_desc(smem_u32(smem_p)), pd1 = make_smem_desc(smem_u32(smem_p + BM * BK));
+            uint32_t li = 0, lh = 0;                                      // local tile / head counters
+            int prev_stage = -1, prev_last = 0;
+            uint32_t hd = blockIdx.x;
+            bool more = hd < n_heads;
+            int mt = 0;
+            for (;; ++li) {
+                const int stage = (int)(lh % STAGES);
+                if (more) {
+                    // ---- scores of tile li, as soon as the softmax warps hold tile li - 1 in registers
+                    mbar_wait_backoff(smem_u32(sempty_bar), (li & 1u) ^ 1u);
+                    if (mt == 0) mbar_wait_backoff(smem_u32(full_bar + stage), (lh / STAGES) & 1u);
+                    tc_fence_after();
+                    uint8_t* st = smem + stage * STAGE_BYTES;
+                    const uint64_t qd = make_smem_desc(smem_u32(st + mt * Q_BYTES)), kd = make_smem_desc(smem_u32(st + 2 * Q_BYTES));
+                    const uint32_t d_s = tmem_base;
+                    if (leader) {
                         for (int k = 0; k < ks1; ++k) mma_i8(d_s, qd + (uint64_t)(k * 2), kd + (uint64_t)(k * 2), id_s, k > 0 ? 1u : 0u);
 #pragma unroll
                         for (int c = 0; c < 2; ++c)
@@ -287,17 +293,19 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
                                 for (int k = 0; k < ks1; ++k) mma_i8(d_s, ca + (uint64_t)(c * 2), kd + (uint64_t)(k * 2), id_s, 1u);
                         tc_commit(smem_u32(sfull_bar));
                     }
-                    if (li > 0) {
-                        // ---- context of tile li - 1: P is in shared memory, the accumulator buffer is free
-                        const uint32_t lp = li - 1;
-                        const uint32_t ob = lp & 1u;                      // context accumulator buffer of that tile
-                        mbar_wait_backoff(smem_u32(pfull_bar), lp & 1u);
-                        mbar_wait_backoff(smem_u32(oempty_bar + ob), ((lp >> 1) & 1u) ^ 1u);
-                        tc_fence_after();
-                        uint8_t* st = smem + prev_stage * STAGE_BYTES;
-                        const uint64_t vd0 = make_smem_desc(smem_u32(st + 2 * Q_BYTES + K_BYTES));
-                        const uint64_t vd1 = make_smem_desc(smem_u32(st + 2 * Q_BYTES + K_BYTES + BN2 * BK));
-                        const uint32_t d_o = tmem_base + (uint32_t)(O_COL + BN2 * ob);
+                }
+                if (li > 0) {
+                    // ---- context of tile li - 1: P is in shared memory, the accumulator buffer is free
+                    const uint32_t lp = li - 1;
+                    const uint32_t ob = lp & 1u;                          // context accumulator buffer of that tile
+                    mbar_wait_backoff(smem_u32(pfull_bar), lp & 1u);
+                    mbar_wait_backoff(smem_u32(oempty_bar + ob), ((lp >> 1) & 1u) ^ 1u);
+                    tc_fence_after();
+                    uint8_t* st = smem + prev_stage * STAGE_BYTES;
+                    const uint64_t vd0 = make_smem_desc(smem_u32(st + 2 * Q_BYTES + K_BYTES));
+                    const uint64_t vd1 = make_smem_desc(smem_u32(st + 2 * Q_BYTES + K_BYTES + BN2 * BK));
+                    const uint32_t d_o = tmem_base + (uint32_t)(O_COL + BN2 * ob);
+                    if (leader) {
                         for (int k = 0; k < ks2; ++k) {
                             const uint64_t off = (uint64_t)((k & 3) * 2);
                             mma_i8(d_o, (k < 4 ? pd0 : pd1) + off, (k < 4 ? vd0 : vd1) + off, id_pu, k > 0 ? 1u : 0u);
@@ -314,15 +322,15 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
                         if (prev_last) tc_commit(smem_u32(empty_bar + prev_stage));   // Q / K / V of that head no longer needed
                         tc_commit(smem_u32(ofull_bar + ob));
                     }
-                    if (!more) break;
-                    prev_stage = stage;
-                    prev_last = (mt == m_tiles - 1);
-                    if (++mt == m_tiles) {
-                        mt = 0;
-                        ++lh;
-                        hd += gridDim.x;
-                        more = hd < n_heads;
-                    }
+                }
+                if (!more) break;
+                prev_stage = stage;
+                prev_last = (mt == m_tiles - 1);
+                if (++mt == m_tiles) {
+                    mt = 0;
+                    ++lh;
+                    hd += gridDim.x;
+                    more = hd < n_heads;
                 }
             }
             __syncwarp();
