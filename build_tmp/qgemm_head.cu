@@ -93,11 +93,6 @@ struct GemmParams {
     uint32_t cv_C, cv_KW, cv_OW, cv_OH, cv_sw, cv_sh;
 };
 
-// Measurement hooks (benchmarks/probe_epilogue_parts.py, probe_tile_trace.py) exist only in builds with -DNQ_GEMM_DEBUG
-// (NQ_EXTRA_NVCC_FLAGS=-DNQ_GEMM_DEBUG python -m numpy_quant_b200.build): the shipped kernel carries neither the
-// NQ_GEMM_DBG tests nor the clock stamps in its per-chunk loops.
-#ifdef NQ_GEMM_DEBUG
-#define NQ_DBG(bit_) ((p.dbg & (bit_)) != 0)
 #define NQ_TRACE_KB(li_, kb_, ev_)                                                                                   \
     do {                                                                                                             \
         if (p.trace && blockIdx.x == 0 && (li_) == 5u && (kb_) < 16u) p.trace[512 + (kb_) * 4 + (ev_)] = clock64();     \
@@ -106,11 +101,6 @@ struct GemmParams {
     do {                                                                                       \
         if (p.trace && blockIdx.x == 0 && (li_) < 64u) p.trace[(li_) * 8 + (ev_)] = clock64(); \
     } while (0)
-#else
-#define NQ_DBG(bit_) false
-#define NQ_TRACE_KB(li_, kb_, ev_) do { } while (0)
-#define NQ_TRACE(li_, ev_) do { } while (0)
-#endif
 
 // ------------------------------------------------------------------ epilogue math
 // dequantize with 32-bit zero-point arithmetic: identical bits to f32(f64(d) * f64(scale)).
@@ -311,7 +301,7 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
             const uint32_t t = p.reverse ? total_tiles - 1u - ts : ts;
             const uint32_t b = fd_div(t, fd_tpb), r = t - b * tiles_per_batch;
             const uint32_t mt = fd_div(r, fd_nt), nt = r - mt * n_tiles;
-            if (leader && !NQ_DBG(256)) NQ_TRACE(pli, 0);
+            if (leader && !(p.dbg & 256)) NQ_TRACE(pli, 0);
             // pair: this CTA stages its own 128 rows of A and its half of the B rows
             const int m0 = (int)mt * BMT + (int)cta_rank * BM;
             const int n0 = (int)nt * BN + (TWO ? (int)cta_rank * (BN / 2) : 0);
@@ -340,7 +330,7 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                                                (uint16_t)(tap % p.cv_KW), (uint16_t)(tap / p.cv_KW), fb);
                             tma_load_3d(sb + j * (C::B_BYTES / 2), &tmap_b, (int)k0, n0, bb, fb);
                         }
-                    } else if (NQ_DBG(32)) {
+                    } else if (p.dbg & 32) {
                         mbar_arrive(fb);                                  // measurement only: no operand traffic at all
                     } else {
                         mbar_expect_tx(fb, C::STAGE_BYTES);
@@ -354,7 +344,7 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                     phase ^= 1;
                 }
             }
-            if (leader && !NQ_DBG(256)) NQ_TRACE(pli, 1);
+            if (leader && !(p.dbg & 256)) NQ_TRACE(pli, 1);
         }
         __syncwarp();
     } else if (warp == 1) {
@@ -370,11 +360,11 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
             // K tail: only the 32-byte steps that hold real data (TMA zero-filled the rest of the box)
             const uint32_t krem_last = (uint32_t)p.K - (k_blocks - 1) * BK;
             const int ksteps_last = krem_last >= (uint32_t)BK ? BK / UMMA_K : (int)((krem_last + UMMA_K - 1) / UMMA_K);
-            const bool conv = !TWO && p.conv, no_mma = NQ_DBG(8);
+            const bool conv = !TWO && p.conv, no_mma = (p.dbg & 8) != 0;
             for (uint32_t t = tile_first; t < total_tiles; t += tile_step, ++mli) {
                 mbar_wait(smem_u32(tempty_bar + acc), acc_phase ^ 1);     // epilogue drained this buffer
                 tc_fence_after();
-                if (leader && !NQ_DBG(256)) NQ_TRACE(mli, 2);
+                if (leader && !(p.dbg & 256)) NQ_TRACE(mli, 2);
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
                 for (uint32_t kb = 0; kb < k_blocks; ++kb) {
                     mbar_wait(smem_u32(full_bar + stage), phase);
@@ -421,7 +411,7 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                 if (leader) {
                     if constexpr (TWO) tc_commit_pair(smem_u32(tfull_bar + acc));   // both CTAs' epilogues
                     else tc_commit(smem_u32(tfull_bar + acc));            // accumulator ready
-                    if (!NQ_DBG(256)) NQ_TRACE(mli, 3);
+                    if (!(p.dbg & 256)) NQ_TRACE(mli, 3);
                 }
                 if (++acc == C::NACC) {
                     acc = 0;
@@ -555,10 +545,10 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                 if (p.q_rowsum)
                     row_rs = (int64_t)bo * p.q_rs[0] + (int64_t)bi * p.q_rs[1] + (int64_t)mb * p.q_rs[2] + (int64_t)ms * p.q_rs[3];
                 __syncwarp();
-                if (warp == 4 && lane == 0 && !NQ_DBG(256)) NQ_TRACE(li, 4);
+                if (warp == 4 && lane == 0 && !(p.dbg & 256)) NQ_TRACE(li, 4);
                 mbar_wait(smem_u32(tfull_bar + acc), acc_phase);
                 tc_fence_after();
-                if (warp == 4 && lane == 0 && !NQ_DBG(256)) NQ_TRACE(li, 5);
+                if (warp == 4 && lane == 0 && !(p.dbg & 256)) NQ_TRACE(li, 5);
                 const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
                 const int rm = 0x4B400000 - (int32_t)rowterm;             // int -> float magic folded into the row term
                 int rs_acc = 0;                                           // ROWS: code sum of the current head
@@ -571,32 +561,22 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                     }
                 };
                 uint32_t nh = fd_div((uint32_t)(n0 + wcol0), fd_D), nd = (uint32_t)(n0 + wcol0) - nh * p.q_D;
-                // Everything the chunk loop needs that does not depend on the chunk is formed here, once per tile, and
-                // pinned in registers (the compiler otherwise re-derives thread index, row bound and shared-memory
-                // window for every chunk): destination row, row predicate, chunk count, TMEM / shared addresses.
-                const int rem_cols = (int)(p.N - (n0 + wcol0));
-                int nchunks = rem_cols <= 0 ? 0 : min(CPW, (rem_cols + 15) >> 4);   // warp-uniform (N % 16 == 0)
-                if (NQ_DBG(16)) nchunks = 0;
-                int8_t* dst_row = reinterpret_cast<int8_t*>(p.C) + row_off;
-                int row_ok_i = row_ok ? 1 : 0;
-                uint32_t t_col = t_row + (uint32_t)wcol0, ctw_s = smem_u32(ctw);
-                const uint32_t q_off4 = (uint32_t)p.q_off[4];             // host: (N / q_D + 1) * q_off[4] < 2^31
-                asm volatile("" : "+r"(row_ok_i), "+r"(t_col), "+r"(ctw_s), "+l"(dst_row));
 #pragma unroll 1
-                for (int i = 0; i < nchunks; ++i) {
-                    const int64_t nc = n0 + wcol0 + i * 16;
+                for (int i = 0; i < CPW; ++i) {
+                    const int cw = wcol0 + i * 16;
+                    const int64_t nc = n0 + cw;
+                    if (nc >= p.N) break;                                 // warp-uniform (N % 16 == 0)
                     uint32_t v[16];
-                    if (!NQ_DBG(2)) tmem_ld_32x32b_x16(t_col, v);
+                    if (p.dbg & 16) continue;
+                    if (!(p.dbg & 2)) tmem_ld_32x32b_x16(t_row + (uint32_t)cw, v);
                     else {
 #pragma unroll
                         for (int j = 0; j < 16; ++j) v[j] = (uint32_t)(i + j);
                     }
-                    t_col += 16;
-                    const uint32_t cs = ctw_s + (uint32_t)i * 64u;        // this step's 16 column terms; + 256: its bias columns
                     int ct[16];
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
-                        const int4 c4 = lds_v4(cs + g * 16);
+                        const int4 c4 = *reinterpret_cast<const int4*>(ctw + i * 16 + g * 4);
                         ct[4 * g] = c4.x; ct[4 * g + 1] = c4.y; ct[4 * g + 2] = c4.z; ct[4 * g + 3] = c4.w;
                     }
                     tmem_ld_wait();
@@ -654,14 +634,12 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                     // pattern only grows, which saturates correctly.
                     const float2 r2 = make_float2(qz.sd.r, qz.sd.r), nb2 = make_float2(-qz.sd.b, -qz.sd.b), mg2 = make_float2(qz.magic, qz.magic);
                     uint32_t w[4];
-                    if (NQ_DBG(1)) {
+                    if (p.dbg & 1) {
                         w[0] = __float_as_uint(f[0]); w[1] = __float_as_uint(f[5]); w[2] = __float_as_uint(f[10]); w[3] = __float_as_uint(f[15]);
                     } else
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
-                        const int4 b4i = lds_v4(cs + 256 + g * 16);       // bias columns of this step (bsw = ctw + 64 words)
-                        const float4 b4 = make_float4(__int_as_float(b4i.x), __int_as_float(b4i.y), __int_as_float(b4i.z),
-                                                      __int_as_float(b4i.w));
+                        const float4 b4 = *reinterpret_cast<const float4*>(bsw + i * 16 + g * 4);
                         float2 ta, tb;
                         if constexpr (EMODE == EM_Q8_GELU) {
                             // float glue (1e-5 contract): dequant * scale + bias as one FMA, GELU, and the
@@ -736,8 +714,9 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                             }
                         }
                     } else {
-                        if (row_ok_i && !NQ_DBG(4))
-                            *reinterpret_cast<int4*>(dst_row + (nh * q_off4 + nd)) = make_int4((int)w[0], (int)w[1], (int)w[2], (int)w[3]);
+                        if (row_ok && !(p.dbg & 4))
+                            *reinterpret_cast<int4*>(reinterpret_cast<int8_t*>(p.C) + row_off + (int64_t)nh * p.q_off[4] + nd) =
+                                make_int4((int)w[0], (int)w[1], (int)w[2], (int)w[3]);
                         if (p.q_rowsum) {
                             if (nh != rs_nh) {
                                 flush_rowsum();
@@ -751,7 +730,7 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                 if (EMODE != EM_Q8_COLS && p.q_rowsum) flush_rowsum();
                 tc_fence_before();
                 __syncwarp();
-                if (NQ_DBG(256)) {                                        // alternative trace: release stamps of warps 4..7 / 16..19
+                if (p.dbg & 256) {                                        // alternative trace: release stamps of warps 4..7 / 16..19
                     if (lane == 0 && warp < 8) NQ_TRACE(li, warp);
                     if (lane == 0 && warp >= 16) NQ_TRACE(li, warp - 16);
                 } else if (lane == 0 && (warp == 4 || warp == 19)) NQ_TRACE(li, warp == 4 ? 6 : 7);
@@ -1479,8 +1458,6 @@ static int qgemm_run(const int8_t* A, const int8_t* B, void* Cout, int64_t M, in
             for (int i = 0; i < 5; ++i)
                 NQ_REQUIRE(ep->q_off[i] % 16 == 0, "nq_qgemm_s8: QUANT row layout needs q_off[0..4] multiples of 16 bytes");
             NQ_REQUIRE(((uintptr_t)Cout & 15) == 0, "nq_qgemm_s8: QUANT destination must be 16-byte aligned");
-            NQ_REQUIRE(ep->q_off[4] >= 0 && (long double)(N / ep->q_cols_per_head + 1) * (long double)ep->q_off[4] < 2147483648.0L,
-                       "nq_qgemm_s8: QUANT row layout: the head part of a destination offset must fit 31 bits");
             NQ_REQUIRE(!ep->q_rowsum || ep->q_rs[5] == 0, "nq_qgemm_s8: QUANT row layout sums codes along n (q_rs[5] == 0)");
             // one warp owns 64 consecutive columns of a row: a (row, head) slot has a single writer when
             // the heads tile that span and the slot does not depend on the batch-inner / other tiles

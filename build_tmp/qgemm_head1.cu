@@ -80,8 +80,7 @@ struct GemmParams {
     int two_cta;                     // CTA-pair kernel (256-row tiles, cta_group::2)
     int deq_wide;                    // DEQUANT: alignment / extent conditions of the 32-column epilogue hold (host-checked)
     int dbg;                         // NQ_GEMM_DBG bit mask (measurement only, benchmarks/probe_epilogue_parts.py): 1 no epilogue
-                                     // math, 2 no TMEM loads, 4 no stores, 8 no MMAs, 16 no epilogue chunks, 32 no TMA loads -- garbage results
-    long long* trace;                // NQ_GEMM_TRACE (measurement only): clock64 stamps of CTA 0's first 64 tiles, 8 per tile
+                                     // math, 2 no TMEM loads, 4 no stores, 8 no MMAs, 16 no epilogue chunks -- garbage results
     int reverse;                     // tile i of the schedule is output tile total - 1 - i (L2 reuse of the producer's tail)
     int req_rows;                    // REQUANT: 32-bit windows and alignment of the thread-per-row epilogue hold (host-checked)
     int sm_noclamp;                  // SOFTMAX: out_zp >= lo: p / s_out + zp (p in [0, 1]) needs no lower clamp
@@ -92,25 +91,6 @@ struct GemmParams {
     int conv;
     uint32_t cv_C, cv_KW, cv_OW, cv_OH, cv_sw, cv_sh;
 };
-
-// Measurement hooks (benchmarks/probe_epilogue_parts.py, probe_tile_trace.py) exist only in builds with -DNQ_GEMM_DEBUG
-// (NQ_EXTRA_NVCC_FLAGS=-DNQ_GEMM_DEBUG python -m numpy_quant_b200.build): the shipped kernel carries neither the
-// NQ_GEMM_DBG tests nor the clock stamps in its per-chunk loops.
-#ifdef NQ_GEMM_DEBUG
-#define NQ_DBG(bit_) ((p.dbg & (bit_)) != 0)
-#define NQ_TRACE_KB(li_, kb_, ev_)                                                                                   \
-    do {                                                                                                             \
-        if (p.trace && blockIdx.x == 0 && (li_) == 5u && (kb_) < 16u) p.trace[512 + (kb_) * 4 + (ev_)] = clock64();     \
-    } while (0)
-#define NQ_TRACE(li_, ev_)                                                                     \
-    do {                                                                                       \
-        if (p.trace && blockIdx.x == 0 && (li_) < 64u) p.trace[(li_) * 8 + (ev_)] = clock64(); \
-    } while (0)
-#else
-#define NQ_DBG(bit_) false
-#define NQ_TRACE_KB(li_, kb_, ev_) do { } while (0)
-#define NQ_TRACE(li_, ev_) do { } while (0)
-#endif
 
 // ------------------------------------------------------------------ epilogue math
 // dequantize with 32-bit zero-point arithmetic: identical bits to f32(f64(d) * f64(scale)).
@@ -209,21 +189,6 @@ __device__ __noinline__ int requant_slow(int acc, int64_t rowterm, const AccZp z
     return asym_out ? requantize_one<true>(d, inv_out_scale, out_zp, lo, hi) : requantize_one<false>(d, inv_out_scale, 0.0, lo, hi);
 }
 
-// Division of n < 2^31 by a divisor fixed for the launch (Granlund / Montgomery round-up method): one multiply-high,
-// one add, one shift instead of the ~25-instruction emulated 32-bit divide -- the tile bookkeeping of every role runs
-// once per tile per warp and used to be a quarter of the epilogue warps' instruction stream.
-struct UDiv {
-    uint32_t d, m, l;
-};
-__device__ __forceinline__ UDiv make_udiv(uint32_t d) {
-    UDiv f;
-    f.d = d;
-    f.l = d > 1u ? 32u - (uint32_t)__clz((int)(d - 1u)) : 0u;             // ceil(log2 d)
-    f.m = (uint32_t)(((((uint64_t)1 << f.l) - d) << 32) / d) + 1u;
-    return f;
-}
-__device__ __forceinline__ uint32_t fd_div(uint32_t n, const UDiv& f) { return (__umulhi(f.m, n) + n) >> f.l; }
-
 template <int BN, int EMODE, bool TWO = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
@@ -252,7 +217,6 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
     const uint32_t m_tiles = (uint32_t)((p.M + BMT - 1) / BMT), n_tiles = (uint32_t)((p.N + BN - 1) / BN);
     const uint32_t tiles_per_batch = m_tiles * n_tiles, total_tiles = tiles_per_batch * (uint32_t)p.batch;
     const uint32_t k_blocks = (uint32_t)((p.K + BK - 1) / BK);
-    const UDiv fd_tpb = make_udiv(tiles_per_batch), fd_nt = make_udiv(n_tiles);
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
@@ -294,135 +258,106 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
     // warpgroups grow to 104 (128 * 56 + 512 * 104 = 60416 <= 61440; an over-subscribed .inc would block forever).
     if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-    // Both single-issuer roles walk the schedule with the WHOLE warp in uniform control flow and let one elected lane
-    // execute only the TMA / tcgen05 instructions: addresses, coordinates and descriptors then live in uniform
-    // registers.  Inside an `if (lane == 0)` region the compiler wraps every such instruction in a per-lane
-    // register -> uniform-register loop; the MMA role then spent ~1300 cycles issuing the four MMAs (512 tensor
-    // cycles) of one K block and took a quarter of its sub-partition's issue slots from the epilogue warps
-    // (benchmarks/probe_tile_trace.py).
     if (warp == 0) {
         // ===================== TMA producer =====================
-        const bool leader = elect_one_sync();
-        int stage = 0;
-        uint32_t phase = 0;
-        uint32_t pli = 0;
-        const uint32_t conv_pix = p.conv ? p.cv_OW * p.cv_OH : 1u;
-        for (uint32_t ts = tile_first; ts < total_tiles; ts += tile_step, ++pli) {
-            const uint32_t t = p.reverse ? total_tiles - 1u - ts : ts;
-            const uint32_t b = fd_div(t, fd_tpb), r = t - b * tiles_per_batch;
-            const uint32_t mt = fd_div(r, fd_nt), nt = r - mt * n_tiles;
-            if (leader && !NQ_DBG(256)) NQ_TRACE(pli, 0);
-            // pair: this CTA stages its own 128 rows of A and its half of the B rows
-            const int m0 = (int)mt * BMT + (int)cta_rank * BM;
-            const int n0 = (int)nt * BN + (TWO ? (int)cta_rank * (BN / 2) : 0);
-            const int ba = p.a_batched ? (int)b : 0, bb = p.b_batched ? (int)b : 0;
-            // conv: the base pixel of row m0 is (ow * sw, oh * sh) of image m0 / (OH * OW)
-            const uint32_t pix = (uint32_t)m0 % conv_pix, img = (uint32_t)m0 / conv_pix;
-            const int w0 = p.conv ? (int)((pix % p.cv_OW) * p.cv_sw) : 0, h0 = p.conv ? (int)((pix / p.cv_OW) * p.cv_sh) : 0;
-            for (uint32_t kb = 0; kb < k_blocks; ++kb) {
-                mbar_wait(smem_u32(empty_bar + stage), phase ^ 1);
-                const uint32_t fb = smem_u32(full_bar + stage);
-                const uint32_t sa = smem_u32(smem_a + stage * C::A_BYTES), sb = smem_u32(smem_b + stage * C::B_BYTES);
-                if (leader) {
-                    NQ_TRACE_KB(pli, kb, 2);
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (uint32_t ts = tile_first; ts < total_tiles; ts += tile_step) {
+                const uint32_t t = p.reverse ? total_tiles - 1u - ts : ts;
+                const uint32_t b = t / tiles_per_batch, r = t % tiles_per_batch;
+                // pair: this CTA stages its own 128 rows of A and its half of the B rows
+                const int m0 = (int)(r / n_tiles) * BMT + (int)cta_rank * BM;
+                const int n0 = (int)(r % n_tiles) * BN + (TWO ? (int)cta_rank * (BN / 2) : 0);
+                const int ba = p.a_batched ? (int)b : 0, bb = p.b_batched ? (int)b : 0;
+                for (uint32_t kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait_backoff(smem_u32(empty_bar + stage), phase ^ 1);
+                    const uint32_t fb = smem_u32(full_bar + stage);
                     if constexpr (TWO) {
                         if (cta_rank == 0) mbar_expect_tx(fb, 2 * C::STAGE_BYTES);   // bytes of both CTAs land here
-                        tma_load_3d_pair(sa, &tmap_a, (int)(kb * BK), m0, ba, fb);
-                        tma_load_3d_pair(sb, &tmap_b, (int)(kb * BK), n0, bb, fb);
+                        tma_load_3d_pair(smem_u32(smem_a + stage * C::A_BYTES), &tmap_a, (int)(kb * BK), m0, ba, fb);
+                        tma_load_3d_pair(smem_u32(smem_b + stage * C::B_BYTES), &tmap_b, (int)(kb * BK), n0, bb, fb);
                     } else if (p.conv) {
                         // two 64-byte K slices per stage: (filter tap, 64 channels) of 128 output pixels each,
-                        // 64B-swizzled sub-tiles
+                        // 64B-swizzled sub-tiles; the base pixel of row m0 is (ow * sw, oh * sh) of image m0 / (OH * OW)
+                        const uint32_t pix = (uint32_t)m0 % (p.cv_OW * p.cv_OH), img = (uint32_t)m0 / (p.cv_OW * p.cv_OH);
+                        const int w0 = (int)((pix % p.cv_OW) * p.cv_sw), h0 = (int)((pix / p.cv_OW) * p.cv_sh);
                         const uint32_t nsub = ((uint32_t)p.K - kb * BK) >= (uint32_t)BK ? 2u : 1u;
                         mbar_expect_tx(fb, nsub * (C::STAGE_BYTES / 2));
                         for (uint32_t j = 0; j < nsub; ++j) {
                             const uint32_t k0 = kb * BK + j * 64, tap = k0 / p.cv_C;
-                            tma_load_im2col_4d(sa + j * (C::A_BYTES / 2), &tmap_a, (int)(k0 % p.cv_C), w0, h0, (int)img,
-                                               (uint16_t)(tap % p.cv_KW), (uint16_t)(tap / p.cv_KW), fb);
-                            tma_load_3d(sb + j * (C::B_BYTES / 2), &tmap_b, (int)k0, n0, bb, fb);
+                            tma_load_im2col_4d(smem_u32(smem_a + stage * C::A_BYTES + j * (C::A_BYTES / 2)), &tmap_a,
+                                               (int)(k0 % p.cv_C), w0, h0, (int)img, (uint16_t)(tap % p.cv_KW),
+                                               (uint16_t)(tap / p.cv_KW), fb);
+                            tma_load_3d(smem_u32(smem_b + stage * C::B_BYTES + j * (C::B_BYTES / 2)), &tmap_b, (int)k0, n0, bb, fb);
                         }
-                    } else if (NQ_DBG(32)) {
-                        mbar_arrive(fb);                                  // measurement only: no operand traffic at all
                     } else {
                         mbar_expect_tx(fb, C::STAGE_BYTES);
-                        tma_load_3d(sa, &tmap_a, (int)(kb * BK), m0, ba, fb);
-                        tma_load_3d(sb, &tmap_b, (int)(kb * BK), n0, bb, fb);
-                    }
-                    NQ_TRACE_KB(pli, kb, 3);
-                }
-                if (++stage == C::STAGES) {
-                    stage = 0;
-                    phase ^= 1;
-                }
-            }
-            if (leader && !NQ_DBG(256)) NQ_TRACE(pli, 1);
-        }
-        __syncwarp();
-    } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (cta_rank == 0) {                                              // pair: the leader CTA issues for both
-            const bool leader = elect_one_sync();
-            constexpr uint32_t idesc = make_idesc(BN, BMT);
-            int stage = 0;
-            uint32_t phase = 0;
-            int acc = 0;
-            uint32_t acc_phase = 0;
-            uint32_t mli = 0;
-            // K tail: only the 32-byte steps that hold real data (TMA zero-filled the rest of the box)
-            const uint32_t krem_last = (uint32_t)p.K - (k_blocks - 1) * BK;
-            const int ksteps_last = krem_last >= (uint32_t)BK ? BK / UMMA_K : (int)((krem_last + UMMA_K - 1) / UMMA_K);
-            const bool conv = !TWO && p.conv, no_mma = NQ_DBG(8);
-            for (uint32_t t = tile_first; t < total_tiles; t += tile_step, ++mli) {
-                mbar_wait(smem_u32(tempty_bar + acc), acc_phase ^ 1);     // epilogue drained this buffer
-                tc_fence_after();
-                if (leader && !NQ_DBG(256)) NQ_TRACE(mli, 2);
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-                for (uint32_t kb = 0; kb < k_blocks; ++kb) {
-                    mbar_wait(smem_u32(full_bar + stage), phase);
-                    tc_fence_after();
-                    const uint32_t sa = smem_u32(smem_a + stage * C::A_BYTES), sb = smem_u32(smem_b + stage * C::B_BYTES);
-                    const int ksteps = (kb + 1 == k_blocks) ? ksteps_last : BK / UMMA_K;
-                    if (leader) {
-                        NQ_TRACE_KB(mli, kb, 0);
-                        if (conv) {
-                            // 64B-swizzled sub-tiles (one per 64-channel slice), two 32-byte K steps each
-#pragma unroll
-                            for (int k = 0; k < BK / UMMA_K; ++k) {
-                                if (k < ksteps) {
-                                    const int j = k >> 1;
-                                    mma_i8(d_tmem, make_smem_desc_sw64(sa + j * (C::A_BYTES / 2)) + (uint64_t)((k & 1) * 2),
-                                           make_smem_desc_sw64(sb + j * (C::B_BYTES / 2)) + (uint64_t)((k & 1) * 2), idesc,
-                                           (kb > 0 || k > 0) ? 1u : 0u);
-                                }
-                            }
-                        } else if (!no_mma) {
-                            const uint64_t adesc = make_smem_desc(sa), bdesc = make_smem_desc(sb);
-#pragma unroll
-                            for (int k = 0; k < BK / UMMA_K; ++k) {
-                                // advance 32 bytes along K inside the swizzle atom: +2 in 16-byte units
-                                if (k < ksteps) {
-                                    if constexpr (TWO)
-                                        mma_i8_pair(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
-                                                    (kb > 0 || k > 0) ? 1u : 0u);
-                                    else
-                                        mma_i8(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
-                                               (kb > 0 || k > 0) ? 1u : 0u);
-                                }
-                            }
-                        }
-                        if constexpr (TWO) tc_commit_pair(smem_u32(empty_bar + stage));   // frees the slot in both CTAs
-                        else tc_commit(smem_u32(empty_bar + stage));      // smem slot free once MMAs retire
-                        NQ_TRACE_KB(mli, kb, 1);
+                        tma_load_3d(smem_u32(smem_a + stage * C::A_BYTES), &tmap_a, (int)(kb * BK), m0, ba, fb);
+                        tma_load_3d(smem_u32(smem_b + stage * C::B_BYTES), &tmap_b, (int)(kb * BK), n0, bb, fb);
                     }
                     if (++stage == C::STAGES) {
                         stage = 0;
                         phase ^= 1;
                     }
                 }
-                if (leader) {
-                    if constexpr (TWO) tc_commit_pair(smem_u32(tfull_bar + acc));   // both CTAs' epilogues
-                    else tc_commit(smem_u32(tfull_bar + acc));            // accumulator ready
-                    if (!NQ_DBG(256)) NQ_TRACE(mli, 3);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0 && cta_rank == 0) {                                // pair: the leader CTA issues for both
+            constexpr uint32_t idesc = make_idesc(BN, BMT);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (uint32_t t = tile_first; t < total_tiles; t += tile_step) {
+                mbar_wait_backoff(smem_u32(tempty_bar + acc), acc_phase ^ 1);   // epilogue drained this buffer
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                for (uint32_t kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait_backoff(smem_u32(full_bar + stage), phase);
+                    tc_fence_after();
+                    const uint64_t adesc = make_smem_desc(smem_u32(smem_a + stage * C::A_BYTES));
+                    const uint64_t bdesc = make_smem_desc(smem_u32(smem_b + stage * C::B_BYTES));
+                    // K tail: only the 32-byte steps that hold real data (TMA zero-filled the rest of the box)
+                    const uint32_t krem = (uint32_t)p.K - kb * BK;
+                    const int ksteps = krem >= (uint32_t)BK ? BK / UMMA_K : (int)((krem + UMMA_K - 1) / UMMA_K);
+                    if (!TWO && p.conv) {
+                        // 64B-swizzled sub-tiles (one per 64-channel slice), two 32-byte K steps each
+#pragma unroll
+                        for (int k = 0; k < BK / UMMA_K; ++k) {
+                            if (k < ksteps) {
+                                const int j = k >> 1;
+                                mma_i8(d_tmem,
+                                       make_smem_desc_sw64(smem_u32(smem_a + stage * C::A_BYTES + j * (C::A_BYTES / 2))) + (uint64_t)((k & 1) * 2),
+                                       make_smem_desc_sw64(smem_u32(smem_b + stage * C::B_BYTES + j * (C::B_BYTES / 2))) + (uint64_t)((k & 1) * 2),
+                                       idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                            }
+                        }
+                    } else
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        // advance 32 bytes along K inside the swizzle atom: +2 in 16-byte units
+                        if (k < ksteps && !(p.dbg & 8)) {
+                            if constexpr (TWO)
+                                mma_i8_pair(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
+                                            (kb > 0 || k > 0) ? 1u : 0u);
+                            else
+                                mma_i8(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
+                                       (kb > 0 || k > 0) ? 1u : 0u);
+                        }
+                    }
+                    if constexpr (TWO) tc_commit_pair(smem_u32(empty_bar + stage));   // frees the slot in both CTAs
+                    else tc_commit(smem_u32(empty_bar + stage));          // smem slot free once MMAs retire
+                    if (++stage == C::STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
                 }
+                if constexpr (TWO) tc_commit_pair(smem_u32(tfull_bar + acc));   // both CTAs' epilogues
+                else tc_commit(smem_u32(tfull_bar + acc));                // accumulator ready
                 if (++acc == C::NACC) {
                     acc = 0;
                     acc_phase ^= 1;
@@ -462,22 +397,18 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
         constexpr bool REQ = (EMODE == EM_REQ_ROWS);                     // Gemm: int bias + requantize, plain [M, N] int8 rows
         constexpr bool Q8 = (EMODE == EM_Q8_ROWS || EMODE == EM_Q8_COLS || EMODE == EM_Q8_GELU || REQ);
         const Quantizer qz(p.qargs);
-        const UDiv fd_S = make_udiv(Q8 ? p.q_S : 1u), fd_D = make_udiv(Q8 ? p.q_D : 1u), fd_ci = make_udiv((uint32_t)p.c_inner);
         const int qlo = (int)p.qargs.lo, qhi = (int)p.qargs.hi;          // integer code range of the QUANT epilogues
         constexpr bool SOFTMAX = (EMODE == EM_SOFTMAX_SYM || EMODE == EM_SOFTMAX_ASYM);
         // Per-tile operands of the zero-point correction (this row's rowsum(A), this warp's colsum(B) and bias
         // columns) are fetched ONE TILE AHEAD: with 227 KB of smem there is no L1 to hit, so each of these
         // loads is an L2 round trip that would otherwise sit at the head of every tile's critical path.
-        struct TilePre { int rowsum, c0, c1, b0, b1, wide; uint32_t b, m0, n0; };
+        struct TilePre { int rowsum, c0, c1, b0, b1, wide; };
         auto prefetch_tile = [&](uint32_t tt, TilePre& o) {
             o.rowsum = o.c0 = o.c1 = o.b0 = o.b1 = o.wide = 0;
-            o.b = o.m0 = o.n0 = 0;
             if (tt >= total_tiles) return;
             if (p.reverse) tt = total_tiles - 1u - tt;
-            const uint32_t pb = fd_div(tt, fd_tpb), pr = tt - pb * tiles_per_batch;
-            const uint32_t pmt = fd_div(pr, fd_nt);
-            const uint32_t pm0 = pmt * BMT + cta_rank * BM, pn0 = (pr - pmt * n_tiles) * BN;
-            o.b = pb; o.m0 = pm0; o.n0 = pn0;
+            const uint32_t pb = tt / tiles_per_batch, pr = tt - pb * tiles_per_batch;
+            const uint32_t pm0 = (pr / n_tiles) * BMT + cta_rank * BM, pn0 = (pr % n_tiles) * BN;
             const int64_t pm = (int64_t)pm0 + q * 32 + lane;
             if (z.use_row && pm < p.M) o.rowsum = ldg_s32(z.rowsum_a + (int64_t)pb * p.M + pm);
             if constexpr (SOFTMAX || Q8) {
@@ -509,15 +440,17 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
         // this CTA's (pair's) i-th tile is t = tile_first + i * tile_step, lives in accumulator buffer i % NACC and is
         // drained by group i % GROUPS
         for (uint32_t li = grp, ts = tile_first + grp * tile_step; ts < total_tiles; li += C::GROUPS, ts += C::GROUPS * tile_step) {
+            const uint32_t t = p.reverse ? total_tiles - 1u - ts : ts;
             const int acc = (int)(li % C::NACC);
             const uint32_t acc_phase = (li / C::NACC) & 1u;
-            const TilePre cur = nxt;                                      // coordinates and operands of this tile
-            const int64_t b = cur.b;
-            const int64_t m0 = cur.m0, n0 = cur.n0;
+            const int64_t b = t / tiles_per_batch;
+            const uint32_t r = t % tiles_per_batch;
+            const int64_t m0 = (int64_t)(r / n_tiles) * BMT + cta_rank * BM, n0 = (int64_t)(r % n_tiles) * BN;
             const int64_t mrow0 = m0 + q * 32;
             const int64_t m = mrow0 + lane;                               // this thread's accumulator row
             const bool row_ok = m < p.M;
             const int32_t* cs_b = z.use_col ? z.colsum_b + b * z.cs_stride : nullptr;
+            const TilePre cur = nxt;
             prefetch_tile(ts + C::GROUPS * tile_step, nxt);
             int64_t rowterm = -z.kterm;
             if (z.use_row && row_ok) rowterm += (int64_t)cur.rowsum * z.zp_b;
@@ -547,18 +480,15 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                 const bool wide_bias = REQ && __any_sync(0xffffffffu, cur.wide != 0);   // some |bias| >= 2^29: general route
                 // row part of the scatter offsets (m = mb * S + ms, batch = bo * inner + bi)
                 const uint32_t mu = (uint32_t)(row_ok ? m : p.M - 1);
-                const uint32_t mb = fd_div(mu, fd_S), ms = mu - mb * p.q_S;
-                const uint32_t bu = (uint32_t)b, bo = fd_div(bu, fd_ci), bi = bu - bo * (uint32_t)p.c_inner;
+                const uint32_t mb = mu / p.q_S, ms = mu - mb * p.q_S;
+                const uint32_t bu = (uint32_t)b, bo = bu / (uint32_t)p.c_inner, bi = bu - bo * (uint32_t)p.c_inner;
                 const int64_t row_off = (int64_t)bo * p.q_off[0] + (int64_t)bi * p.q_off[1] + (int64_t)mb * p.q_off[2] +
                                         (int64_t)ms * p.q_off[3];
-                int64_t row_rs = 0;
-                if (p.q_rowsum)
-                    row_rs = (int64_t)bo * p.q_rs[0] + (int64_t)bi * p.q_rs[1] + (int64_t)mb * p.q_rs[2] + (int64_t)ms * p.q_rs[3];
+                const int64_t row_rs = (int64_t)bo * p.q_rs[0] + (int64_t)bi * p.q_rs[1] + (int64_t)mb * p.q_rs[2] +
+                                       (int64_t)ms * p.q_rs[3];
                 __syncwarp();
-                if (warp == 4 && lane == 0 && !NQ_DBG(256)) NQ_TRACE(li, 4);
                 mbar_wait(smem_u32(tfull_bar + acc), acc_phase);
                 tc_fence_after();
-                if (warp == 4 && lane == 0 && !NQ_DBG(256)) NQ_TRACE(li, 5);
                 const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
                 const int rm = 0x4B400000 - (int32_t)rowterm;             // int -> float magic folded into the row term
                 int rs_acc = 0;                                           // ROWS: code sum of the current head
@@ -570,33 +500,23 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                         else atomicAdd(slot, rs_acc);
                     }
                 };
-                uint32_t nh = fd_div((uint32_t)(n0 + wcol0), fd_D), nd = (uint32_t)(n0 + wcol0) - nh * p.q_D;
-                // Everything the chunk loop needs that does not depend on the chunk is formed here, once per tile, and
-                // pinned in registers (the compiler otherwise re-derives thread index, row bound and shared-memory
-                // window for every chunk): destination row, row predicate, chunk count, TMEM / shared addresses.
-                const int rem_cols = (int)(p.N - (n0 + wcol0));
-                int nchunks = rem_cols <= 0 ? 0 : min(CPW, (rem_cols + 15) >> 4);   // warp-uniform (N % 16 == 0)
-                if (NQ_DBG(16)) nchunks = 0;
-                int8_t* dst_row = reinterpret_cast<int8_t*>(p.C) + row_off;
-                int row_ok_i = row_ok ? 1 : 0;
-                uint32_t t_col = t_row + (uint32_t)wcol0, ctw_s = smem_u32(ctw);
-                const uint32_t q_off4 = (uint32_t)p.q_off[4];             // host: (N / q_D + 1) * q_off[4] < 2^31
-                asm volatile("" : "+r"(row_ok_i), "+r"(t_col), "+r"(ctw_s), "+l"(dst_row));
+                uint32_t nh = (uint32_t)(n0 + wcol0) / p.q_D, nd = (uint32_t)(n0 + wcol0) - nh * p.q_D;
 #pragma unroll 1
-                for (int i = 0; i < nchunks; ++i) {
-                    const int64_t nc = n0 + wcol0 + i * 16;
+                for (int i = 0; i < CPW; ++i) {
+                    const int cw = wcol0 + i * 16;
+                    const int64_t nc = n0 + cw;
+                    if (nc >= p.N) break;                                 // warp-uniform (N % 16 == 0)
                     uint32_t v[16];
-                    if (!NQ_DBG(2)) tmem_ld_32x32b_x16(t_col, v);
+                    if (p.dbg & 16) continue;
+                    if (!(p.dbg & 2)) tmem_ld_32x32b_x16(t_row + (uint32_t)cw, v);
                     else {
 #pragma unroll
                         for (int j = 0; j < 16; ++j) v[j] = (uint32_t)(i + j);
                     }
-                    t_col += 16;
-                    const uint32_t cs = ctw_s + (uint32_t)i * 64u;        // this step's 16 column terms; + 256: its bias columns
                     int ct[16];
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
-                        const int4 c4 = lds_v4(cs + g * 16);
+                        const int4 c4 = *reinterpret_cast<const int4*>(ctw + i * 16 + g * 4);
                         ct[4 * g] = c4.x; ct[4 * g + 1] = c4.y; ct[4 * g + 2] = c4.z; ct[4 * g + 3] = c4.w;
                     }
                     tmem_ld_wait();
@@ -654,14 +574,12 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                     // pattern only grows, which saturates correctly.
                     const float2 r2 = make_float2(qz.sd.r, qz.sd.r), nb2 = make_float2(-qz.sd.b, -qz.sd.b), mg2 = make_float2(qz.magic, qz.magic);
                     uint32_t w[4];
-                    if (NQ_DBG(1)) {
+                    if (p.dbg & 1) {
                         w[0] = __float_as_uint(f[0]); w[1] = __float_as_uint(f[5]); w[2] = __float_as_uint(f[10]); w[3] = __float_as_uint(f[15]);
                     } else
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
-                        const int4 b4i = lds_v4(cs + 256 + g * 16);       // bias columns of this step (bsw = ctw + 64 words)
-                        const float4 b4 = make_float4(__int_as_float(b4i.x), __int_as_float(b4i.y), __int_as_float(b4i.z),
-                                                      __int_as_float(b4i.w));
+                        const float4 b4 = *reinterpret_cast<const float4*>(bsw + i * 16 + g * 4);
                         float2 ta, tb;
                         if constexpr (EMODE == EM_Q8_GELU) {
                             // float glue (1e-5 contract): dequant * scale + bias as one FMA, GELU, and the
@@ -736,8 +654,9 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                             }
                         }
                     } else {
-                        if (row_ok_i && !NQ_DBG(4))
-                            *reinterpret_cast<int4*>(dst_row + (nh * q_off4 + nd)) = make_int4((int)w[0], (int)w[1], (int)w[2], (int)w[3]);
+                        if (row_ok && !(p.dbg & 4))
+                            *reinterpret_cast<int4*>(reinterpret_cast<int8_t*>(p.C) + row_off + (int64_t)nh * p.q_off[4] + nd) =
+                                make_int4((int)w[0], (int)w[1], (int)w[2], (int)w[3]);
                         if (p.q_rowsum) {
                             if (nh != rs_nh) {
                                 flush_rowsum();
@@ -751,10 +670,6 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                 if (EMODE != EM_Q8_COLS && p.q_rowsum) flush_rowsum();
                 tc_fence_before();
                 __syncwarp();
-                if (NQ_DBG(256)) {                                        // alternative trace: release stamps of warps 4..7 / 16..19
-                    if (lane == 0 && warp < 8) NQ_TRACE(li, warp);
-                    if (lane == 0 && warp >= 16) NQ_TRACE(li, warp - 16);
-                } else if (lane == 0 && (warp == 4 || warp == 19)) NQ_TRACE(li, warp == 4 ? 6 : 7);
                 if (lane == 0) { if constexpr (TWO) mbar_arrive_cluster(smem_u32(tempty_bar + acc), 0); else mbar_arrive(smem_u32(tempty_bar + acc)); }
                 continue;
             }
@@ -1479,8 +1394,6 @@ static int qgemm_run(const int8_t* A, const int8_t* B, void* Cout, int64_t M, in
             for (int i = 0; i < 5; ++i)
                 NQ_REQUIRE(ep->q_off[i] % 16 == 0, "nq_qgemm_s8: QUANT row layout needs q_off[0..4] multiples of 16 bytes");
             NQ_REQUIRE(((uintptr_t)Cout & 15) == 0, "nq_qgemm_s8: QUANT destination must be 16-byte aligned");
-            NQ_REQUIRE(ep->q_off[4] >= 0 && (long double)(N / ep->q_cols_per_head + 1) * (long double)ep->q_off[4] < 2147483648.0L,
-                       "nq_qgemm_s8: QUANT row layout: the head part of a destination offset must fit 31 bits");
             NQ_REQUIRE(!ep->q_rowsum || ep->q_rs[5] == 0, "nq_qgemm_s8: QUANT row layout sums codes along n (q_rs[5] == 0)");
             // one warp owns 64 consecutive columns of a row: a (row, head) slot has a single writer when
             // the heads tile that span and the slot does not depend on the batch-inner / other tiles
@@ -1511,7 +1424,6 @@ static int qgemm_run(const int8_t* A, const int8_t* B, void* Cout, int64_t M, in
     p.bias_q = ep->bias_q;
     p.dbg = getenv("NQ_GEMM_DBG") ? atoi(getenv("NQ_GEMM_DBG")) : 0;
     p.reverse = ep->reverse_tiles != 0;
-    p.trace = getenv("NQ_GEMM_TRACE") ? (long long*)strtoull(getenv("NQ_GEMM_TRACE"), nullptr, 10) : nullptr;
     p.c_inner = ep->c_batch_inner > 1 ? ep->c_batch_inner : 1;
     p.stride_c_inner = ep->c_batch_inner > 1 ? ep->stride_c_inner : 0;
     NQ_REQUIRE(p.c_inner == 1 || (batch % p.c_inner == 0 && ep->mode != NQ_EPI_REQUANT),

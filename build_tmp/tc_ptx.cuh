@@ -185,13 +185,6 @@ __device__ __forceinline__ int4 ldg_v4(const void* p) {
     asm volatile("ld.global.nc.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
     return r;
 }
-// 16 bytes from a 32-bit shared-memory address (no generic -> shared conversion in the loop that uses it); ordered
-// after the shared-memory stores that precede it in program order ("memory")
-__device__ __forceinline__ int4 lds_v4(uint32_t saddr) {
-    int4 r;
-    asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(saddr) : "memory");
-    return r;
-}
 __device__ __forceinline__ int ldg_s32(const void* p) {
     int r;
     asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(r) : "l"(p));
