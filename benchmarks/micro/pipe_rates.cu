@@ -34,6 +34,8 @@ __global__ void __launch_bounds__(512) k(float* out, long long* cyc, float a, fl
                 r[i] = __ffma2_rn(r[i], a2, b2); n[(i + 3) & 7] = max(n[(i + 3) & 7], n[i]); r[i] = __ffma2_rn(r[i], b2, a2);
             }
             if (MODE == 12) { r[i].x = __fmaf_rn(r[i].x, a, b); n[i] = n[i] + it; r[i].y = __fmaf_rn(r[i].y, a, b); n[i] ^= 0x4b000000; }   // 2 FFMA + 2 ALU
+            if (MODE == 14) { r[i].x += __int2float_rn(n[i]); n[i] += it; }                                   // I2FP + FADD + IADD
+            if (MODE == 15) { r[i].x += __int_as_float(n[i]); n[i] += it; }                                   // FADD + IADD (reference for 14)
             if (MODE == 13) { asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(r[i].x)); n[i] = n[i] + it; n[i] ^= 0x4b000000; n[(i + 3) & 7] = max(n[(i + 3) & 7], n[i]); n[i] += 3; }   // MUFU + 4 ALU
         }
     }
@@ -72,6 +74,8 @@ int main() {
         run<11>("mix 4 FFMA2 + 3 ALU + 1 MUFU", 8, th);
         run<12>("2 FFMA + 2 ALU interleaved", 4, th);
         run<13>("1 MUFU + 4 ALU", 5, th);
+        run<14>("I2FP + FADD + IADD", 3, th);
+        run<15>("FADD + IADD", 2, th);
     }
     return 0;
 }

@@ -165,10 +165,12 @@ __device__ __forceinline__ float2 gelu_fast2(float2 x, float p_rdiv, float nl2e_
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(z.x));
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(z.y));
     y = __ffma2_rn(y, e, make_float2(1.0f, 1.0f));                        // 1 - poly(t) * exp(-u^2)
-    const float2 erf_u = make_float2(__int_as_float(__float_as_int(y.x) ^ (__float_as_int(x.x) & 0x80000000)),
-                                     __int_as_float(__float_as_int(y.y) ^ (__float_as_int(x.y) & 0x80000000)));
+    // (sign(x) erf|u| + c2) * x * c = erf|u| * |x c| + c2 * (x c) for c = c3 / s_out > 0 (host-checked): the sign never
+    // has to be copied onto the erf value, and |.| is an operand modifier.  Same FMA inputs up to two cancelling signs.
     const float2 xc = __fmul2_rn(x, make_float2(c_out, c_out));
-    return __ffma2_rn(erf_u, xc, __fmul2_rn(xc, make_float2(c_add, c_add)));   // (erf + c2) * x * (c3 / s_out)
+    const float2 axc = make_float2(fabsf(xc.x), fabsf(xc.y));
+    (void)c_add;                                                          // == 1 (host-checked): c2 * (x c) is x c itself
+    return __ffma2_rn(y, axc, xc);
 }
 
 // Exact re-evaluation of one lane's share of a 32 x 32 step of the wide dequant epilogue (rare: some value left the
@@ -693,8 +695,14 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                             ta = __ffma2_rn(ea, r2, ta);
                             tb = __ffma2_rn(eb, r2, tb);
                         }
-                        ta = __fadd2_rn(make_float2(fmaxf(ta.x, -4194304.0f), fmaxf(ta.y, -4194304.0f)), mg2);
-                        tb = __fadd2_rn(make_float2(fmaxf(tb.x, -4194304.0f), fmaxf(tb.y, -4194304.0f)), mg2);
+                        if constexpr (EMODE == EM_Q8_GELU) {
+                            // GELU >= -0.2403 c1 c3: the quotient cannot leave the magic window downwards (host-checked)
+                            ta = __fadd2_rn(ta, mg2);
+                            tb = __fadd2_rn(tb, mg2);
+                        } else {
+                            ta = __fadd2_rn(make_float2(fmaxf(ta.x, -4194304.0f), fmaxf(ta.y, -4194304.0f)), mg2);
+                            tb = __fadd2_rn(make_float2(fmaxf(tb.x, -4194304.0f), fmaxf(tb.y, -4194304.0f)), mg2);
+                        }
                         int n0q = __float_as_int(ta.x) - 0x4B400000, n1q = __float_as_int(ta.y) - 0x4B400000;
                         int n2q = __float_as_int(tb.x) - 0x4B400000, n3q = __float_as_int(tb.y) - 0x4B400000;
                         if (qlo != -128) {                                 // codes narrower than 8 bits (warp-uniform)
@@ -1501,6 +1509,12 @@ static int qgemm_run(const int8_t* A, const int8_t* B, void* Cout, int64_t M, in
         if (ep->mode == NQ_EPI_GELU_QUANT) {
             NQ_REQUIRE(ep->gelu_div != 0.f && isfinite(ep->gelu_div), "nq_qgemm_s8: GELU divisor must be finite and non-zero");
             NQ_REQUIRE(ep->gelu_div > 0.f, "nq_qgemm_s8: GELU epilogue needs a positive divisor (sign(x / c1) = sign(x))");
+            // (erf(x / c1) + 1) * x * c3 >= -0.2403 * c1 * c3: with c2 = 1 and c3 > 0 the quotient by the output scale is
+            // bounded below and the epilogue drops the sign copy and the lower clamp; anything else is not a GELU
+            NQ_REQUIRE(ep->gelu_add == 1.0f && ep->gelu_mul > 0.f && isfinite(ep->gelu_mul),
+                       "nq_qgemm_s8: GELU epilogue needs Add constant 1 and a positive Mul constant");
+            NQ_REQUIRE(0.25 * (double)ep->gelu_div * (double)ep->gelu_mul / (double)ep->out_scale < 4.0e6,
+                       "nq_qgemm_s8: GELU epilogue: c1 * c3 / out_scale too large for the single-add rounding");
             p.g_prdiv = (float)(0.3275911 / (double)ep->gelu_div);
             p.g_nl2e = (float)(-1.4426950408889634 / ((double)ep->gelu_div * (double)ep->gelu_div));
             p.g_add = ep->gelu_add;

@@ -430,6 +430,23 @@ def test_qgemm_gelu_epilogue(zp):
     assert (np.abs(gc - t) <= tol).all(), float((np.abs(gc - t) - tol).max())
 
 
+def test_qgemm_gelu_epilogue_rejects_chains_that_are_not_a_gelu():
+    """The fused epilogue drops the sign copy and the lower clamp, which needs Add constant 1 and positive Div / Mul
+    constants (a GELU is bounded below); other constants are refused so that the caller keeps the node-by-node route."""
+    rng = np.random.default_rng(3)
+    M, N, Kd = 128, 64, 64
+    a = rng.integers(-128, 128, size=(1, M, Kd)).astype(np.int8)
+    w = rng.integers(-128, 128, size=(1, Kd, N)).astype(np.int8)
+    bias = dev(rng.normal(size=N).astype(np.float32))
+    oa, ob = K.operand_from_codes(dev(a), "A", False), K.operand_from_codes(dev(w), "B", True)
+    azp = K.AccZeroPoint(5, None, Kd, None, ob.rowsum, True)
+    for c in ((1.4142135381698608, 0.5, 0.5), (1.4142135381698608, 1.0, -0.5), (-1.4142135381698608, 1.0, 0.5)):
+        with pytest.raises(_lib.NqError):
+            K.qgemm_to_operand(oa, ob, 2.0e-5, azp, bias, 8, 0.03, None, "rows", 1, M, False, gelu=c)
+    with pytest.raises(_lib.NqError):                                     # c1 * c3 / out_scale outside the rounding window
+        K.qgemm_to_operand(oa, ob, 2.0e-5, azp, bias, 8, 1.0e-8, None, "rows", 1, M, False, gelu=(1.4142135381698608, 1.0, 0.5))
+
+
 def _softmax_chain_oracle(q8, kt8, sq, zq, sk, zk, div):
     """Reference chain up to the float32 probabilities (numpy_quantization.py:44-61, :37-41, Div, tensor.py:139-146) plus
     the float64 evaluation of the same chain on the exact integer scores (the contract's centre)."""
