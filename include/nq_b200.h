@@ -230,6 +230,14 @@ int nq_qgemm_s8_simt(const int8_t* A, const int8_t* B, int32_t* C,
 int nq_nhwc_pad(const void* x, int elem_bytes, int64_t B, int64_t C, int64_t H, int64_t W, int ph0, int pw0, int ph1, int pw1,
                 int pad_code, int bits, float scale, int has_zp, int64_t zp, int8_t* out, void* stream);
 
+/* Conv whose patches tile the image (kernel == stride, no padding -- the ViT patch embedding, reference
+ * numpy_helper.py:18-92 reached from model.py:95-100): the patch matrix is a re-indexing of the image, so the input
+ * quantizer (numpy_quantization.py:24-34) writes it directly: x[B,C,H,W] float32 ->
+ * out[(b, oh, ow)][(c, kh, kw)] int8 (row stride ldo bytes), the K-major left operand of nq_qgemm_s8 against the
+ * filters in their natural [O][C*KH*KW] order.  No nq_im2col pass.  KW % 4 == 0, H % KH == 0, W % KW == 0. */
+int nq_quantize_patches_f32(const float* x, int64_t B, int64_t C, int64_t H, int64_t W, int64_t KH, int64_t KW,
+                            int bit_width, float scale, int has_zp, int64_t zp, int8_t* out, int64_t ldo, void* stream);
+
 /* ---- K6: im2col for Conv (numpy_helper.py:18-92, tensor.py:256-264) ----------------------
  * x[B,C,H,W] (int8 codes or float32; elem_bytes 1 or 4) -> patches
  * out[B*OH*OW][kh][kw][c] with row stride ldo elements; positions that fall in the

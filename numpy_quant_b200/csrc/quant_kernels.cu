@@ -45,6 +45,42 @@ __global__ void __launch_bounds__(256) quantize_scalar_kernel(const float* __res
         out[i] = (int8_t)qz.code<QMODE>(x[i]);
 }
 
+// Non-overlapping patches (Conv with kernel == stride and no padding: the ViT stem): the patch matrix is a pure
+// re-indexing of the image, so the quantizer writes it directly -- x[B, C, H, W] float32 -> out[(b, oh, ow)][(c, kh, kw)]
+// int8, the K-major A operand of the convolution GEMM (weights in their natural [O][C][KH][KW] order).  One thread
+// = one (patch, c, kh) run of KW floats: consecutive threads are consecutive kh / c of one patch, so a warp writes one
+// contiguous span of the operand row and reads whole 32-byte sectors of the image.
+template <int QMODE>
+__global__ void __launch_bounds__(1024) quantize_patches_kernel(const float* __restrict__ x, int64_t n_rows, int C, int H, int W,
+                                                               int KH, int KW, QArgs a, int8_t* __restrict__ out, int64_t ldo) {
+    // CTA = one row of patches (b, oh); thread = one float4 slot (c, kh, j) of the patch, fixed for the whole launch, so
+    // the loops below carry no index arithmetic: along ow the source advances by KW floats and the destination by one
+    // operand row.  Consecutive threads read consecutive 16 bytes of a KW-float run, then the next kh / c, and write
+    // consecutive 4-byte groups of the operand row; four patches in flight per thread.
+    const Quantizer qz(a);
+    const int OH = H / KH, OW = W / KW, kw4 = KW >> 2, vec_per_patch = C * KH * kw4;
+    for (int t = threadIdx.x; t < vec_per_patch; t += blockDim.x) {
+        const int ck = t / kw4, j = t - ck * kw4, c = ck / KH, kh = ck - c * KH;
+        for (int64_t row = blockIdx.x; row < n_rows; row += gridDim.x) {
+            const int64_t b = row / OH;
+            const int oh = (int)(row - b * OH);
+            const float4* src = reinterpret_cast<const float4*>(x + ((b * C + c) * H + (int64_t)oh * KH + kh) * W) + j;
+            int* dst = reinterpret_cast<int*>(out + row * OW * ldo + (int64_t)ck * KW) + j;
+            const int64_t dstep = ldo >> 2;
+            for (int ow0 = 0; ow0 < OW; ow0 += 4) {
+                float4 val[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) val[u] = __ldcs(src + (int64_t)min(ow0 + u, OW - 1) * kw4);
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (ow0 + u < OW)
+                        dst[(ow0 + u) * dstep] = pack4_codes(qz.code<QMODE>(val[u].x), qz.code<QMODE>(val[u].y),
+                                                            qz.code<QMODE>(val[u].z), qz.code<QMODE>(val[u].w));
+            }
+        }
+    }
+}
+
 // wide symmetric/asymmetric quantize to int64 codes (4*bit_width-bit biases, model.py:383-389, 405-410)
 __global__ void quantize_i64_kernel(const float* __restrict__ x, int64_t n, float scale, int has_zp, double zp,
                                     float lo, float hi, double dlo, double dhi, int64_t* __restrict__ out) {
@@ -568,6 +604,27 @@ extern "C" int nq_quantize_f32(const float* x, int64_t n, int bit_width, float s
         NQ_DISPATCH_QMODE(qmode, quantize_scalar_kernel, <<<grid, 256, 0, s>>>(x, n, a, out));
     }
     NQ_CHECK_LAUNCH("nq_quantize_f32");
+    return NQ_OK;
+}
+
+extern "C" int nq_quantize_patches_f32(const float* x, int64_t B, int64_t C, int64_t H, int64_t W, int64_t KH, int64_t KW,
+                                       int bit_width, float scale, int has_zp, int64_t zp, int8_t* out, int64_t ldo,
+                                       void* stream) {
+    NQ_REQUIRE(bit_width >= 2 && bit_width <= 8, "nq_quantize_patches_f32: bit_width %d outside 2..8", bit_width);
+    NQ_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && KH > 0 && KW > 0, "nq_quantize_patches_f32: empty geometry");
+    NQ_REQUIRE(H % KH == 0 && W % KW == 0, "nq_quantize_patches_f32: the patches must tile the image (H %% KH == 0, W %% KW == 0)");
+    NQ_REQUIRE(KW % 4 == 0 && ((uintptr_t)x & 15) == 0, "nq_quantize_patches_f32: KW %% 4 == 0 and a 16-byte aligned image are required");
+    NQ_REQUIRE(ldo >= C * KH * KW && ldo % 4 == 0 && ((uintptr_t)out & 3) == 0, "nq_quantize_patches_f32: ldo < C*KH*KW or unaligned output");
+    NQ_REQUIRE(C * KH < (1ll << 31) && H < (1ll << 31) && W < (1ll << 31), "nq_quantize_patches_f32: extent too large");
+    int qmode;
+    const QArgs a = make_qargs(bit_width, scale, has_zp, zp, &qmode);
+    const int64_t n_rows = B * (H / KH), vec_per_patch = C * KH * (KW / 4);
+    const int threads = (int)(vec_per_patch >= 1024 ? 1024 : ((vec_per_patch + 31) / 32) * 32);
+    const int64_t cap = (int64_t)sm_count() * (2048 / threads) * 4;
+    const int grid = (int)(n_rows < cap ? n_rows : cap);
+    cudaStream_t s = (cudaStream_t)stream;
+    NQ_DISPATCH_QMODE(qmode, quantize_patches_kernel, <<<grid, threads, 0, s>>>(x, n_rows, (int)C, (int)H, (int)W, (int)KH, (int)KW, a, out, ldo));
+    NQ_CHECK_LAUNCH("nq_quantize_patches_f32");
     return NQ_OK;
 }
 

@@ -57,6 +57,27 @@ def quantize(x: torch.Tensor, bits: int, scale, zp) -> torch.Tensor:
     return out
 
 
+def quantize_patches(x: torch.Tensor, kh: int, kw: int, bits: int, scale, zp) -> "Operand":
+    """float32 NCHW image -> quantized patch matrix [(b, oh, ow)][(c, kh, kw)] of a Conv whose kernel == stride and
+    pads == 0, written straight into the K-major A operand of the convolution GEMM (no im2col pass)."""
+    _need_cuda(x, torch.float32)
+    x = materialize(x)
+    B, Cc, H, W = (int(v) for v in x.shape)
+    k = Cc * kh * kw
+    ld = round_up(k, 16)
+    rows = B * (H // kh) * (W // kw)
+    out = torch.empty((1, rows, ld), dtype=torch.int8, device=x.device) if ld == k else \
+        torch.zeros((1, rows, ld), dtype=torch.int8, device=x.device)
+    call("nq_quantize_patches_f32", x.data_ptr(), B, Cc, H, W, kh, kw, bits, float(scale), int(zp is not None),
+         0 if zp is None else int(zp), out.data_ptr(), ld, _stream())
+    _count()
+    return Operand(out, (), rows, k, ld, None)
+
+
+def can_quantize_patches(shape, kh: int, kw: int) -> bool:
+    return len(shape) == 4 and kw % 4 == 0 and shape[2] % kh == 0 and shape[3] % kw == 0
+
+
 def quantize_i64(x: torch.Tensor, bits: int, scale, zp=None) -> torch.Tensor:
     """Wide quantize (4*bit_width-bit biases; 9..32 bit codes) -> int64 codes; `zp` as in numpy_quantization.py:24-34."""
     _need_cuda(x, torch.float32)

@@ -21,6 +21,7 @@ from . import _lib, kernels as K
 from . import onnx_lite
 from .numpy_quantization import quant_parameters
 from .tensor import (FTensor, ITensor, QTensor, Tensor, concat, fconv2d, qconv2d, qtensor_from_operand, quantize_tensor_nhwc,
+                     quantize_tensor_patches,
                      quantize_tensor, where, _to_device)
 
 
@@ -645,6 +646,17 @@ class QModel(Model):
             return d[1]
         return value.data.dequantize()
 
+    def _conv_input_tiling(self, value: Value):
+        """(kh, kw) if every Conv consuming `value` (see _conv_input_pads) has kernel == strides == (kh, kw), else None."""
+        kernel = None
+        for n in value.outputs:
+            w = n.inputs[1].data
+            k = tuple(int(v) for v in w.shape[2:])
+            if len(k) != 2 or tuple(int(v) for v in n.attrs["strides"]) != k or (kernel is not None and k != kernel):
+                return None
+            kernel = k
+        return kernel
+
     def _conv_input_pads(self, value: Value):
         """The common `pads` of the Conv nodes consuming `value` as their image, or None if anything else reads it
         (model outputs included) or the quantized weights are not symmetric 8-bit-or-narrower codes."""
@@ -961,8 +973,13 @@ class QModel(Model):
                 pads = self._conv_input_pads(variable)
                 q = None
                 if pads is not None:
-                    # consumed only by Conv nodes: quantized straight into the padded NHWC image their TMA reads
-                    q = quantize_tensor_nhwc(FTensor(array), self.bit_width, qparams.scale, qparams.zero_point, pads)
+                    tiling = self._conv_input_tiling(variable) if not any(pads) else None
+                    if tiling is not None:
+                        # kernel == stride, no padding (patch embedding): quantized straight into the patch matrix
+                        q = quantize_tensor_patches(FTensor(array), self.bit_width, qparams.scale, qparams.zero_point, tiling)
+                    if q is None:
+                        # consumed only by Conv nodes: quantized straight into the padded NHWC image their TMA reads
+                        q = quantize_tensor_nhwc(FTensor(array), self.bit_width, qparams.scale, qparams.zero_point, pads)
                 variable.data = q if q is not None else \
                     quantize_tensor(FTensor(array), self.bit_width, qparams.scale, qparams.zero_point)
             elif array.dtype == np.int64:

@@ -265,6 +265,9 @@ class QTensor:
                 operand layout of the GEMM (written there directly by quantize_tensor)
       _nhwc     (padded NHWC image, pads, logical NCHW shape): codes of a Conv input that so far exist only in
                 the layout nq_qconv2d_s8 reads (written there by quantize_tensor_nhwc)
+      _patches  (patch-matrix Operand, (kh, kw), logical NCHW shape): codes of the input of a Conv whose patches tile
+                the image (kernel == stride, no padding), written by quantize_tensor_patches in the layout the
+                convolution GEMM reads
       _lazy     pending GEMM of a matmul result (operands + optional int bias)
       _packed   (role, packed bitstream, operand geometry, row sums): sub-byte storage of a weight -- the K-major
                 operand buffer packed to bit_width bits per code (nq_pack_s8); unpacked into a transient int8
@@ -275,6 +278,7 @@ class QTensor:
         self._lazy = None
         self._oplayout = None
         self._nhwc = None
+        self._patches = None
         self._ops: dict = {}           # cached K-major GEMM operands by role
         self._packed = None
         self._src = None               # base QTensor when this is the 2-D transpose of it
@@ -335,6 +339,8 @@ class QTensor:
             return tuple(self._oplayout[2])
         if self._nhwc is not None:
             return tuple(self._nhwc[2])
+        if self._patches is not None:
+            return tuple(self._patches[2])
         if self._packed is not None:
             return tuple(self._packed["logical"])
         L = self._lazy
@@ -362,6 +368,10 @@ class QTensor:
             elif self._nhwc is not None:
                 img, (ph0, pw0, _, _), shape = self._nhwc
                 self._q = K.materialize(img[:, ph0:ph0 + shape[2], pw0:pw0 + shape[3], :].permute(0, 3, 1, 2))
+            elif self._patches is not None:
+                op, (kh, kw), (b, c, h, w) = self._patches
+                v = op.data[0, :, : op.k].view(b, h // kh, w // kw, c, kh, kw).permute(0, 3, 1, 4, 2, 5)
+                self._q = K.materialize(v).view(b, c, h, w)
             else:
                 L = self._lazy
                 acc = K.qgemm(L["a"], L["b"])
@@ -699,6 +709,23 @@ def quantize_tensor_nhwc(tensor: FTensor, bit_width: int, scale: np.float32, zer
     return out
 
 
+def quantize_tensor_patches(tensor: FTensor, bit_width: int, scale: np.float32, zero_point, kernel) -> Optional[QTensor]:
+    """quantize_tensor for a value consumed only by Conv nodes whose patches tile the image (kernel == stride, no
+    padding: the ViT patch embedding): the float32 image is quantized straight into the patch matrix the convolution
+    GEMM reads, so the Conv is a reshape + MatMul and no im2col pass runs.  None when the geometry is not served."""
+    t = tensor.device_tensor
+    zi = _as_opt_int(zero_point)
+    kh, kw = (int(v) for v in kernel)
+    lo, hi = -(1 << (bit_width - 1)), (1 << (bit_width - 1)) - 1
+    if t.dim() != 4 or not (2 <= bit_width <= 8) or not K.can_quantize_patches(tuple(t.shape), kh, kw) \
+            or (zi is not None and not lo <= zi <= hi):
+        return None
+    op = K.quantize_patches(t, kh, kw, bit_width, float(scale), zi)
+    out = QTensor(None, bit_width, scale=scale, zero_point=zero_point)
+    out._patches = (op, (kh, kw), tuple(int(v) for v in t.shape))
+    return out
+
+
 def qtensor_from_operand(op: K.Operand, role: str, shape: tuple, bit_width: int, scale, zero_point) -> QTensor:
     """Wrap codes that exist only in the K-major GEMM operand layout (`.data` un-pads on demand)."""
     out = QTensor(None, bit_width, scale=scale, zero_point=zero_point)
@@ -801,6 +828,20 @@ def qconv2d(x: QTensor, w: QTensor, b: FTensor, pads, strides) -> FTensor:
     o, c, kh, kw = (int(s) for s in wq.shape)
     xshape = tuple(int(v) for v in x.shape)
     k = kh * kw * c
+    if x._patches is not None and x._patches[1] == (kh, kw) and tuple(int(s) for s in strides) == (kh, kw) \
+            and not any(int(p) for p in pads):
+        # the patches tile the image: the input was quantized straight into the patch matrix (rows (b, oh, ow), columns
+        # (c, kh, kw)), the filters are used in their natural [O, C*KH*KW] order -- reshape + MatMul, nothing else
+        opa = x._patches[0]
+        opw = w._ops.get("conv_chw")
+        if opw is None:
+            opw = K.operand_from_codes(wq.reshape(o, k), "A", True)        # rows = O, rowsum = colsum(B)
+            w._ops["conv_chw"] = opw
+        azp_p = K.AccZeroPoint(zx, None, k, None, opw.rowsum, True)
+        y = K.qgemm(opa, opw, _lib.EPI_DEQUANT, float(np.float32(x.scale) * np.float32(w.scale)), azp_p,
+                    bias_f32=b.device_tensor.contiguous())
+        n_img, oh, ow = xshape[0], xshape[2] // kh, xshape[3] // kw
+        return FTensor(y.view(n_img, oh, ow, o).permute(0, 3, 1, 2))
     opb = w._ops.get("conv")
     if opb is None:
         wk = K.materialize(wq.permute(0, 2, 3, 1)).view(o, k)            # [O, kh*kw*c] == K-major B operand

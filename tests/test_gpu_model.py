@@ -134,6 +134,41 @@ def test_conv_block_config3_geometry_vs_oracle():
     np.testing.assert_array_equal(q([x], retain=False)[0], got)
 
 
+@pytest.mark.parametrize("bits", [8, 4])
+def test_patch_embedding_conv_is_a_reshape(bits, monkeypatch):
+    """Conv with kernel == stride and no padding (the ViT patch embedding, C = 3): the input is quantized straight
+    into the patch matrix (nq_quantize_patches_f32) and the Conv runs as a MatMul against the filters in their natural
+    order -- no im2col pass.  Quantized input codes are the oracle's bit for bit, the output equals the reference's
+    fake-quant float conv within float32 summation rounding, and it is bit-identical to the im2col route."""
+    from numpy_quant_b200 import kernels as K
+    proto = zoo.conv_graph(3, 3, (32, 48), 40, (8, 16), (0, 0, 0, 0), (8, 16), seed=1)
+    x = np.random.default_rng(2).normal(size=(3, 3, 32, 48)).astype(np.float32)
+    m = Model.from_onnx(proto)
+    plan = rg.calibrate(rg.import_graph(proto, ol), [x], bits)
+    q = m.quantize([x], bits)
+    inject_oracle_params(q, m, plan)
+    before = K.LAUNCHES
+    got = q([x])[0]
+    launches = K.LAUNCHES - before
+    want = rg.run_quant(plan, [x])[0]
+    np.testing.assert_allclose(got, want, rtol=1e-5, atol=2e-3)
+    xin = {v.name: v for v in q.values}["input"].data
+    assert xin._patches is not None                                       # the new route ran
+    np.testing.assert_array_equal(xin.data, plan_quantized_input(plan, x, bits))
+    np.testing.assert_array_equal(q([x], retain=False)[0], got)
+    monkeypatch.setattr(K, "can_quantize_patches", lambda *a, **k: False)  # the nq_im2col + nq_qgemm_s8 route
+    before = K.LAUNCHES
+    ref = q([x])[0]
+    assert K.LAUNCHES - before > launches                                 # one pass (im2col) more
+    np.testing.assert_array_equal(got, ref)
+
+
+def plan_quantized_input(plan, x, bits):
+    s, z = plan.qparams["input"]
+    from oracle import ref_quant as rq
+    return rq.quantize(x, bits, s, z)
+
+
 VIT_CFG = dict(batch=2, image_size=32, patch_size=16, hidden=32, heads=4, intermediate=64, layers=2, classes=10)
 
 
