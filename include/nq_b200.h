@@ -230,6 +230,13 @@ int nq_qgemm_s8_simt(const int8_t* A, const int8_t* B, int32_t* C,
 int nq_nhwc_pad(const void* x, int elem_bytes, int64_t B, int64_t C, int64_t H, int64_t W, int ph0, int pw0, int ph1, int pw1,
                 int pad_code, int bits, float scale, int has_zp, int64_t zp, int8_t* out, void* stream);
 
+/* Batched byte transpose out[b][c][r] = in[b][r][c] (b < batch, r < R, c < C; row strides ld_in / ld_out bytes, batch
+ * strides in bytes; bytes r in [R, ld_out) of every output row are written as 0).  Turns the [head][S][D] codes the V
+ * projection writes through the row-layout NQ_EPI_QUANT epilogue into the K-major [head][D][S] right operand of the
+ * P.V MatMul (the graph's Transpose of V, tensor.py:74 / model.py Transpose node, as a 1-byte-per-element pass). */
+int nq_transpose_s8(const int8_t* in, int64_t batch, int64_t R, int64_t C, int64_t ld_in, int64_t stride_in,
+                    int8_t* out, int64_t ld_out, int64_t stride_out, void* stream);
+
 /* Conv whose patches tile the image (kernel == stride, no padding -- the ViT patch embedding, reference
  * numpy_helper.py:18-92 reached from model.py:95-100): the patch matrix is a re-indexing of the image, so the input
  * quantizer (numpy_quantization.py:24-34) writes it directly: x[B,C,H,W] float32 ->

@@ -53,6 +53,7 @@ _SIGNATURES = {
     "nq_device_info": [C.POINTER(C.c_int)],
     "nq_quantize_f32": [vp, i64, C.c_int, f32, C.c_int, i64, vp, vp],
     "nq_quantize_f32_i64": [vp, i64, C.c_int, f32, C.c_int, i64, vp, vp],
+    "nq_transpose_s8": [vp, i64, i64, i64, i64, i64, vp, i64, i64, vp],
     "nq_quantize_patches_f32": [vp, i64, i64, i64, i64, i64, i64, C.c_int, f32, C.c_int, i64, vp, i64, vp],
     "nq_quantize_f32_4d": [vp, i64, i64, i64, i64, i64, i64, i64, i64, C.c_int, f32, C.c_int, i64, vp, i64, vp, vp],
     "nq_dequantize": [vp, C.c_int, i64, f32, C.c_int, i64, vp, vp],

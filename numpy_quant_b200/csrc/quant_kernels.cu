@@ -1,5 +1,6 @@
 // K1 quantize, K2 dequantize, K3 requantize, K10 min/max, K11 pack/unpack, row sums.
 // All HBM-bound: 16-byte vector accesses, grid-stride over whole waves of the 148 SMs.
+#include <algorithm>
 #include "common.cuh"
 
 namespace nq {
@@ -77,6 +78,59 @@ __global__ void __launch_bounds__(1024) quantize_patches_kernel(const float* __r
                         dst[(ow0 + u) * dstep] = pack4_codes(qz.code<QMODE>(val[u].x), qz.code<QMODE>(val[u].y),
                                                             qz.code<QMODE>(val[u].z), qz.code<QMODE>(val[u].w));
             }
+        }
+    }
+}
+
+// Batched byte transpose out[b][c][r] = in[b][r][c] (the V operand of the attention: the projection GEMM writes V
+// as [head][S][D] through its fast row-layout epilogue, the P.V MatMul wants the contraction axis S contiguous).
+// Tile 128 r x 64 c through shared memory: 16-byte coalesced loads, 4 x 4 byte blocks transposed in registers
+// (8 PRMT), 4-byte stores that are contiguous along r across a warp.  Word columns are XOR-swizzled with the row
+// group so that the column-wise read-back has at most 2-way bank conflicts.  Rows r in [R, ld_out) are written as 0.
+__global__ void __launch_bounds__(256) transpose_s8_kernel(const int8_t* __restrict__ in, int R, int Cc, int64_t ld_in,
+                                                          int64_t stride_in, int8_t* __restrict__ out, int64_t ld_out,
+                                                          int64_t stride_out, int r_tiles, int c_tiles) {
+    __shared__ uint32_t tile[128 * 16];
+    const int ct = blockIdx.x % c_tiles, rt = (blockIdx.x / c_tiles) % r_tiles;
+    const int64_t b = blockIdx.x / (c_tiles * r_tiles);
+    const int r0 = rt * 128, c0 = ct * 64;
+    const int8_t* src = in + b * stride_in;
+    for (int i = threadIdx.x; i < 128 * 4; i += 256) {
+        const int r = i >> 2, q4 = i & 3, c = c0 + q4 * 16;
+        int4 v = make_int4(0, 0, 0, 0);
+        if (r0 + r < R && c < Cc) {
+            const int8_t* p = src + (int64_t)(r0 + r) * ld_in + c;
+            if (c + 16 <= Cc && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) v = *reinterpret_cast<const int4*>(p);
+            else {
+                int w[4] = {0, 0, 0, 0};
+                for (int k = 0; k < 16 && c + k < Cc; ++k) w[k >> 2] |= (int)(uint8_t)p[k] << ((k & 3) * 8);
+                v = make_int4(w[0], w[1], w[2], w[3]);
+            }
+        }
+        const int sw = (r >> 2) & 15;
+        uint32_t* row = tile + r * 16;
+        row[(q4 * 4 + 0) ^ sw] = (uint32_t)v.x;
+        row[(q4 * 4 + 1) ^ sw] = (uint32_t)v.y;
+        row[(q4 * 4 + 2) ^ sw] = (uint32_t)v.z;
+        row[(q4 * 4 + 3) ^ sw] = (uint32_t)v.w;
+    }
+    __syncthreads();
+    int8_t* dst = out + b * stride_out;
+    for (int i = threadIdx.x; i < 32 * 16; i += 256) {
+        const int sg = i & 31, dg = i >> 5;                                // lanes: consecutive row groups
+        const int sw = sg & 15;
+        const uint32_t a0 = tile[(sg * 4 + 0) * 16 + (dg ^ sw)], a1 = tile[(sg * 4 + 1) * 16 + (dg ^ sw)];
+        const uint32_t a2 = tile[(sg * 4 + 2) * 16 + (dg ^ sw)], a3 = tile[(sg * 4 + 3) * 16 + (dg ^ sw)];
+        const uint32_t t0 = __byte_perm(a0, a1, 0x5140), t1 = __byte_perm(a2, a3, 0x5140);
+        const uint32_t t2 = __byte_perm(a0, a1, 0x7362), t3 = __byte_perm(a2, a3, 0x7362);
+        const uint32_t o[4] = {__byte_perm(t0, t1, 0x5410), __byte_perm(t0, t1, 0x7632), __byte_perm(t2, t3, 0x5410),
+                               __byte_perm(t2, t3, 0x7632)};
+        const int r = r0 + sg * 4;
+        if (r >= ld_out) continue;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int c = c0 + dg * 4 + k;
+            if (c < Cc) *reinterpret_cast<uint32_t*>(dst + (int64_t)c * ld_out + r) = o[k];
         }
     }
 }
@@ -604,6 +658,20 @@ extern "C" int nq_quantize_f32(const float* x, int64_t n, int bit_width, float s
         NQ_DISPATCH_QMODE(qmode, quantize_scalar_kernel, <<<grid, 256, 0, s>>>(x, n, a, out));
     }
     NQ_CHECK_LAUNCH("nq_quantize_f32");
+    return NQ_OK;
+}
+
+extern "C" int nq_transpose_s8(const int8_t* in, int64_t batch, int64_t R, int64_t Cc, int64_t ld_in, int64_t stride_in,
+                               int8_t* out, int64_t ld_out, int64_t stride_out, void* stream) {
+    NQ_REQUIRE(batch > 0 && R > 0 && Cc > 0, "nq_transpose_s8: empty problem");
+    NQ_REQUIRE(ld_in >= Cc && ld_out >= R && ld_out % 4 == 0 && stride_out % 4 == 0 && ((uintptr_t)out & 3) == 0,
+               "nq_transpose_s8: ld_in >= C, ld_out >= R, ld_out / stride_out multiples of 4 and a 4-byte aligned output are required");
+    NQ_REQUIRE(R < (1ll << 30) && Cc < (1ll << 30), "nq_transpose_s8: extent too large");
+    const int64_t r_tiles = (std::max<int64_t>(R, ld_out) + 127) / 128, c_tiles = (Cc + 63) / 64;
+    NQ_REQUIRE(batch * r_tiles * c_tiles < (1ll << 31), "nq_transpose_s8: too many tiles");
+    transpose_s8_kernel<<<(unsigned)(batch * r_tiles * c_tiles), 256, 0, (cudaStream_t)stream>>>(
+        in, (int)R, (int)Cc, ld_in, stride_in, out, ld_out, stride_out, (int)r_tiles, (int)c_tiles);
+    NQ_CHECK_LAUNCH("nq_transpose_s8");
     return NQ_OK;
 }
 

@@ -361,6 +361,9 @@ def qconv2d(x_nhwc: torch.Tensor, w: Operand, kh: int, kw: int, strides, mode: i
     return out, OH, OW
 
 
+SPLIT_COLS_VIA_TRANSPOSE = os.environ.get("NQ_SPLIT_COLS_EPILOGUE") is None     # A/B switch: the column-layout epilogue
+
+
 def qgemm_to_operand(a: Operand, b: Operand, scale: float, azp: AccZeroPoint, bias_f32: Optional[torch.Tensor],
                      bits: int, out_scale, out_zp, kind: str, heads: int, seq: int, want_rowsum: bool,
                      gelu: Optional[tuple] = None) -> Operand:
@@ -378,6 +381,19 @@ def qgemm_to_operand(a: Operand, b: Operand, scale: float, azp: AccZeroPoint, bi
     batch = max(a.batch, b.batch)
     M, N, Kd = a.rows, b.rows, a.k
     dev = a.data.device
+    if kind == "split_cols" and SPLIT_COLS_VIA_TRANSPOSE and gelu is None and N % heads == 0 and (N // heads) % 16 == 0:
+        # V of the attention: written as [head][S][D] through the row-layout epilogue (the byte-scattering column
+        # layout costs 70 us per ViT-B layer against 37 us), then one 1-byte-per-element transpose into [head][D][S]
+        rows_op = qgemm_to_operand(a, b, scale, azp, bias_f32, bits, out_scale, out_zp, "split_rows", heads, seq, False)
+        BH, S, D = rows_op.batch, rows_op.rows, rows_op.k
+        ld = round_up(S, 16)
+        out = torch.empty((BH, D, ld), dtype=torch.int8, device=dev)
+        call("nq_transpose_s8", rows_op.data.data_ptr(), BH, S, D, rows_op.ld, S * rows_op.ld, out.data_ptr(), ld, D * ld, _stream())
+        _count()
+        res = Operand(out, rows_op.batch_shape, D, S, ld, None)
+        if want_rowsum:
+            res.rowsum = rowsum(res)
+        return res
     ep = Epilogue()
     ep.mode = _lib.EPI_QUANT
     ep.scale = float(scale)

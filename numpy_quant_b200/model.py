@@ -1321,7 +1321,10 @@ class QModel(Model):
             other_asym = self.quant_params[other.name].zero_point is not None
         perm = [int(x) for x in spec["transpose"].attrs["perm"]]
         logical = tuple([B, S, H, D][p] for p in perm)
-        q = acc.quantize_into_operand(bias, self.bit_width, qp.scale, qp.zero_point, spec["kind"], H, S, other_asym,
+        # column sums of V: the fused attention kernel does not read them (its zero-point terms come from constant-
+        # operand MMAs) and QTensor._operand computes them on demand for the two-GEMM route
+        want_rs = other_asym and spec["kind"] != "split_cols"
+        q = acc.quantize_into_operand(bias, self.bit_width, qp.scale, qp.zero_point, spec["kind"], H, S, want_rs,
                                       role, logical)
         if q is None:
             return False

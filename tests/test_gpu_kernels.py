@@ -430,6 +430,39 @@ def test_qgemm_gelu_epilogue(zp):
     assert (np.abs(gc - t) <= tol).all(), float((np.abs(gc - t) - tol).max())
 
 
+@pytest.mark.parametrize("shape", [(5, 197, 64, 64, 208), (3, 130, 48, 64, 144), (2, 7, 20, 32, 16), (1, 300, 100, 112, 304)])
+def test_transpose_s8(shape):
+    """nq_transpose_s8: out[b][c][r] = in[b][r][c], padding bytes r in [R, ld_out) zero, ragged R / C / unaligned ld_in."""
+    bt, R, Cc, ld_in, ld_out = shape
+    rng = np.random.default_rng(R)
+    a = rng.integers(-128, 128, size=(bt, R, ld_in)).astype(np.int8)
+    src = dev(a)
+    out = torch.full((bt, Cc, ld_out), 55, dtype=torch.int8, device=src.device)
+    _lib.call("nq_transpose_s8", src.data_ptr(), bt, R, Cc, ld_in, R * ld_in, out.data_ptr(), ld_out, Cc * ld_out, 0)
+    torch.cuda.synchronize()
+    got = host(out)
+    np.testing.assert_array_equal(got[:, :, :R], a[:, :, :Cc].transpose(0, 2, 1))
+    assert (got[:, :, R:] == 0).all()
+
+
+def test_split_cols_operand_via_transpose_equals_the_column_epilogue(monkeypatch):
+    """The V operand [head][D][S] produced by the row-layout epilogue + nq_transpose_s8 carries exactly the codes of
+    the column-layout (byte-scattering) epilogue."""
+    rng = np.random.default_rng(8)
+    B, S, H, D, Kd = 3, 197, 4, 64, 96
+    a = rng.integers(-128, 128, size=(1, B * S, Kd)).astype(np.int8)
+    w = rng.integers(-128, 128, size=(1, Kd, H * D)).astype(np.int8)
+    bias = dev(rng.normal(size=H * D).astype(np.float32))
+    oa, ob = K.operand_from_codes(dev(a), "A", False), K.operand_from_codes(dev(w), "B", True)
+    azp = K.AccZeroPoint(-9, None, Kd, None, ob.rowsum, True)
+    new = K.qgemm_to_operand(oa, ob, 3.0e-5, azp, bias, 8, 0.04, 6, "split_cols", H, S, False)
+    monkeypatch.setattr(K, "SPLIT_COLS_VIA_TRANSPOSE", False)
+    old = K.qgemm_to_operand(oa, ob, 3.0e-5, azp, bias, 8, 0.04, 6, "split_cols", H, S, True)
+    assert new.rows == old.rows == D and new.k == old.k == S and new.ld == old.ld
+    np.testing.assert_array_equal(host(new.data)[:, :, :S], host(old.data)[:, :, :S])
+    np.testing.assert_array_equal(host(K.rowsum(new)), host(old.rowsum))
+
+
 def test_qgemm_gelu_epilogue_rejects_chains_that_are_not_a_gelu():
     """The fused epilogue drops the sign copy and the lower clamp, which needs Add constant 1 and positive Div / Mul
     constants (a GELU is bounded below); other constants are refused so that the caller keeps the node-by-node route."""
