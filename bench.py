@@ -643,7 +643,8 @@ def run_own_arm(args) -> None:
         n = sum(tr["launches_per_step"].values())
         traffic = sum(tr["per_launch_bytes"][k] * c for k, c in tr["launches_per_step"].items()) / n
         traffic_note = (f"mean DRAM bytes per launch over the {n} of {len(gemm) // max(args.steps, 1)} GEMM launches per step "
-                        "whose shape has an ncu --set full capture (profiles/r01_gemm_dram_traffic.json)")
+                        "whose shape has an ncu --set full capture (profiles/r01_gemm_dram_traffic.json: round-1 captures, the operand "
+                        "and output bytes of these shapes have not changed)")
     except Exception:
         pass
     achieved = gemm_ops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
@@ -665,10 +666,12 @@ def run_own_arm(args) -> None:
                      "frac_all_denominators": tops_fractions(achieved, peaks, lib_tops) if achieved else None,
                      "library_int8_tops_8192": lib_tops,
                      "bound_note": ("the int8 GEMMs of this graph carry fused epilogues (dequantize / GELU / quantize for the next "
-                                    "MatMul). Ablation (NQ_GEMM_DBG, profiles/r02_gemm_ablation.md): the N = K = 768 launches have a ~40 us "
-                                    "operand-feed floor (L2 -> SM) under a ~45 us epilogue that only partly overlap; MLP-1 "
-                                    "(N = 3072, GELU + quantize) is epilogue-bound with the MUFU pipe as its floor; MLP-2 "
-                                    "(K = 3072) runs closest to the tensor pipe"),
+                                    "MatMul) and are epilogue-bound: ablation and per-tile clock traces (profiles/r02_gemm_ablation.md, "
+                                    "r02_gemm_tile_trace.md) put the MLP-1 launch at 175 us with the main loop switched off against "
+                                    "189 us complete; the epilogue runs at ~0.7 warp instructions per cycle per scheduler, the rate "
+                                    "its FFMA2 / ALU / MUFU mix issues at (r02_pipe_rates.md), so instructions per element are the "
+                                    "lever (r02_fc1_gelu_ncu_full.md); the float32 + residual epilogues (output projection, MLP-2) "
+                                    "are bound by the residual stream"),
                      "kernel": "nq::qgemm_kernel<BN, epilogue> (all instantiations launched in the step: the int8 GEMMs)",
                      "launches_per_step": len(gemm) // max(args.steps, 1),
                      "share_of_step": gemm_ms / eager_ms if eager_ms else None,
