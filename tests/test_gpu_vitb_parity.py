@@ -210,7 +210,7 @@ def test_teacher_forced_stem_and_head(bits):
     ref = c.env[conv].a
     err = float(np.abs(got - ref).max() / np.abs(ref).max())
     record("vitb_stem_conv", bits=bits, max_err_rel_to_range=err)
-    assert err < 2e-5
+    assert err < 3e-6                                                     # measured 6e-7
     # classifier: quantize(token) -> Gemm -> requantize, all integer / single-op arithmetic: bit-exact logits codes
     tok = c.env["/Gather_output_0"]
     s_t, z_t = c.plan.qparams["/Gather_output_0"]
@@ -249,7 +249,7 @@ def test_teacher_forced_layernorm_quantize(bits, which):
         got = op.data.cpu().numpy().astype(np.int64).reshape(B * S, -1)[:, :HID]
         d = np.abs(got - want)
         record("layernorm_quantize_flips", bits=bits, which=which, float_glue=str(glue), flip_fraction=np.mean(d != 0), max_step=d.max())
-        assert d.max() <= 1 and np.mean(d != 0) < 2e-3, (int(d.max()), float(np.mean(d != 0)))
+        assert d.max() <= 1 and np.mean(d != 0) < 3e-5, (int(d.max()), float(np.mean(d != 0)))   # measured <= 6.6e-6 (2 codes)
         assert contract_excess(got, v64, s, z, bits) <= 0
         np.testing.assert_array_equal(op.rowsum.cpu().numpy().reshape(-1), got.sum(-1))
 
@@ -304,7 +304,7 @@ def test_teacher_forced_attention(bits):
     P_ref = c.codes(names["p"])
     d = np.abs(Pc - P_ref)
     record("vitb_attention_P_flips", bits=bits, flip_fraction=np.mean(d != 0), max_step=d.max(), p_zp=str(zp))
-    assert d.max() <= 1 and np.mean(d != 0) < 3e-3, (int(d.max()), float(np.mean(d != 0)))
+    assert d.max() <= 1 and np.mean(d != 0) < 2e-5, (int(d.max()), float(np.mean(d != 0)))       # measured 5.4e-6 (5 codes)
     acc2, sc2, z2 = rq.q_matmul(Pc, sp, None if zp is None else np.int64(zp), vc, sv, None if zv is None else np.int64(zv))
     ctx = rq.dequantize(acc2, sc2, z2).transpose(0, 2, 1, 3).reshape(B, S, H * D)
     want = rq.quantize(ctx, bits, so, None if zo is None else np.int64(zo))
@@ -314,7 +314,7 @@ def test_teacher_forced_attention(bits):
     ref = c.codes(names["o"])
     dd = np.abs(gc - ref)
     record("vitb_attention_context_flips", bits=bits, flip_fraction=np.mean(dd != 0), max_step=dd.max())
-    assert dd.max() <= 1 and np.mean(dd != 0) < 0.05, (int(dd.max()), float(np.mean(dd != 0)))
+    assert dd.max() <= 1 and np.mean(dd != 0) < 1e-4, (int(dd.max()), float(np.mean(dd != 0)))   # measured 3.3e-5 (10 codes)
     # the two-GEMM route of the executor's fallback gives the oracle's P.V arithmetic as well
     qP = QTensor(P_ref, bits, sp, None if zp is None else np.int64(zp))
     qV = QTensor(vc, bits, sv, None if zv is None else np.int64(zv))
@@ -356,7 +356,7 @@ def test_teacher_forced_mlp1_gelu(bits):
     want = c.codes(out).reshape(B * S, -1)
     d = np.abs(got - want)
     record("vitb_gelu_flips", bits=bits, flip_fraction=np.mean(d != 0), max_step=d.max())
-    assert d.max() <= 1 and np.mean(d != 0) < 5e-3, (int(d.max()), float(np.mean(d != 0)))
+    assert d.max() <= 1 and np.mean(d != 0) < 4e-5, (int(d.max()), float(np.mean(d != 0)))       # measured 1.07e-5 (13 codes)
     h = c.env[L0 + "/intermediate/dense/Add_output_0"].a.astype(np.float64).reshape(B * S, -1)      # exact input of the chain
     g64 = (rq.erf_poly((h / 1.4142135381698608).astype(np.float32)).astype(np.float64) + 1.0) * h * 0.5
     assert contract_excess(got, g64, s, None if z is None else int(z), bits) <= 1e-3
