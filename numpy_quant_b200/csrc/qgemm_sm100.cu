@@ -1558,7 +1558,8 @@ static int qgemm_run(const int8_t* A, const int8_t* B, void* Cout, int64_t M, in
         const long double za = (long double)llabs(p.zp.zp_a), zb = (long double)llabs(p.zp.zp_b);
         const long double bound = 16384.0L * K + 128.0L * K * (za + zb) + za * zb * K;
         static const bool no_fast = getenv("NQ_NO_FAST_REQUANT") != nullptr;      // A/B switch
-        p.req_rows = !no_fast && qmode != 2 && bound < 536870000.0L && N % 16 == 0 && ldc % 16 == 0 && stride_c % 16 == 0 &&
+        // ragged N: the last 16-column step stores into the row's padding, which the caller provides (ldc >= round_up(N, 16))
+        p.req_rows = !no_fast && qmode != 2 && bound < 536870000.0L && ldc >= (N + 15) / 16 * 16 && ldc % 16 == 0 && stride_c % 16 == 0 &&
                      ((uintptr_t)Cout % 16 == 0) && p.c_inner == 1 && M < (1ll << 31);
         if (p.req_rows) {
             p.q_S = (uint32_t)M;                                          // one "image" of M rows, one "head" of N columns

@@ -276,7 +276,8 @@ def qgemm(a: Operand, b: Operand, mode: int = _lib.EPI_RAW, scale: float = 1.0,
     dtype = {_lib.EPI_RAW: torch.int32, _lib.EPI_DEQUANT: torch.float32, _lib.EPI_REQUANT: torch.int8}[mode]
     # 32-bit outputs get rows padded to a 16-byte multiple so the epilogue can use its vector-store
     # path for ragged N (attention scores, N = 197); callers see a [batch, M, N] view of it
-    ldn = N if (simt or mode == _lib.EPI_REQUANT or N % 4 == 0) else round_up(N, 4)
+    # (int8 REQUANT rows: padded to 16 bytes so that the thread-per-row epilogue applies to ragged N, e.g. 1000 classes)
+    ldn = N if (simt or N % 16 == 0) else round_up(N, 16) if mode == _lib.EPI_REQUANT else N if N % 4 == 0 else round_up(N, 4)
     if heads:
         assert batch % heads == 0 and N % 4 == 0 and mode != _lib.EPI_REQUANT and not simt and residual is None
         out = torch.empty((batch // heads, M, heads, N), dtype=dtype, device=a.data.device)
