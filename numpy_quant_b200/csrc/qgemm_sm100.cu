@@ -246,6 +246,7 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
     uint64_t* tfull_bar = bars + 2 * C::STAGES;
     uint64_t* tempty_bar = bars + 2 * C::STAGES + 8;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 16);
+    volatile uint32_t* pace = tmem_slot + 1;                              // tiles issued by the MMA warp (residual prefetcher)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -270,6 +271,7 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
             // one arrival per epilogue warp of the group (pair: the warps of both CTAs arrive on the leader's barrier)
             mbar_init(smem_u32(tempty_bar + i), (TWO ? 2 : 1) * NUM_EPI_WARPS / C::GROUPS);
         }
+        *pace = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -423,12 +425,42 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                 if (leader) {
                     if constexpr (TWO) tc_commit_pair(smem_u32(tfull_bar + acc));   // both CTAs' epilogues
                     else tc_commit(smem_u32(tfull_bar + acc));            // accumulator ready
+                    if constexpr (EMODE == EM_DEQ_WIDE_RES && !TWO) *pace = mli + 1;
                     if (!NQ_DBG(256)) NQ_TRACE(mli, 3);
                 }
                 if (++acc == C::NACC) {
                     acc = 0;
                     acc_phase ^= 1;
                 }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 3) {
+        // ===================== residual prefetcher (float32 + residual epilogue only) =====================
+        // The epilogue warps can hold only a few residual loads in flight each (registers), so the residual stream's
+        // HBM latency was exposed about four times per tile: the output projection took 86 us against 45 us without the
+        // residual Add (benchmarks/probe_residual_gemm.py).  This otherwise idle warp pulls the residual block of the
+        // tile that is being multiplied into L2 (one bulk prefetch per row), one tile ahead of the epilogue and paced by
+        // the accumulator barriers, so that the epilogue's loads are L2 hits.
+        // (not for CTA pairs: the K >= 1024 launches they serve are not bound by the residual stream -- MLP-2 measured
+        // 113.8 us without and 117.6 us with the prefetcher)
+        if constexpr (EMODE == EM_DEQ_WIDE_RES && !TWO) {
+            uint32_t li = 0;
+            for (uint32_t ts = tile_first; ts < total_tiles; ts += tile_step, ++li) {
+                const uint32_t t = p.reverse ? total_tiles - 1u - ts : ts;
+                const uint32_t b = fd_div(t, fd_tpb), r = t - b * tiles_per_batch;
+                const uint32_t mt = fd_div(r, fd_nt), nt = r - mt * n_tiles;
+                const int64_t m0 = (int64_t)mt * BMT + cta_rank * BM, n0 = (int64_t)nt * BN;
+                const int64_t cols = (p.N - n0) < BN ? (p.N - n0) : BN;
+                const float* base = p.residual + (int64_t)b * p.stride_r + n0;
+                // pace: the MMA warp has issued tile li - 1 (a monotonic counter: this warp may lag without harm)
+                for (uint32_t spin = 0; li >= 1; ++spin) {
+                    if (*pace >= li) break;
+                    __nanosleep(200);
+                    if (spin > (1u << 24)) __trap();
+                }
+                for (int rr = lane; rr < BM; rr += 32)
+                    if (m0 + rr < p.M) prefetch_l2_bulk(base + (m0 + rr) * p.ldr, (uint32_t)(cols * 4));
             }
         }
         __syncwarp();

@@ -185,6 +185,10 @@ __device__ __forceinline__ int4 ldg_v4(const void* p) {
     asm volatile("ld.global.nc.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
     return r;
 }
+// Pull `bytes` (multiple of 16, 16-byte aligned address) of global memory into L2; no destination, no completion
+__device__ __forceinline__ void prefetch_l2_bulk(const void* gptr, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
+}
 // 16 bytes from a 32-bit shared-memory address (no generic -> shared conversion in the loop that uses it); ordered
 // after the shared-memory stores that precede it in program order ("memory")
 __device__ __forceinline__ int4 lds_v4(uint32_t saddr) {
