@@ -398,6 +398,22 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                                            (kb > 0 || k > 0) ? 1u : 0u);
                                 }
                             }
+                        } else if (!no_mma && ksteps == BK / UMMA_K) {
+                            // full K block (every block but a ragged last one): four unconditional MMAs, nothing else --
+                            // the issuing warp's own instruction stream must stay well under the 512 cycles the tensor
+                            // pipe needs for them, or the pipe idles (the general loop below costs ~110 instructions)
+                            const uint64_t adesc = make_smem_desc(sa), bdesc = make_smem_desc(sb);
+                            if constexpr (TWO) {
+                                mma_i8_pair(d_tmem, adesc, bdesc, idesc, kb > 0 ? 1u : 0u);
+                                mma_i8_pair(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
+                                mma_i8_pair(d_tmem, adesc + 4, bdesc + 4, idesc, 1u);
+                                mma_i8_pair(d_tmem, adesc + 6, bdesc + 6, idesc, 1u);
+                            } else {
+                                mma_i8(d_tmem, adesc, bdesc, idesc, kb > 0 ? 1u : 0u);
+                                mma_i8(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
+                                mma_i8(d_tmem, adesc + 4, bdesc + 4, idesc, 1u);
+                                mma_i8(d_tmem, adesc + 6, bdesc + 6, idesc, 1u);
+                            }
                         } else if (!no_mma) {
                             const uint64_t adesc = make_smem_desc(sa), bdesc = make_smem_desc(sb);
 #pragma unroll
