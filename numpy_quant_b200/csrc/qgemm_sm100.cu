@@ -57,6 +57,7 @@ struct GemmParams {
     int a_batched, b_batched;        // 0 -> operand shared across the batch (TMA batch coord 0)
     int mode;
     int fast32;                      // zero-point arithmetic provably fits int32 (host-checked bound)
+    int fast24;                      // ... and |acc - zero-point terms| < 2^24: int -> float conversion is exact
     float scale;
     AccZp zp;
     const float* bias_f32;
@@ -610,7 +611,8 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                 tc_fence_after();
                 if (warp == 4 && lane == 0 && !NQ_DBG(256)) NQ_TRACE(li, 5);
                 const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
-                const int rm = 0x4B400000 - (int32_t)rowterm;             // int -> float magic folded into the row term
+                const bool f24 = !REQ && p.fast24 != 0;                   // host bound: exact int -> float conversion (I2FP)
+                const int rm = (f24 ? 0 : 0x4B400000) - (int32_t)rowterm; // else: int -> float magic folded into the row term
                 int rs_acc = 0;                                           // ROWS: code sum of the current head
                 uint32_t rs_nh = 0xffffffffu;
                 auto flush_rowsum = [&]() {
@@ -652,12 +654,23 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                     tmem_ld_wait();
                     int x[16];
                     uint32_t bad = 0;
+                    float f[16];
+                    if (f24) {
+                        // |acc - zero-point terms| < 2^24 proved on the host: the plain conversion is exact, no window test
+                        const float2 sc2 = make_float2(p.scale, p.scale);
+#pragma unroll
+                        for (int j = 0; j < 16; j += 2) {
+                            float2 t = make_float2(__int2float_rn((int)v[j] + rm - ct[j]), __int2float_rn((int)v[j + 1] + rm - ct[j + 1]));
+                            if constexpr (EMODE != EM_Q8_GELU) t = __fmul2_rn(t, sc2);       // GELU: scaled below
+                            f[j] = t.x;
+                            f[j + 1] = t.y;
+                        }
+                    } else {
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
                         x[j] = (int)v[j] + rm - ct[j];
                         bad |= (uint32_t)(x[j] ^ 0x4B000000);
                     }
-                    float f[16];
                     if constexpr (REQ) {
                         if (__builtin_expect(wide_bias || __any_sync(0xffffffffu, (bad & 0xFF800000u) != 0), 0)) {
                             // general 64-bit route for this 16-column step (whole warp: the store below is per thread)
@@ -693,6 +706,7 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                             f[j] = t.x;
                             f[j + 1] = t.y;
                         }
+                    }
                     }
                     const bool gelu_scaled = (bad & 0xFF800000u) != 0;    // warp-divergent only on the rare slow route
                     // Quantizer tail, two columns per instruction: the quotient t = y / s_out (ROWS / COLS: correctly
@@ -1473,6 +1487,8 @@ static int qgemm_run(const int8_t* A, const int8_t* B, void* Cout, int64_t M, in
         p.fast32 = (ep->mode == NQ_EPI_DEQUANT || ep->mode == NQ_EPI_QUANT || ep->mode == NQ_EPI_SOFTMAX_QUANT ||
                     ep->mode == NQ_EPI_GELU_QUANT) &&
                    bound < 2147483000.0L;
+        static const bool no24 = getenv("NQ_NO_I2F_EPILOGUE") != nullptr;         // A/B switch
+        p.fast24 = !no24 && p.fast32 && bound < 16777216.0L;
     }
     if (ep->mode == NQ_EPI_SOFTMAX_QUANT) {
         NQ_REQUIRE(p.fast32, "nq_qgemm_s8: SOFTMAX epilogue needs the 32-bit zero-point bound");
