@@ -646,6 +646,26 @@ class QModel(Model):
             return d[1]
         return value.data.dequantize()
 
+    def _row_gather_after(self, node: Node):
+        """(Gather node, index) if the only consumer of this LayerNormalization (last axis, 3-D input) is a Gather along
+        axis 1 with one constant scalar index and the normalised value is not a model output, else None."""
+        out = node.outputs[0]
+        x = node.inputs[0].data
+        if out in self.outputs or len(out.outputs) != 1 or not isinstance(x, FTensor) or x.device_tensor.dim() != 3 \
+                or node.attrs.get("axis", -1) not in (-1, 2):
+            return None
+        g = out.outputs[0]
+        if g.op != "Gather" or g.inputs[0] is not out or int(g.attrs.get("axis", 0)) != 1:
+            return None
+        idx = g.inputs[1].data
+        if not isinstance(idx, ITensor) or np.asarray(idx.data).ndim != 0:
+            return None
+        i = int(np.asarray(idx.data))
+        n = int(x.device_tensor.shape[1])
+        if i < 0:
+            i += n
+        return (g, i) if 0 <= i < n else None
+
     def _conv_input_tiling(self, value: Value):
         """(kh, kw) if every Conv consuming `value` (see _conv_input_pads) has kernel == strides == (kh, kw), else None."""
         kernel = None
@@ -1209,6 +1229,20 @@ class QModel(Model):
                 tock("TinyqDequant", t0)
                 t0 = tick()
                 outputs_data = onnx_operator_implementation(node.op, [node.inputs[0].data, node.inputs[1].data, b], node.attrs)
+                tock(node.op, t0)
+            elif fused and node.op == "LayerNormalization" and isinstance(node.inputs[0].data, FTensor) \
+                    and (gsel := self._row_gather_after(node)) is not None:
+                # LayerNormalization -> Gather(axis=1, one index) (the class token in front of the classifier): the
+                # normalisation is row-wise, so gathering first gives the same rows with the same arithmetic and the
+                # other S - 1 rows of the last LayerNorm are never produced (nothing else reads them: retain=False)
+                gnode, idx = gsel
+                t0 = tick()
+                g, b = as_float(node.inputs[1]), as_float(node.inputs[2])
+                xt = node.inputs[0].data.device_tensor
+                sub = FTensor(K.materialize(xt[:, idx:idx + 1, :]))
+                y = onnx_operator_implementation(node.op, [sub, g, b], node.attrs)[0]
+                stash[gnode.name] = FTensor(y.device_tensor.reshape(xt.shape[0], xt.shape[2]))
+                outputs_data = [None]
                 tock(node.op, t0)
             elif fused and node.op == "LayerNormalization" and name in plan["quantize_out"] \
                     and isinstance(node.inputs[0].data, FTensor) \
