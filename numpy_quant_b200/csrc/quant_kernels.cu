@@ -665,6 +665,14 @@ extern "C" int nq_quantize_f32(const float* x, int64_t n, int bit_width, float s
     return NQ_OK;
 }
 
+// Grid of the warp-per-unit accumulator kernels (unit = one row x 512 columns): one unit per warp while that is at most
+// four waves of resident CTAs (a grid-stride loop with 3.46 passes per warp leaves the last pass half empty at 4096^2),
+// the persistent grid for large problems.
+static int acc_units_grid(int64_t rows, int64_t n4) {
+    const int64_t units = rows * ((n4 + 127) / 128), ctas = (units + 7) / 8, cap = (int64_t)sm_count() * 8;
+    return (int)std::max<int64_t>(1, ctas <= 4 * cap ? ctas : cap);
+}
+
 extern "C" int nq_transpose_s8(const int8_t* in, int64_t batch, int64_t R, int64_t Cc, int64_t ld_in, int64_t stride_in,
                                int8_t* out, int64_t ld_out, int64_t stride_out, void* stream) {
     NQ_REQUIRE(batch > 0 && R > 0 && Cc > 0, "nq_transpose_s8: empty problem");
@@ -776,7 +784,7 @@ extern "C" int nq_dequantize_acc(const int32_t* acc, int64_t batch, int64_t M, i
     const bool vec = N % 4 == 0 && ldacc % 4 == 0 && ((uintptr_t)acc % 16 == 0) && ((uintptr_t)out % 16 == 0) && N / 4 < (1ll << 31) &&
                      (!z.use_col || (((uintptr_t)z.colsum_b % 16 == 0) && z.cs_stride % 4 == 0));
     if (vec)
-        acc_post_fast_kernel<1><<<stream_grid(batch * M * (N / 4), 256), 256, 0, (cudaStream_t)stream>>>(
+        acc_post_fast_kernel<1><<<acc_units_grid(batch * M, N / 4), 256, 0, (cudaStream_t)stream>>>(
             acc, batch * M, M, (int)(N / 4), ldacc, scale, z, 0.f, 0.f, 0.f, 0.f, out);
 
     else
@@ -802,7 +810,7 @@ extern "C" int nq_requantize_acc(const int32_t* acc, int64_t batch, int64_t M, i
         const bool vec = N % 4 == 0 && ldacc % 4 == 0 && ((uintptr_t)acc % 16 == 0) && ((uintptr_t)out % 4 == 0) && N / 4 < (1ll << 31) &&
                          (!z.use_col || (((uintptr_t)z.colsum_b % 16 == 0) && z.cs_stride % 4 == 0));
         if (vec) {
-            const int g4 = stream_grid(batch * M * (N / 4), 256);
+            const int g4 = acc_units_grid(batch * M, N / 4);
             const bool f64 = has_out_zp && !(out_zp > -(1 << 20) && out_zp < (1 << 20));
             if (!f64 && !bias_q) {
                 acc_post_fast_kernel<2><<<g4, 256, 0, s>>>(acc, batch * M, M, (int)(N / 4), ldacc, scale, z, inv,
