@@ -158,6 +158,11 @@ def _gloo_worker(rank, ws, port, full, out):
                           shard.reshape(shard.shape[0], -1).max(1).values], dim=1)
         red = nqd.allreduce_minmax(mm).numpy()
         gathered = nqd.gather_outputs(shard.numpy().transpose(1, 0, 2))
+        # group=False: rank-local statistics, no collective -- only rank 0 calls it here, as bench.py's single-rank
+        # configurations do; a collective issued by one rank would dead-lock against the barrier that follows
+        local = nqd.allreduce_minmax(mm, group=False) if rank == 0 else mm
+        assert local is mm
+        dist.barrier()
         out.put((rank, red, None if gathered is None else gathered.shape))
     finally:
         dist.destroy_process_group()
