@@ -639,12 +639,11 @@ def run_own_arm(args) -> None:
     # captured shapes of the step); None if the summary file is missing
     traffic, traffic_note = None, None
     try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_gemm_dram_traffic.json")))
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r02_gemm_dram_traffic.json")))
         n = sum(tr["launches_per_step"].values())
         traffic = sum(tr["per_launch_bytes"][k] * c for k, c in tr["launches_per_step"].items()) / n
         traffic_note = (f"mean DRAM bytes per launch over the {n} of {len(gemm) // max(args.steps, 1)} GEMM launches per step "
-                        "whose shape has an ncu --set full capture (profiles/r01_gemm_dram_traffic.json: round-1 captures, the operand "
-                        "and output bytes of these shapes have not changed)")
+                        "whose shape has an ncu --set full capture (profiles/r02_gemm_dram_traffic.json)")
     except Exception:
         pass
     achieved = gemm_ops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
